@@ -1,0 +1,210 @@
+/*
+ * rspl_ba.h — C-ABI of the B200-native point+line bundle-adjustment solver.
+ *
+ * Drop-in boundary for the reference's g2o_optimization module (RSPL-SLAM):
+ *   LocalmapOptimization(...)  include/g2o_optimization/g2o_optimization.h:15-18  ->  rspl_ba_local_batch()
+ *   FrameOptimization(...)     include/g2o_optimization/g2o_optimization.h:20-22  ->  rspl_ba_frame_batch()
+ * The reference has no FFI for this path (plain C++ free functions linked into air_vo_lib,
+ * CMakeLists.txt:57-77); the binding a maintainer adds is the header-only C++ shim
+ * include/rspl_ba/g2o_optimization_shim.hpp, which keeps the two signatures and flattens the
+ * reference containers (include/g2o_optimization/types.h:19-174) into the structure-of-arrays
+ * batches below. See INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes, fp64 values, int32 indices, uint8 flags; caller owns every buffer;
+ *    the library never keeps a caller pointer after a call returns.
+ *  - "planes": an array documented as [k][n] is k contiguous planes of n values (component-major
+ *    structure-of-arrays), so device loads coalesce and H2D is a straight copy.
+ *  - poses cross the boundary as the caller's Twc (Pose3d: p, q) with Eigen's quaternion storage
+ *    order x,y,z,w (types.h:19-35); inversion to the optimiser's Tcw and back happens on the
+ *    device exactly as g2o_optimization.cc:42,237-239,271,391-393 do.
+ *  - vertex references inside a window/frame are *local indices* into that window's slice of the
+ *    vertex arrays, in ascending-id (std::map) order; the shim compacts ids.
+ *  - every function returns RSPL_BA_OK (0) or a negative RsplBaStatus; no exceptions, no aborts.
+ *  - one context per calling thread; a context owns a non-blocking CUDA stream and grow-only
+ *    device workspaces; no call performs a device-wide synchronisation.
+ *  - there is NO CPU fallback: without a CUDA device every entry point fails with
+ *    RSPL_BA_ERR_CUDA.
+ */
+#ifndef RSPL_BA_H_
+#define RSPL_BA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSPL_BA_VERSION 100 /* 0.1.0 */
+
+typedef enum RsplBaStatus {
+  RSPL_BA_OK = 0,
+  RSPL_BA_ERR_INVALID = -1,     /* malformed input (null pointer, index out of range, bad offsets) */
+  RSPL_BA_ERR_CUDA = -2,        /* CUDA runtime error / no device */
+  RSPL_BA_ERR_UNSUPPORTED = -3, /* problem exceeds a documented limit of this path */
+  RSPL_BA_ERR_STATE = -4        /* staged call out of order (solve before upload, ...) */
+} RsplBaStatus;
+
+typedef struct RsplBaContext RsplBaContext;
+
+/* OptimizationConfig (include/read_configs.h:50-56; `rate` is never read by the optimiser) plus the
+ * schedules the reference hard-codes. */
+typedef struct RsplBaOptions {
+  double thr_mono_point;   /* cfg.mono_point   (chi2 threshold; Huber delta = (float)sqrt) */
+  double thr_stereo_point; /* cfg.stereo_point */
+  double thr_mono_line;    /* cfg.mono_line    */
+  double thr_stereo_line;  /* cfg.stereo_line  */
+  int32_t local_iters_pass1; /* 10, g2o_optimization.cc:173 */
+  int32_t local_iters_pass2; /*  5, g2o_optimization.cc:210 */
+  int32_t frame_rounds;      /*  4, g2o_optimization.cc:339 */
+  int32_t frame_iters;       /* 10, g2o_optimization.cc:336 */
+  int32_t stereo_bf_float;   /* 1: g2o's EdgeStereoSE3ProjectXYZ::cam_project(xyz, const float& bf) */
+  int32_t reserved;
+} RsplBaOptions;
+
+/* Per-problem statistics (optional outputs). */
+typedef struct RsplBaStats {
+  int32_t iters[4];          /* outer LM iterations per pass (local: 2 used) / per round (frame) */
+  int32_t trials[4];         /* inner LM trials per pass / round */
+  int64_t edges_linearized;  /* sum over buildSystem passes of active edges */
+  int64_t edges_evaluated;   /* sum over error-evaluation passes of active edges */
+  double final_chi2;         /* robust chi2 of the last accepted state of the last pass */
+  double final_lambda;
+} RsplBaStats;
+
+/* ---------------------------------------------------------------------------------------------
+ * FrameOptimization batch (pose-only): n_frames independent frames.
+ * Per frame f: mono edges  [mono_begin[f],   mono_begin[f+1])   (VectorOfMonoPointConstraints order)
+ *              stereo edges[stereo_begin[f], stereo_begin[f+1]) (VectorOfStereoPointConstraints order)
+ * Each edge carries its world point Xw (the reference copies points[id].p into the edge,
+ * g2o_optimization.cc:305,328).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct RsplFrameBatch {
+  int32_t n_frames;
+  int32_t n_cameras;
+  const double* cameras;        /* [n_cameras][5] fx, fy, cx, cy, bf (camera.h:25-29) */
+  const double* pose_twc;       /* [7][n_frames] planes px,py,pz,qx,qy,qz,qw */
+  const int32_t* mono_begin;    /* [n_frames+1] */
+  const int32_t* stereo_begin;  /* [n_frames+1] */
+  const double* mono_meas;      /* [2][n_mono]   x_left, y_left */
+  const double* mono_xw;        /* [3][n_mono] */
+  const int32_t* mono_cam;      /* [n_mono] or NULL (all 0) */
+  const uint8_t* mono_inlier;   /* [n_mono] initial ->inlier flags, or NULL (all 1; map_builder.cc:569) */
+  const double* stereo_meas;    /* [3][n_stereo] x_left, y_left, x_right */
+  const double* stereo_xw;      /* [3][n_stereo] */
+  const int32_t* stereo_cam;    /* [n_stereo] or NULL */
+  const uint8_t* stereo_inlier; /* [n_stereo] or NULL */
+} RsplFrameBatch;
+
+typedef struct RsplFrameBatchResult {
+  double* pose_twc;        /* [7][n_frames] optimised Twc */
+  uint8_t* mono_inlier;    /* [n_mono] */
+  uint8_t* stereo_inlier;  /* [n_stereo] */
+  int32_t* num_inliers;    /* [n_frames] FrameOptimization's return value, or NULL */
+  RsplBaStats* stats;      /* [n_frames] or NULL */
+} RsplFrameBatchResult;
+
+/* ---------------------------------------------------------------------------------------------
+ * LocalmapOptimization batch: n_windows independent local windows.
+ * Window w owns poses [pose_begin[w], pose_begin[w+1]) etc.; edge vertex indices are local to
+ * the window. Edges may arrive in any order (the reference happens to emit them landmark-major,
+ * map.cc:609-707; the library builds its own landmark-major and pose-major CSR on the device).
+ * Line3d is g2o::Line3D storage [w(3), d(3)] (types.h:108-121).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct RsplLocalBatch {
+  int32_t n_windows;
+  int32_t n_cameras;
+  const double* cameras;          /* [n_cameras][5] */
+  const int32_t* pose_begin;      /* [n_windows+1] */
+  const int32_t* point_begin;     /* [n_windows+1] */
+  const int32_t* line_begin;      /* [n_windows+1] */
+  const int32_t* mono_pt_begin;   /* [n_windows+1] */
+  const int32_t* stereo_pt_begin; /* [n_windows+1] */
+  const int32_t* mono_ln_begin;   /* [n_windows+1] */
+  const int32_t* stereo_ln_begin; /* [n_windows+1] */
+  const double* pose_twc;         /* [7][n_poses] */
+  const uint8_t* pose_fixed;      /* [n_poses] Pose3d::fixed */
+  const double* point_xyz;        /* [3][n_points] */
+  const double* line_wd;          /* [6][n_lines] */
+  /* mono point edges */
+  const int32_t* mp_pose;  const int32_t* mp_point; const int32_t* mp_cam; /* mp_cam may be NULL */
+  const double* mp_meas;          /* [2][n_mp] */
+  /* stereo point edges */
+  const int32_t* sp_pose;  const int32_t* sp_point; const int32_t* sp_cam;
+  const double* sp_meas;          /* [3][n_sp] */
+  /* mono line edges */
+  const int32_t* ml_pose;  const int32_t* ml_line;  const int32_t* ml_cam;
+  const double* ml_meas;          /* [4][n_ml] x1,y1,x2,y2 (left) */
+  /* stereo line edges */
+  const int32_t* sl_pose;  const int32_t* sl_line;  const int32_t* sl_cam;
+  const double* sl_meas;          /* [8][n_sl] left x1,y1,x2,y2, right x1,y1,x2,y2 (map.cc:686) */
+} RsplLocalBatch;
+
+typedef struct RsplLocalBatchResult {
+  double* pose_twc;    /* [7][n_poses] */
+  double* point_xyz;   /* [3][n_points] */
+  double* line_wd;     /* [6][n_lines] */
+  uint8_t* mp_inlier;  /* [n_mp] */
+  uint8_t* sp_inlier;  /* [n_sp] */
+  uint8_t* ml_inlier;  /* [n_ml] */
+  uint8_t* sl_inlier;  /* [n_sl] */
+  RsplBaStats* stats;  /* [n_windows] or NULL */
+} RsplLocalBatchResult;
+
+/* --- lifecycle ------------------------------------------------------------------------------ */
+int rspl_ba_version(void);
+void rspl_ba_default_options(RsplBaOptions* opt); /* thresholds 50/75/50/75 (configs_euroc.yaml:57-60), 10/5, 4x10 */
+/* device < 0: current device. stream: a cudaStream_t to run on, or NULL to create an own
+ * non-blocking stream. */
+int rspl_ba_create(int device, void* stream, RsplBaContext** out);
+void rspl_ba_destroy(RsplBaContext* ctx);
+const char* rspl_ba_last_error(const RsplBaContext* ctx);
+void* rspl_ba_stream(const RsplBaContext* ctx); /* the cudaStream_t all work of this context is ordered on */
+int rspl_ba_device(const RsplBaContext* ctx);
+
+/* --- FrameOptimization ---------------------------------------------------------------------- */
+/* One call = upload + solve + download with host buffers (what the shim uses). */
+int rspl_ba_frame_batch(RsplBaContext* ctx, const RsplFrameBatch* in, const RsplBaOptions* opt,
+                        RsplFrameBatchResult* out);
+/* Staged variant: inputs stay resident in HBM; solve may be repeated (it restarts from the
+ * uploaded inputs every time); all three are ordered on the context stream, upload/download
+ * block the host until their copies finished, solve is asynchronous. */
+int rspl_ba_frame_batch_upload(RsplBaContext* ctx, const RsplFrameBatch* in);
+int rspl_ba_frame_batch_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
+int rspl_ba_frame_batch_download(RsplBaContext* ctx, RsplFrameBatchResult* out);
+
+/* --- LocalmapOptimization ------------------------------------------------------------------- */
+int rspl_ba_local_batch(RsplBaContext* ctx, const RsplLocalBatch* in, const RsplBaOptions* opt,
+                        RsplLocalBatchResult* out);
+int rspl_ba_local_batch_upload(RsplBaContext* ctx, const RsplLocalBatch* in);
+int rspl_ba_local_batch_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
+int rspl_ba_local_batch_download(RsplBaContext* ctx, RsplLocalBatchResult* out);
+
+/* --- pinned host memory (optional; any host pointer is accepted, pinned ones copy faster) ---- */
+void* rspl_ba_alloc_pinned(size_t bytes);
+void rspl_ba_free_pinned(void* p);
+
+/* --- introspection for benchmarks ----------------------------------------------------------- */
+/* Number of kernel launches issued by this context since creation. */
+int64_t rspl_ba_launch_count(const RsplBaContext* ctx);
+/* Block the host until all work queued on the context stream has finished. */
+int rspl_ba_sync(RsplBaContext* ctx);
+
+/* --- unit-level device entry points (used by the parity tests) ------------------------------- */
+/* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
+ * line, 3 stereo line. pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]
+ * (3 used for points); meas [n][8]; cam5 [5]. Outputs (host): err [n][4], Jl [n][16], Jp [n][24]
+ * (row-major dim x ld / dim x 6), chi2 [n]. */
+int rspl_ba_eval_edges(RsplBaContext* ctx, int edge_type, int32_t n, const double* pose7,
+                       const double* lm, const double* meas, const double* cam5,
+                       int32_t stereo_bf_float, double* err, double* Jl, double* Jp, double* chi2);
+/* Applies the manifold updates on the device: kind 0 pose (state 7, update 6), 1 point (3,3),
+ * 2 line (6,4). state [n][7], upd [n][6], out [n][7]. */
+int rspl_ba_oplus(RsplBaContext* ctx, int kind, int32_t n, const double* state, const double* upd,
+                  double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSPL_BA_H_ */

@@ -1,0 +1,150 @@
+/*
+ * oracle/oracle.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * C interface of the CPU oracle: a dependency-free restatement of the algorithm the
+ * reference's g2o_optimization module runs (reference: src/g2o_optimization/g2o_optimization.cc:21-397,
+ * edge_project_line.cc:21-42, edge_project_stereo_line.cc:22-51, vertex_line3d.h:26-43) plus the
+ * slice of g2o it exercises (un-vendored by the reference; semantics per SURVEY.md §9).
+ *
+ * PARITY UNPINNED: the reference ships no tests / golden vectors for this path and g2o + Eigen
+ * are not installable here, so this oracle is checked only against (i) closed-form known-answer
+ * geometry and (ii) an independent numpy restatement (oracle/np_oracle.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library. The product (rspl_slam_b200/, include/rspl_ba.h) never links or calls it.
+ *
+ * Data model mirrors the reference's boundary types (include/g2o_optimization/types.h): vertices
+ * are addressed by *id* (std::map keys), constraints carry id_pose / id_point / id_camera and an
+ * in/out `inlier` flag, everything is mutated in place.
+ */
+#ifndef RSPL_ORACLE_H_
+#define RSPL_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcTraceRow {
+  int32_t pass;      /* local BA: 0/1; pose-only: round index */
+  int32_t iter;      /* outer LM iteration */
+  int32_t trial;     /* inner trial */
+  int32_t accepted;  /* 1 = step kept */
+  double chi_before; /* currentChi */
+  double chi_after;  /* tempChi */
+  double lambda;     /* lambda used for this trial */
+  double rho;
+} OrcTraceRow;
+
+typedef struct OrcStats {
+  int32_t iters[4];        /* outer iterations executed per pass / round */
+  int32_t trials[4];       /* inner trials per pass / round */
+  int64_t edges_linearized;/* sum over buildSystem calls of active edges */
+  int64_t edges_evaluated; /* sum over computeActiveErrors calls of active edges */
+  double final_chi2;       /* activeRobustChi2 of the last accepted state of the last pass */
+  int32_t n_trace;         /* rows written to trace (<= trace_cap) */
+  int32_t trace_cap;
+  OrcTraceRow* trace;      /* optional, caller-owned */
+} OrcStats;
+
+/* Mirrors OptimizationConfig (include/read_configs.h:50-56) + the schedules hard-coded in
+ * g2o_optimization.cc:173,210,336,339. */
+typedef struct OrcConfig {
+  double mono_point, stereo_point, mono_line, stereo_line;
+  int32_t iters_pass1, iters_pass2; /* 10, 5 */
+  int32_t rounds, iters_round;      /* 4, 10 */
+  int32_t stereo_bf_float;          /* 1: EdgeStereoSE3ProjectXYZ::cam_project takes bf as float (g2o) */
+} OrcConfig;
+
+typedef struct OrcLocalProblem {
+  /* MapOfPoses (types.h:19-35): id -> {fixed, p, q(x,y,z,w)}; ids ascending */
+  int32_t n_poses;
+  const int32_t* pose_id;
+  double* pose_p; /* [n][3] in/out, Twc */
+  double* pose_q; /* [n][4] x,y,z,w in/out */
+  const uint8_t* pose_fixed;
+  /* MapOfPoints3d (types.h:38-51) */
+  int32_t n_points;
+  const int32_t* point_id;
+  double* point_p; /* [n][3] in/out */
+  /* MapOfLine3d (types.h:108-121): g2o::Line3D = [w(3), d(3)] */
+  int32_t n_lines;
+  const int32_t* line_id;
+  double* line_L; /* [n][6] in/out */
+  /* camera_list: fx, fy, cx, cy, bf */
+  int32_t n_cams;
+  const double* cams; /* [n][5] */
+  /* constraints (types.h:54-174), insertion order */
+  int32_t n_mono_pt;
+  const int32_t *mp_id_pose, *mp_id_point, *mp_id_cam;
+  const double* mp_kp; /* [n][2] */
+  uint8_t* mp_inlier;
+  int32_t n_stereo_pt;
+  const int32_t *sp_id_pose, *sp_id_point, *sp_id_cam;
+  const double* sp_kp; /* [n][3] */
+  uint8_t* sp_inlier;
+  int32_t n_mono_ln;
+  const int32_t *ml_id_pose, *ml_id_line, *ml_id_cam;
+  const double* ml_l2d; /* [n][4] */
+  uint8_t* ml_inlier;
+  int32_t n_stereo_ln;
+  const int32_t *sl_id_pose, *sl_id_line, *sl_id_cam;
+  const double* sl_l2d; /* [n][8] */
+  uint8_t* sl_inlier;
+} OrcLocalProblem;
+
+typedef struct OrcFrameProblem {
+  /* poses.size()==1 (g2o_optimization.cc:259) */
+  double* pose_p; /* [3] in/out */
+  double* pose_q; /* [4] x,y,z,w in/out */
+  int32_t n_points;
+  const int32_t* point_id;
+  const double* point_p; /* [n][3] */
+  int32_t n_cams;
+  const double* cams;
+  int32_t n_mono_pt;
+  const int32_t *mp_id_point, *mp_id_cam;
+  const double* mp_kp;
+  uint8_t* mp_inlier;
+  int32_t n_stereo_pt;
+  const int32_t *sp_id_point, *sp_id_cam;
+  const double* sp_kp;
+  uint8_t* sp_inlier;
+} OrcFrameProblem;
+
+/* LocalmapOptimization (g2o_optimization.cc:21-252). Returns 0, or <0 on malformed input. */
+int orc_local_ba(OrcLocalProblem* prob, const OrcConfig* cfg, OrcStats* stats);
+/* FrameOptimization (g2o_optimization.cc:256-397). Returns the reference's int (#inliers), <0 on error. */
+int orc_frame_opt(OrcFrameProblem* prob, const OrcConfig* cfg, OrcStats* stats);
+
+/* Batched drivers for the CPU baseline: one problem per OpenMP thread (n_threads<=0: all). */
+int orc_frame_opt_batch(int32_t n, OrcFrameProblem* probs, const OrcConfig* cfg, OrcStats* stats,
+                        int32_t* ret, int32_t n_threads);
+int orc_local_ba_batch(int32_t n, OrcLocalProblem* probs, const OrcConfig* cfg, OrcStats* stats,
+                       int32_t n_threads);
+int orc_max_threads(void);
+
+/* ---- unit-level entry points (per-edge KATs and GPU unit tests) ---- */
+/* pose7 = g2o vertex estimate Tcw as [qx,qy,qz,qw,tx,ty,tz]. */
+void orc_pose_from_twc(const double* p3, const double* q4, double* pose7); /* SE3Quat(q,p).inverse() */
+void orc_pose_to_twc(const double* pose7, double* p3, double* q4);
+void orc_se3_exp(const double* u6, double* pose7);
+void orc_pose_oplus(const double* pose7, const double* u6, double* out7); /* exp(u)*T */
+void orc_line_oplus(const double* L6, const double* v4, double* out6);
+void orc_line_from_cartesian(const double* pv6, double* out6);
+void orc_line_transform(const double* pose7, const double* L6, double* out6);
+/* edge_type: 0 mono point, 1 stereo point, 2 mono line, 3 stereo line (binary edges);
+ * 4 mono pose-only, 5 stereo pose-only (landmark = Xw constant).
+ * cam5 = fx,fy,cx,cy,bf. err[4]; Jl[dim*ld] (ld = 3 points / 4 lines, row-major), Jp[dim*6].
+ * Jacobians follow g2o: analytic for points, numeric central differences
+ * delta=1e-9 for lines (§9.8). Returns the residual dimension. */
+int orc_edge_eval(int edge_type, const double* pose7, const double* lm, const double* meas,
+                  const double* cam5, int stereo_bf_float, double* err, double* Jl, double* Jp);
+/* Huber (§9.5): delta = (float)sqrt(thr); out rho[3] */
+void orc_huber(double chi2, double thr, double* rho3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSPL_ORACLE_H_ */

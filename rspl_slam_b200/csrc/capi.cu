@@ -1,0 +1,532 @@
+// capi.cu — the C-ABI of include/rspl_ba.h: context, device workspaces, validation, launches.
+//
+// Host side of the drop-in boundary for /root/reference/src/g2o_optimization/g2o_optimization.cc
+// (LocalmapOptimization :21-252, FrameOptimization :256-397). Everything numeric happens in the
+// kernels of frame_kernel.cuh / local_kernel.cuh; this file only moves bytes and launches.
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/rspl_ba.h"
+#include "ba_math.cuh"
+#include "frame_kernel.cuh"
+#include "local_kernel.cuh"
+
+static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
+
+namespace {
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// bump allocator over one DevBuf so a batch is a single allocation (256-byte aligned slices:
+// every plane starts 16-byte aligned for 128-bit loads)
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+};
+
+} // namespace
+
+struct RsplBaContext {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  char err[512] = {0};
+  int num_sms = 0;
+  size_t smem_optin = 0;
+
+  // ---- frame batch state
+  DevBuf frame_buf;
+  ba::FrameDev fd{};
+  bool frame_uploaded = false;
+  bool frame_solved = false;
+  int f_n_frames = 0, f_n_mono = 0, f_n_stereo = 0;
+
+  // ---- local batch state
+  DevBuf local_buf;
+  ba::LocalDev ld{};
+  bool local_uploaded = false;
+  bool local_solved = false;
+  int l_n_windows = 0, l_np = 0, l_npt = 0, l_nln = 0, l_n[4] = {0, 0, 0, 0};
+  int l_max_free_poses = 0, l_max_poses = 0;
+
+  // ---- unit-level scratch
+  DevBuf unit_buf;
+};
+
+namespace {
+
+int fail(RsplBaContext* c, int code, const char* fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                              \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return fail(ctx, RSPL_BA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+bool offsets_ok(const int32_t* b, int n) {
+  if (!b || b[0] != 0) return false;
+  for (int i = 0; i < n; ++i)
+    if (b[i + 1] < b[i]) return false;
+  return true;
+}
+
+bool indices_ok(const int32_t* idx, const int32_t* ebeg, const int32_t* vbeg, int n_units) {
+  // every edge of unit u references a vertex in [0, vbeg[u+1]-vbeg[u])
+  for (int u = 0; u < n_units; ++u) {
+    const int nv = vbeg[u + 1] - vbeg[u];
+    for (int e = ebeg[u]; e < ebeg[u + 1]; ++e)
+      if (idx[e] < 0 || idx[e] >= nv) return false;
+  }
+  return true;
+}
+
+bool cams_ok(const int32_t* cam, int n, int n_cameras) {
+  if (!cam) return true;
+  for (int i = 0; i < n; ++i)
+    if (cam[i] < 0 || cam[i] >= n_cameras) return false;
+  return true;
+}
+
+struct SetDevice {
+  int prev = -1;
+  bool ok = true;
+  explicit SetDevice(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~SetDevice() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+ba::FrameOpt make_frame_opt(const RsplBaOptions& o) {
+  ba::FrameOpt f;
+  f.thr_mono = o.thr_mono_point;
+  f.thr_stereo = o.thr_stereo_point;
+  f.delta_mono = (double)(float)sqrt(o.thr_mono_point);     // const float deltaMonoPoint = sqrt(cfg.mono_point) (:282)
+  f.delta_stereo = (double)(float)sqrt(o.thr_stereo_point); // (:283)
+  f.rounds = o.frame_rounds;
+  f.iters = o.frame_iters;
+  return f;
+}
+
+} // namespace
+
+// ================================================================================================
+// lifecycle
+// ================================================================================================
+extern "C" int rspl_ba_version(void) { return RSPL_BA_VERSION; }
+
+extern "C" void rspl_ba_default_options(RsplBaOptions* o) {
+  if (!o) return;
+  o->thr_mono_point = 50.0; // configs/configs_euroc.yaml:57-60
+  o->thr_stereo_point = 75.0;
+  o->thr_mono_line = 50.0;
+  o->thr_stereo_line = 75.0;
+  o->local_iters_pass1 = 10;
+  o->local_iters_pass2 = 5;
+  o->frame_rounds = 4;
+  o->frame_iters = 10;
+  o->stereo_bf_float = 1;
+  o->reserved = 0;
+}
+
+extern "C" int rspl_ba_create(int device, void* stream, RsplBaContext** out) {
+  if (!out) return RSPL_BA_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return RSPL_BA_ERR_CUDA; // no device: the product has no CPU path
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return RSPL_BA_ERR_CUDA;
+  }
+  if (device >= count) return RSPL_BA_ERR_INVALID;
+  RsplBaContext* c = new (std::nothrow) RsplBaContext();
+  if (!c) return RSPL_BA_ERR_CUDA;
+  c->device = device;
+  SetDevice guard(device);
+  if (!guard.ok) {
+    delete c;
+    return RSPL_BA_ERR_CUDA;
+  }
+  if (stream) {
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return RSPL_BA_ERR_CUDA;
+    }
+    c->own_stream = true;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RSPL_BA_ERR_CUDA;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = c;
+  return RSPL_BA_OK;
+}
+
+extern "C" void rspl_ba_destroy(RsplBaContext* c) {
+  if (!c) return;
+  SetDevice guard(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->frame_buf.release();
+  c->local_buf.release();
+  c->unit_buf.release();
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* rspl_ba_last_error(const RsplBaContext* c) { return c ? c->err : "null context"; }
+extern "C" void* rspl_ba_stream(const RsplBaContext* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int rspl_ba_device(const RsplBaContext* c) { return c ? c->device : -1; }
+extern "C" int64_t rspl_ba_launch_count(const RsplBaContext* c) { return c ? c->launches : 0; }
+extern "C" int rspl_ba_sync(RsplBaContext* c) {
+  if (!c) return RSPL_BA_ERR_INVALID;
+  SetDevice guard(c->device);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RSPL_BA_OK;
+}
+
+extern "C" void* rspl_ba_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+extern "C" void rspl_ba_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ================================================================================================
+// FrameOptimization batch
+// ================================================================================================
+extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch* in) {
+  if (!c || !in) return RSPL_BA_ERR_INVALID;
+  c->frame_uploaded = c->frame_solved = false;
+  const int F = in->n_frames;
+  if (F < 0 || in->n_cameras < 1 || !in->cameras) return fail(c, RSPL_BA_ERR_INVALID, "frame batch: bad header");
+  if (F == 0) {
+    c->f_n_frames = c->f_n_mono = c->f_n_stereo = 0;
+    c->frame_uploaded = true;
+    return RSPL_BA_OK;
+  }
+  if (!in->pose_twc || !offsets_ok(in->mono_begin, F) || !offsets_ok(in->stereo_begin, F))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame batch: bad pose pointer or edge offsets");
+  const int nm = in->mono_begin[F], ns = in->stereo_begin[F];
+  if ((nm && (!in->mono_meas || !in->mono_xw)) || (ns && (!in->stereo_meas || !in->stereo_xw)))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame batch: null edge arrays");
+  if (!cams_ok(in->mono_cam, nm, in->n_cameras) || !cams_ok(in->stereo_cam, ns, in->n_cameras))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame batch: id_camera out of range");
+  if (in->n_cameras > 1 && ((nm && !in->mono_cam) || (ns && !in->stereo_cam)))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame batch: several cameras but no per-edge camera index");
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+
+  Arena a;
+  const size_t o_cam = a.take(sizeof(double) * 5 * in->n_cameras);
+  const size_t o_pose = a.take(sizeof(double) * 7 * F);
+  const size_t o_mb = a.take(sizeof(int) * (F + 1));
+  const size_t o_sb = a.take(sizeof(int) * (F + 1));
+  const size_t o_mm = a.take(sizeof(double) * 2 * nm);
+  const size_t o_mx = a.take(sizeof(double) * 3 * nm);
+  const size_t o_mc = a.take(sizeof(int) * nm);
+  const size_t o_mi = a.take(nm);
+  const size_t o_sm = a.take(sizeof(double) * 3 * ns);
+  const size_t o_sx = a.take(sizeof(double) * 3 * ns);
+  const size_t o_sc = a.take(sizeof(int) * ns);
+  const size_t o_si = a.take(ns);
+  // outputs / work
+  const size_t o_op = a.take(sizeof(double) * 7 * F);
+  const size_t o_omi = a.take(nm);
+  const size_t o_osi = a.take(ns);
+  const size_t o_ml = a.take(nm);
+  const size_t o_sl = a.take(ns);
+  const size_t o_ni = a.take(sizeof(int) * F);
+  const size_t o_st = a.take(sizeof(ba::DevStats) * F);
+  CU_TRY(c, c->frame_buf.reserve(a.off));
+  char* base = c->frame_buf.as<char>();
+  cudaStream_t s = c->stream;
+#define H2D(off, src, bytes)                                                                \
+  do {                                                                                      \
+    if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  H2D(o_cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
+  H2D(o_pose, in->pose_twc, sizeof(double) * 7 * F);
+  H2D(o_mb, in->mono_begin, sizeof(int) * (F + 1));
+  H2D(o_sb, in->stereo_begin, sizeof(int) * (F + 1));
+  H2D(o_mm, in->mono_meas, sizeof(double) * 2 * nm);
+  H2D(o_mx, in->mono_xw, sizeof(double) * 3 * nm);
+  if (in->mono_cam) H2D(o_mc, in->mono_cam, sizeof(int) * nm);
+  if (in->mono_inlier) H2D(o_mi, in->mono_inlier, (size_t)nm);
+  H2D(o_sm, in->stereo_meas, sizeof(double) * 3 * ns);
+  H2D(o_sx, in->stereo_xw, sizeof(double) * 3 * ns);
+  if (in->stereo_cam) H2D(o_sc, in->stereo_cam, sizeof(int) * ns);
+  if (in->stereo_inlier) H2D(o_si, in->stereo_inlier, (size_t)ns);
+#undef H2D
+  CU_TRY(c, cudaStreamSynchronize(s)); // caller buffers may be reused after return
+
+  ba::FrameDev& d = c->fd;
+  d.n_frames = F;
+  d.n_cameras = in->n_cameras;
+  d.cameras = (const double*)(base + o_cam);
+  d.pose_twc = (const double*)(base + o_pose);
+  d.mono_begin = (const int*)(base + o_mb);
+  d.stereo_begin = (const int*)(base + o_sb);
+  d.n_mono = nm;
+  d.n_stereo = ns;
+  d.mono_meas = (const double*)(base + o_mm);
+  d.mono_xw = (const double*)(base + o_mx);
+  d.mono_cam = in->mono_cam ? (const int*)(base + o_mc) : nullptr;
+  d.mono_inl_in = in->mono_inlier ? (const uint8_t*)(base + o_mi) : nullptr;
+  d.stereo_meas = (const double*)(base + o_sm);
+  d.stereo_xw = (const double*)(base + o_sx);
+  d.stereo_cam = in->stereo_cam ? (const int*)(base + o_sc) : nullptr;
+  d.stereo_inl_in = in->stereo_inlier ? (const uint8_t*)(base + o_si) : nullptr;
+  d.out_pose_twc = (double*)(base + o_op);
+  d.mono_inl = (uint8_t*)(base + o_omi);
+  d.stereo_inl = (uint8_t*)(base + o_osi);
+  d.mono_lvl = (uint8_t*)(base + o_ml);
+  d.stereo_lvl = (uint8_t*)(base + o_sl);
+  d.num_inliers = (int*)(base + o_ni);
+  d.stats = (void*)(base + o_st);
+  c->f_n_frames = F;
+  c->f_n_mono = nm;
+  c->f_n_stereo = ns;
+  c->frame_uploaded = true;
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_frame_batch_solve(RsplBaContext* c, const RsplBaOptions* opt) {
+  if (!c || !opt) return RSPL_BA_ERR_INVALID;
+  if (!c->frame_uploaded) return fail(c, RSPL_BA_ERR_STATE, "frame_batch_solve before upload");
+  if (opt->frame_rounds < 0 || opt->frame_iters < 1)
+    return fail(c, RSPL_BA_ERR_INVALID, "frame_rounds must be >= 0 and frame_iters >= 1");
+  c->frame_solved = true;
+  if (c->f_n_frames == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  ba::FrameOpt fo = make_frame_opt(*opt);
+  ba::frame_opt_kernel<<<c->f_n_frames, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_frame_batch_download(RsplBaContext* c, RsplFrameBatchResult* out) {
+  if (!c || !out) return RSPL_BA_ERR_INVALID;
+  if (!c->frame_solved) return fail(c, RSPL_BA_ERR_STATE, "frame_batch_download before solve");
+  const int F = c->f_n_frames, nm = c->f_n_mono, ns = c->f_n_stereo;
+  if (F == 0) return RSPL_BA_OK;
+  if (!out->pose_twc || (nm && !out->mono_inlier) || (ns && !out->stereo_inlier))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame result: null output arrays");
+  SetDevice guard(c->device);
+  cudaStream_t s = c->stream;
+  const ba::FrameDev& d = c->fd;
+  CU_TRY(c, cudaMemcpyAsync(out->pose_twc, d.out_pose_twc, sizeof(double) * 7 * F, cudaMemcpyDeviceToHost, s));
+  if (nm) CU_TRY(c, cudaMemcpyAsync(out->mono_inlier, d.mono_inl, nm, cudaMemcpyDeviceToHost, s));
+  if (ns) CU_TRY(c, cudaMemcpyAsync(out->stereo_inlier, d.stereo_inl, ns, cudaMemcpyDeviceToHost, s));
+  if (out->num_inliers)
+    CU_TRY(c, cudaMemcpyAsync(out->num_inliers, d.num_inliers, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
+  if (out->stats)
+    CU_TRY(c, cudaMemcpyAsync(out->stats, d.stats, sizeof(RsplBaStats) * F, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, const RsplBaOptions* opt,
+                                   RsplFrameBatchResult* out) {
+  int rc = rspl_ba_frame_batch_upload(c, in);
+  if (rc != RSPL_BA_OK) return rc;
+  rc = rspl_ba_frame_batch_solve(c, opt);
+  if (rc != RSPL_BA_OK) return rc;
+  return rspl_ba_frame_batch_download(c, out);
+}
+
+// ================================================================================================
+// unit-level device entry points (parity tests)
+// ================================================================================================
+namespace ba {
+
+__global__ void eval_edges_kernel(int type, int n, const double* pose7, const double* lm, const double* meas, Cam cam,
+                                  int bf_float, double* err, double* Jl, double* Jp, double* chi2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* p = pose7 + 7 * i;
+  double R[9];
+  quat_to_R(p, R);
+  const double t[3] = {p[4], p[5], p[6]};
+  const double* X = lm + 6 * i;
+  const double* m = meas + 8 * i;
+  double r[4] = {0, 0, 0, 0}, jl[16], jp[24];
+  for (int k = 0; k < 16; ++k) jl[k] = 0;
+  for (int k = 0; k < 24; ++k) jp[k] = 0;
+  double info = 1.0;
+  int dim = 0;
+  if (type == 0 || type == 1) {
+    double Xc[3];
+    transform_point(R, t, X, Xc);
+    if (type == 1) {
+      const double bf_res = bf_float ? (double)(float)cam.bf : cam.bf;
+      point_residual<true>(cam, bf_res, Xc, m, r);
+      point_jac_pose<true>(cam, Xc, jp);
+      double j9[9];
+      point_jac_point<true>(cam, R, Xc, j9);
+      for (int k = 0; k < 9; ++k) jl[k] = j9[k];
+      dim = 3;
+    } else {
+      point_residual<false>(cam, cam.bf, Xc, m, r);
+      point_jac_pose<false>(cam, Xc, jp);
+      double j6[9];
+      point_jac_point<false>(cam, R, Xc, j6);
+      for (int k = 0; k < 6; ++k) jl[k] = j6[k];
+      dim = 2;
+    }
+  } else if (type == 2) {
+    line_linearize<false>(cam, R, t, X, m, r, jp, jl);
+    dim = 2;
+    info = 0.1;
+  } else {
+    line_linearize<true>(cam, R, t, X, m, r, jp, jl);
+    dim = 4;
+    info = 0.1;
+  }
+  double c2 = 0;
+  for (int k = 0; k < dim; ++k) c2 += r[k] * info * r[k];
+  for (int k = 0; k < 4; ++k) err[4 * i + k] = r[k];
+  for (int k = 0; k < 16; ++k) Jl[16 * i + k] = jl[k];
+  for (int k = 0; k < 24; ++k) Jp[24 * i + k] = jp[k];
+  chi2[i] = c2;
+}
+
+__global__ void oplus_kernel(int kind, int n, const double* state, const double* upd, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* s = state + 7 * i;
+  const double* u = upd + 6 * i;
+  double* o = out + 7 * i;
+  for (int k = 0; k < 7; ++k) o[k] = 0;
+  if (kind == 0) {
+    Pose T;
+    for (int k = 0; k < 4; ++k) T.q[k] = s[k];
+    for (int k = 0; k < 3; ++k) T.t[k] = s[4 + k];
+    Pose Tn = pose_oplus(T, u);
+    for (int k = 0; k < 4; ++k) o[k] = Tn.q[k];
+    for (int k = 0; k < 3; ++k) o[4 + k] = Tn.t[k];
+  } else if (kind == 1) {
+    for (int k = 0; k < 3; ++k) o[k] = s[k] + u[k];
+  } else {
+    line_oplus(s, u, o);
+  }
+}
+
+} // namespace ba
+
+extern "C" int rspl_ba_eval_edges(RsplBaContext* c, int edge_type, int32_t n, const double* pose7, const double* lm,
+                                  const double* meas, const double* cam5, int32_t stereo_bf_float, double* err,
+                                  double* Jl, double* Jp, double* chi2) {
+  if (!c || n < 0 || edge_type < 0 || edge_type > 3 || !pose7 || !lm || !meas || !cam5 || !err || !Jl || !Jp || !chi2)
+    return RSPL_BA_ERR_INVALID;
+  if (n == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  Arena a;
+  const size_t o_p = a.take(sizeof(double) * 7 * n), o_l = a.take(sizeof(double) * 6 * n);
+  const size_t o_m = a.take(sizeof(double) * 8 * n), o_e = a.take(sizeof(double) * 4 * n);
+  const size_t o_jl = a.take(sizeof(double) * 16 * n), o_jp = a.take(sizeof(double) * 24 * n);
+  const size_t o_c = a.take(sizeof(double) * n);
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_p, pose7, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemcpyAsync(base + o_l, lm, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemcpyAsync(base + o_m, meas, sizeof(double) * 8 * n, cudaMemcpyHostToDevice, s));
+  ba::Cam cam{cam5[0], cam5[1], cam5[2], cam5[3], cam5[4]};
+  ba::eval_edges_kernel<<<(n + 127) / 128, 128, 0, s>>>(edge_type, n, (const double*)(base + o_p),
+                                                        (const double*)(base + o_l), (const double*)(base + o_m), cam,
+                                                        stereo_bf_float, (double*)(base + o_e), (double*)(base + o_jl),
+                                                        (double*)(base + o_jp), (double*)(base + o_c));
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(err, base + o_e, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(Jl, base + o_jl, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(Jp, base + o_jp, sizeof(double) * 24 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(chi2, base + o_c, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_oplus(RsplBaContext* c, int kind, int32_t n, const double* state, const double* upd,
+                             double* out) {
+  if (!c || n < 0 || kind < 0 || kind > 2 || !state || !upd || !out) return RSPL_BA_ERR_INVALID;
+  if (n == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  Arena a;
+  const size_t o_s = a.take(sizeof(double) * 7 * n), o_u = a.take(sizeof(double) * 6 * n);
+  const size_t o_o = a.take(sizeof(double) * 7 * n);
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_s, state, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemcpyAsync(base + o_u, upd, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, s));
+  ba::oplus_kernel<<<(n + 127) / 128, 128, 0, s>>>(kind, n, (const double*)(base + o_s), (const double*)(base + o_u),
+                                                   (double*)(base + o_o));
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(out, base + o_o, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  return RSPL_BA_OK;
+}
+
+#include "local_capi.inl"
