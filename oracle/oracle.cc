@@ -806,7 +806,8 @@ struct Graph {
         A[k * n + j] = s / ukk;
       }
     }
-    std::vector<double> y(n);
+    static thread_local std::vector<double> y;
+    y.resize(n);
     for (int i = 0; i < n; ++i) { // U^T y = b
       double s = b[i];
       for (int p = 0; p < i; ++p) s -= A[p * n + i] * y[p];
@@ -824,7 +825,8 @@ struct Graph {
   bool solver_solve() {
     const int n = size_poses;
     if (!do_schur) {
-      std::vector<double> H((size_t)n * n, 0.0);
+      std::vector<double>& H = Hschur;
+      H.assign((size_t)n * n, 0.0);
       for (int k = 0; k < n_pose_act; ++k) {
         const Vertex& v = V[ivmap[k]];
         for (int i = 0; i < 6; ++i)
@@ -1057,9 +1059,24 @@ void set_cam(Edge& e, const double* c) {
 // ================================================================================================
 // LocalmapOptimization — g2o_optimization.cc:21-252
 // ================================================================================================
+// One reusable graph per worker thread: vectors keep their capacity across problems, so a batch
+// does not hammer mmap/munmap (large allocations serialise threads on the process mm lock).
+static Graph& tls_graph() {
+  static thread_local Graph g;
+  g.V.clear();
+  g.E.clear();
+  g.act_edges.clear();
+  g.ivmap.clear();
+  g.stats = nullptr;
+  g.cur_pass = 0;
+  g.lambda = 0;
+  g.ni = 2;
+  return g;
+}
+
 extern "C" int orc_local_ba(OrcLocalProblem* P, const OrcConfig* cfg, OrcStats* stats) {
   stats_reset(stats);
-  Graph G;
+  Graph& G = tls_graph();
   G.stats = stats;
   G.bf_float = cfg->stereo_bf_float != 0;
   std::map<int, int> pose_of, point_of, line_of;
@@ -1228,7 +1245,7 @@ extern "C" int orc_local_ba(OrcLocalProblem* P, const OrcConfig* cfg, OrcStats* 
 // ================================================================================================
 extern "C" int orc_frame_opt(OrcFrameProblem* P, const OrcConfig* cfg, OrcStats* stats) {
   stats_reset(stats);
-  Graph G;
+  Graph& G = tls_graph();
   G.stats = stats;
   G.bf_float = cfg->stereo_bf_float != 0;
   std::map<int, int> point_of;

@@ -359,7 +359,7 @@ extern "C" int rspl_ba_frame_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
   ba::FrameOpt fo = make_frame_opt(*opt);
-  ba::frame_opt_kernel<<<c->f_n_frames, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  ba::frame_opt_kernel<<<(c->f_n_frames + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;

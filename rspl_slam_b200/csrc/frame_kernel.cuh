@@ -1,13 +1,14 @@
 // frame_kernel.cuh — K7: batched pose-only optimisation, the whole FrameOptimization
-// (/root/reference/src/g2o_optimization/g2o_optimization.cc:256-397) of one frame per CTA.
+// (/root/reference/src/g2o_optimization/g2o_optimization.cc:256-397) of one frame per WARP.
 //
 // One launch runs, for every frame of the batch, the reference's 4 rounds x LM(10) with Huber
 // reweighting, chi2 re-classification between rounds (the (float)chi2 comparison of :351-352,
 // the pose reset of :340, the kernel drop after round index 2, :364) and the g2o Levenberg
 // accept/reject logic entirely on the device. Edges are read from
 // structure-of-arrays planes (coalesced); the 6x6 system is reduced with a fixed-order
-// shuffle tree + fixed-order cross-warp sum (bitwise deterministic), solved by warp 0 with an
-// in-register Cholesky, and the only HBM writes are the final flags, pose and stats.
+// shuffle butterfly (bitwise deterministic), solved redundantly by every lane with an in-register
+// Cholesky (no broadcast, no block barrier: a warp never waits for another frame), and the only
+// HBM writes are the final flags, pose and stats.
 #pragma once
 
 #include <float.h>
@@ -58,19 +59,15 @@ struct DevStats { // layout == RsplBaStats
   double final_lambda;
 };
 
-constexpr int FRAME_THREADS = 128;
+constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
 constexpr int FRAME_WARPS = FRAME_THREADS / 32;
 constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
 
-struct FrameSmem {
-  double red[FRAME_WARPS][NACC];
-  double R[9], t[3];      // current pose (rotation matrix form) used by the edge passes
-  double Re[9], te[3];    // pose at which edge errors were last evaluated (stale-error semantics, §9.12)
-  Pose T, Tbackup, T0;
+// per-warp (= per-frame) state that is touched once per trial: kept in shared memory so the
+// edge loops keep their registers
+struct WarpState {
+  Pose T0, Tbackup, Te; // initial pose; LM backup; pose of the last error evaluation (stale-error semantics, §9.12)
   double H[21], b[6], x[6];
-  double lambda, ni, chi_cur;
-  int verdict;            // 0: iteration ok, continue; 1: retry trial; 2: terminate optimize()
-  int n_out;
 };
 
 BA_DEV void load_cam(const double* cams, int idx, Cam& c) {
@@ -104,36 +101,17 @@ BA_DEV void accumulate_pose_only(const double* J, const double* r, double w, dou
   }
 }
 
-// deterministic block reduction of N doubles per thread; result valid in every lane of warp 0
-template <int N>
-BA_DEV void block_reduce(double* acc, FrameSmem& s, int lane, int warp) {
+// fixed-order butterfly: every lane ends with the same bitwise-deterministic sum
+BA_DEV double warp_allreduce(double v) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    acc[k] = v;
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) s.red[warp][k] = acc[k];
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      double v = s.red[0][k];
-#pragma unroll
-      for (int wv = 1; wv < FRAME_WARPS; ++wv) v += s.red[wv][k];
-      acc[k] = v;
-    }
-  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 // 6x6 Cholesky solve of (H + lambda I) x = b, H packed upper. Returns false iff a pivot <= 0
-// (LinearSolverEigen / SimplicialLLT failure rule, §9.11).
+// (LinearSolverEigen / SimplicialLLT failure rule, §9.11); x is left untouched then.
 BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) {
-  double U[6][6];
+  double U[6][6], inv[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -144,16 +122,16 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
     double d = U[k][k];
 #pragma unroll
     for (int p = 0; p < k; ++p) d -= U[p][k] * U[p][k];
-    if (!(d > 0.0) && !(d != d)) ok = false; // d <= 0 (NaN falls through like Eigen's test)
-    const double ukk = sqrt(d);
-    U[k][k] = ukk;
-    const double inv = 1.0 / ukk;
+    if (d <= 0.0) ok = false; // NaN falls through like Eigen's test
+    const double r = rsqrt(d);
+    inv[k] = r;
+    U[k][k] = d * r;
 #pragma unroll
     for (int j = k + 1; j < 6; ++j) {
       double sacc = U[k][j];
 #pragma unroll
       for (int p = 0; p < k; ++p) sacc -= U[p][k] * U[p][j];
-      U[k][j] = sacc * inv;
+      U[k][j] = sacc * r;
     }
   }
   if (!ok) return false;
@@ -163,37 +141,25 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
     double sacc = b[i];
 #pragma unroll
     for (int p = 0; p < i; ++p) sacc -= U[p][i] * y[p];
-    y[i] = sacc / U[i][i];
+    y[i] = sacc * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double sacc = y[i];
 #pragma unroll
     for (int p = i + 1; p < 6; ++p) sacc -= U[i][p] * x[p];
-    x[i] = sacc / U[i][i];
+    x[i] = sacc * inv[i];
   }
   return true;
 }
 
-BA_DEV void publish_pose(FrameSmem& s, const Pose& T) {
-  s.T = T;
-  double R[9];
-  quat_to_R(T.q, R);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) s.R[i] = R[i];
-  s.t[0] = T.t[0];
-  s.t[1] = T.t[1];
-  s.t[2] = T.t[2];
-}
-
-// One pass over the frame's active edges at the pose in (R,t).
+// One pass of a warp over its frame's active edges at the pose (R,t).
 //  LINEARIZE: accumulate H, b and the robust chi2 (= computeActiveErrors + activeRobustChi2 + buildSystem)
 //  else      : robust chi2 only (= computeActiveErrors + activeRobustChi2)
 template <bool LINEARIZE>
 BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int s0, int s1, const double* R,
-                      const double* t, bool robust, bool single_cam, const Cam& cam0, double* acc) {
-  const int tid = threadIdx.x;
-  for (int e = m0 + tid; e < m1; e += FRAME_THREADS) {
+                      const double* t, bool robust, bool single_cam, const Cam& cam0, int lane, double* acc) {
+  for (int e = m0 + lane; e < m1; e += 32) {
     if (d.mono_lvl[e]) continue;
     Cam cam = cam0;
     if (!single_cam) load_cam(d.cameras, d.mono_cam[e], cam);
@@ -212,7 +178,7 @@ BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int 
       accumulate_pose_only<2>(J, r, w, acc);
     }
   }
-  for (int e = s0 + tid; e < s1; e += FRAME_THREADS) {
+  for (int e = s0 + lane; e < s1; e += 32) {
     if (d.stereo_lvl[e]) continue;
     Cam cam = cam0;
     if (!single_cam) load_cam(d.cameras, d.stereo_cam[e], cam);
@@ -233,10 +199,21 @@ BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int 
   }
 }
 
+BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
+  quat_to_R(T.q, R);
+  t[0] = T.t[0];
+  t[1] = T.t[1];
+  t[2] = T.t[2];
+}
+
+// One warp per frame: every lane carries the same pose / LM scalars (computed redundantly, so no
+// broadcast and no block barrier is ever needed); lanes stride over the frame's edges.
 __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, FrameOpt o) {
-  __shared__ FrameSmem s;
-  const int f = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ WarpState wstate[FRAME_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = blockIdx.x * FRAME_WARPS + warp;
+  if (f >= d.n_frames) return;
+  WarpState& ws = wstate[warp];
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];
   const int n_edges = (m1 - m0) + (s1 - s0);
@@ -245,36 +222,28 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
   load_cam(d.cameras, 0, cam0);
 
   // ---- setup: pose (g2o_optimization.cc:271), flags, levels
-  if (warp == 0) {
+  Pose T;
+  {
     const double p[3] = {d.pose_twc[f], d.pose_twc[d.n_frames + f], d.pose_twc[2 * d.n_frames + f]};
     const double q[4] = {d.pose_twc[3 * d.n_frames + f], d.pose_twc[4 * d.n_frames + f],
                          d.pose_twc[5 * d.n_frames + f], d.pose_twc[6 * d.n_frames + f]};
-    Pose T0 = pose_from_twc(p, q);
-    if (lane == 0) {
-      s.T0 = T0;
-      publish_pose(s, T0);
-#pragma unroll
-      for (int i = 0; i < 9; ++i) s.Re[i] = s.R[i];
-      s.te[0] = s.t[0];
-      s.te[1] = s.t[1];
-      s.te[2] = s.t[2];
-      s.lambda = 0;
-      s.ni = 2;
-      s.chi_cur = 0;
-      s.n_out = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) s.x[i] = 0;
-    }
+    T = pose_from_twc(p, q);
   }
-  for (int e = m0 + tid; e < m1; e += FRAME_THREADS) {
+  if (lane == 0) {
+    ws.T0 = T;
+    ws.Te = T;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ws.x[i] = 0;
+  }
+  for (int e = m0 + lane; e < m1; e += 32) {
     d.mono_lvl[e] = 0;
     d.mono_inl[e] = d.mono_inl_in ? d.mono_inl_in[e] : 1;
   }
-  for (int e = s0 + tid; e < s1; e += FRAME_THREADS) {
+  for (int e = s0 + lane; e < s1; e += 32) {
     d.stereo_lvl[e] = 0;
     d.stereo_inl[e] = d.stereo_inl_in ? d.stereo_inl_in[e] : 1;
   }
-  __syncthreads();
+  __syncwarp();
 
   DevStats st;
 #pragma unroll
@@ -286,129 +255,116 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
   bool robust = true;
   int n_active = n_edges; // every edge starts at level 0
   int num_outlier = 0;
-  double acc[NACC];
+  double lambda = 0, ni = 2, chi_cur = 0;
+  double R[9], t[3];
 
   for (int round = 0; round < o.rounds; ++round) {
     const int sr = round < 4 ? round : 3;
-    // frame_vertex->setEstimate(initial) (:340)
-    if (tid == 0) publish_pose(s, s.T0);
-    __syncthreads();
+    T = ws.T0; // frame_vertex->setEstimate(initial) (:340)
+    pose_to_Rt(T, R, t);
     if (n_active > 0) {
       // ---------------- optimizer.optimize(iters) ----------------
       for (int it = 0; it < o.iters; ++it) {
+        {
+          double acc[NACC];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = 0;
-        edge_pass<true>(d, o, m0, m1, s0, s1, s.R, s.t, robust, single_cam, cam0, acc);
-        block_reduce<NACC>(acc, s, lane, warp);
-        st.edges_linearized += n_active;
-        st.edges_evaluated += n_active;
-        if (warp == 0) {
+          for (int k = 0; k < NACC; ++k) acc[k] = 0;
+          edge_pass<true>(d, o, m0, m1, s0, s1, R, t, robust, single_cam, cam0, lane, acc);
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
             double mx = 0;
 #pragma unroll
             for (int i = 0; i < 6; ++i) mx = fmax(fabs(acc[up6(i, i)]), mx);
-            if (lane == 0) {
-              s.lambda = 1e-5 * mx;
-              s.ni = 2;
-            }
+            lambda = 1e-5 * mx;
+            ni = 2;
           }
+          chi_cur = acc[NACC - 1];
+          __syncwarp();
           if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 21; ++k) s.H[k] = acc[k];
+            for (int k = 0; k < 21; ++k) ws.H[k] = acc[k];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s.b[k] = acc[21 + k];
-            s.chi_cur = acc[NACC - 1];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) s.Re[i] = s.R[i];
-            s.te[0] = s.t[0];
-            s.te[1] = s.t[1];
-            s.te[2] = s.t[2];
+            for (int k = 0; k < 6; ++k) ws.b[k] = acc[21 + k];
+            ws.Te = T;
           }
+          __syncwarp();
         }
-        __syncthreads();
+        st.edges_linearized += n_active;
+        st.edges_evaluated += n_active;
         int qmax = 0;
-        int verdict;
+        double rho = 0;
+        bool retry;
         do {
-          // ---- trial: backup, solve, update (warp 0, lane-redundant), then evaluate
-          if (warp == 0) {
-            double H[21], b[6], x[6];
+          // ---- trial: backup, solve, update, evaluate
+          double x[6], b[6];
+          bool ok;
+          {
+            double H[21];
 #pragma unroll
-            for (int k = 0; k < 21; ++k) H[k] = s.H[k];
+            for (int k = 0; k < 21; ++k) H[k] = ws.H[k];
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-              b[k] = s.b[k];
-              x[k] = s.x[k]; // stale x survives a failed factorisation (LinearSolverEigen returns early)
+              b[k] = ws.b[k];
+              x[k] = ws.x[k]; // stale x survives a failed factorisation (LinearSolverEigen returns early)
             }
-            const bool ok = solve6(H, b, s.lambda, x);
-            Pose Tn = pose_oplus(s.T, x);
-            __syncwarp();
-            if (lane == 0) {
-              s.Tbackup = s.T;
-#pragma unroll
-              for (int k = 0; k < 6; ++k) s.x[k] = x[k];
-              publish_pose(s, Tn);
-              s.verdict = ok ? 0 : -1;
-            }
+            ok = solve6(H, b, lambda, x);
           }
-          __syncthreads();
-          acc[0] = 0;
+          const Pose Tn = pose_oplus(T, x);
+          __syncwarp();
+          if (lane == 0) {
+            ws.Tbackup = T;
+            ws.Te = Tn;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ws.x[k] = x[k];
+          }
+          __syncwarp();
+          T = Tn;
+          pose_to_Rt(T, R, t);
+          double tempChi;
           {
             double a2[NACC];
             a2[NACC - 1] = 0;
-            edge_pass<false>(d, o, m0, m1, s0, s1, s.R, s.t, robust, single_cam, cam0, a2);
-            acc[0] = a2[NACC - 1];
+            edge_pass<false>(d, o, m0, m1, s0, s1, R, t, robust, single_cam, cam0, lane, a2);
+            tempChi = warp_allreduce(a2[NACC - 1]);
           }
-          block_reduce<1>(acc, s, lane, warp);
           st.edges_evaluated += n_active;
           st.trials[sr]++;
-          if (warp == 0 && lane == 0) {
-            double tempChi = acc[0];
-            if (s.verdict < 0) tempChi = DBL_MAX;
-            double rho = s.chi_cur - tempChi;
-            double scale = 0;
+          if (!ok) tempChi = DBL_MAX;
+          rho = chi_cur - tempChi;
+          double scale = 0;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) scale += s.x[j] * (s.lambda * s.x[j] + s.b[j]);
-            scale += 1e-3;
-            rho /= scale;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) s.Re[i] = s.R[i];
-            s.te[0] = s.t[0];
-            s.te[1] = s.t[1];
-            s.te[2] = s.t[2];
-            bool stop_lambda = false;
-            if (rho > 0 && isfinite(tempChi)) {
-              double alpha = 1. - pow((2 * rho - 1), 3);
-              alpha = fmin(alpha, 2. / 3.);
-              const double scaleFactor = fmax(1. / 3., alpha);
-              s.lambda *= scaleFactor;
-              s.ni = 2;
-              s.chi_cur = tempChi;
-            } else {
-              s.lambda *= s.ni;
-              s.ni *= 2;
-              publish_pose(s, s.Tbackup);
-              if (!isfinite(s.lambda)) stop_lambda = true;
-            }
-            const int q1 = stop_lambda ? qmax : qmax + 1;
-            int v;
-            if (!stop_lambda && rho < 0 && q1 < 10) v = 1; // retry
-            else if (q1 == 10 || rho == 0 || !isfinite(s.lambda)) v = 2; // Terminate
-            else v = 0;
-            s.verdict = v;
+          for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+          scale += 1e-3;
+          rho /= scale;
+          bool stop_lambda = false;
+          if (rho > 0 && isfinite(tempChi)) {
+            const double c = 2 * rho - 1;
+            double alpha = 1. - c * c * c;
+            alpha = fmin(alpha, 2. / 3.);
+            const double scaleFactor = fmax(1. / 3., alpha);
+            lambda *= scaleFactor;
+            ni = 2;
+            chi_cur = tempChi;
+          } else {
+            lambda *= ni;
+            ni *= 2;
+            T = ws.Tbackup;
+            pose_to_Rt(T, R, t);
+            if (!isfinite(lambda)) stop_lambda = true;
           }
-          __syncthreads();
-          verdict = s.verdict;
-          qmax++;
-        } while (verdict == 1);
+          if (!stop_lambda) qmax++;
+          retry = !stop_lambda && rho < 0 && qmax < 10;
+        } while (retry);
         st.iters[sr]++;
-        if (verdict == 2) break;
+        if (qmax == 10 || rho == 0 || !isfinite(lambda)) break; // Terminate
       }
     }
     // ---------------- classification (:344-385) ----------------
-    if (tid == 0) s.n_out = 0;
-    __syncthreads();
+    double Re[9], te[3];
+    pose_to_Rt(ws.Te, Re, te);
     int my_out = 0;
-    for (int e = m0 + tid; e < m1; e += FRAME_THREADS) {
+    for (int e = m0 + lane; e < m1; e += 32) {
       Cam cam = cam0;
       if (!single_cam) load_cam(d.cameras, d.mono_cam[e], cam);
       const double X[3] = {d.mono_xw[e], d.mono_xw[d.n_mono + e], d.mono_xw[2 * d.n_mono + e]};
@@ -418,8 +374,8 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
       const bool recompute = !d.mono_inl[e];
       const bool was_active = !d.mono_lvl[e] && n_active > 0;
       double Xc[3], r[2];
-      if (recompute || !was_active) transform_point(s.R, s.t, X, Xc);
-      else transform_point(s.Re, s.te, X, Xc);
+      if (recompute || !was_active) transform_point(R, t, X, Xc);
+      else transform_point(Re, te, X, Xc);
       point_residual<false>(cam, cam.bf, Xc, m, r);
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1]);
       const bool out = (double)chi2 > o.thr_mono;
@@ -427,7 +383,7 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
       d.mono_lvl[e] = out ? 1 : 0;
       my_out += out;
     }
-    for (int e = s0 + tid; e < s1; e += FRAME_THREADS) {
+    for (int e = s0 + lane; e < s1; e += 32) {
       Cam cam = cam0;
       if (!single_cam) load_cam(d.cameras, d.stereo_cam[e], cam);
       const double X[3] = {d.stereo_xw[e], d.stereo_xw[d.n_stereo + e], d.stereo_xw[2 * d.n_stereo + e]};
@@ -435,8 +391,8 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
       const bool recompute = !d.stereo_inl[e];
       const bool was_active = !d.stereo_lvl[e] && n_active > 0;
       double Xc[3], r[3];
-      if (recompute || !was_active) transform_point(s.R, s.t, X, Xc);
-      else transform_point(s.Re, s.te, X, Xc);
+      if (recompute || !was_active) transform_point(R, t, X, Xc);
+      else transform_point(Re, te, X, Xc);
       point_residual<true>(cam, cam.bf, Xc, m, r);
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
       const bool out = (double)chi2 > o.thr_stereo;
@@ -444,18 +400,17 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
       d.stereo_lvl[e] = out ? 1 : 0;
       my_out += out;
     }
-    if (my_out) atomicAdd(&s.n_out, my_out);
-    __syncthreads();
-    num_outlier = s.n_out;
+    num_outlier = __reduce_add_sync(0xffffffffu, my_out);
     n_active = n_edges - num_outlier;
     if (round == 2) robust = false; // e->setRobustKernel(0) (:364,:384)
-    __syncthreads();
+    __syncwarp(); // level / inlier flags written above are read by other lanes' next passes? no: each lane
+                  // re-reads only the edges it wrote (same stride), the barrier just orders the round
     if (n_edges < 10) break; // optimizer.edges().size() < 10 (:387)
   }
 
   // ---- recover optimized data (:391-396)
-  if (tid == 0) {
-    Pose Twc = pose_inverse(s.T);
+  if (lane == 0) {
+    const Pose Twc = pose_inverse(T);
     d.out_pose_twc[f] = Twc.t[0];
     d.out_pose_twc[d.n_frames + f] = Twc.t[1];
     d.out_pose_twc[2 * d.n_frames + f] = Twc.t[2];
@@ -464,8 +419,8 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
     d.out_pose_twc[5 * d.n_frames + f] = Twc.q[2];
     d.out_pose_twc[6 * d.n_frames + f] = Twc.q[3];
     d.num_inliers[f] = n_edges - num_outlier;
-    st.final_chi2 = s.chi_cur;
-    st.final_lambda = s.lambda;
+    st.final_chi2 = chi_cur;
+    st.final_lambda = lambda;
     if (d.stats) reinterpret_cast<DevStats*>(d.stats)[f] = st;
   }
 }

@@ -291,7 +291,7 @@ def make_frame_problem(seed: int, n_points: int = 400, stereo_frac: float = 1.0,
         mp_inlier=np.ones(int(mo.sum()), dtype=U8),
         sp_id_point=ids[stereo], sp_id_cam=np.zeros(int(stereo.sum()), dtype=I32), sp_kp=m[stereo],
         sp_inlier=np.ones(int(stereo.sum()), dtype=U8),
-        truth=dict(Rwc=Rwc, twc=twc, gross=gross, seed=seed)).normalise()
+        truth=dict(Rwc=Rwc, twc=twc, gross=gross, stereo=stereo, seed=seed)).normalise()
 
 
 def make_frame_batch(config: int, n_frames: int, first_instance: int = 0, n_points: int = 400,

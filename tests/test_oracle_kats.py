@@ -160,7 +160,7 @@ def test_frame_optimization_recovers_pose_and_flags_outliers(orc):
     q = p.copy()
     st = orc.frame_opt(q, trace=True)
     assert np.linalg.norm(q.pose_p - p.truth["twc"]) < 0.01 < np.linalg.norm(p.pose_p - p.truth["twc"])
-    gross = p.truth["gross"]
+    gross = p.truth["gross"][p.truth["stereo"]]
     # every flagged outlier is a gross one or a 1-px-noise tail event; most gross ones are caught
     assert (q.sp_inlier[gross] == 0).mean() > 0.9 and (q.sp_inlier[~gross] == 1).mean() > 0.99
     assert st["ret"] == int(q.sp_inlier.sum()) + int(q.mp_inlier.sum())
