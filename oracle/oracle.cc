@@ -386,6 +386,7 @@ struct Graph {
   std::vector<Vertex> V;
   std::vector<Edge> E;
   bool bf_float = true;
+  double num_delta = 1e-9;
   OrcStats* stats = nullptr;
   int cur_pass = 0;
 
@@ -552,7 +553,7 @@ struct Graph {
     }
     // line edges: BaseBinaryEdge numeric linearizeOplus, central differences delta = 1e-9 (§9.8)
     Vertex& vl = V[e.v_lm];
-    const double delta = 1e-9, scalar = 1 / (2 * delta);
+    const double delta = num_delta, scalar = 1 / (2 * delta);
     double err_before[4];
     std::memcpy(err_before, e.err, sizeof(err_before));
     double ep[4];
@@ -1071,6 +1072,7 @@ static Graph& tls_graph() {
   g.cur_pass = 0;
   g.lambda = 0;
   g.ni = 2;
+  g.num_delta = 1e-9;
   return g;
 }
 
@@ -1079,6 +1081,7 @@ extern "C" int orc_local_ba(OrcLocalProblem* P, const OrcConfig* cfg, OrcStats* 
   Graph& G = tls_graph();
   G.stats = stats;
   G.bf_float = cfg->stereo_bf_float != 0;
+  G.num_delta = cfg->numeric_delta > 0 ? cfg->numeric_delta : 1e-9;
   std::map<int, int> pose_of, point_of, line_of;
   // frame vertices (:39-48); ids must be ascending (std::map order)
   for (int i = 0; i < P->n_poses; ++i) {

@@ -55,6 +55,9 @@ typedef struct OrcConfig {
   int32_t iters_pass1, iters_pass2; /* 10, 5 */
   int32_t rounds, iters_round;      /* 4, 10 */
   int32_t stereo_bf_float;          /* 1: EdgeStereoSE3ProjectXYZ::cam_project takes bf as float (g2o) */
+  int32_t reserved;
+  double numeric_delta;             /* step of the numeric line Jacobians; <= 0 means g2o's 1e-9.
+                                       Tests use 1e-6 to separate difference-quotient noise from real deviations. */
 } OrcConfig;
 
 typedef struct OrcLocalProblem {

@@ -34,7 +34,8 @@ class OrcStats(C.Structure):
 class OrcConfig(C.Structure):
     _fields_ = [("mono_point", C.c_double), ("stereo_point", C.c_double), ("mono_line", C.c_double),
                 ("stereo_line", C.c_double), ("iters_pass1", C.c_int32), ("iters_pass2", C.c_int32),
-                ("rounds", C.c_int32), ("iters_round", C.c_int32), ("stereo_bf_float", C.c_int32)]
+                ("rounds", C.c_int32), ("iters_round", C.c_int32), ("stereo_bf_float", C.c_int32),
+                ("reserved", C.c_int32), ("numeric_delta", C.c_double)]
 
 
 class OrcLocalProblem(C.Structure):
@@ -107,9 +108,9 @@ def _p(a: np.ndarray, ct):
     return a.ctypes.data_as(ct)
 
 
-def make_config(cfg=None, iters=(10, 5), rounds=4, iters_round=10, stereo_bf_float=1) -> OrcConfig:
+def make_config(cfg=None, iters=(10, 5), rounds=4, iters_round=10, stereo_bf_float=1, numeric_delta=0.0) -> OrcConfig:
     mp, sp, ml, sl = (50.0, 75.0, 50.0, 75.0) if cfg is None else (cfg.mono_point, cfg.stereo_point, cfg.mono_line, cfg.stereo_line)
-    return OrcConfig(mp, sp, ml, sl, iters[0], iters[1], rounds, iters_round, stereo_bf_float)
+    return OrcConfig(mp, sp, ml, sl, iters[0], iters[1], rounds, iters_round, stereo_bf_float, 0, numeric_delta)
 
 
 def _local_struct(p) -> OrcLocalProblem:

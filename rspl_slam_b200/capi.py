@@ -86,6 +86,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_eval_edges", "rspl_ba_oplus")
 
 _lib = None
+LOCAL_BA_READY = True
 
 
 class RsplBaError(RuntimeError):

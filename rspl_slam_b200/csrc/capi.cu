@@ -75,6 +75,7 @@ struct RsplBaContext {
   bool frame_uploaded = false;
   bool frame_solved = false;
   int f_n_frames = 0, f_n_mono = 0, f_n_stereo = 0;
+  ba::Cam f_cam0{};
 
   // ---- local batch state
   DevBuf local_buf;
@@ -342,6 +343,7 @@ extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch
   d.stereo_lvl = (uint8_t*)(base + o_sl);
   d.num_inliers = (int*)(base + o_ni);
   d.stats = (void*)(base + o_st);
+  c->f_cam0 = ba::Cam{in->cameras[0], in->cameras[1], in->cameras[2], in->cameras[3], in->cameras[4]};
   c->f_n_frames = F;
   c->f_n_mono = nm;
   c->f_n_stereo = ns;
@@ -359,7 +361,11 @@ extern "C" int rspl_ba_frame_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
   ba::FrameOpt fo = make_frame_opt(*opt);
-  ba::frame_opt_kernel<<<(c->f_n_frames + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  const int grid = (c->f_n_frames + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
+  const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr);
+  fo.cam0 = c->f_cam0;
+  if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;

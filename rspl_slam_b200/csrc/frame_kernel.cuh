@@ -48,6 +48,7 @@ struct FrameOpt {
   double thr_mono, thr_stereo;
   double delta_mono, delta_stereo; // (float)sqrt(thr) widened
   int rounds, iters;
+  Cam cam0;                        // camera 0, read straight from the constant bank when SINGLE_CAM
 };
 
 struct DevStats { // layout == RsplBaStats
@@ -66,8 +67,9 @@ constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
 // per-warp (= per-frame) state that is touched once per trial: kept in shared memory so the
 // edge loops keep their registers
 struct WarpState {
-  Pose T0, Tbackup, Te; // initial pose; LM backup; pose of the last error evaluation (stale-error semantics, §9.12)
+  Pose T, T0, Tbackup, Te; // current / initial pose; LM backup; pose of the last error evaluation (§9.12)
   double H[21], b[6], x[6];
+  DevStats st;
 };
 
 BA_DEV void load_cam(const double* cams, int idx, Cam& c) {
@@ -156,13 +158,14 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
 // One pass of a warp over its frame's active edges at the pose (R,t).
 //  LINEARIZE: accumulate H, b and the robust chi2 (= computeActiveErrors + activeRobustChi2 + buildSystem)
 //  else      : robust chi2 only (= computeActiveErrors + activeRobustChi2)
-template <bool LINEARIZE>
+template <bool LINEARIZE, bool SINGLE_CAM>
 BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int s0, int s1, const double* R,
-                      const double* t, bool robust, bool single_cam, const Cam& cam0, int lane, double* acc) {
+                      const double* t, bool robust, int lane, double* acc) {
   for (int e = m0 + lane; e < m1; e += 32) {
     if (d.mono_lvl[e]) continue;
-    Cam cam = cam0;
-    if (!single_cam) load_cam(d.cameras, d.mono_cam[e], cam);
+    Cam camv;
+    if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
+    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
     const double X[3] = {d.mono_xw[e], d.mono_xw[d.n_mono + e], d.mono_xw[2 * d.n_mono + e]};
     const double m[2] = {d.mono_meas[e], d.mono_meas[d.n_mono + e]};
     double Xc[3], r[2];
@@ -180,8 +183,9 @@ BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int 
   }
   for (int e = s0 + lane; e < s1; e += 32) {
     if (d.stereo_lvl[e]) continue;
-    Cam cam = cam0;
-    if (!single_cam) load_cam(d.cameras, d.stereo_cam[e], cam);
+    Cam camv;
+    if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
+    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
     const double X[3] = {d.stereo_xw[e], d.stereo_xw[d.n_stereo + e], d.stereo_xw[2 * d.n_stereo + e]};
     const double m[3] = {d.stereo_meas[e], d.stereo_meas[d.n_stereo + e], d.stereo_meas[2 * d.n_stereo + e]};
     double Xc[3], r[3];
@@ -208,7 +212,9 @@ BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
 
 // One warp per frame: every lane carries the same pose / LM scalars (computed redundantly, so no
 // broadcast and no block barrier is ever needed); lanes stride over the frame's edges.
-__global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, FrameOpt o) {
+template <bool SINGLE_CAM>
+__global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __grid_constant__ FrameDev d,
+                                                                      const __grid_constant__ FrameOpt o) {
   __shared__ WarpState wstate[FRAME_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = blockIdx.x * FRAME_WARPS + warp;
@@ -217,9 +223,6 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];
   const int n_edges = (m1 - m0) + (s1 - s0);
-  const bool single_cam = (d.n_cameras == 1) || (d.mono_cam == nullptr && d.stereo_cam == nullptr);
-  Cam cam0;
-  load_cam(d.cameras, 0, cam0);
 
   // ---- setup: pose (g2o_optimization.cc:271), flags, levels
   Pose T;
@@ -234,6 +237,9 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
     ws.Te = T;
 #pragma unroll
     for (int i = 0; i < 6; ++i) ws.x[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ws.st.iters[i] = ws.st.trials[i] = 0;
+    ws.st.edges_linearized = ws.st.edges_evaluated = 0;
   }
   for (int e = m0 + lane; e < m1; e += 32) {
     d.mono_lvl[e] = 0;
@@ -244,13 +250,6 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
     d.stereo_inl[e] = d.stereo_inl_in ? d.stereo_inl_in[e] : 1;
   }
   __syncwarp();
-
-  DevStats st;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) st.iters[i] = st.trials[i] = 0;
-  st.edges_linearized = st.edges_evaluated = 0;
-  st.final_chi2 = 0;
-  st.final_lambda = 0;
 
   bool robust = true;
   int n_active = n_edges; // every edge starts at level 0
@@ -269,7 +268,7 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
           double acc[NACC];
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
-          edge_pass<true>(d, o, m0, m1, s0, s1, R, t, robust, single_cam, cam0, lane, acc);
+          edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, R, t, robust, lane, acc);
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
@@ -290,8 +289,10 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
           }
           __syncwarp();
         }
-        st.edges_linearized += n_active;
-        st.edges_evaluated += n_active;
+        if (lane == 0) {
+          ws.st.edges_linearized += n_active;
+          ws.st.edges_evaluated += n_active;
+        }
         int qmax = 0;
         double rho = 0;
         bool retry;
@@ -325,11 +326,13 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
           {
             double a2[NACC];
             a2[NACC - 1] = 0;
-            edge_pass<false>(d, o, m0, m1, s0, s1, R, t, robust, single_cam, cam0, lane, a2);
+            edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, R, t, robust, lane, a2);
             tempChi = warp_allreduce(a2[NACC - 1]);
           }
-          st.edges_evaluated += n_active;
-          st.trials[sr]++;
+          if (lane == 0) {
+            ws.st.edges_evaluated += n_active;
+            ws.st.trials[sr]++;
+          }
           if (!ok) tempChi = DBL_MAX;
           rho = chi_cur - tempChi;
           double scale = 0;
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
           if (!stop_lambda) qmax++;
           retry = !stop_lambda && rho < 0 && qmax < 10;
         } while (retry);
-        st.iters[sr]++;
+        if (lane == 0) ws.st.iters[sr]++;
         if (qmax == 10 || rho == 0 || !isfinite(lambda)) break; // Terminate
       }
     }
@@ -365,8 +368,9 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
     pose_to_Rt(ws.Te, Re, te);
     int my_out = 0;
     for (int e = m0 + lane; e < m1; e += 32) {
-      Cam cam = cam0;
-      if (!single_cam) load_cam(d.cameras, d.mono_cam[e], cam);
+      Cam camv;
+      if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
+      const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
       const double X[3] = {d.mono_xw[e], d.mono_xw[d.n_mono + e], d.mono_xw[2 * d.n_mono + e]};
       const double m[2] = {d.mono_meas[e], d.mono_meas[d.n_mono + e]};
       // active edges keep the error of their last evaluation; the reference recomputes only
@@ -384,8 +388,9 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
       my_out += out;
     }
     for (int e = s0 + lane; e < s1; e += 32) {
-      Cam cam = cam0;
-      if (!single_cam) load_cam(d.cameras, d.stereo_cam[e], cam);
+      Cam camv;
+      if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
+      const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
       const double X[3] = {d.stereo_xw[e], d.stereo_xw[d.n_stereo + e], d.stereo_xw[2 * d.n_stereo + e]};
       const double m[3] = {d.stereo_meas[e], d.stereo_meas[d.n_stereo + e], d.stereo_meas[2 * d.n_stereo + e]};
       const bool recompute = !d.stereo_inl[e];
@@ -419,9 +424,9 @@ __global__ void __launch_bounds__(FRAME_THREADS) frame_opt_kernel(FrameDev d, Fr
     d.out_pose_twc[5 * d.n_frames + f] = Twc.q[2];
     d.out_pose_twc[6 * d.n_frames + f] = Twc.q[3];
     d.num_inliers[f] = n_edges - num_outlier;
-    st.final_chi2 = chi_cur;
-    st.final_lambda = lambda;
-    if (d.stats) reinterpret_cast<DevStats*>(d.stats)[f] = st;
+    ws.st.final_chi2 = chi_cur;
+    ws.st.final_lambda = lambda;
+    if (d.stats) reinterpret_cast<DevStats*>(d.stats)[f] = ws.st;
   }
 }
 

@@ -1,4 +1,323 @@
-extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch*) { return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local BA not built yet"); }
-extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions*) { return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local BA not built yet"); }
-extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResult*) { return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local BA not built yet"); }
-extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch*, const RsplBaOptions*, RsplLocalBatchResult*) { return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local BA not built yet"); }
+// local_capi.inl — C-ABI entry points of the LocalmapOptimization batch (included by capi.cu).
+// Reference boundary: LocalmapOptimization(...) /root/reference/include/g2o_optimization/g2o_optimization.h:15-18.
+
+namespace {
+
+struct KindHost { // host view of one landmark kind of an RsplLocalBatch
+  const int32_t* lm_begin;
+  const int32_t* cls_begin[2];
+  const int32_t* cls_pose[2];
+  const int32_t* cls_lm[2];
+  const int32_t* cls_cam[2];
+  const double* cls_meas[2];
+  const double* lm_in;
+  int md[2]; // measurement planes per class
+};
+
+KindHost kind_host(const RsplLocalBatch* in, int kind) {
+  KindHost h;
+  if (kind == 0) {
+    h.lm_begin = in->point_begin;
+    h.cls_begin[0] = in->mono_pt_begin;
+    h.cls_begin[1] = in->stereo_pt_begin;
+    h.cls_pose[0] = in->mp_pose;
+    h.cls_pose[1] = in->sp_pose;
+    h.cls_lm[0] = in->mp_point;
+    h.cls_lm[1] = in->sp_point;
+    h.cls_cam[0] = in->mp_cam;
+    h.cls_cam[1] = in->sp_cam;
+    h.cls_meas[0] = in->mp_meas;
+    h.cls_meas[1] = in->sp_meas;
+    h.lm_in = in->point_xyz;
+    h.md[0] = 2;
+    h.md[1] = 3;
+  } else {
+    h.lm_begin = in->line_begin;
+    h.cls_begin[0] = in->mono_ln_begin;
+    h.cls_begin[1] = in->stereo_ln_begin;
+    h.cls_pose[0] = in->ml_pose;
+    h.cls_pose[1] = in->sl_pose;
+    h.cls_lm[0] = in->ml_line;
+    h.cls_lm[1] = in->sl_line;
+    h.cls_cam[0] = in->ml_cam;
+    h.cls_cam[1] = in->sl_cam;
+    h.cls_meas[0] = in->ml_meas;
+    h.cls_meas[1] = in->sl_meas;
+    h.lm_in = in->line_wd;
+    h.md[0] = 4;
+    h.md[1] = 8;
+  }
+  return h;
+}
+
+} // namespace
+
+extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch* in) {
+  if (!c || !in) return RSPL_BA_ERR_INVALID;
+  c->local_uploaded = c->local_solved = false;
+  const int W = in->n_windows;
+  if (W < 0 || in->n_cameras < 1 || in->n_cameras > 255 || !in->cameras)
+    return fail(c, RSPL_BA_ERR_INVALID, "local batch: bad header");
+  if (W == 0) {
+    c->l_n_windows = 0;
+    c->local_uploaded = true;
+    return RSPL_BA_OK;
+  }
+  if (!offsets_ok(in->pose_begin, W) || !offsets_ok(in->point_begin, W) || !offsets_ok(in->line_begin, W) ||
+      !offsets_ok(in->mono_pt_begin, W) || !offsets_ok(in->stereo_pt_begin, W) || !offsets_ok(in->mono_ln_begin, W) ||
+      !offsets_ok(in->stereo_ln_begin, W))
+    return fail(c, RSPL_BA_ERR_INVALID, "local batch: bad offsets");
+  const int NP = in->pose_begin[W];
+  if (NP <= 0 || !in->pose_twc || !in->pose_fixed) return fail(c, RSPL_BA_ERR_INVALID, "local batch: no poses");
+  KindHost kh[2] = {kind_host(in, 0), kind_host(in, 1)};
+  int n_lm[2], n_cls[2][2];
+  for (int k = 0; k < 2; ++k) {
+    n_lm[k] = kh[k].lm_begin[W];
+    if (n_lm[k] && !kh[k].lm_in) return fail(c, RSPL_BA_ERR_INVALID, "local batch: null landmark array");
+    for (int cl = 0; cl < 2; ++cl) {
+      n_cls[k][cl] = kh[k].cls_begin[cl][W];
+      if (n_cls[k][cl] && (!kh[k].cls_pose[cl] || !kh[k].cls_lm[cl] || !kh[k].cls_meas[cl]))
+        return fail(c, RSPL_BA_ERR_INVALID, "local batch: null edge array");
+      if (n_cls[k][cl]) {
+        if (!indices_ok(kh[k].cls_pose[cl], kh[k].cls_begin[cl], in->pose_begin, W) ||
+            !indices_ok(kh[k].cls_lm[cl], kh[k].cls_begin[cl], kh[k].lm_begin, W))
+          return fail(c, RSPL_BA_ERR_INVALID, "local batch: edge references a vertex outside its window");
+        if (!cams_ok(kh[k].cls_cam[cl], n_cls[k][cl], in->n_cameras))
+          return fail(c, RSPL_BA_ERR_INVALID, "local batch: id_camera out of range");
+        if (in->n_cameras > 1 && !kh[k].cls_cam[cl])
+          return fail(c, RSPL_BA_ERR_INVALID, "local batch: several cameras but no per-edge camera index");
+      }
+    }
+  }
+  // per-window limits of the shared-memory path
+  int max_poses = 1, max_free = 1;
+  for (int w = 0; w < W; ++w) {
+    const int a = in->pose_begin[w], b = in->pose_begin[w + 1];
+    int nf = 0;
+    for (int p = a; p < b; ++p) nf += in->pose_fixed[p] ? 0 : 1;
+    if (b - a > max_poses) max_poses = b - a;
+    if (nf > max_free) max_free = nf;
+  }
+  if (max_poses > 255)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: %d poses in one window (limit 255)", max_poses);
+  const size_t smem = ba::local_smem_bytes(max_poses, max_free);
+  if (smem > c->smem_optin)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED,
+                "local batch: %d free poses in one window need %zu B of shared memory (limit %zu); use the global-BA path",
+                max_free, smem, c->smem_optin);
+
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  Arena a;
+  const size_t o_cam = a.take(sizeof(double) * 5 * in->n_cameras);
+  const size_t o_pb = a.take(sizeof(int) * (W + 1));
+  const size_t o_ptw = a.take(sizeof(double) * 7 * NP);
+  const size_t o_pfx = a.take(NP);
+  const size_t o_tcw = a.take(sizeof(double) * 7 * NP);
+  const size_t o_pout = a.take(sizeof(double) * 7 * NP);
+  const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
+  const size_t o_err = a.take(sizeof(int));
+  const int slot_stride = (max_free + 3) & ~3;
+  struct KOff {
+    size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
+    size_t meas, info, lm, src, chi2, lvl, Wb, Zb, ebeg, cursor, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
+  } ko[2];
+  for (int k = 0; k < 2; ++k) {
+    const int LD = k ? 4 : 3, SD = k ? 6 : 3, MD = k ? 8 : 3, HD = k ? 10 : 6, WD = 6 * LD;
+    const size_t ne = (size_t)n_cls[k][0] + n_cls[k][1], nl = n_lm[k];
+    KOff& o = ko[k];
+    o.lm_begin = a.take(sizeof(int) * (W + 1));
+    for (int cl = 0; cl < 2; ++cl) {
+      o.cls_begin[cl] = a.take(sizeof(int) * (W + 1));
+      o.cls_pose[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_lm[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_cam[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_meas[cl] = a.take(sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
+      o.out_inl[cl] = a.take(n_cls[k][cl]);
+    }
+    o.lm_in = a.take(sizeof(double) * SD * nl);
+    o.meas = a.take(sizeof(double) * MD * ne);
+    o.info = a.take(sizeof(int) * ne);
+    o.lm = a.take(sizeof(int) * ne);
+    o.src = a.take(sizeof(int) * ne);
+    o.chi2 = a.take(sizeof(double) * ne);
+    o.lvl = a.take(ne);
+    o.Wb = a.take(sizeof(double) * WD * ne);
+    o.Zb = a.take(sizeof(double) * WD * ne);
+    o.ebeg = a.take(sizeof(int) * (nl + 1));
+    o.cursor = a.take(sizeof(int) * nl);
+    o.x = a.take(sizeof(double) * SD * nl);
+    o.xb = a.take(sizeof(double) * SD * nl);
+    o.H = a.take(sizeof(double) * HD * nl);
+    o.b = a.take(sizeof(double) * LD * nl);
+    o.y = a.take(sizeof(double) * LD * nl);
+    o.act = a.take(nl);
+    o.slot = a.take(nl * (size_t)slot_stride);
+    o.plist = a.take(sizeof(int) * ne);
+    o.pbeg = a.take(sizeof(int) * (NP + 1));
+    o.lm_out = a.take(sizeof(double) * SD * nl);
+  }
+  CU_TRY(c, c->local_buf.reserve(a.off));
+  char* base = c->local_buf.as<char>();
+  cudaStream_t s = c->stream;
+#define H2D(off, src, bytes)                                                                              \
+  do {                                                                                                    \
+    if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s)); \
+  } while (0)
+  H2D(o_cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
+  H2D(o_pb, in->pose_begin, sizeof(int) * (W + 1));
+  H2D(o_ptw, in->pose_twc, sizeof(double) * 7 * NP);
+  H2D(o_pfx, in->pose_fixed, (size_t)NP);
+  for (int k = 0; k < 2; ++k) {
+    const int SD = k ? 6 : 3;
+    H2D(ko[k].lm_begin, kh[k].lm_begin, sizeof(int) * (W + 1));
+    H2D(ko[k].lm_in, kh[k].lm_in, sizeof(double) * SD * n_lm[k]);
+    for (int cl = 0; cl < 2; ++cl) {
+      H2D(ko[k].cls_begin[cl], kh[k].cls_begin[cl], sizeof(int) * (W + 1));
+      H2D(ko[k].cls_pose[cl], kh[k].cls_pose[cl], sizeof(int) * n_cls[k][cl]);
+      H2D(ko[k].cls_lm[cl], kh[k].cls_lm[cl], sizeof(int) * n_cls[k][cl]);
+      if (kh[k].cls_cam[cl]) H2D(ko[k].cls_cam[cl], kh[k].cls_cam[cl], sizeof(int) * n_cls[k][cl]);
+      H2D(ko[k].cls_meas[cl], kh[k].cls_meas[cl], sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
+    }
+  }
+#undef H2D
+  CU_TRY(c, cudaStreamSynchronize(s));
+
+  ba::LocalDev& d = c->ld;
+  d.n_windows = W;
+  d.n_cameras = in->n_cameras;
+  d.n_poses = NP;
+  d.cameras = (const double*)(base + o_cam);
+  d.pose_begin = (const int*)(base + o_pb);
+  d.pose_twc = (const double*)(base + o_ptw);
+  d.pose_fixed = (const uint8_t*)(base + o_pfx);
+  d.pose_tcw = (double*)(base + o_tcw);
+  d.pose_out = (double*)(base + o_pout);
+  d.slot_stride = slot_stride;
+  d.stats = (void*)(base + o_stats);
+  d.err = (int*)(base + o_err);
+  for (int k = 0; k < 2; ++k) {
+    ba::KindDev& kd = d.k[k];
+    const KOff& o = ko[k];
+    kd.n_lm = n_lm[k];
+    kd.n_edge = n_cls[k][0] + n_cls[k][1];
+    kd.lm_begin = (const int*)(base + o.lm_begin);
+    for (int cl = 0; cl < 2; ++cl) {
+      kd.cls_begin[cl] = (const int*)(base + o.cls_begin[cl]);
+      kd.cls_pose[cl] = (const int*)(base + o.cls_pose[cl]);
+      kd.cls_lm[cl] = (const int*)(base + o.cls_lm[cl]);
+      kd.cls_cam[cl] = kh[k].cls_cam[cl] ? (const int*)(base + o.cls_cam[cl]) : nullptr;
+      kd.cls_meas[cl] = (const double*)(base + o.cls_meas[cl]);
+      kd.cls_n[cl] = n_cls[k][cl];
+      kd.out_inl[cl] = (uint8_t*)(base + o.out_inl[cl]);
+    }
+    kd.lm_in = (const double*)(base + o.lm_in);
+    kd.meas = (double*)(base + o.meas);
+    kd.info = (int*)(base + o.info);
+    kd.lm = (int*)(base + o.lm);
+    kd.src = (int*)(base + o.src);
+    kd.chi2 = (double*)(base + o.chi2);
+    kd.lvl = (uint8_t*)(base + o.lvl);
+    kd.W = (double*)(base + o.Wb);
+    kd.Z = (double*)(base + o.Zb);
+    kd.ebeg = (int*)(base + o.ebeg);
+    kd.cursor = (int*)(base + o.cursor);
+    kd.x = (double*)(base + o.x);
+    kd.xb = (double*)(base + o.xb);
+    kd.H = (double*)(base + o.H);
+    kd.b = (double*)(base + o.b);
+    kd.y = (double*)(base + o.y);
+    kd.act = (uint8_t*)(base + o.act);
+    kd.slot = (uint8_t*)(base + o.slot);
+    kd.plist = (int*)(base + o.plist);
+    kd.pbeg = (int*)(base + o.pbeg);
+    kd.lm_out = (double*)(base + o.lm_out);
+  }
+  c->l_n_windows = W;
+  c->l_np = NP;
+  c->l_npt = n_lm[0];
+  c->l_nln = n_lm[1];
+  c->l_n[0] = n_cls[0][0];
+  c->l_n[1] = n_cls[0][1];
+  c->l_n[2] = n_cls[1][0];
+  c->l_n[3] = n_cls[1][1];
+  c->l_max_poses = max_poses;
+  c->l_max_free_poses = max_free;
+  c->local_uploaded = true;
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* opt) {
+  if (!c || !opt) return RSPL_BA_ERR_INVALID;
+  if (!c->local_uploaded) return fail(c, RSPL_BA_ERR_STATE, "local_batch_solve before upload");
+  if (opt->local_iters_pass1 < 0 || opt->local_iters_pass2 < 0)
+    return fail(c, RSPL_BA_ERR_INVALID, "negative iteration count");
+  c->local_solved = true;
+  if (c->l_n_windows == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  ba::LocalOpt lo;
+  lo.thr[0] = opt->thr_mono_point;
+  lo.thr[1] = opt->thr_stereo_point;
+  lo.thr[2] = opt->thr_mono_line;
+  lo.thr[3] = opt->thr_stereo_line;
+  for (int i = 0; i < 4; ++i) lo.delta[i] = (double)(float)sqrt(lo.thr[i]); // const float thHuber* = sqrt(cfg.*) (:77-78,:125-126)
+  lo.iters[0] = opt->local_iters_pass1;
+  lo.iters[1] = opt->local_iters_pass2;
+  lo.bf_float = opt->stereo_bf_float;
+  lo.max_poses = c->l_max_poses;
+  lo.max_free = c->l_max_free_poses;
+  const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
+  CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int), c->stream));
+  ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ba::local_solve_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, smem, c->stream>>>(c->ld, lo);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResult* out) {
+  if (!c || !out) return RSPL_BA_ERR_INVALID;
+  if (!c->local_solved) return fail(c, RSPL_BA_ERR_STATE, "local_batch_download before solve");
+  if (c->l_n_windows == 0) return RSPL_BA_OK;
+  const ba::LocalDev& d = c->ld;
+  if (!out->pose_twc || (c->l_npt && !out->point_xyz) || (c->l_nln && !out->line_wd) ||
+      (c->l_n[0] && !out->mp_inlier) || (c->l_n[1] && !out->sp_inlier) || (c->l_n[2] && !out->ml_inlier) ||
+      (c->l_n[3] && !out->sl_inlier))
+    return fail(c, RSPL_BA_ERR_INVALID, "local result: null output arrays");
+  SetDevice guard(c->device);
+  cudaStream_t s = c->stream;
+  int err = 0;
+#define D2H(dst, src, bytes)                                                                        \
+  do {                                                                                              \
+    if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); \
+  } while (0)
+  D2H(&err, d.err, sizeof(int));
+  D2H(out->pose_twc, d.pose_out, sizeof(double) * 7 * c->l_np);
+  D2H(out->point_xyz, d.k[0].lm_out, sizeof(double) * 3 * c->l_npt);
+  D2H(out->line_wd, d.k[1].lm_out, sizeof(double) * 6 * c->l_nln);
+  D2H(out->mp_inlier, d.k[0].out_inl[0], (size_t)c->l_n[0]);
+  D2H(out->sp_inlier, d.k[0].out_inl[1], (size_t)c->l_n[1]);
+  D2H(out->ml_inlier, d.k[1].out_inl[0], (size_t)c->l_n[2]);
+  D2H(out->sl_inlier, d.k[1].out_inl[1], (size_t)c->l_n[3]);
+  if (out->stats) D2H(out->stats, d.stats, sizeof(RsplBaStats) * c->l_n_windows);
+#undef D2H
+  CU_TRY(c, cudaStreamSynchronize(s));
+  if (err & ba::LOCAL_ERR_DUP_EDGE)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: two constraints join the same (pose, landmark) pair");
+  if (err & ba::LOCAL_ERR_DEGREE)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: a landmark has more than 254 observations");
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch* in, const RsplBaOptions* opt,
+                                   RsplLocalBatchResult* out) {
+  int rc = rspl_ba_local_batch_upload(c, in);
+  if (rc != RSPL_BA_OK) return rc;
+  rc = rspl_ba_local_batch_solve(c, opt);
+  if (rc != RSPL_BA_OK) return rc;
+  return rspl_ba_local_batch_download(c, out);
+}
