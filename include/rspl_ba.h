@@ -191,6 +191,11 @@ int64_t rspl_ba_launch_count(const RsplBaContext* ctx);
 /* Block the host until all work queued on the context stream has finished. */
 int rspl_ba_sync(RsplBaContext* ctx);
 
+/* Diagnostics: SM cycles per phase of the last local solve summed over windows. out8: 0 linearise,
+ * 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky, 5 update/back-substitution/evaluation,
+ * 6 LM decision/restore, 7 other. */
+int rspl_ba_local_phase_cycles(RsplBaContext* ctx, double* out8);
+
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
  * line, 3 stereo line. pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]

@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus")
+    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_local_phase_cycles")
 
 _lib = None
 LOCAL_BA_READY = True
@@ -145,6 +145,8 @@ def load_library() -> C.CDLL:
     L.rspl_ba_eval_edges.restype = C.c_int
     L.rspl_ba_oplus.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p, c_f64p]
     L.rspl_ba_oplus.restype = C.c_int
+    L.rspl_ba_local_phase_cycles.argtypes = [ctx, c_f64p]
+    L.rspl_ba_local_phase_cycles.restype = C.c_int
     _lib = L
     return L
 
@@ -322,6 +324,11 @@ class Context:
     def local_batch_download(self, out: LocalBatchResult) -> LocalBatchResult:
         r = self._local_result_struct(out)
         self._check(self._L.rspl_ba_local_batch_download(self._ctx, C.byref(r)))
+        return out
+
+    def local_phase_cycles(self) -> np.ndarray:
+        out = np.zeros(8)
+        self._check(self._L.rspl_ba_local_phase_cycles(self._ctx, _p(out, c_f64p)))
         return out
 
     # ---------------- unit-level ----------------

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -17,6 +18,7 @@
 #include "ba_math.cuh"
 #include "frame_kernel.cuh"
 #include "local_kernel.cuh"
+#include "local_batched.cuh"
 
 static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
 
@@ -84,6 +86,15 @@ struct RsplBaContext {
   bool local_solved = false;
   int l_n_windows = 0, l_np = 0, l_npt = 0, l_nln = 0, l_n[4] = {0, 0, 0, 0};
   int l_max_free_poses = 0, l_max_poses = 0;
+  // batched (multi-kernel) path of the local batch
+  DevBuf batch_buf;
+  ba::BatchDev bd{};
+  bool batch_ready = false;
+  std::vector<int> l_nf_begin;          // [W+1] free poses per window (prefix)
+  std::vector<long long> l_pair_base;   // [W+1] capacity prefix of the pair lists
+  int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
+  int l_last_path = 0;                  // 1 persistent, 2 batched (diagnostics)
+  int l_super_steps = 0;
 
   // ---- unit-level scratch
   DevBuf unit_buf;
@@ -223,6 +234,7 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   cudaStreamSynchronize(c->stream);
   c->frame_buf.release();
   c->local_buf.release();
+  c->batch_buf.release();
   c->unit_buf.release();
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;

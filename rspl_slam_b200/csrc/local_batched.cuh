@@ -1,0 +1,973 @@
+// local_batched.cuh — batched LocalmapOptimization: one kernel per LM phase over ALL windows.
+//
+// Same algorithm, data layout and device functions as local_kernel.cuh (the one-CTA-per-window
+// persistent kernel), reorganised for throughput on large batches (BASELINE config C4: 1024
+// windows): every phase is a grid over (window, chunk) work items with a small register
+// footprint, so tens of thousands of CTAs keep HBM busy instead of 8 warps per SM chasing
+// dependent loads. Each window carries its own Levenberg-Marquardt state machine in HBM
+// (WinState); all accept/reject decisions are taken on the device (k_decide). The host only
+// replays the fixed kernel sequence of a "super-step" and polls one integer (number of windows
+// still iterating) every few super-steps.
+//
+//   super-step = k_linearize -> k_pose_blocks -> k_begin_trial -> k_schur_prep -> k_schur_reduce
+//                -> k_solve -> k_backsub -> k_decide -> k_restore
+// A window in stage NEED_LIN executes all of them (a new LM iteration), a window in stage
+// NEED_TRIAL (rejected step, new lambda) skips the first two, a DONE window skips everything.
+// All reductions use fixed work assignments and fixed-order trees: results are bitwise
+// reproducible and independent of how many windows share the batch (or the GPU count).
+#pragma once
+
+#include "local_kernel.cuh"
+
+namespace ba {
+
+constexpr int BT = 128; // threads per CTA of the per-landmark / per-pair kernels
+constexpr int BW = BT / 32;
+
+enum { STAGE_NEED_LIN = 0, STAGE_NEED_TRIAL = 1, STAGE_DONE = 2 };
+
+struct WinState {
+  int stage, pass, it, qmax, n_sys, solve_ok, prep_fail, restore;
+  int robust, iters, nf, pad;
+  double lambda, ni, chi_cur, scale_pose, nact;
+  DevStats st;
+};
+
+struct BatchDev { // extra state of the batched path (all in HBM)
+  WinState* ws;   // [W]
+  double* P_q;    // [NP][4]
+  double* P_t;    // [NP][3]
+  double* P_R;    // [NP][9]
+  double* P_bq;   // [NP][4]
+  double* P_bt;   // [NP][3]
+  int* free_idx;  // [NP] window-local free index or -1
+  int* pact;      // [NP] #active edges per pose in the current pass
+  int* nf_begin;  // [W+1] offsets into the free-pose arrays
+  int* pose_of;   // [NF] window-local pose of a free index
+  int* sys_idx;   // [NF] block index in the reduced system or -1
+  double* Hpp;    // [NF][21]
+  double* bp;     // [NF][6]
+  double* xp;     // [NF][6] pose increments by free index
+  double* hs_part; // [W][Pmax][42]
+  double* part;   // [W][C][4] per-chunk partial sums
+  int* pair_beg;  // [W][2*Pmax+1] entry offsets: point entries, line entries per pair
+  int2* pairs;    // pair entries (e_i, e_j) into the sorted edge arrays
+  const long long* pair_base; // [W+1] region of each window inside `pairs`
+  int* n_active;  // device counter for the host poll
+  int Cp, Cl, C;  // landmark chunks per window: points, lines, total
+  int Pmax, NFmax;
+};
+
+BA_DEV void pair_decode(int p, int nf, int& fi, int& fj) {
+  int row = 0, rem = p;
+  while (rem >= nf - row) {
+    rem -= nf - row;
+    ++row;
+  }
+  fi = row;
+  fj = row + rem;
+}
+BA_DEV int pair_index(int fi, int fj, int nf) { return fi * nf - fi * (fi - 1) / 2 + (fj - fi); }
+
+// deterministic CTA reduction of N doubles per thread (BT threads); thread q < N ends with sum q
+template <int N>
+BA_DEV void cta_reduce(double* v, double* smem /* [BW][N] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < N; ++q) v[q] = warp_allreduce(v[q]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) smem[warp * N + q] = v[q];
+  }
+  __syncthreads();
+}
+template <int N>
+BA_DEV double cta_reduce_get(const double* smem, int q) {
+  double s = smem[q];
+#pragma unroll
+  for (int w = 1; w < BW; ++w) s += smem[w * N + q];
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup: free-pose tables, optimiser poses, pair lists
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BT) kb_init(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                              const __grid_constant__ LocalOpt o) {
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  const int f0 = b.nf_begin[w];
+  if (tid == 0) {
+    int nf = 0;
+    for (int p = 0; p < np; ++p) {
+      if (d.pose_fixed[p0 + p]) {
+        b.free_idx[p0 + p] = -1;
+      } else {
+        b.free_idx[p0 + p] = nf;
+        b.pose_of[f0 + nf] = p;
+        ++nf;
+      }
+    }
+    WinState& s = b.ws[w];
+    s.stage = STAGE_DONE;
+    s.pass = 0;
+    s.it = s.qmax = s.n_sys = 0;
+    s.solve_ok = 1;
+    s.prep_fail = 0;
+    s.restore = 0;
+    s.robust = 1;
+    s.iters = 0;
+    s.nf = nf;
+    s.lambda = 0;
+    s.ni = 2;
+    s.chi_cur = 0;
+    s.scale_pose = 0;
+    s.nact = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.st.iters[i] = s.st.trials[i] = 0;
+    s.st.edges_linearized = s.st.edges_evaluated = 0;
+    s.st.final_chi2 = s.st.final_lambda = 0;
+  }
+  for (int p = tid; p < np; p += BT) {
+    double q[4], R[9];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = b.P_q[4 * (size_t)(p0 + p) + i] = d.pose_tcw[(size_t)i * d.n_poses + p0 + p];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b.P_t[3 * (size_t)(p0 + p) + i] = d.pose_tcw[(size_t)(4 + i) * d.n_poses + p0 + p];
+    quat_to_R(q, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) b.P_R[9 * (size_t)(p0 + p) + i] = R[i];
+  }
+}
+
+// pair lists: one warp per (window, pair); MODE 0 counts, MODE 1 fills (ballot compaction: deterministic)
+template <int KIND, int MODE>
+BA_DEV int pair_scan_kind(const LocalDev& d, const BatchDev& b, const KindDev& k, int w, int pose_i, int fj, bool diag,
+                          int lane, int2* out) {
+  const int l0 = k.lm_begin[w];
+  const int p0 = d.pose_begin[w];
+  const int a = k.pbeg[p0 + pose_i], e_end = k.pbeg[p0 + pose_i + 1];
+  int n = 0;
+  for (int base = a; base < e_end; base += 32) {
+    const int it = base + lane;
+    bool hit = false;
+    int e = 0, e2 = 0;
+    if (it < e_end) {
+      e = k.plist[it];
+      if (diag) {
+        hit = true;
+        e2 = e;
+      } else {
+        const int l = l0 + k.lm[e];
+        const int sl = k.slot[(size_t)l * d.slot_stride + fj];
+        if (sl != SLOT_NONE) {
+          hit = true;
+          e2 = k.ebeg[l] + sl;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (MODE == 1 && hit) out[n + __popc(m & ((1u << lane) - 1))] = make_int2(e, e2);
+    n += __popc(m);
+  }
+  return n;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BT) kb_pairs(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nf = b.ws[w].nf;
+  const int np_pairs = nf * (nf + 1) / 2;
+  int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
+  if (MODE == 1 && threadIdx.x == 0) {
+    // exclusive scan of the counts written by MODE 0 (counts sit in pb[2p], pb[2p+1])
+    long long run = b.pair_base[w];
+    const long long cap = b.pair_base[w + 1];
+    for (int q = 0; q < 2 * np_pairs; ++q) {
+      const int c = pb[q];
+      pb[q] = (int)run;
+      run += c;
+    }
+    pb[2 * np_pairs] = (int)run;
+    if (run > cap) { // only possible with duplicate (pose, landmark) edges, which are rejected anyway
+      atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
+      for (int q = 0; q <= 2 * np_pairs; ++q) pb[q] = (int)b.pair_base[w];
+    }
+  }
+  if (MODE == 1) __syncthreads();
+  if (MODE == 1 && (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  for (int p = warp; p < np_pairs; p += BW) {
+    int fi, fj;
+    pair_decode(p, nf, fi, fj);
+    const int pose_i = b.pose_of[b.nf_begin[w] + fi];
+    const bool diag = fi == fj;
+    if (MODE == 0) {
+      const int n0 = pair_scan_kind<0, 0>(d, b, d.k[0], w, pose_i, fj, diag, lane, nullptr);
+      const int n1 = pair_scan_kind<1, 0>(d, b, d.k[1], w, pose_i, fj, diag, lane, nullptr);
+      if (lane == 0) {
+        pb[2 * p] = n0;
+        pb[2 * p + 1] = n1;
+      }
+    } else {
+      pair_scan_kind<0, 1>(d, b, d.k[0], w, pose_i, fj, diag, lane, b.pairs + pb[2 * p]);
+      pair_scan_kind<1, 1>(d, b, d.k[1], w, pose_i, fj, diag, lane, b.pairs + pb[2 * p + 1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass begin: active sets (§9.12), reduced-system indices
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k, int w) {
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  const int p0 = d.pose_begin[w];
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    const int l = l0 + i;
+    int any = 0;
+    for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e) {
+      if (k.lvl[e]) continue;
+      any = 1;
+      atomicAdd(&b.pact[p0 + (k.info[e] & 0xffff)], 1);
+    }
+    k.act[l] = (uint8_t)any;
+  }
+}
+
+__global__ void __launch_bounds__(256) kb_begin_pass(const __grid_constant__ LocalDev d,
+                                                     const __grid_constant__ BatchDev b,
+                                                     const __grid_constant__ LocalOpt o, int pass) {
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  for (int p = tid; p < np; p += blockDim.x) b.pact[p0 + p] = 0;
+  __syncthreads();
+  mark_active_b<0>(d, b, d.k[0], w);
+  mark_active_b<1>(d, b, d.k[1], w);
+  __syncthreads();
+  if (tid == 0) {
+    WinState& s = b.ws[w];
+    const int f0 = b.nf_begin[w];
+    int nsys = 0;
+    for (int fi = 0; fi < s.nf; ++fi) b.sys_idx[f0 + fi] = b.pact[p0 + b.pose_of[f0 + fi]] > 0 ? nsys++ : -1;
+    s.n_sys = nsys;
+    s.pass = pass;
+    s.it = 0;
+    s.qmax = 0;
+    s.lambda = 0;
+    s.ni = 2;
+    s.robust = pass == 0 ? 1 : 0;
+    s.iters = o.iters[pass];
+    s.restore = 0;
+    s.stage = s.iters > 0 ? STAGE_NEED_LIN : STAGE_DONE;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: linearise, one thread per landmark (edges of a landmark in g2o order)
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+BA_DEV void linearize_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o, const KindDev& k, int w, int l,
+                          bool robust, double& chi_part, double& maxdiag_part, double& nact_part) {
+  // The pose x landmark block W = Jp^T (rho1 Omega) Jl is NOT materialised here: kb_schur_prep
+  // recomputes it from the edge record (~200 flop) instead of a 144/192 B round trip through HBM.
+  using T = KT<KIND>;
+  const int p0 = d.pose_begin[w];
+  double X[T::SD];
+  load_lm<KIND>(k, l, X);
+  double H[T::HD], bb[T::LD];
+#pragma unroll
+  for (int q = 0; q < T::HD; ++q) H[q] = 0;
+#pragma unroll
+  for (int q = 0; q < T::LD; ++q) bb[q] = 0;
+  const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  for (int e = ea; e < eb; ++e) {
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double m[T::MD], r[4], Jp[24], Jl[16];
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, true>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, m, r,
+                          Jp, Jl);
+    const double c2 = edge_chi2<KIND>(r);
+    k.chi2[e] = c2;
+    double wgt = 1.0;
+    const double rho0 = robust ? huber(c2, o.delta[2 * KIND + (stereo ? 1 : 0)], wgt) : c2;
+    chi_part += rho0;
+    nact_part += 1.0;
+    const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < T::LD; ++a) {
+      double g = 0;
+#pragma unroll
+      for (int rr = 0; rr < T::ROWS; ++rr) g += Jl[rr * T::LD + a] * r[rr];
+      bb[a] -= wo * g;
+#pragma unroll
+      for (int c = a; c < T::LD; ++c) {
+        double h = 0;
+#pragma unroll
+        for (int rr = 0; rr < T::ROWS; ++rr) h += Jl[rr * T::LD + a] * Jl[rr * T::LD + c];
+        H[q++] += wo * h;
+      }
+    }
+  }
+  int q = 0;
+#pragma unroll
+  for (int a = 0; a < T::LD; ++a)
+#pragma unroll
+    for (int c = a; c < T::LD; ++c) {
+      if (c == a) maxdiag_part = fmax(maxdiag_part, fabs(H[q]));
+      k.H[(size_t)q * k.n_lm + l] = H[q];
+      ++q;
+    }
+#pragma unroll
+  for (int a = 0; a < T::LD; ++a) k.b[(size_t)a * k.n_lm + l] = bb[a];
+}
+
+// grid (chunks of this kind, windows): the chunk index is the fastest-varying block index so the
+// CTAs of one window run together and share its poses / edges in L1 / L2
+template <int KIND>
+__global__ void __launch_bounds__(BT) kb_linearize(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                   const __grid_constant__ LocalOpt o) {
+  __shared__ double red[BW * 3];
+  const int w = blockIdx.y;
+  const int c = blockIdx.x + (KIND ? b.Cp : 0); // slot in the per-window partial-sum table
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_LIN) return;
+  const bool robust = s.robust;
+  double v[3] = {0, 0, 0}; // chi, nact, maxdiag
+  double mx = 0;
+  {
+    const KindDev& k = d.k[KIND];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i < nl && k.act[l0 + i]) linearize_one<KIND>(d, b, o, k, w, l0 + i, robust, v[0], mx, v[1]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  v[2] = 0;
+  cta_reduce<3>(v, red);
+  __shared__ double redmx[BW];
+  if ((threadIdx.x & 31) == 0) redmx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m2 = redmx[0];
+#pragma unroll
+    for (int q = 1; q < BW; ++q) m2 = fmax(m2, redmx[q]);
+    double* pp = b.part + ((size_t)w * b.C + c) * 4;
+    pp[0] = cta_reduce_get<3>(red, 0);
+    pp[1] = cta_reduce_get<3>(red, 1);
+    pp[2] = m2;
+  }
+}
+
+// K1': Hpp, bp per free pose; one CTA per (window, free pose)
+template <int KIND>
+BA_DEV void pose_block_kind(const LocalDev& d, const BatchDev& b, const LocalOpt& o, const KindDev& k, int w, int p,
+                            bool robust, double* acc) {
+  using T = KT<KIND>;
+  const int l0 = k.lm_begin[w];
+  const int p0 = d.pose_begin[w];
+  const int a = k.pbeg[p0 + p], e_end = k.pbeg[p0 + p + 1];
+  const double* R = b.P_R + 9 * (size_t)(p0 + p);
+  const double* t = b.P_t + 3 * (size_t)(p0 + p);
+  for (int it = a + threadIdx.x; it < e_end; it += BT) {
+    const int e = k.plist[it];
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double X[T::SD], m[T::MD], r[4], Jp[24], Jl[16];
+    load_lm<KIND>(k, l0 + k.lm[e], X);
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, true>(cam, o.bf_float, stereo, R, t, X, m, r, Jp, Jl);
+    double wgt = 1.0;
+    if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
+    const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double g = 0;
+#pragma unroll
+      for (int rr = 0; rr < T::ROWS; ++rr) g += Jp[rr * 6 + i] * r[rr];
+      acc[21 + i] -= wo * g;
+#pragma unroll
+      for (int j = i; j < 6; ++j) {
+        double h = 0;
+#pragma unroll
+        for (int rr = 0; rr < T::ROWS; ++rr) h += Jp[rr * 6 + i] * Jp[rr * 6 + j];
+        acc[up6(i, j)] += wo * h;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BT) kb_pose_blocks(const __grid_constant__ LocalDev d,
+                                                     const __grid_constant__ BatchDev b,
+                                                     const __grid_constant__ LocalOpt o) {
+  __shared__ double red[BW * 27];
+  const int w = blockIdx.y, fi = blockIdx.x;
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_LIN || fi >= s.nf) return;
+  const int f0 = b.nf_begin[w];
+  if (b.sys_idx[f0 + fi] < 0) return;
+  const int p = b.pose_of[f0 + fi];
+  double acc[27];
+#pragma unroll
+  for (int q = 0; q < 27; ++q) acc[q] = 0;
+  pose_block_kind<0>(d, b, o, d.k[0], w, p, s.robust, acc);
+  pose_block_kind<1>(d, b, o, d.k[1], w, p, s.robust, acc);
+  cta_reduce<27>(acc, red);
+  if (threadIdx.x < 27) {
+    const double v = cta_reduce_get<27>(red, threadIdx.x);
+    if (threadIdx.x < 21) b.Hpp[(size_t)(f0 + fi) * 21 + threadIdx.x] = v;
+    else b.bp[(size_t)(f0 + fi) * 6 + threadIdx.x - 21] = v;
+  }
+}
+
+// one thread per window: chi0, lambda init (computeLambdaInit), stage NEED_LIN -> NEED_TRIAL
+__global__ void __launch_bounds__(128) kb_begin_trial(const __grid_constant__ LocalDev d,
+                                                      const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.n_windows) return;
+  WinState& s = b.ws[w];
+  s.restore = 0;
+  s.prep_fail = 0;
+  if (s.stage != STAGE_NEED_LIN) return;
+  double chi = 0, nact = 0, mx = 0;
+  for (int c = 0; c < b.C; ++c) {
+    const double* pp = b.part + ((size_t)w * b.C + c) * 4;
+    chi += pp[0];
+    nact += pp[1];
+    mx = fmax(mx, pp[2]);
+  }
+  if (nact == 0.0) { // no active edge: optimize() returns without iterating
+    s.stage = STAGE_DONE;
+    return;
+  }
+  if (s.it == 0) {
+    const int f0 = b.nf_begin[w];
+    for (int fi = 0; fi < s.nf; ++fi) {
+      if (b.sys_idx[f0 + fi] < 0) continue;
+      for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(b.Hpp[(size_t)(f0 + fi) * 21 + up6(i, i)]));
+    }
+    s.lambda = 1e-5 * mx;
+    s.ni = 2;
+  }
+  s.chi_cur = chi;
+  s.nact = nact;
+  s.qmax = 0;
+  s.st.edges_linearized += (long long)nact;
+  s.st.edges_evaluated += (long long)nact;
+  s.stage = STAGE_NEED_TRIAL;
+}
+
+// K3: per landmark L = chol(Hll + lambda), y = L^-1 bl, Z_e = W_e L^-T
+template <int KIND>
+BA_DEV void schur_prep_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o, const KindDev& k, int w, int l,
+                           double lambda, bool robust, int& fail) {
+  using T = KT<KIND>;
+  constexpr int LD = T::LD;
+  const int p0 = d.pose_begin[w], f0 = b.nf_begin[w];
+  double X[T::SD];
+  load_lm<KIND>(k, l, X);
+  double Hup[T::HD], Lf[LD * (LD + 1) / 2], inv[LD];
+#pragma unroll
+  for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+  if (!small_chol<LD>(Hup, lambda, Lf, inv)) fail = 1;
+  double y[LD];
+#pragma unroll
+  for (int a = 0; a < LD; ++a) {
+    double v = k.b[(size_t)a * k.n_lm + l];
+#pragma unroll
+    for (int p = 0; p < a; ++p) v -= Lf[a * (a + 1) / 2 + p] * y[p];
+    y[a] = v * inv[a];
+    k.y[(size_t)a * k.n_lm + l] = y[a];
+  }
+  const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  for (int e = ea; e < eb; ++e) {
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const int fi = b.free_idx[p0 + p];
+    if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
+    double* Ze = k.Z + (size_t)e * T::WD;
+    double wv[T::WD];
+    if (k.lvl[e]) { // excluded edge (level 1): no contribution
+#pragma unroll
+      for (int q = 0; q < T::WD; q += 2) *reinterpret_cast<double2*>(Ze + q) = make_double2(0.0, 0.0);
+      continue;
+    }
+    { // W = Jp^T (rho1 Omega) Jl, recomputed from the edge record
+      const bool stereo = (info >> 30) & 1;
+      Cam cam;
+      load_cam(d.cameras, (info >> 16) & 0xff, cam);
+      double m[T::MD], r[4], Jp[24], Jl[16];
+      load_edge<KIND>(k, e, m);
+      eval_edge<KIND, true>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, m, r,
+                            Jp, Jl);
+      double wgt = 1.0;
+      if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
+      const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < LD; ++c) {
+          double h = 0;
+#pragma unroll
+          for (int rr = 0; rr < T::ROWS; ++rr) h += Jp[rr * 6 + a] * Jl[rr * LD + c];
+          wv[a * LD + c] = wo * h;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      double z[LD];
+#pragma unroll
+      for (int c = 0; c < LD; ++c) {
+        double v = wv[a * LD + c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) v -= Lf[c * (c + 1) / 2 + p] * z[p];
+        z[c] = v * inv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < LD; ++c) wv[a * LD + c] = z[c];
+    }
+#pragma unroll
+    for (int q = 0; q < T::WD; q += 2) *reinterpret_cast<double2*>(Ze + q) = make_double2(wv[q], wv[q + 1]);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BT) kb_schur_prep(const __grid_constant__ LocalDev d,
+                                                    const __grid_constant__ BatchDev b,
+                                                    const __grid_constant__ LocalOpt o) {
+  const int w = blockIdx.y;
+  WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  int fail = 0;
+  const KindDev& k = d.k[KIND];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  const int i = blockIdx.x * BT + threadIdx.x;
+  if (i < nl && k.act[l0 + i]) schur_prep_one<KIND>(d, b, o, k, w, l0 + i, s.lambda, s.robust, fail);
+  if (fail) atomicOr(&s.prep_fail, 1);
+}
+
+// K3': one CTA per (window, pose pair): sum_e Z_i Z_j^T (and Z_i y on the diagonal) over the pair list
+template <int KIND>
+BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, double* acc) {
+  using T = KT<KIND>;
+  constexpr int LD = T::LD;
+  const int l0 = k.lm_begin[w];
+  for (int it = threadIdx.x; it < n; it += BT) {
+    const int2 ee = ent[it];
+    const int l = l0 + k.lm[ee.x];
+    if (!k.act[l]) continue;
+    double Zi[T::WD], Zj[T::WD];
+    const double* zi = k.Z + (size_t)ee.x * T::WD;
+#pragma unroll
+    for (int q = 0; q < T::WD; q += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(zi + q);
+      Zi[q] = v.x;
+      Zi[q + 1] = v.y;
+    }
+    if (diag) {
+#pragma unroll
+      for (int q = 0; q < T::WD; ++q) Zj[q] = Zi[q];
+    } else {
+      const double* zj = k.Z + (size_t)ee.y * T::WD;
+#pragma unroll
+      for (int q = 0; q < T::WD; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(zj + q);
+        Zj[q] = v.x;
+        Zj[q + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < LD; ++q) v += Zi[r * LD + q] * Zj[c * LD + q];
+        acc[r * 6 + c] += v;
+      }
+    if (diag) {
+      double y[LD];
+#pragma unroll
+      for (int q = 0; q < LD; ++q) y[q] = k.y[(size_t)q * k.n_lm + l];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < LD; ++q) v += Zi[r * LD + q] * y[q];
+        acc[36 + r] += v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BT) kb_schur_reduce(const __grid_constant__ LocalDev d,
+                                                      const __grid_constant__ BatchDev b) {
+  __shared__ double red[BW * 42];
+  // pair index fastest: the ~NF(NF+1)/2 CTAs of one window run together, so the window's Z blocks
+  // (each read by every pair that contains its pose) are fetched from HBM once and then hit in L2
+  const int w = blockIdx.y, p = blockIdx.x;
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  const int nf = s.nf;
+  if (p >= nf * (nf + 1) / 2) return;
+  int fi, fj;
+  pair_decode(p, nf, fi, fj);
+  const int f0 = b.nf_begin[w];
+  if (b.sys_idx[f0 + fi] < 0 || b.sys_idx[f0 + fj] < 0) return;
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
+  const bool diag = fi == fj;
+  double acc[42];
+#pragma unroll
+  for (int q = 0; q < 42; ++q) acc[q] = 0;
+  schur_pair_entries<0>(d.k[0], w, b.pairs + pb[0], pb[1] - pb[0], diag, acc);
+  schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, acc);
+  cta_reduce<42>(acc, red);
+  if (threadIdx.x < 42) b.hs_part[((size_t)w * b.Pmax + p) * 42 + threadIdx.x] = cta_reduce_get<42>(red, threadIdx.x);
+}
+
+// K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory
+__global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = blockIdx.x, tid = threadIdx.x;
+  WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  const int nf = s.nf, f0 = b.nf_begin[w], p0 = d.pose_begin[w];
+  const int n = 6 * s.n_sys;
+  double* Hs = reinterpret_cast<double*>(smem_raw);
+  double* bs = Hs + (size_t)n * n;
+  double* xs = bs + n;
+  double* sc_part = xs + n; // [nf] pose part of the LM scale
+  __shared__ int s_ok;
+  const double lambda = s.lambda;
+  // assemble upper blocks
+  const int npairs = nf * (nf + 1) / 2;
+  for (int idx = tid; idx < npairs * 36; idx += blockDim.x) {
+    const int p = idx / 36, rc = idx % 36, r = rc / 6, c = rc % 6;
+    int fi, fj;
+    pair_decode(p, nf, fi, fj);
+    const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
+    if (si < 0 || sj < 0) continue;
+    double v = -b.hs_part[((size_t)w * b.Pmax + p) * 42 + rc];
+    if (fi == fj) {
+      const int rr = r < c ? r : c, cc = r < c ? c : r;
+      v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? lambda : 0.0);
+    }
+    Hs[(size_t)(6 * si + r) * n + 6 * sj + c] = v;
+  }
+  for (int idx = tid; idx < nf * 6; idx += blockDim.x) {
+    const int fi = idx / 6, r = idx % 6;
+    const int si = b.sys_idx[f0 + fi];
+    if (si < 0) continue;
+    const int p = pair_index(fi, fi, nf);
+    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + p) * 42 + 36 + r];
+  }
+  __syncthreads();
+  if (n > 0) {
+    WinSmem ws2; // cholesky_solve reports through sc->solve_ok
+    ws2.Hs = Hs;
+    ws2.bs = bs;
+    ws2.xp = xs;
+    __shared__ WinScalars sc_local;
+    ws2.sc = &sc_local;
+    cholesky_solve(ws2, n);
+    __syncthreads();
+    if (tid == 0) s_ok = sc_local.solve_ok && !s.prep_fail;
+  } else if (tid == 0) {
+    s_ok = !s.prep_fail;
+  }
+  __syncthreads();
+  const bool ok = s_ok;
+  if (ok) {
+    for (int fi = tid; fi < nf; fi += blockDim.x) {
+      const int si = b.sys_idx[f0 + fi];
+      double part = 0;
+      if (si >= 0) {
+        const size_t gp = (size_t)(p0 + b.pose_of[f0 + fi]);
+        Pose T;
+        double x6[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          x6[q] = xs[6 * si + q];
+          b.xp[(size_t)(f0 + fi) * 6 + q] = x6[q];
+          part += x6[q] * (lambda * x6[q] + b.bp[(size_t)(f0 + fi) * 6 + q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) T.q[q] = b.P_bq[4 * gp + q] = b.P_q[4 * gp + q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) T.t[q] = b.P_bt[3 * gp + q] = b.P_t[3 * gp + q];
+        const Pose Tn = pose_oplus(T, x6);
+        double Rn[9];
+        quat_to_R(Tn.q, Rn);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b.P_q[4 * gp + q] = Tn.q[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) b.P_t[3 * gp + q] = Tn.t[q];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) b.P_R[9 * gp + q] = Rn[q];
+      }
+      sc_part[fi] = part;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double sp = 0;
+    if (ok)
+      for (int fi = 0; fi < nf; ++fi) sp += sc_part[fi];
+    s.scale_pose = sp;
+    s.solve_ok = ok ? 1 : 0;
+  }
+}
+
+// K5/K6: back-substitution, manifold update, re-evaluation; one thread per landmark
+template <int KIND>
+BA_DEV void backsub_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o, const KindDev& k, int w, int l,
+                        double lambda, bool robust, double& chi_part, double& scale_part) {
+  using T = KT<KIND>;
+  constexpr int LD = T::LD;
+  const int p0 = d.pose_begin[w], f0 = b.nf_begin[w];
+  double v[LD];
+#pragma unroll
+  for (int a = 0; a < LD; ++a) v[a] = k.y[(size_t)a * k.n_lm + l];
+  const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  for (int e = ea; e < eb; ++e) {
+    const int fi = b.free_idx[p0 + (k.info[e] & 0xffff)];
+    if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
+    const double* Ze = k.Z + (size_t)e * T::WD;
+    const double* xv = b.xp + (size_t)(f0 + fi) * 6;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      const double xr = xv[r];
+#pragma unroll
+      for (int a = 0; a < LD; ++a) v[a] -= Ze[r * LD + a] * xr;
+    }
+  }
+  double Hup[T::HD], Lf[LD * (LD + 1) / 2], inv[LD], xl[LD];
+#pragma unroll
+  for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+  small_chol<LD>(Hup, lambda, Lf, inv);
+#pragma unroll
+  for (int a = LD - 1; a >= 0; --a) {
+    double t2 = v[a];
+#pragma unroll
+    for (int p = a + 1; p < LD; ++p) t2 -= Lf[p * (p + 1) / 2 + a] * xl[p];
+    xl[a] = t2 * inv[a];
+  }
+#pragma unroll
+  for (int a = 0; a < LD; ++a) scale_part += xl[a] * (lambda * xl[a] + k.b[(size_t)a * k.n_lm + l]);
+  double X[T::SD], Xn[T::SD];
+  load_lm<KIND>(k, l, X);
+#pragma unroll
+  for (int q = 0; q < T::SD; ++q) k.xb[(size_t)q * k.n_lm + l] = X[q];
+  if (KIND == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Xn[q] = X[q] + xl[q];
+  } else {
+    line_oplus(X, xl, Xn);
+  }
+#pragma unroll
+  for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = Xn[q];
+  for (int e = ea; e < eb; ++e) {
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double m[T::MD], r[4];
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, false>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), Xn, m, r,
+                           nullptr, nullptr);
+    const double c2 = edge_chi2<KIND>(r);
+    k.chi2[e] = c2;
+    double wgt;
+    chi_part += robust ? huber(c2, o.delta[2 * KIND + (stereo ? 1 : 0)], wgt) : c2;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BT) kb_backsub(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                 const __grid_constant__ LocalOpt o) {
+  __shared__ double red[BW * 2];
+  const int w = blockIdx.y;
+  const int c = blockIdx.x + (KIND ? b.Cp : 0);
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL || !s.solve_ok) return;
+  double v[2] = {0, 0}; // chi1, scale
+  {
+    const KindDev& k = d.k[KIND];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i < nl && k.act[l0 + i]) backsub_one<KIND>(d, b, o, k, w, l0 + i, s.lambda, s.robust, v[0], v[1]);
+  }
+  cta_reduce<2>(v, red);
+  if (threadIdx.x == 0) {
+    double* pp = b.part + ((size_t)w * b.C + c) * 4;
+    pp[0] = cta_reduce_get<2>(red, 0);
+    pp[1] = cta_reduce_get<2>(red, 1);
+  }
+}
+
+// one thread per window: the Levenberg accept / reject logic (§9.9) and the window's next stage
+__global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.n_windows) return;
+  WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  const bool ok = s.solve_ok;
+  double chi1 = 0, scale = s.scale_pose;
+  if (ok) {
+    for (int c = 0; c < b.C; ++c) {
+      const double* pp = b.part + ((size_t)w * b.C + c) * 4;
+      chi1 += pp[0];
+      scale += pp[1];
+    }
+  }
+  const double tempChi = ok ? chi1 : DBL_MAX; // a failed factorisation is a rejected step
+  double rho = s.chi_cur - tempChi;
+  rho /= (ok ? scale : 0.0) + 1e-3;
+  bool stop_lambda = false, accepted = false;
+  if (rho > 0 && isfinite(tempChi)) {
+    const double c = 2 * rho - 1;
+    double alpha = 1. - c * c * c;
+    alpha = fmin(alpha, 2. / 3.);
+    s.lambda *= fmax(1. / 3., alpha);
+    s.ni = 2;
+    s.chi_cur = tempChi;
+    accepted = true;
+  } else {
+    s.lambda *= s.ni;
+    s.ni *= 2;
+    if (!isfinite(s.lambda)) stop_lambda = true;
+  }
+  const int q1 = stop_lambda ? s.qmax : s.qmax + 1;
+  s.qmax = q1;
+  s.st.trials[s.pass]++;
+  if (ok) s.st.edges_evaluated += (long long)s.nact;
+  if (!accepted && ok) { // pop(): poses here, landmarks in kb_restore
+    const int p0 = d.pose_begin[w], f0 = b.nf_begin[w];
+    for (int fi = 0; fi < s.nf; ++fi) {
+      if (b.sys_idx[f0 + fi] < 0) continue;
+      const size_t gp = (size_t)(p0 + b.pose_of[f0 + fi]);
+      double q[4], R[9];
+      for (int i = 0; i < 4; ++i) q[i] = b.P_q[4 * gp + i] = b.P_bq[4 * gp + i];
+      for (int i = 0; i < 3; ++i) b.P_t[3 * gp + i] = b.P_bt[3 * gp + i];
+      quat_to_R(q, R);
+      for (int i = 0; i < 9; ++i) b.P_R[9 * gp + i] = R[i];
+    }
+    s.restore = 1;
+  }
+  if (!stop_lambda && rho < 0 && q1 < 10) {
+    s.stage = STAGE_NEED_TRIAL; // retry with the larger lambda
+    return;
+  }
+  s.st.iters[s.pass]++;
+  s.it++;
+  const bool terminate = (q1 == 10 || rho == 0 || !isfinite(s.lambda));
+  s.stage = (terminate || s.it >= s.iters) ? STAGE_DONE : STAGE_NEED_LIN;
+}
+
+// grid (Cp + Cl, windows): chunk < Cp restores points, else lines
+__global__ void __launch_bounds__(BT) kb_restore(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, c = blockIdx.x;
+  if (!b.ws[w].restore) return;
+  if (c < b.Cp) {
+    const KindDev& k = d.k[0];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = c * BT + threadIdx.x;
+    if (i < nl && k.act[l0 + i]) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) k.x[(size_t)q * k.n_lm + l0 + i] = k.xb[(size_t)q * k.n_lm + l0 + i];
+    }
+  } else {
+    const KindDev& k = d.k[1];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = (c - b.Cp) * BT + threadIdx.x;
+    if (i < nl && k.act[l0 + i]) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) k.x[(size_t)q * k.n_lm + l0 + i] = k.xb[(size_t)q * k.n_lm + l0 + i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) kb_count_active(const __grid_constant__ LocalDev d,
+                                                       const __grid_constant__ BatchDev b) {
+  int n = 0;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < d.n_windows; w += gridDim.x * blockDim.x)
+    n += b.ws[w].stage != STAGE_DONE;
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(b.n_active, n);
+}
+
+// flagging / write-back, edge-parallel
+template <int KIND, bool FINAL>
+BA_DEV void flag_edges(const LocalDev& d, const BatchDev& b, const LocalOpt& o, const KindDev& k, int w, int chunk,
+                       int nchunks) {
+  const int l0 = k.lm_begin[w];
+  const int p0 = d.pose_begin[w];
+  const int e0 = edge_base(k, w), e1 = edge_base(k, w + 1);
+  for (int e = e0 + chunk * blockDim.x + threadIdx.x; e < e1; e += nchunks * blockDim.x) {
+    const int info = k.info[e];
+    const bool stereo = (info >> 30) & 1;
+    const double thr = o.thr[2 * KIND + (stereo ? 1 : 0)];
+    bool depth_ok = true;
+    if (KIND == 0) {
+      const int p = info & 0xffff;
+      double X[3], Xc[3];
+      load_lm<0>(k, l0 + k.lm[e], X);
+      transform_point(b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, Xc);
+      depth_ok = Xc[2] > 0.0;
+    }
+    if (FINAL) {
+      const int key = k.src[e];
+      k.out_inl[key >> 30][key & 0x3fffffff] = (k.chi2[e] <= thr && depth_ok) ? 1 : 0; // :213-231
+    } else {
+      k.lvl[e] = (k.chi2[e] > thr || !depth_ok) ? 1 : 0; // :176-206
+    }
+  }
+}
+
+template <bool FINAL>
+__global__ void __launch_bounds__(256) kb_flag(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                               const __grid_constant__ LocalOpt o) {
+  const int w = blockIdx.x;
+  flag_edges<0, FINAL>(d, b, o, d.k[0], w, blockIdx.y, gridDim.y);
+  flag_edges<1, FINAL>(d, b, o, d.k[1], w, blockIdx.y, gridDim.y);
+}
+
+__global__ void __launch_bounds__(256) kb_writeback(const __grid_constant__ LocalDev d,
+                                                    const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.x, tid = threadIdx.x;
+  write_landmarks<0>(d.k[0], w);
+  write_landmarks<1>(d.k[1], w);
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  for (int p = tid; p < np; p += blockDim.x) {
+    Pose T;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) T.q[i] = b.P_q[4 * (size_t)(p0 + p) + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T.t[i] = b.P_t[3 * (size_t)(p0 + p) + i];
+    const Pose Twc = pose_inverse(T);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d.pose_out[(size_t)i * d.n_poses + p0 + p] = Twc.t[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.pose_out[(size_t)(3 + i) * d.n_poses + p0 + p] = Twc.q[i];
+  }
+  if (tid == 0 && d.stats) {
+    WinState& s = b.ws[w];
+    s.st.final_chi2 = s.chi_cur;
+    s.st.final_lambda = s.lambda;
+    reinterpret_cast<DevStats*>(d.stats)[w] = s.st;
+  }
+}
+
+} // namespace ba

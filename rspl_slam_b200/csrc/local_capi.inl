@@ -91,12 +91,27 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   }
   // per-window limits of the shared-memory path
   int max_poses = 1, max_free = 1;
+  c->batch_ready = false;
+  c->l_nf_begin.assign(W + 1, 0);
+  c->l_pair_base.assign(W + 1, 0);
+  c->l_max_pts = c->l_max_lns = c->l_max_edges = 0;
   for (int w = 0; w < W; ++w) {
     const int a = in->pose_begin[w], b = in->pose_begin[w + 1];
     int nf = 0;
     for (int p = a; p < b; ++p) nf += in->pose_fixed[p] ? 0 : 1;
     if (b - a > max_poses) max_poses = b - a;
     if (nf > max_free) max_free = nf;
+    c->l_nf_begin[w + 1] = c->l_nf_begin[w] + nf;
+    const int npt = in->point_begin[w + 1] - in->point_begin[w], nln = in->line_begin[w + 1] - in->line_begin[w];
+    const long long ne = (long long)(in->mono_pt_begin[w + 1] - in->mono_pt_begin[w]) +
+                         (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]) +
+                         (in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) +
+                         (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]);
+    if (npt > c->l_max_pts) c->l_max_pts = npt;
+    if (nln > c->l_max_lns) c->l_max_lns = nln;
+    if (ne > c->l_max_edges) c->l_max_edges = (int)ne;
+    // a landmark with k free observers yields k(k+1)/2 <= k(nf+1)/2 pair entries
+    c->l_pair_base[w + 1] = c->l_pair_base[w] + (ne * (nf + 1) + 1) / 2 + 2;
   }
   if (max_poses > 255)
     return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: %d poses in one window (limit 255)", max_poses);
@@ -117,6 +132,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const size_t o_pout = a.take(sizeof(double) * 7 * NP);
   const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
   const size_t o_err = a.take(sizeof(int));
+  const size_t o_phase = a.take(sizeof(long long) * 8 * W);
   const int slot_stride = (max_free + 3) & ~3;
   struct KOff {
     size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
@@ -196,6 +212,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.slot_stride = slot_stride;
   d.stats = (void*)(base + o_stats);
   d.err = (int*)(base + o_err);
+  d.phase = (long long*)(base + o_phase);
   for (int k = 0; k < 2; ++k) {
     ba::KindDev& kd = d.k[k];
     const KOff& o = ko[k];
@@ -247,6 +264,144 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   return RSPL_BA_OK;
 }
 
+namespace {
+
+// Allocates (grow-only) and wires the HBM state of the batched path for the uploaded batch.
+int batched_prepare(RsplBaContext* c) {
+  if (c->batch_ready) return RSPL_BA_OK;
+  const int W = c->l_n_windows, NP = c->l_np;
+  const int NF = c->l_nf_begin[W];
+  const int NFmax = c->l_max_free_poses;
+  const int Pmax = NFmax * (NFmax + 1) / 2;
+  const int Cp = (c->l_max_pts + ba::BT - 1) / ba::BT, Cl = (c->l_max_lns + ba::BT - 1) / ba::BT;
+  const int C = Cp + Cl > 0 ? Cp + Cl : 1;
+  const long long n_pairs = c->l_pair_base[W];
+  if (n_pairs > 0x7fffffffLL) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: pair lists exceed 2^31 entries");
+  if (C > 65535 || Pmax > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: window too large for the batched path");
+  Arena a;
+  const size_t o_ws = a.take(sizeof(ba::WinState) * W);
+  const size_t o_q = a.take(sizeof(double) * 4 * NP), o_t = a.take(sizeof(double) * 3 * NP);
+  const size_t o_R = a.take(sizeof(double) * 9 * NP);
+  const size_t o_bq = a.take(sizeof(double) * 4 * NP), o_bt = a.take(sizeof(double) * 3 * NP);
+  const size_t o_fi = a.take(sizeof(int) * NP), o_pact = a.take(sizeof(int) * NP);
+  const size_t o_nfb = a.take(sizeof(int) * (W + 1));
+  const size_t o_pof = a.take(sizeof(int) * (NF + 1)), o_sys = a.take(sizeof(int) * (NF + 1));
+  const size_t o_hpp = a.take(sizeof(double) * 21 * (NF + 1)), o_bp = a.take(sizeof(double) * 6 * (NF + 1));
+  const size_t o_xp = a.take(sizeof(double) * 6 * (NF + 1));
+  const size_t o_hsp = a.take(sizeof(double) * 42 * (size_t)W * (Pmax > 0 ? Pmax : 1));
+  const size_t o_part = a.take(sizeof(double) * 4 * (size_t)W * C);
+  const size_t o_pbeg = a.take(sizeof(int) * (size_t)W * (2 * Pmax + 1));
+  const size_t o_pairs = a.take(sizeof(int2) * (size_t)(n_pairs + 1));
+  const size_t o_pbase = a.take(sizeof(long long) * (W + 1));
+  const size_t o_nact = a.take(sizeof(int));
+  CU_TRY(c, c->batch_buf.reserve(a.off));
+  char* base = c->batch_buf.as<char>();
+  CU_TRY(c, cudaMemcpyAsync(base + o_nfb, c->l_nf_begin.data(), sizeof(int) * (W + 1), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(base + o_pbase, c->l_pair_base.data(), sizeof(long long) * (W + 1), cudaMemcpyHostToDevice,
+                            c->stream));
+  CU_TRY(c, cudaMemsetAsync(base + o_part, 0, sizeof(double) * 4 * (size_t)W * C, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  ba::BatchDev& b = c->bd;
+  b.ws = (ba::WinState*)(base + o_ws);
+  b.P_q = (double*)(base + o_q);
+  b.P_t = (double*)(base + o_t);
+  b.P_R = (double*)(base + o_R);
+  b.P_bq = (double*)(base + o_bq);
+  b.P_bt = (double*)(base + o_bt);
+  b.free_idx = (int*)(base + o_fi);
+  b.pact = (int*)(base + o_pact);
+  b.nf_begin = (int*)(base + o_nfb);
+  b.pose_of = (int*)(base + o_pof);
+  b.sys_idx = (int*)(base + o_sys);
+  b.Hpp = (double*)(base + o_hpp);
+  b.bp = (double*)(base + o_bp);
+  b.xp = (double*)(base + o_xp);
+  b.hs_part = (double*)(base + o_hsp);
+  b.part = (double*)(base + o_part);
+  b.pair_beg = (int*)(base + o_pbeg);
+  b.pairs = (int2*)(base + o_pairs);
+  b.pair_base = (const long long*)(base + o_pbase);
+  b.n_active = (int*)(base + o_nact);
+  b.Cp = Cp;
+  b.Cl = Cl;
+  b.C = C;
+  b.Pmax = Pmax > 0 ? Pmax : 1;
+  b.NFmax = NFmax;
+  c->batch_ready = true;
+  return RSPL_BA_OK;
+}
+
+// The batched LocalmapOptimization: fixed kernel sequence per super-step, per-window LM state
+// machines on the device, host polls the number of still-iterating windows.
+int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
+  int rc = batched_prepare(c);
+  if (rc != RSPL_BA_OK) return rc;
+  c->l_last_path = 2;
+  c->l_super_steps = 0;
+  const ba::LocalDev& d = c->ld;
+  const ba::BatchDev& b = c->bd;
+  const int W = c->l_n_windows;
+  cudaStream_t s = c->stream;
+  if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
+  // (chunk | pose | pair) index fastest, window on grid.y: the CTAs of one window run together
+  const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair(b.Pmax, W),
+      g_win((W + 127) / 128);
+  const int n_max = 6 * b.NFmax;
+  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
+  if (smem_solve > c->smem_optin) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "reduced system does not fit shared memory");
+  CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+#define LAUNCH(kern, grid, block, shm, ...)            \
+  do {                                                 \
+    kern<<<grid, block, shm, s>>>(__VA_ARGS__);        \
+    c->launches++;                                     \
+  } while (0)
+  LAUNCH(ba::kb_init, W, ba::BT, 0, d, b, lo);
+  LAUNCH(ba::kb_pairs<0>, W, ba::BT, 0, d, b);
+  LAUNCH(ba::kb_pairs<1>, W, ba::BT, 0, d, b);
+  CU_TRY(c, cudaGetLastError());
+  const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
+  for (int pass = 0; pass < 2; ++pass) {
+    LAUNCH(ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
+    const int worst = lo.iters[pass] * 10 + 1; // <= 10 trials per LM iteration (§9.9)
+    int done_steps = 0;
+    while (done_steps < worst) {
+      const int burst = done_steps == 0 ? (lo.iters[pass] < 4 ? lo.iters[pass] : 4) : 4;
+      for (int k = 0; k < burst && done_steps < worst; ++k, ++done_steps) {
+        if (b.Cp) LAUNCH(ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+        LAUNCH(ba::kb_begin_trial, g_win, 128, 0, d, b);
+        if (b.Cp) LAUNCH(ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
+        LAUNCH(ba::kb_solve, W, 256, smem_solve, d, b);
+        if (b.Cp) LAUNCH(ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(ba::kb_decide, g_win, 128, 0, d, b);
+        if (b.C) LAUNCH(ba::kb_restore, g_lm, ba::BT, 0, d, b);
+        c->l_super_steps++;
+      }
+      CU_TRY(c, cudaGetLastError());
+      if (lo.iters[pass] == 0) break;
+      // poll: how many windows are still iterating?
+      int n_active = 0;
+      CU_TRY(c, cudaMemsetAsync(b.n_active, 0, sizeof(int), s));
+      LAUNCH(ba::kb_count_active, 32, 256, 0, d, b);
+      CU_TRY(c, cudaMemcpyAsync(&n_active, b.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CU_TRY(c, cudaStreamSynchronize(s));
+      if (n_active == 0) break;
+    }
+    if (pass == 0) LAUNCH(ba::kb_flag<false>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+  }
+  LAUNCH(ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+  LAUNCH(ba::kb_writeback, W, 256, 0, d, b);
+#undef LAUNCH
+  CU_TRY(c, cudaGetLastError());
+  return RSPL_BA_OK;
+}
+
+} // namespace
+
 extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* opt) {
   if (!c || !opt) return RSPL_BA_ERR_INVALID;
   if (!c->local_uploaded) return fail(c, RSPL_BA_ERR_STATE, "local_batch_solve before upload");
@@ -272,6 +427,17 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
+  // Path: a handful of windows -> one persistent CTA per window (whole LM loop in one kernel, no
+  // host involvement: the latency path of configs C1/C3); a large batch -> one kernel per LM phase
+  // over all windows (the throughput path of config C4). RSPL_BA_LOCAL_PATH=persistent|batched
+  // forces one of them (tests run both).
+  bool batched = c->l_n_windows >= 2 * c->num_sms;
+  if (const char* env = getenv("RSPL_BA_LOCAL_PATH")) {
+    if (!strcmp(env, "persistent")) batched = false;
+    else if (!strcmp(env, "batched")) batched = true;
+  }
+  if (batched) return local_solve_batched(c, lo);
+  c->l_last_path = 1;
   CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ba::local_solve_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, smem, c->stream>>>(c->ld, lo);
   c->launches++;
@@ -320,4 +486,21 @@ extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch* in, c
   rc = rspl_ba_local_batch_solve(c, opt);
   if (rc != RSPL_BA_OK) return rc;
   return rspl_ba_local_batch_download(c, out);
+}
+
+// Diagnostics: cycles per phase of the last local solve, summed over windows (thread-0 clock64
+// deltas): 0 linearise (landmark-major), 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky,
+// 5 update + back-substitution + evaluation, 6 LM decision / restore, 7 everything else.
+extern "C" int rspl_ba_local_phase_cycles(RsplBaContext* c, double* out8) {
+  if (!c || !out8) return RSPL_BA_ERR_INVALID;
+  if (!c->local_solved) return fail(c, RSPL_BA_ERR_STATE, "local_phase_cycles before solve");
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (c->l_n_windows == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  std::vector<long long> h((size_t)8 * c->l_n_windows);
+  CU_TRY(c, cudaMemcpyAsync(h.data(), c->ld.phase, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < c->l_n_windows; ++w)
+    for (int i = 0; i < 8; ++i) out8[i] += (double)h[(size_t)w * 8 + i];
+  return RSPL_BA_OK;
 }

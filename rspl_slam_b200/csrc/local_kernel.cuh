@@ -93,6 +93,7 @@ struct LocalDev {
   KindDev k[2];
   void* stats;
   int* err; // device error flag
+  long long* phase; // [n_windows][8] cycles per phase (diagnostics), may be null
 };
 
 struct LocalOpt {
@@ -267,6 +268,8 @@ __global__ void __launch_bounds__(LOCAL_THREADS) local_setup_kernel(const __grid
 // solve: shared-memory window state
 // ------------------------------------------------------------------------------------------------
 struct WinScalars {
+  long long ph[8];
+  long long t_last;
   double lambda, ni, chi_cur, chi_tmp, scale, maxdiag;
   int verdict, n_sys, solve_ok, n_active_edges;
   DevStats st;
@@ -338,6 +341,15 @@ BA_DEV WinSmem carve(unsigned char* base, int NP, int NF) {
   ip += NF;
   s.pose_of = ip;
   return s;
+}
+
+// phase timer (thread 0 only; diagnostics)
+BA_DEV void tick(const WinSmem& s, int phase) {
+  if (threadIdx.x == 0) {
+    const long long now = clock64();
+    s.sc->ph[phase] += now - s.sc->t_last;
+    s.sc->t_last = now;
+  }
 }
 
 // deterministic block sum of one double per thread; result returned to every thread
@@ -995,9 +1007,14 @@ BA_DEV void lm_pass(const LocalDev& d, const LocalOpt& o, int w, const WinSmem& 
     // ---- computeActiveErrors + activeRobustChi2 + buildSystem
     double chi_part = 0, maxd = 0;
     int nact = 0;
+    tick(s, 7);
     linearize_landmarks<0>(d, o, d.k[0], w, s, robust, chi_part, maxd, nact);
     linearize_landmarks<1>(d, o, d.k[1], w, s, robust, chi_part, maxd, nact);
+    __syncthreads();
+    tick(s, 0);
     accumulate_poses(d, o, w, s, nf, robust);
+    __syncthreads();
+    tick(s, 1);
     const double chi0 = block_sum(chi_part, s.red);
     const double nact_all = block_sum((double)nact, s.red);
     if (nact_all == 0.0) break; // no active edge: g2o's optimize() returns without iterating
@@ -1027,11 +1044,14 @@ BA_DEV void lm_pass(const LocalDev& d, const LocalOpt& o, int w, const WinSmem& 
       schur_prep<0>(d, d.k[0], w, s, lambda, fail);
       schur_prep<1>(d, d.k[1], w, s, lambda, fail);
       const int any_fail = __syncthreads_or(fail);
+      tick(s, 2);
       if (n > 0) {
         schur_reduce(d, w, s, nf, n, lambda);
         __syncthreads();
+        tick(s, 3);
         cholesky_solve(s, n);
         __syncthreads();
+        tick(s, 4);
       } else if (tid == 0) {
         sc.solve_ok = 1;
       }
@@ -1070,6 +1090,7 @@ BA_DEV void lm_pass(const LocalDev& d, const LocalOpt& o, int w, const WinSmem& 
       }
       const double chi1 = block_sum(chi_part2, s.red);
       const double scale = block_sum(scale_part, s.red);
+      tick(s, 5);
       if (tid == 0) {
         // a failed factorisation is a rejected step (tempChi = DBL_MAX, §9.9); the states were not touched
         const double tempChi = ok ? chi1 : DBL_MAX;
@@ -1119,6 +1140,7 @@ BA_DEV void lm_pass(const LocalDev& d, const LocalOpt& o, int w, const WinSmem& 
         restore_landmarks<1>(d.k[1], w);
       }
       __syncthreads();
+      tick(s, 6);
       qmax++;
     } while (verdict == 1);
     if (tid == 0) sc.st.iters[pass]++;
@@ -1155,6 +1177,9 @@ __global__ void __launch_bounds__(LOCAL_THREADS) local_solve_kernel(const __grid
     sc.st.final_lambda = 0;
     sc.chi_cur = 0;
     sc.lambda = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc.ph[i] = 0;
+    sc.t_last = clock64();
   }
   for (int p = tid; p < np; p += LOCAL_THREADS) {
     double q[4], R[9];
@@ -1193,6 +1218,12 @@ __global__ void __launch_bounds__(LOCAL_THREADS) local_solve_kernel(const __grid
     for (int i = 0; i < 3; ++i) d.pose_out[(size_t)i * d.n_poses + p0 + p] = Twc.t[i];
 #pragma unroll
     for (int i = 0; i < 4; ++i) d.pose_out[(size_t)(3 + i) * d.n_poses + p0 + p] = Twc.q[i];
+  }
+  __syncthreads();
+  tick(s, 7);
+  if (tid == 0 && d.phase) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.phase[(size_t)w * 8 + i] = s.sc->ph[i];
   }
   if (tid == 0 && d.stats) {
     s.sc->st.final_chi2 = s.sc->chi_cur;
