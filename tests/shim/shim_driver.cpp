@@ -1,0 +1,110 @@
+// shim_driver.cpp — calls the reference-signature LocalmapOptimization / FrameOptimization provided
+// by include/rspl_ba/g2o_optimization_shim.hpp on a problem read from a flat float64 file and writes
+// the mutated containers back. TEST INFRASTRUCTURE (see tests/test_shim.py).
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "mock_types.h"
+#define RSPL_BA_DEFINE_REFERENCE_ENTRY_POINTS
+#include "rspl_ba/g2o_optimization_shim.hpp"
+
+static std::vector<double> read_all(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { perror(path); exit(2); }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<double> v(n / 8);
+  if (fread(v.data(), 8, v.size(), f) != v.size()) exit(2);
+  fclose(f);
+  return v;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  const std::vector<double> in = read_all(argv[1]);
+  size_t k = 0;
+  auto next = [&]() { return in[k++]; };
+  const int kind = (int)next();
+  const int np = (int)next(), npt = (int)next(), nln = (int)next();
+  const int nmp = (int)next(), nsp = (int)next(), nml = (int)next(), nsl = (int)next();
+  OptimizationConfig cfg{next(), next(), next(), next(), 0.5};
+  std::vector<CameraPtr> cams{std::make_shared<Camera>(Camera{next(), next(), next(), next(), next()})};
+  MapOfPoses poses;
+  MapOfPoints3d points;
+  MapOfLine3d lines;
+  for (int i = 0; i < np; ++i) {
+    const int id = (int)next();
+    Pose3d p;
+    p.fixed = next() != 0;
+    for (int c = 0; c < 3; ++c) p.p(c) = next();
+    p.q.x() = next(); p.q.y() = next(); p.q.z() = next(); p.q.w() = next();
+    poses[id] = p;
+  }
+  for (int i = 0; i < npt; ++i) {
+    const int id = (int)next();
+    Position3d p;
+    p.fixed = false;
+    for (int c = 0; c < 3; ++c) p.p(c) = next();
+    points[id] = p;
+  }
+  for (int i = 0; i < nln; ++i) {
+    const int id = (int)next();
+    Line3d l;
+    l.fixed = false;
+    for (int c = 0; c < 6; ++c) l.line_3d(c) = next();
+    lines[id] = l;
+  }
+  VectorOfMonoPointConstraints mp;
+  VectorOfStereoPointConstraints sp;
+  VectorOfMonoLineConstraints ml;
+  VectorOfStereoLineConstraints sl;
+  for (int i = 0; i < nmp; ++i) {
+    auto c = std::make_shared<MonoPointConstraint>();
+    c->id_pose = (int)next(); c->id_point = (int)next(); c->id_camera = 0; c->inlier = next() != 0; c->pixel_sigma = 0.8;
+    for (int q = 0; q < 2; ++q) c->keypoint(q) = next();
+    mp.push_back(c);
+  }
+  for (int i = 0; i < nsp; ++i) {
+    auto c = std::make_shared<StereoPointConstraint>();
+    c->id_pose = (int)next(); c->id_point = (int)next(); c->id_camera = 0; c->inlier = next() != 0; c->pixel_sigma = 0.8;
+    for (int q = 0; q < 3; ++q) c->keypoint(q) = next();
+    sp.push_back(c);
+  }
+  for (int i = 0; i < nml; ++i) {
+    auto c = std::make_shared<MonoLineConstraint>();
+    c->id_pose = (int)next(); c->id_line = (int)next(); c->id_camera = 0; c->inlier = next() != 0; c->pixel_sigma = 0.8;
+    for (int q = 0; q < 4; ++q) c->line_2d(q) = next();
+    ml.push_back(c);
+  }
+  for (int i = 0; i < nsl; ++i) {
+    auto c = std::make_shared<StereoLineConstraint>();
+    c->id_pose = (int)next(); c->id_line = (int)next(); c->id_camera = 0; c->inlier = next() != 0; c->pixel_sigma = 0.8;
+    for (int q = 0; q < 8; ++q) c->line_2d(q) = next();
+    sl.push_back(c);
+  }
+  double ret = 0;
+  if (kind == 0) {
+    LocalmapOptimization(poses, points, lines, cams, mp, sp, ml, sl, cfg);
+  } else {
+    ret = FrameOptimization(poses, points, cams, mp, sp, cfg);
+  }
+  std::vector<double> out;
+  out.push_back(ret);
+  for (auto& kv : poses) {
+    for (int c = 0; c < 3; ++c) out.push_back(kv.second.p(c));
+    out.push_back(kv.second.q.x()); out.push_back(kv.second.q.y()); out.push_back(kv.second.q.z()); out.push_back(kv.second.q.w());
+  }
+  for (auto& kv : points) for (int c = 0; c < 3; ++c) out.push_back(kv.second.p(c));
+  for (auto& kv : lines) for (int c = 0; c < 6; ++c) out.push_back(kv.second.line_3d(c));
+  for (auto& c : mp) out.push_back(c->inlier ? 1 : 0);
+  for (auto& c : sp) out.push_back(c->inlier ? 1 : 0);
+  for (auto& c : ml) out.push_back(c->inlier ? 1 : 0);
+  for (auto& c : sl) out.push_back(c->inlier ? 1 : 0);
+  FILE* f = fopen(argv[2], "wb");
+  if (!f) return 2;
+  fwrite(out.data(), 8, out.size(), f);
+  fclose(f);
+  return 0;
+}
