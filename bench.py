@@ -278,16 +278,44 @@ def run_ours(args):
         value = edges_lin_all * args.steps / dev_s_max
         e2e_value = edges_lin_all * e2e_steps / e2e_s_max
         peak, peak_src = _peaks()
-        # roofline of the dominant (only) kernel, rank 0's launch: algorithmic bytes / measured duration
+        # roofline of the dominant kernel class: algorithmic bytes / CUDA-event time of
+        # that class, measured in a separate profiled pass (event pairs around every launch)
+        prof_steps = max(1, min(args.steps, 5))
+        ctx.set_profiling(True)
+        for _ in range(prof_steps):
+            solve(opt)
+        prof = ctx.get_profile()
+        ctx.set_profiling(False)
+        per_kernel = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
+                      for k, v in prof.items() if v[1]}
         if args.workload == "c2":
             n_st, n_mo = int(batch.stereo_begin[-1]), int(batch.mono_begin[-1])
             frac_st = n_st / max(n_st + n_mo, 1)
             alg_bytes = edges_eval * (BYTES_POSE_ONLY_STEREO * frac_st + BYTES_POSE_ONLY_MONO * (1 - frac_st))
+            dom_ms = prof["frame_opt"][0] / prof_steps
+            dom_launches = prof["frame_opt"][1] / prof_steps
+            dom_name = kernel
         else:
-            from rspl_slam_b200.roofline import local_algorithmic_bytes
-            alg_bytes = local_algorithmic_bytes(batch, stats)
-        launch_s = dev_s / max(gpu_launches, 1)
-        achieved = alg_bytes / launch_s / 1e9
+            from rspl_slam_b200.roofline import local_class_bytes
+            cls_bytes = local_class_bytes(batch, stats)  # bytes per step of the linearise / Schur / back-sub classes
+            groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
+                      "schur (kb_schur_prep + kb_schur_reduce + kb_solve)": (("schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
+                      "backsub (kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"]),
+                      "persistent (local_solve_kernel)": (("local_solve_persistent",), sum(cls_bytes.values()))}
+            best = None
+            for name, (classes, nbytes) in groups.items():
+                ms = sum(prof[c][0] for c in classes) / prof_steps
+                nl = sum(prof[c][1] for c in classes) / prof_steps
+                if nl == 0:
+                    continue
+                per_kernel[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
+                                    "achieved_GBs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+                if best is None or ms > best[1]:
+                    best = (name, ms, nl, nbytes)
+            dom_name, dom_ms, dom_launches, alg_bytes = best
+        launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
+        alg_per_launch = alg_bytes / max(dom_launches, 1)
+        achieved = alg_per_launch / launch_s / 1e9
         cpu = cpu_baseline(args)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -303,10 +331,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(out.d2h_bytes()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
                     "api": "rspl_ba_%s_batch (pinned host buffers in, pinned host buffers out)" % ("frame" if args.workload == "c2" else "local")},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": 1e3 * launch_s,
-                         "note": "contract bytes (SURVEY 8d) per evaluation; the kernel keeps the LM loop on chip, so real HBM traffic is far lower and the kernel is FP64-issue bound (see DESIGN.md)"},
+                         "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": 1e3 * launch_s,
+                         "launches_per_step": dom_launches, "per_kernel": per_kernel,
+                         "note": "achieved = SURVEY 8(d) contract bytes (materialised-W formulation) / CUDA-event time of the kernel class; "
+                                 "the kernels recompute instead of materialising, so real DRAM traffic (`traffic`) is lower, see DESIGN.md"},
             "cpu_baseline": cpu,
             "clocks": clk.summary(),
             "wall_s_timed_region": wall_max,

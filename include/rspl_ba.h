@@ -191,6 +191,14 @@ int64_t rspl_ba_launch_count(const RsplBaContext* ctx);
 /* Block the host until all work queued on the context stream has finished. */
 int rspl_ba_sync(RsplBaContext* ctx);
 
+/* Per-kernel-class timing with CUDA events on the context stream (what bench.py's roofline uses).
+ * Classes: 0 frame_opt, 1 local_setup, 2 local_solve (persistent), 3 init + pair lists, 4 linearize,
+ * 5 pose blocks, 6 Schur prep, 7 Schur reduce, 8 reduced solve, 9 back-substitution / update /
+ * evaluation, 10 LM control kernels, 11 flagging + write-back. get_profile synchronises the
+ * stream, returns milliseconds and launch counts accumulated since the last call and resets them. */
+int rspl_ba_set_profiling(RsplBaContext* ctx, int enabled);
+int rspl_ba_get_profile(RsplBaContext* ctx, double* ms12, int64_t* launches12);
+
 /* Diagnostics: SM cycles per phase of the last local solve summed over windows. out8: 0 linearise,
  * 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky, 5 update/back-substitution/evaluation,
  * 6 LM decision/restore, 7 other. */

@@ -83,7 +83,8 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_local_phase_cycles")
+    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_local_phase_cycles",
+    "rspl_ba_set_profiling", "rspl_ba_get_profile")
 
 _lib = None
 LOCAL_BA_READY = True
@@ -147,6 +148,10 @@ def load_library() -> C.CDLL:
     L.rspl_ba_oplus.restype = C.c_int
     L.rspl_ba_local_phase_cycles.argtypes = [ctx, c_f64p]
     L.rspl_ba_local_phase_cycles.restype = C.c_int
+    L.rspl_ba_set_profiling.argtypes = [ctx, C.c_int]
+    L.rspl_ba_set_profiling.restype = C.c_int
+    L.rspl_ba_get_profile.argtypes = [ctx, c_f64p, C.POINTER(C.c_int64)]
+    L.rspl_ba_get_profile.restype = C.c_int
     _lib = L
     return L
 
@@ -325,6 +330,19 @@ class Context:
         r = self._local_result_struct(out)
         self._check(self._L.rspl_ba_local_batch_download(self._ctx, C.byref(r)))
         return out
+
+    PROFILE_CLASSES = ("frame_opt", "local_setup", "local_solve_persistent", "init_pairs", "linearize", "pose_blocks",
+                       "schur_prep", "schur_reduce", "reduced_solve", "backsub_update_eval", "lm_control", "flag_writeback")
+
+    def set_profiling(self, enabled: bool):
+        self._check(self._L.rspl_ba_set_profiling(self._ctx, 1 if enabled else 0))
+
+    def get_profile(self) -> dict:
+        """{class: (milliseconds, launches)} accumulated since the last call (CUDA events on the context stream)."""
+        ms = np.zeros(12)
+        n = np.zeros(12, dtype=np.int64)
+        self._check(self._L.rspl_ba_get_profile(self._ctx, _p(ms, c_f64p), n.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 
     def local_phase_cycles(self) -> np.ndarray:
         out = np.zeros(8)

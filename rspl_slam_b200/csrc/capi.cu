@@ -96,6 +96,15 @@ struct RsplBaContext {
   int l_last_path = 0;                  // 1 persistent, 2 batched (diagnostics)
   int l_super_steps = 0;
 
+  // ---- optional per-kernel-class timing with CUDA events on the context stream (rspl_ba_set_profiling)
+  bool prof = false;
+  struct ProfEv {
+    cudaEvent_t a, b;
+    int cls;
+  };
+  std::vector<ProfEv> prof_pool;
+  size_t prof_used = 0;
+
   // ---- unit-level scratch
   DevBuf unit_buf;
 };
@@ -251,6 +260,59 @@ extern "C" int rspl_ba_sync(RsplBaContext* c) {
   return RSPL_BA_OK;
 }
 
+// ---- kernel-class profiling -----------------------------------------------------------------------
+namespace {
+enum ProfClass {
+  PC_FRAME = 0, PC_LOCAL_SETUP, PC_LOCAL_PERSISTENT, PC_PAIRS, PC_LINEARIZE, PC_POSE_BLOCKS, PC_SCHUR_PREP,
+  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COUNT
+};
+// records an event pair around one launch when profiling is on
+struct ProfScope {
+  RsplBaContext* c;
+  int idx = -1;
+  ProfScope(RsplBaContext* ctx, int cls) : c(ctx) {
+    if (!c->prof) return;
+    if (c->prof_used == c->prof_pool.size()) {
+      RsplBaContext::ProfEv e;
+      if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+      c->prof_pool.push_back(e);
+    }
+    idx = (int)c->prof_used++;
+    c->prof_pool[idx].cls = cls;
+    cudaEventRecord(c->prof_pool[idx].a, c->stream);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(c->prof_pool[idx].b, c->stream);
+  }
+};
+} // namespace
+
+extern "C" int rspl_ba_set_profiling(RsplBaContext* c, int enabled) {
+  if (!c) return RSPL_BA_ERR_INVALID;
+  c->prof = enabled != 0;
+  c->prof_used = 0;
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_get_profile(RsplBaContext* c, double* ms12, int64_t* launches12) {
+  if (!c || !ms12 || !launches12) return RSPL_BA_ERR_INVALID;
+  SetDevice guard(c->device);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < PC_COUNT; ++i) {
+    ms12[i] = 0;
+    launches12[i] = 0;
+  }
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->prof_pool[i].a, c->prof_pool[i].b) == cudaSuccess) {
+      ms12[c->prof_pool[i].cls] += ms;
+      launches12[c->prof_pool[i].cls] += 1;
+    }
+  }
+  c->prof_used = 0;
+  return RSPL_BA_OK;
+}
+
 extern "C" void* rspl_ba_alloc_pinned(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -376,8 +438,11 @@ extern "C" int rspl_ba_frame_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   const int grid = (c->f_n_frames + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
   const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr);
   fo.cam0 = c->f_cam0;
-  if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
-  else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  {
+    ProfScope ps(c, PC_FRAME);
+    if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+    else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
+  }
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;

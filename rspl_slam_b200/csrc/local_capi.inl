@@ -350,35 +350,36 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
   if (smem_solve > c->smem_optin) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "reduced system does not fit shared memory");
   CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-#define LAUNCH(kern, grid, block, shm, ...)            \
+#define LAUNCH(cls, kern, grid, block, shm, ...)       \
   do {                                                 \
+    ProfScope ps_(c, cls);                             \
     kern<<<grid, block, shm, s>>>(__VA_ARGS__);        \
     c->launches++;                                     \
   } while (0)
-  LAUNCH(ba::kb_init, W, ba::BT, 0, d, b, lo);
-  LAUNCH(ba::kb_pairs<0>, W, ba::BT, 0, d, b);
-  LAUNCH(ba::kb_pairs<1>, W, ba::BT, 0, d, b);
+  LAUNCH(PC_PAIRS, ba::kb_init, W, ba::BT, 0, d, b, lo);
+  LAUNCH(PC_PAIRS, ba::kb_pairs<0>, W, ba::BT, 0, d, b);
+  LAUNCH(PC_PAIRS, ba::kb_pairs<1>, W, ba::BT, 0, d, b);
   CU_TRY(c, cudaGetLastError());
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   for (int pass = 0; pass < 2; ++pass) {
-    LAUNCH(ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
+    LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
     const int worst = lo.iters[pass] * 10 + 1; // <= 10 trials per LM iteration (§9.9)
     int done_steps = 0;
     while (done_steps < worst) {
       const int burst = done_steps == 0 ? (lo.iters[pass] < 4 ? lo.iters[pass] : 4) : 4;
       for (int k = 0; k < burst && done_steps < worst; ++k, ++done_steps) {
-        if (b.Cp) LAUNCH(ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
-        LAUNCH(ba::kb_begin_trial, g_win, 128, 0, d, b);
-        if (b.Cp) LAUNCH(ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
-        LAUNCH(ba::kb_solve, W, 256, smem_solve, d, b);
-        if (b.Cp) LAUNCH(ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(ba::kb_decide, g_win, 128, 0, d, b);
-        if (b.C) LAUNCH(ba::kb_restore, g_lm, ba::BT, 0, d, b);
+        if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(PC_POSE_BLOCKS, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+        LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
+        if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
+        LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
+        if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
+        if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+        LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
+        if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
         c->l_super_steps++;
       }
       CU_TRY(c, cudaGetLastError());
@@ -386,15 +387,15 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       // poll: how many windows are still iterating?
       int n_active = 0;
       CU_TRY(c, cudaMemsetAsync(b.n_active, 0, sizeof(int), s));
-      LAUNCH(ba::kb_count_active, 32, 256, 0, d, b);
+      LAUNCH(PC_CONTROL, ba::kb_count_active, 32, 256, 0, d, b);
       CU_TRY(c, cudaMemcpyAsync(&n_active, b.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
       CU_TRY(c, cudaStreamSynchronize(s));
       if (n_active == 0) break;
     }
-    if (pass == 0) LAUNCH(ba::kb_flag<false>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+    if (pass == 0) LAUNCH(PC_FLAG_WRITEBACK, ba::kb_flag<false>, dim3(W, edge_chunks), 256, 0, d, b, lo);
   }
-  LAUNCH(ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
-  LAUNCH(ba::kb_writeback, W, 256, 0, d, b);
+  LAUNCH(PC_FLAG_WRITEBACK, ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+  LAUNCH(PC_FLAG_WRITEBACK, ba::kb_writeback, W, 256, 0, d, b);
 #undef LAUNCH
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;
@@ -424,7 +425,10 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   lo.max_free = c->l_max_free_poses;
   const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
   CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int), c->stream));
-  ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+  {
+    ProfScope ps(c, PC_LOCAL_SETUP);
+    ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+  }
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   // Path: a handful of windows -> one persistent CTA per window (whole LM loop in one kernel, no
@@ -439,7 +443,10 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   if (batched) return local_solve_batched(c, lo);
   c->l_last_path = 1;
   CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ba::local_solve_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, smem, c->stream>>>(c->ld, lo);
+  {
+    ProfScope ps(c, PC_LOCAL_PERSISTENT);
+    ba::local_solve_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, smem, c->stream>>>(c->ld, lo);
+  }
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;

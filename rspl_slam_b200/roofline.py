@@ -49,3 +49,15 @@ def local_algorithmic_bytes(batch, stats) -> float:
     trials = stats["trials"].sum(axis=1).astype(np.float64)
     trial_passes = float((trials * win_edges).sum()) / edges     # edge-weighted number of Schur/back-sub passes
     return pb["linearize"] * lin_passes + (pb["schur"] + pb["backsub"]) * trial_passes
+
+
+def local_class_bytes(batch, stats) -> dict:
+    """Algorithmic bytes per solve of the three kernel classes (linearise / Schur / back-substitution)."""
+    pb = local_pass_bytes(batch)
+    edges = max(pb["edges"], 1)
+    lin_passes = float(stats["edges_linearized"].sum()) / edges
+    win_edges = batch.window_edges().astype(np.float64)
+    trials = stats["trials"].sum(axis=1).astype(np.float64)
+    trial_passes = float((trials * win_edges).sum()) / edges
+    return {"linearize": pb["linearize"] * lin_passes, "schur": pb["schur"] * trial_passes,
+            "backsub": pb["backsub"] * trial_passes}
