@@ -556,13 +556,13 @@ __global__ void __launch_bounds__(BT) kb_schur_prep(const __grid_constant__ Loca
   if (fail) atomicOr(&s.prep_fail, 1);
 }
 
-// K3': one CTA per (window, pose pair): sum_e Z_i Z_j^T (and Z_i y on the diagonal) over the pair list
+// K3': one WARP per (window, pose pair): sum_e Z_i Z_j^T (and Z_i y on the diagonal) over the pair list
 template <int KIND>
-BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, double* acc) {
+BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, int lane, double* acc) {
   using T = KT<KIND>;
   constexpr int LD = T::LD;
   const int l0 = k.lm_begin[w];
-  for (int it = threadIdx.x; it < n; it += BT) {
+  for (int it = lane; it < n; it += 32) {
     const int2 ee = ent[it];
     const int l = l0 + k.lm[ee.x];
     if (!k.act[l]) continue;
@@ -610,12 +610,29 @@ BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, 
   }
 }
 
+// Reduces 64 per-lane values across the warp with 62 shuffles instead of 64 x 5: at every step a
+// lane keeps one half of its values and trades the other half with its partner. Fixed pattern =>
+// bitwise deterministic. On return lane L holds the totals of elements 2L (v[0]) and 2L+1 (v[1]).
+BA_DEV void warp_transpose_reduce64(double* v, int lane) {
+#pragma unroll
+  for (int off = 16, n = 64; off >= 1; off >>= 1, n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(BT) kb_schur_reduce(const __grid_constant__ LocalDev d,
                                                       const __grid_constant__ BatchDev b) {
-  __shared__ double red[BW * 42];
-  // pair index fastest: the ~NF(NF+1)/2 CTAs of one window run together, so the window's Z blocks
-  // (each read by every pair that contains its pose) are fetched from HBM once and then hit in L2
-  const int w = blockIdx.y, p = blockIdx.x;
+  // pair index fastest: the warps of one window run together, so the window's Z blocks (each read by
+  // every pair that contains its pose) are fetched from HBM once and then hit in L2
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.y, p = blockIdx.x * BW + (threadIdx.x >> 5);
   const WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const int nf = s.nf;
@@ -626,13 +643,17 @@ __global__ void __launch_bounds__(BT) kb_schur_reduce(const __grid_constant__ Lo
   if (b.sys_idx[f0 + fi] < 0 || b.sys_idx[f0 + fj] < 0) return;
   const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
   const bool diag = fi == fj;
-  double acc[42];
+  double acc[64];
 #pragma unroll
-  for (int q = 0; q < 42; ++q) acc[q] = 0;
-  schur_pair_entries<0>(d.k[0], w, b.pairs + pb[0], pb[1] - pb[0], diag, acc);
-  schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, acc);
-  cta_reduce<42>(acc, red);
-  if (threadIdx.x < 42) b.hs_part[((size_t)w * b.Pmax + p) * 42 + threadIdx.x] = cta_reduce_get<42>(red, threadIdx.x);
+  for (int q = 0; q < 64; ++q) acc[q] = 0;
+  schur_pair_entries<0>(d.k[0], w, b.pairs + pb[0], pb[1] - pb[0], diag, lane, acc);
+  schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, lane, acc);
+  warp_transpose_reduce64(acc, lane);
+  if (2 * lane < 42) {
+    double* out = b.hs_part + ((size_t)w * b.Pmax + p) * 42 + 2 * lane;
+    out[0] = acc[0];
+    out[1] = acc[1];
+  }
 }
 
 // K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory

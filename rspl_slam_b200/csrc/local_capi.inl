@@ -344,7 +344,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   cudaStream_t s = c->stream;
   if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   // (chunk | pose | pair) index fastest, window on grid.y: the CTAs of one window run together
-  const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair(b.Pmax, W),
+  const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
       g_win((W + 127) / 128);
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
