@@ -212,6 +212,11 @@ def run_ours(args):
         oneshot = lambda b: ctx.local_batch(b, opt, out)
         workload = f"C4 batched LocalmapOptimization ({n_units} windows of 10 KF/3k pts/300 lines per GPU, LM 10+5)"
         kernel = "ba::local_ba_kernel"
+    if args.workload == "c2" and len(batch.cameras) == 1:
+        # one camera and all ->inlier flags true are the ABI defaults: pass NULL instead of copying 8 MB of zeros / ones
+        batch.mono_cam = batch.stereo_cam = None
+        if batch.mono_inlier.all() and batch.stereo_inlier.all():
+            batch.mono_inlier = batch.stereo_inlier = None
     pinned = _pin_batch(batch, capi)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2

@@ -78,6 +78,10 @@ struct RsplBaContext {
   bool frame_solved = false;
   int f_n_frames = 0, f_n_mono = 0, f_n_stereo = 0;
   ba::Cam f_cam0{};
+  std::vector<int32_t> f_mb, f_sb; // host copies of the frame edge offsets
+  cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined one-shot call
+  cudaStream_t s_cmp[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk kernels may overlap each other
+  std::vector<cudaEvent_t> pipe_ev;
 
   // ---- local batch state
   DevBuf local_buf;
@@ -245,6 +249,15 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   c->local_buf.release();
   c->batch_buf.release();
   c->unit_buf.release();
+  for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
+  for (auto& pe : c->prof_pool) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  for (int i = 0; i < 4; ++i)
+    if (c->s_cmp[i]) cudaStreamDestroy(c->s_cmp[i]);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -328,14 +341,19 @@ extern "C" void rspl_ba_free_pinned(void* p) {
 // ================================================================================================
 // FrameOptimization batch
 // ================================================================================================
-extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch* in) {
-  if (!c || !in) return RSPL_BA_ERR_INVALID;
+namespace {
+
+struct FrameOffsets {
+  size_t cam, pose, mb, sb, mm, mx, mc, mi, sm, sx, sc, si, op, omi, osi, ml, sl, ni, st;
+};
+
+// validates the batch, sizes the device arena and wires the kernel argument block (no copies yet)
+int frame_prepare(RsplBaContext* c, const RsplFrameBatch* in, FrameOffsets& o) {
   c->frame_uploaded = c->frame_solved = false;
   const int F = in->n_frames;
   if (F < 0 || in->n_cameras < 1 || !in->cameras) return fail(c, RSPL_BA_ERR_INVALID, "frame batch: bad header");
   if (F == 0) {
     c->f_n_frames = c->f_n_mono = c->f_n_stereo = 0;
-    c->frame_uploaded = true;
     return RSPL_BA_OK;
   }
   if (!in->pose_twc || !offsets_ok(in->mono_begin, F) || !offsets_ok(in->stereo_begin, F))
@@ -347,80 +365,154 @@ extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch
     return fail(c, RSPL_BA_ERR_INVALID, "frame batch: id_camera out of range");
   if (in->n_cameras > 1 && ((nm && !in->mono_cam) || (ns && !in->stereo_cam)))
     return fail(c, RSPL_BA_ERR_INVALID, "frame batch: several cameras but no per-edge camera index");
-  SetDevice guard(c->device);
-  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
-
   Arena a;
-  const size_t o_cam = a.take(sizeof(double) * 5 * in->n_cameras);
-  const size_t o_pose = a.take(sizeof(double) * 7 * F);
-  const size_t o_mb = a.take(sizeof(int) * (F + 1));
-  const size_t o_sb = a.take(sizeof(int) * (F + 1));
-  const size_t o_mm = a.take(sizeof(double) * 2 * nm);
-  const size_t o_mx = a.take(sizeof(double) * 3 * nm);
-  const size_t o_mc = a.take(sizeof(int) * nm);
-  const size_t o_mi = a.take(nm);
-  const size_t o_sm = a.take(sizeof(double) * 3 * ns);
-  const size_t o_sx = a.take(sizeof(double) * 3 * ns);
-  const size_t o_sc = a.take(sizeof(int) * ns);
-  const size_t o_si = a.take(ns);
-  // outputs / work
-  const size_t o_op = a.take(sizeof(double) * 7 * F);
-  const size_t o_omi = a.take(nm);
-  const size_t o_osi = a.take(ns);
-  const size_t o_ml = a.take(nm);
-  const size_t o_sl = a.take(ns);
-  const size_t o_ni = a.take(sizeof(int) * F);
-  const size_t o_st = a.take(sizeof(ba::DevStats) * F);
+  o.cam = a.take(sizeof(double) * 5 * in->n_cameras);
+  o.pose = a.take(sizeof(double) * 7 * F);
+  o.mb = a.take(sizeof(int) * (F + 1));
+  o.sb = a.take(sizeof(int) * (F + 1));
+  o.mm = a.take(sizeof(double) * 2 * nm);
+  o.mx = a.take(sizeof(double) * 3 * nm);
+  o.mc = a.take(sizeof(int) * nm);
+  o.mi = a.take(nm);
+  o.sm = a.take(sizeof(double) * 3 * ns);
+  o.sx = a.take(sizeof(double) * 3 * ns);
+  o.sc = a.take(sizeof(int) * ns);
+  o.si = a.take(ns);
+  o.op = a.take(sizeof(double) * 7 * F);
+  o.omi = a.take(nm);
+  o.osi = a.take(ns);
+  o.ml = a.take(nm);
+  o.sl = a.take(ns);
+  o.ni = a.take(sizeof(int) * F);
+  o.st = a.take(sizeof(ba::DevStats) * F);
   CU_TRY(c, c->frame_buf.reserve(a.off));
   char* base = c->frame_buf.as<char>();
-  cudaStream_t s = c->stream;
-#define H2D(off, src, bytes)                                                                \
-  do {                                                                                      \
-    if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s)); \
-  } while (0)
-  H2D(o_cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
-  H2D(o_pose, in->pose_twc, sizeof(double) * 7 * F);
-  H2D(o_mb, in->mono_begin, sizeof(int) * (F + 1));
-  H2D(o_sb, in->stereo_begin, sizeof(int) * (F + 1));
-  H2D(o_mm, in->mono_meas, sizeof(double) * 2 * nm);
-  H2D(o_mx, in->mono_xw, sizeof(double) * 3 * nm);
-  if (in->mono_cam) H2D(o_mc, in->mono_cam, sizeof(int) * nm);
-  if (in->mono_inlier) H2D(o_mi, in->mono_inlier, (size_t)nm);
-  H2D(o_sm, in->stereo_meas, sizeof(double) * 3 * ns);
-  H2D(o_sx, in->stereo_xw, sizeof(double) * 3 * ns);
-  if (in->stereo_cam) H2D(o_sc, in->stereo_cam, sizeof(int) * ns);
-  if (in->stereo_inlier) H2D(o_si, in->stereo_inlier, (size_t)ns);
-#undef H2D
-  CU_TRY(c, cudaStreamSynchronize(s)); // caller buffers may be reused after return
-
   ba::FrameDev& d = c->fd;
   d.n_frames = F;
   d.n_cameras = in->n_cameras;
-  d.cameras = (const double*)(base + o_cam);
-  d.pose_twc = (const double*)(base + o_pose);
-  d.mono_begin = (const int*)(base + o_mb);
-  d.stereo_begin = (const int*)(base + o_sb);
+  d.cameras = (const double*)(base + o.cam);
+  d.pose_twc = (const double*)(base + o.pose);
+  d.mono_begin = (const int*)(base + o.mb);
+  d.stereo_begin = (const int*)(base + o.sb);
   d.n_mono = nm;
   d.n_stereo = ns;
-  d.mono_meas = (const double*)(base + o_mm);
-  d.mono_xw = (const double*)(base + o_mx);
-  d.mono_cam = in->mono_cam ? (const int*)(base + o_mc) : nullptr;
-  d.mono_inl_in = in->mono_inlier ? (const uint8_t*)(base + o_mi) : nullptr;
-  d.stereo_meas = (const double*)(base + o_sm);
-  d.stereo_xw = (const double*)(base + o_sx);
-  d.stereo_cam = in->stereo_cam ? (const int*)(base + o_sc) : nullptr;
-  d.stereo_inl_in = in->stereo_inlier ? (const uint8_t*)(base + o_si) : nullptr;
-  d.out_pose_twc = (double*)(base + o_op);
-  d.mono_inl = (uint8_t*)(base + o_omi);
-  d.stereo_inl = (uint8_t*)(base + o_osi);
-  d.mono_lvl = (uint8_t*)(base + o_ml);
-  d.stereo_lvl = (uint8_t*)(base + o_sl);
-  d.num_inliers = (int*)(base + o_ni);
-  d.stats = (void*)(base + o_st);
+  d.mono_meas = (const double*)(base + o.mm);
+  d.mono_xw = (const double*)(base + o.mx);
+  d.mono_cam = in->mono_cam ? (const int*)(base + o.mc) : nullptr;
+  d.mono_inl_in = in->mono_inlier ? (const uint8_t*)(base + o.mi) : nullptr;
+  d.stereo_meas = (const double*)(base + o.sm);
+  d.stereo_xw = (const double*)(base + o.sx);
+  d.stereo_cam = in->stereo_cam ? (const int*)(base + o.sc) : nullptr;
+  d.stereo_inl_in = in->stereo_inlier ? (const uint8_t*)(base + o.si) : nullptr;
+  d.out_pose_twc = (double*)(base + o.op);
+  d.mono_inl = (uint8_t*)(base + o.omi);
+  d.stereo_inl = (uint8_t*)(base + o.osi);
+  d.mono_lvl = (uint8_t*)(base + o.ml);
+  d.stereo_lvl = (uint8_t*)(base + o.sl);
+  d.num_inliers = (int*)(base + o.ni);
+  d.stats = (void*)(base + o.st);
   c->f_cam0 = ba::Cam{in->cameras[0], in->cameras[1], in->cameras[2], in->cameras[3], in->cameras[4]};
   c->f_n_frames = F;
   c->f_n_mono = nm;
   c->f_n_stereo = ns;
+  return RSPL_BA_OK;
+}
+
+// H2D of the frames [f0, f1) on stream s: their slice of every plane (+ the small header arrays if `header`)
+int frame_copy_in(RsplBaContext* c, const RsplFrameBatch* in, const FrameOffsets& o, int f0, int f1, bool header,
+                  cudaStream_t s) {
+  char* base = c->frame_buf.as<char>();
+  const int F = in->n_frames, nm = c->f_n_mono, ns = c->f_n_stereo;
+#define H2D(off, src, bytes)                                                                             \
+  do {                                                                                                   \
+    if ((bytes) > 0)                                                                                     \
+      CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s));               \
+  } while (0)
+  if (header) {
+    H2D(o.cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
+    H2D(o.pose, in->pose_twc, sizeof(double) * 7 * F);
+    H2D(o.mb, in->mono_begin, sizeof(int) * (F + 1));
+    H2D(o.sb, in->stereo_begin, sizeof(int) * (F + 1));
+  }
+  const size_t m0 = in->mono_begin[f0], m1 = in->mono_begin[f1], s0 = in->stereo_begin[f0], s1 = in->stereo_begin[f1];
+  for (int k = 0; k < 2; ++k) H2D(o.mm + sizeof(double) * ((size_t)k * nm + m0), in->mono_meas + (size_t)k * nm + m0, sizeof(double) * (m1 - m0));
+  for (int k = 0; k < 3; ++k) H2D(o.mx + sizeof(double) * ((size_t)k * nm + m0), in->mono_xw + (size_t)k * nm + m0, sizeof(double) * (m1 - m0));
+  if (in->mono_cam) H2D(o.mc + sizeof(int) * m0, in->mono_cam + m0, sizeof(int) * (m1 - m0));
+  if (in->mono_inlier) H2D(o.mi + m0, in->mono_inlier + m0, m1 - m0);
+  for (int k = 0; k < 3; ++k) H2D(o.sm + sizeof(double) * ((size_t)k * ns + s0), in->stereo_meas + (size_t)k * ns + s0, sizeof(double) * (s1 - s0));
+  for (int k = 0; k < 3; ++k) H2D(o.sx + sizeof(double) * ((size_t)k * ns + s0), in->stereo_xw + (size_t)k * ns + s0, sizeof(double) * (s1 - s0));
+  if (in->stereo_cam) H2D(o.sc + sizeof(int) * s0, in->stereo_cam + s0, sizeof(int) * (s1 - s0));
+  if (in->stereo_inlier) H2D(o.si + s0, in->stereo_inlier + s0, s1 - s0);
+#undef H2D
+  return RSPL_BA_OK;
+}
+
+int frame_launch(RsplBaContext* c, const RsplBaOptions* opt, int f0, int f1, cudaStream_t stream = nullptr) {
+  if (!stream) stream = c->stream;
+  ba::FrameOpt fo = make_frame_opt(*opt);
+  fo.cam0 = c->f_cam0;
+  fo.frame0 = f0;
+  fo.frame1 = f1;
+  const int grid = (f1 - f0 + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
+  const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr);
+  {
+    ProfScope ps(c, PC_FRAME);
+    if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+  }
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return RSPL_BA_OK;
+}
+
+// D2H of the results of frames [f0, f1) on stream s. mb / sb: host copies of the edge offsets.
+int frame_copy_out(RsplBaContext* c, RsplFrameBatchResult* out, const int32_t* mb, const int32_t* sb, int f0, int f1,
+                   cudaStream_t s) {
+  const ba::FrameDev& d = c->fd;
+  const int F = c->f_n_frames;
+  const size_t m0 = mb[f0], m1 = mb[f1], s0 = sb[f0], s1 = sb[f1];
+  for (int k = 0; k < 7; ++k)
+    CU_TRY(c, cudaMemcpyAsync(out->pose_twc + (size_t)k * F + f0, d.out_pose_twc + (size_t)k * F + f0,
+                              sizeof(double) * (f1 - f0), cudaMemcpyDeviceToHost, s));
+  if (m1 > m0) CU_TRY(c, cudaMemcpyAsync(out->mono_inlier + m0, d.mono_inl + m0, m1 - m0, cudaMemcpyDeviceToHost, s));
+  if (s1 > s0) CU_TRY(c, cudaMemcpyAsync(out->stereo_inlier + s0, d.stereo_inl + s0, s1 - s0, cudaMemcpyDeviceToHost, s));
+  if (out->num_inliers)
+    CU_TRY(c, cudaMemcpyAsync(out->num_inliers + f0, d.num_inliers + f0, sizeof(int) * (f1 - f0), cudaMemcpyDeviceToHost, s));
+  if (out->stats)
+    CU_TRY(c, cudaMemcpyAsync(out->stats + f0, (const RsplBaStats*)d.stats + f0, sizeof(RsplBaStats) * (f1 - f0),
+                              cudaMemcpyDeviceToHost, s));
+  return RSPL_BA_OK;
+}
+
+int ensure_pipeline(RsplBaContext* c, int n_chunks) {
+  if (!c->s_in) CU_TRY(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  if (!c->s_out) CU_TRY(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i)
+    if (!c->s_cmp[i]) CU_TRY(c, cudaStreamCreateWithFlags(&c->s_cmp[i], cudaStreamNonBlocking));
+  while ((int)c->pipe_ev.size() < 2 * n_chunks) {
+    cudaEvent_t e;
+    CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->pipe_ev.push_back(e);
+  }
+  return RSPL_BA_OK;
+}
+
+} // namespace
+
+extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch* in) {
+  if (!c || !in) return RSPL_BA_ERR_INVALID;
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  FrameOffsets o;
+  int rc = frame_prepare(c, in, o);
+  if (rc != RSPL_BA_OK) return rc;
+  if (c->f_n_frames > 0) {
+    rc = frame_copy_in(c, in, o, 0, c->f_n_frames, true, c->stream);
+    if (rc != RSPL_BA_OK) return rc;
+    CU_TRY(c, cudaStreamSynchronize(c->stream)); // caller buffers may be reused after return
+    c->f_mb.assign(in->mono_begin, in->mono_begin + c->f_n_frames + 1);
+    c->f_sb.assign(in->stereo_begin, in->stereo_begin + c->f_n_frames + 1);
+  }
   c->frame_uploaded = true;
   return RSPL_BA_OK;
 }
@@ -434,18 +526,7 @@ extern "C" int rspl_ba_frame_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   if (c->f_n_frames == 0) return RSPL_BA_OK;
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
-  ba::FrameOpt fo = make_frame_opt(*opt);
-  const int grid = (c->f_n_frames + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
-  const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr);
-  fo.cam0 = c->f_cam0;
-  {
-    ProfScope ps(c, PC_FRAME);
-    if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
-    else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, c->stream>>>(c->fd, fo);
-  }
-  c->launches++;
-  CU_TRY(c, cudaGetLastError());
-  return RSPL_BA_OK;
+  return frame_launch(c, opt, 0, c->f_n_frames);
 }
 
 extern "C" int rspl_ba_frame_batch_download(RsplBaContext* c, RsplFrameBatchResult* out) {
@@ -456,26 +537,58 @@ extern "C" int rspl_ba_frame_batch_download(RsplBaContext* c, RsplFrameBatchResu
   if (!out->pose_twc || (nm && !out->mono_inlier) || (ns && !out->stereo_inlier))
     return fail(c, RSPL_BA_ERR_INVALID, "frame result: null output arrays");
   SetDevice guard(c->device);
-  cudaStream_t s = c->stream;
-  const ba::FrameDev& d = c->fd;
-  CU_TRY(c, cudaMemcpyAsync(out->pose_twc, d.out_pose_twc, sizeof(double) * 7 * F, cudaMemcpyDeviceToHost, s));
-  if (nm) CU_TRY(c, cudaMemcpyAsync(out->mono_inlier, d.mono_inl, nm, cudaMemcpyDeviceToHost, s));
-  if (ns) CU_TRY(c, cudaMemcpyAsync(out->stereo_inlier, d.stereo_inl, ns, cudaMemcpyDeviceToHost, s));
-  if (out->num_inliers)
-    CU_TRY(c, cudaMemcpyAsync(out->num_inliers, d.num_inliers, sizeof(int) * F, cudaMemcpyDeviceToHost, s));
-  if (out->stats)
-    CU_TRY(c, cudaMemcpyAsync(out->stats, d.stats, sizeof(RsplBaStats) * F, cudaMemcpyDeviceToHost, s));
-  CU_TRY(c, cudaStreamSynchronize(s));
+  int rc = frame_copy_out(c, out, c->f_mb.data(), c->f_sb.data(), 0, F, c->stream);
+  if (rc != RSPL_BA_OK) return rc;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
   return RSPL_BA_OK;
 }
 
+// One call with host buffers. Frames are independent, so the batch is cut into chunks and the
+// three stages run as a pipeline on three streams: H2D of chunk k+1 and D2H of chunk k-1 overlap
+// the kernel of chunk k (B200 has separate copy engines per direction). Returns when every result
+// is in the caller's buffers.
 extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, const RsplBaOptions* opt,
                                    RsplFrameBatchResult* out) {
-  int rc = rspl_ba_frame_batch_upload(c, in);
+  if (!c || !in || !opt || !out) return RSPL_BA_ERR_INVALID;
+  if (opt->frame_rounds < 0 || opt->frame_iters < 1)
+    return fail(c, RSPL_BA_ERR_INVALID, "frame_rounds must be >= 0 and frame_iters >= 1");
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  FrameOffsets o;
+  int rc = frame_prepare(c, in, o);
   if (rc != RSPL_BA_OK) return rc;
-  rc = rspl_ba_frame_batch_solve(c, opt);
+  const int F = c->f_n_frames;
+  c->frame_uploaded = c->frame_solved = true;
+  if (F == 0) return RSPL_BA_OK;
+  if (!out->pose_twc || (c->f_n_mono && !out->mono_inlier) || (c->f_n_stereo && !out->stereo_inlier))
+    return fail(c, RSPL_BA_ERR_INVALID, "frame result: null output arrays");
+  c->f_mb.assign(in->mono_begin, in->mono_begin + F + 1);
+  c->f_sb.assign(in->stereo_begin, in->stereo_begin + F + 1);
+  int n_chunks = F / 512;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 4) n_chunks = 4;
+  rc = ensure_pipeline(c, n_chunks + 1);
   if (rc != RSPL_BA_OK) return rc;
-  return rspl_ba_frame_batch_download(c, out);
+  // everything queued earlier on the context stream completes first
+  CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * n_chunks], c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * n_chunks], 0));
+  for (int k = 0; k < n_chunks; ++k) {
+    const int f0 = (int)((long long)F * k / n_chunks), f1 = (int)((long long)F * (k + 1) / n_chunks);
+    cudaStream_t cs = n_chunks > 1 ? c->s_cmp[k & 3] : c->stream;
+    rc = frame_copy_in(c, in, o, f0, f1, k == 0, c->s_in);
+    if (rc != RSPL_BA_OK) return rc;
+    CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * k], c->s_in));
+    CU_TRY(c, cudaStreamWaitEvent(cs, c->pipe_ev[2 * k], 0));
+    rc = frame_launch(c, opt, f0, f1, cs);
+    if (rc != RSPL_BA_OK) return rc;
+    CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * k + 1], cs));
+    CU_TRY(c, cudaStreamWaitEvent(c->s_out, c->pipe_ev[2 * k + 1], 0));
+    rc = frame_copy_out(c, out, c->f_mb.data(), c->f_sb.data(), f0, f1, c->s_out);
+    if (rc != RSPL_BA_OK) return rc;
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->s_out));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RSPL_BA_OK;
 }
 
 // ================================================================================================

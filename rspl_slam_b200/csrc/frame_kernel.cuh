@@ -49,6 +49,7 @@ struct FrameOpt {
   double delta_mono, delta_stereo; // (float)sqrt(thr) widened
   int rounds, iters;
   Cam cam0;                        // camera 0, read straight from the constant bank when SINGLE_CAM
+  int frame0, frame1;              // frame range of this launch (chunks of a pipelined batch)
 };
 
 struct DevStats { // layout == RsplBaStats
@@ -217,8 +218,8 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
                                                                       const __grid_constant__ FrameOpt o) {
   __shared__ WarpState wstate[FRAME_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f = blockIdx.x * FRAME_WARPS + warp;
-  if (f >= d.n_frames) return;
+  const int f = o.frame0 + blockIdx.x * FRAME_WARPS + warp;
+  if (f >= o.frame1) return;
   WarpState& ws = wstate[warp];
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];

@@ -240,7 +240,7 @@ class FrameBatch:
     def h2d_bytes(self) -> int:
         return sum(int(getattr(self, k).nbytes) for k in (
             "cameras", "pose_twc", "mono_begin", "stereo_begin", "mono_meas", "mono_xw", "mono_cam",
-            "mono_inlier", "stereo_meas", "stereo_xw", "stereo_cam", "stereo_inlier"))
+            "mono_inlier", "stereo_meas", "stereo_xw", "stereo_cam", "stereo_inlier") if getattr(self, k) is not None)
 
 
 @dataclass
