@@ -98,11 +98,11 @@ BA_DEV void pose_normalize(Pose& T) {
     T.q[2] = -T.q[2];
     T.q[3] = -T.q[3];
   }
-  const double n = sqrt(T.q[0] * T.q[0] + T.q[1] * T.q[1] + T.q[2] * T.q[2] + T.q[3] * T.q[3]);
-  T.q[0] /= n;
-  T.q[1] /= n;
-  T.q[2] /= n;
-  T.q[3] /= n;
+  const double inv = rsqrt(T.q[0] * T.q[0] + T.q[1] * T.q[1] + T.q[2] * T.q[2] + T.q[3] * T.q[3]);
+  T.q[0] *= inv;
+  T.q[1] *= inv;
+  T.q[2] *= inv;
+  T.q[3] *= inv;
 }
 
 BA_DEV Pose pose_inverse(const Pose& T) {
@@ -193,9 +193,11 @@ BA_DEV double huber(double e, double delta, double& w) {
     w = 1.0;
     return e;
   }
-  const double sq = sqrt(e);
-  w = delta / sq;
-  return 2 * sq * delta - dsqr;
+  // one rsqrt instead of sqrt + divide (the pair costs ~50 fp64 instructions on the device):
+  // rho1 = delta / sqrt(e), rho0 = 2 delta sqrt(e) - delta^2 with sqrt(e) = e * rsqrt(e)
+  const double rs = rsqrt(e);
+  w = delta * rs;
+  return 2 * (e * rs) * delta - dsqr;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -85,22 +85,68 @@ BA_DEV void load_cam(const double* cams, int idx, Cam& c) {
 // index of (i,j), i<=j, in the packed upper triangle of a 6x6
 __host__ __device__ constexpr int up6(int i, int j) { return i * 6 - i * (i - 1) / 2 + (j - i); }
 
+// H += w J^T J ; b -= w J^T r (information = I, §9.4, §9.7), using the structure of the pose Jacobian of a
+// point edge (§9.3): row0 = [a0 a1 a2 a3 0 a5], row1 = [b0 b1 b2 0 b4 b5], row2 = row0 + [c0 c1 0 0 0 c5]
+// — the zero entries are skipped explicitly (the compiler may not drop 0 * x in IEEE arithmetic).
 template <int ROWS>
 BA_DEV void accumulate_pose_only(const double* J, const double* r, double w, double* acc) {
-  // H += w J^T J ; b -= w J^T r   (information = I, §9.4, §9.7)
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double g = 0;
-#pragma unroll
-    for (int k = 0; k < ROWS; ++k) g += J[6 * k + i] * r[k];
-    acc[21 + i] -= w * g;
-#pragma unroll
-    for (int j = i; j < 6; ++j) {
-      double h = 0;
-#pragma unroll
-      for (int k = 0; k < ROWS; ++k) h += J[6 * k + i] * J[6 * k + j];
-      acc[up6(i, j)] += w * h;
-    }
+  const double* a = J;
+  const double* b = J + 6;
+  const double wr0 = w * r[0], wr1 = w * r[1];
+  // gradient
+  acc[21 + 0] -= a[0] * wr0 + b[0] * wr1;
+  acc[21 + 1] -= a[1] * wr0 + b[1] * wr1;
+  acc[21 + 2] -= a[2] * wr0 + b[2] * wr1;
+  acc[21 + 3] -= a[3] * wr0;
+  acc[21 + 4] -= b[4] * wr1;
+  acc[21 + 5] -= a[5] * wr0 + b[5] * wr1;
+  // row 0 and row 1 outer products (entries with column 4 of row 0 / column 3 of row 1 vanish)
+  const double wa[6] = {w * a[0], w * a[1], w * a[2], w * a[3], 0.0, w * a[5]};
+  const double wb[6] = {w * b[0], w * b[1], w * b[2], 0.0, w * b[4], w * b[5]};
+  acc[up6(0, 0)] += wa[0] * a[0] + wb[0] * b[0];
+  acc[up6(0, 1)] += wa[0] * a[1] + wb[0] * b[1];
+  acc[up6(0, 2)] += wa[0] * a[2] + wb[0] * b[2];
+  acc[up6(0, 3)] += wa[0] * a[3];
+  acc[up6(0, 4)] += wb[0] * b[4];
+  acc[up6(0, 5)] += wa[0] * a[5] + wb[0] * b[5];
+  acc[up6(1, 1)] += wa[1] * a[1] + wb[1] * b[1];
+  acc[up6(1, 2)] += wa[1] * a[2] + wb[1] * b[2];
+  acc[up6(1, 3)] += wa[1] * a[3];
+  acc[up6(1, 4)] += wb[1] * b[4];
+  acc[up6(1, 5)] += wa[1] * a[5] + wb[1] * b[5];
+  acc[up6(2, 2)] += wa[2] * a[2] + wb[2] * b[2];
+  acc[up6(2, 3)] += wa[2] * a[3];
+  acc[up6(2, 4)] += wb[2] * b[4];
+  acc[up6(2, 5)] += wa[2] * a[5] + wb[2] * b[5];
+  acc[up6(3, 3)] += wa[3] * a[3];
+  acc[up6(3, 5)] += wa[3] * a[5];
+  acc[up6(4, 4)] += wb[4] * b[4];
+  acc[up6(4, 5)] += wb[4] * b[5];
+  acc[up6(5, 5)] += wa[5] * a[5] + wb[5] * b[5];
+  if (ROWS == 3) {
+    const double* c = J + 12; // c[4] == 0
+    const double wr2 = w * r[2];
+    acc[21 + 0] -= c[0] * wr2;
+    acc[21 + 1] -= c[1] * wr2;
+    acc[21 + 2] -= c[2] * wr2;
+    acc[21 + 3] -= c[3] * wr2;
+    acc[21 + 5] -= c[5] * wr2;
+    const double wc[6] = {w * c[0], w * c[1], w * c[2], w * c[3], 0.0, w * c[5]};
+    acc[up6(0, 0)] += wc[0] * c[0];
+    acc[up6(0, 1)] += wc[0] * c[1];
+    acc[up6(0, 2)] += wc[0] * c[2];
+    acc[up6(0, 3)] += wc[0] * c[3];
+    acc[up6(0, 5)] += wc[0] * c[5];
+    acc[up6(1, 1)] += wc[1] * c[1];
+    acc[up6(1, 2)] += wc[1] * c[2];
+    acc[up6(1, 3)] += wc[1] * c[3];
+    acc[up6(1, 5)] += wc[1] * c[5];
+    acc[up6(2, 2)] += wc[2] * c[2];
+    acc[up6(2, 3)] += wc[2] * c[3];
+    acc[up6(2, 5)] += wc[2] * c[5];
+    acc[up6(3, 3)] += wc[3] * c[3];
+    acc[up6(3, 5)] += wc[3] * c[5];
+    acc[up6(5, 5)] += wc[5] * c[5];
   }
 }
 

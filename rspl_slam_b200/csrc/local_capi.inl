@@ -361,6 +361,46 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   LAUNCH(PC_PAIRS, ba::kb_pairs<1>, W, ba::BT, 0, d, b);
   CU_TRY(c, cudaGetLastError());
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
+  // one super-step = a fixed sequence of launches with constant arguments
+  auto super_step = [&]() {
+    if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
+    LAUNCH(PC_POSE_BLOCKS, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
+    if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
+    LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
+    if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
+    if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
+  };
+  // ... captured once into a CUDA graph and replayed (launch-bound for small batches: a C1 window
+  // spends ~32 super-steps x 12 tiny kernels). Profiling needs event pairs around every launch,
+  // which a captured graph cannot carry, so it falls back to plain launches.
+  cudaGraphExec_t gexec = nullptr;
+  int64_t launches_per_step = 0;
+  if (!c->prof) {
+    cudaGraph_t graph = nullptr;
+    const int64_t before = c->launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      super_step();
+      if (cudaStreamEndCapture(s, &graph) == cudaSuccess && graph) {
+        if (cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+        cudaGraphDestroy(graph);
+      }
+    }
+    launches_per_step = c->launches - before;
+    c->launches = before;
+    cudaGetLastError();
+  }
+  struct GraphGuard {
+    cudaGraphExec_t& g;
+    ~GraphGuard() {
+      if (g) cudaGraphExecDestroy(g);
+    }
+  } graph_guard{gexec};
   for (int pass = 0; pass < 2; ++pass) {
     LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
     const int worst = lo.iters[pass] * 10 + 1; // <= 10 trials per LM iteration (§9.9)
@@ -368,18 +408,12 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     while (done_steps < worst) {
       const int burst = done_steps == 0 ? (lo.iters[pass] < 4 ? lo.iters[pass] : 4) : 4;
       for (int k = 0; k < burst && done_steps < worst; ++k, ++done_steps) {
-        if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(PC_POSE_BLOCKS, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
-        LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
-        if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
-        LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
-        if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
-        if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
-        LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
-        if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
+        if (gexec) {
+          CU_TRY(c, cudaGraphLaunch(gexec, s));
+          c->launches += launches_per_step;
+        } else {
+          super_step();
+        }
         c->l_super_steps++;
       }
       CU_TRY(c, cudaGetLastError());
@@ -431,11 +465,12 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   }
   c->launches++;
   CU_TRY(c, cudaGetLastError());
-  // Path: a handful of windows -> one persistent CTA per window (whole LM loop in one kernel, no
-  // host involvement: the latency path of configs C1/C3); a large batch -> one kernel per LM phase
-  // over all windows (the throughput path of config C4). RSPL_BA_LOCAL_PATH=persistent|batched
-  // forces one of them (tests run both).
-  bool batched = c->l_n_windows >= 2 * c->num_sms;
+  // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
+  // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent
+  // kernel even for a single window (5.8 ms vs 30 ms), because a lone CTA of 256 threads cannot hide
+  // the latency of its dependent loads. The persistent kernel (whole LM loop in one launch, zero host
+  // involvement) stays selectable with RSPL_BA_LOCAL_PATH=persistent; the tests run both.
+  bool batched = true;
   if (const char* env = getenv("RSPL_BA_LOCAL_PATH")) {
     if (!strcmp(env, "persistent")) batched = false;
     else if (!strcmp(env, "batched")) batched = true;

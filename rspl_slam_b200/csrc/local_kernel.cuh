@@ -797,7 +797,19 @@ BA_DEV void cholesky_solve(const WinSmem& s, int n) {
     double dk = 0;
     for (int j = k + lane; j < n; j += 32) {
       double v = A[(size_t)k * n + j];
-      for (int p = 0; p < k; ++p) v -= A[(size_t)p * n + k] * A[(size_t)p * n + j];
+      {
+        // four independent partial sums hide the shared-memory load latency of the dependent chain
+        double v1 = 0, v2 = 0, v3 = 0;
+        int p = 0;
+        for (; p + 3 < k; p += 4) {
+          v -= A[(size_t)p * n + k] * A[(size_t)p * n + j];
+          v1 -= A[(size_t)(p + 1) * n + k] * A[(size_t)(p + 1) * n + j];
+          v2 -= A[(size_t)(p + 2) * n + k] * A[(size_t)(p + 2) * n + j];
+          v3 -= A[(size_t)(p + 3) * n + k] * A[(size_t)(p + 3) * n + j];
+        }
+        for (; p < k; ++p) v -= A[(size_t)p * n + k] * A[(size_t)p * n + j];
+        v += (v1 + v2) + v3;
+      }
       A[(size_t)k * n + j] = v;
       if (j == k) dk = v;
     }
