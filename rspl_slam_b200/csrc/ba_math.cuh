@@ -184,6 +184,50 @@ BA_DEV Pose pose_exp(const double* u) {
 // VertexSE3Expmap::oplusImpl: T <- exp(u) * T
 BA_DEV Pose pose_oplus(const Pose& T, const double* u) { return pose_mul(pose_exp(u), T); }
 
+// The same update on a rotation-matrix pose, for inner loops that never need the quaternion:
+// R <- dR R, t <- dR t + V upsilon with (dR, V) of SE3Quat::exp. The quaternion round trip and its
+// two normalisations (which keep g2o's estimate on the manifold to rounding level) are skipped; the
+// caller converts back once at the end. One reciprocal replaces the three divisions of the closed form.
+struct PoseRt {
+  double R[9];
+  double t[3];
+};
+BA_DEV void poseRt_oplus(const PoseRt& T, const double* u, PoseRt& out) {
+  const double wx = u[0], wy = u[1], wz = u[2];
+  const double th2 = wx * wx + wy * wy + wz * wz;
+  double a, b, c;
+  if (th2 < 1e-10) { // theta < 1e-5
+    a = 1.0;
+    b = 0.5;
+    c = 1.0 / 6.0;
+  } else {
+    const double theta = sqrt(th2), it = 1.0 / theta;
+    double s, co;
+    sincos(theta, &s, &co);
+    a = s * it;
+    b = (1 - co) * it * it;
+    c = (theta - s) * it * it * it;
+  }
+  const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+  const double O2[9] = {-(wy * wy + wz * wz), wx * wy, wx * wz, wx * wy, -(wx * wx + wz * wz), wy * wz,
+                        wx * wz, wy * wz, -(wx * wx + wy * wy)};
+  double dR[9], V[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+    dR[i] = id + a * O[i] + b * O2[i];
+    V[i] = id + b * O[i] + c * O2[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      out.R[3 * i + j] = dR[3 * i] * T.R[j] + dR[3 * i + 1] * T.R[3 + j] + dR[3 * i + 2] * T.R[6 + j];
+    out.t[i] = dR[3 * i] * T.t[0] + dR[3 * i + 1] * T.t[1] + dR[3 * i + 2] * T.t[2] + V[3 * i] * u[3] +
+               V[3 * i + 1] * u[4] + V[3 * i + 2] * u[5];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Huber (RobustKernelHuber::robustify); returns rho0, writes the weight rho1
 // ------------------------------------------------------------------------------------------------

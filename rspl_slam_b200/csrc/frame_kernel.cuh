@@ -68,7 +68,7 @@ constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
 // per-warp (= per-frame) state that is touched once per trial: kept in shared memory so the
 // edge loops keep their registers
 struct WarpState {
-  Pose T, T0, Tbackup, Te; // current / initial pose; LM backup; pose of the last error evaluation (§9.12)
+  PoseRt T0, Tbackup, Te; // initial pose; LM backup; pose of the last error evaluation (stale errors, §9.12)
   double H[21], b[6], x[6];
   DevStats st;
 };
@@ -272,12 +272,16 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
   const int n_edges = (m1 - m0) + (s1 - s0);
 
   // ---- setup: pose (g2o_optimization.cc:271), flags, levels
-  Pose T;
+  PoseRt T; // optimiser pose Tcw as rotation matrix + translation (quaternion only at the boundary)
   {
     const double p[3] = {d.pose_twc[f], d.pose_twc[d.n_frames + f], d.pose_twc[2 * d.n_frames + f]};
     const double q[4] = {d.pose_twc[3 * d.n_frames + f], d.pose_twc[4 * d.n_frames + f],
                          d.pose_twc[5 * d.n_frames + f], d.pose_twc[6 * d.n_frames + f]};
-    T = pose_from_twc(p, q);
+    const Pose Tq = pose_from_twc(p, q);
+    quat_to_R(Tq.q, T.R);
+    T.t[0] = Tq.t[0];
+    T.t[1] = Tq.t[1];
+    T.t[2] = Tq.t[2];
   }
   if (lane == 0) {
     ws.T0 = T;
@@ -302,12 +306,10 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
   int n_active = n_edges; // every edge starts at level 0
   int num_outlier = 0;
   double lambda = 0, ni = 2, chi_cur = 0;
-  double R[9], t[3];
 
   for (int round = 0; round < o.rounds; ++round) {
     const int sr = round < 4 ? round : 3;
     T = ws.T0; // frame_vertex->setEstimate(initial) (:340)
-    pose_to_Rt(T, R, t);
     if (n_active > 0) {
       // ---------------- optimizer.optimize(iters) ----------------
       for (int it = 0; it < o.iters; ++it) {
@@ -315,7 +317,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
           double acc[NACC];
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
-          edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, R, t, robust, lane, acc);
+          edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
@@ -358,7 +360,8 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
             }
             ok = solve6(H, b, lambda, x);
           }
-          const Pose Tn = pose_oplus(T, x);
+          PoseRt Tn;
+          poseRt_oplus(T, x, Tn);
           __syncwarp();
           if (lane == 0) {
             ws.Tbackup = T;
@@ -368,12 +371,11 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
           }
           __syncwarp();
           T = Tn;
-          pose_to_Rt(T, R, t);
           double tempChi;
           {
             double a2[NACC];
             a2[NACC - 1] = 0;
-            edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, R, t, robust, lane, a2);
+            edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
             tempChi = warp_allreduce(a2[NACC - 1]);
           }
           if (lane == 0) {
@@ -400,7 +402,6 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
             lambda *= ni;
             ni *= 2;
             T = ws.Tbackup;
-            pose_to_Rt(T, R, t);
             if (!isfinite(lambda)) stop_lambda = true;
           }
           if (!stop_lambda) qmax++;
@@ -411,8 +412,9 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
       }
     }
     // ---------------- classification (:344-385) ----------------
-    double Re[9], te[3];
-    pose_to_Rt(ws.Te, Re, te);
+    const PoseRt Tev = ws.Te;
+    const double* Re = Tev.R;
+    const double* te = Tev.t;
     int my_out = 0;
     for (int e = m0 + lane; e < m1; e += 32) {
       Cam camv;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
       const bool recompute = !d.mono_inl[e];
       const bool was_active = !d.mono_lvl[e] && n_active > 0;
       double Xc[3], r[2];
-      if (recompute || !was_active) transform_point(R, t, X, Xc);
+      if (recompute || !was_active) transform_point(T.R, T.t, X, Xc);
       else transform_point(Re, te, X, Xc);
       point_residual<false>(cam, cam.bf, Xc, m, r);
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1]);
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
       const bool recompute = !d.stereo_inl[e];
       const bool was_active = !d.stereo_lvl[e] && n_active > 0;
       double Xc[3], r[3];
-      if (recompute || !was_active) transform_point(R, t, X, Xc);
+      if (recompute || !was_active) transform_point(T.R, T.t, X, Xc);
       else transform_point(Re, te, X, Xc);
       point_residual<true>(cam, cam.bf, Xc, m, r);
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
@@ -462,7 +464,13 @@ __global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __gri
 
   // ---- recover optimized data (:391-396)
   if (lane == 0) {
-    const Pose Twc = pose_inverse(T);
+    Pose Tq;
+    R_to_quat(T.R, Tq.q);
+    Tq.t[0] = T.t[0];
+    Tq.t[1] = T.t[1];
+    Tq.t[2] = T.t[2];
+    pose_normalize(Tq);
+    const Pose Twc = pose_inverse(Tq);
     d.out_pose_twc[f] = Twc.t[0];
     d.out_pose_twc[d.n_frames + f] = Twc.t[1];
     d.out_pose_twc[2 * d.n_frames + f] = Twc.t[2];
