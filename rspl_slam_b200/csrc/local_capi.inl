@@ -357,8 +357,9 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     c->launches++;                                     \
   } while (0)
   LAUNCH(PC_PAIRS, ba::kb_init, W, ba::BT, 0, d, b, lo);
-  LAUNCH(PC_PAIRS, ba::kb_pairs<0>, W, ba::BT, 0, d, b);
-  LAUNCH(PC_PAIRS, ba::kb_pairs<1>, W, ba::BT, 0, d, b);
+  LAUNCH(PC_PAIRS, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
+  LAUNCH(PC_PAIRS, ba::kb_pairs_scan, g_win, 128, 0, d, b);
+  LAUNCH(PC_PAIRS, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
   CU_TRY(c, cudaGetLastError());
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
