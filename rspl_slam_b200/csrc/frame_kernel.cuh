@@ -61,6 +61,9 @@ struct DevStats { // layout == RsplBaStats
   double final_lambda;
 };
 
+#ifndef FRAME_MIN_BLOCKS
+#define FRAME_MIN_BLOCKS 4 // 128 registers: best of {3, 4, 5} measured on B200 (profiles/README.md)
+#endif
 constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
 constexpr int FRAME_WARPS = FRAME_THREADS / 32;
 constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
@@ -260,7 +263,7 @@ BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
 // One warp per frame: every lane carries the same pose / LM scalars (computed redundantly, so no
 // broadcast and no block barrier is ever needed); lanes stride over the frame's edges.
 template <bool SINGLE_CAM>
-__global__ void __launch_bounds__(FRAME_THREADS, 4) frame_opt_kernel(const __grid_constant__ FrameDev d,
+__global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_kernel(const __grid_constant__ FrameDev d,
                                                                       const __grid_constant__ FrameOpt o) {
   __shared__ WarpState wstate[FRAME_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

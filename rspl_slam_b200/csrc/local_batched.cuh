@@ -26,6 +26,14 @@ constexpr int BW = BT / 32;
 
 enum { STAGE_NEED_LIN = 0, STAGE_NEED_TRIAL = 1, STAGE_DONE = 2 };
 
+// Layout of a Z block in the batched path: COLUMN-major, Z[e][q][0..5] with q the landmark coordinate:
+// kb_schur_reduce splits a pair entry by column (Z_i Z_j^T = sum_q z_i,q z_j,q^T).
+constexpr int ZCOL = 6;
+template <int KIND>
+struct ZBlk {
+  static constexpr int N = KT<KIND>::LD * ZCOL; // doubles per block: 18 (points), 24 (lines)
+};
+
 struct WinState {
   int stage, pass, it, qmax, n_sys, solve_ok, prep_fail, restore;
   int robust, iters, nf, pad;
@@ -240,6 +248,13 @@ BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k
       atomicAdd(&b.pact[p0 + (k.info[e] & 0xffff)], 1);
     }
     k.act[l] = (uint8_t)any;
+    if (!any) { // kb_schur_reduce / kb_backsub read Z and y of every listed edge without testing `act`
+      for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e)
+#pragma unroll
+        for (int q = 0; q < ZBlk<KIND>::N; ++q) k.Z[(size_t)e * ZBlk<KIND>::N + q] = 0.0;
+#pragma unroll
+      for (int q = 0; q < KT<KIND>::LD; ++q) k.y[(size_t)q * k.n_lm + l] = 0.0;
+    }
   }
 }
 
@@ -502,11 +517,11 @@ BA_DEV void schur_prep_one(const LocalDev& d, const BatchDev& b, const LocalOpt&
     const int p = info & 0xffff;
     const int fi = b.free_idx[p0 + p];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
-    double* Ze = k.Z + (size_t)e * T::WD;
+    double* Ze = k.Z + (size_t)e * ZBlk<KIND>::N;
     double wv[T::WD];
     if (k.lvl[e]) { // excluded edge (level 1): no contribution
 #pragma unroll
-      for (int q = 0; q < T::WD; q += 2) *reinterpret_cast<double2*>(Ze + q) = make_double2(0.0, 0.0);
+      for (int q = 0; q < ZBlk<KIND>::N; q += 2) *reinterpret_cast<double2*>(Ze + q) = make_double2(0.0, 0.0);
       continue;
     }
     { // W = Jp^T (rho1 Omega) Jl, recomputed from the edge record
@@ -543,8 +558,14 @@ BA_DEV void schur_prep_one(const LocalDev& d, const BatchDev& b, const LocalOpt&
 #pragma unroll
       for (int c = 0; c < LD; ++c) wv[a * LD + c] = z[c];
     }
+    // column-major store (see ZCOL)
 #pragma unroll
-    for (int q = 0; q < T::WD; q += 2) *reinterpret_cast<double2*>(Ze + q) = make_double2(wv[q], wv[q + 1]);
+    for (int c = 0; c < LD; ++c) {
+      double2* col = reinterpret_cast<double2*>(Ze + c * ZCOL);
+      col[0] = make_double2(wv[0 * LD + c], wv[1 * LD + c]);
+      col[1] = make_double2(wv[2 * LD + c], wv[3 * LD + c]);
+      col[2] = make_double2(wv[4 * LD + c], wv[5 * LD + c]);
+    }
   }
 }
 
@@ -563,58 +584,112 @@ __global__ void __launch_bounds__(BT) kb_schur_prep(const __grid_constant__ Loca
   if (fail) atomicOr(&s.prep_fail, 1);
 }
 
-// K3': one WARP per (window, pose pair): sum_e Z_i Z_j^T (and Z_i y on the diagonal) over the pair list
+// K3': one WARP per (window, pose pair): sum_e Z_i Z_j^T (and Z_i y on the diagonal) over the pair list.
+// A lane owns one COLUMN q of one pair entry per iteration and adds the rank-1 update z_i,q z_j,q^T to its
+// private accumulators (all lanes' accumulators are summed at the end anyway). The loop is a gather of
+// 64-byte columns at data-dependent addresses and its first versions were latency-bound: 84 accumulator
+// registers per lane leave room for ~12 warps per SM, too few to cover the L2 round trip with one or two
+// loads in flight per lane. So the columns travel global -> shared memory with cp.async into a
+// lane-private ring of RED_STAGES stages (the 227 KB of shared memory hold the in-flight data instead of
+// registers), entry records are fetched one further iteration ahead, and a lane only ever reads what it
+// copied itself, so no barrier is needed.
+constexpr int RED_STAGES = 4;
+constexpr int RED_RING = RED_STAGES * 6 * 32; // double2 per warp: [stage][piece][lane], conflict-free both ways
+
+BA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BA_DEV void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+BA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+BA_DEV void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+BA_DEV void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 template <int KIND>
-BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, int lane, double* acc) {
-  using T = KT<KIND>;
-  constexpr int LD = T::LD;
+BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, int lane, double* acc,
+                               double2* ring) {
+  constexpr int LD = KT<KIND>::LD, ZB = ZBlk<KIND>::N, S = RED_STAGES;
   const int l0 = k.lm_begin[w];
-  for (int it = lane; it < n; it += 32) {
-    const int2 ee = ent[it];
-    const int l = l0 + k.lm[ee.x];
-    if (!k.act[l]) continue;
-    double Zi[T::WD], Zj[T::WD];
-    const double* zi = k.Z + (size_t)ee.x * T::WD;
+  const int nsub = n * LD;
+  const int nit = (nsub + 31) >> 5;
+  if (nit == 0) return;
+  // register pipeline in front of the copies: entry record (two iterations before its copies are
+  // issued), then -- diagonal pairs only -- the landmark index that locates y (one iteration before)
+  auto fetch = [&](int i) -> int2 {
+    const int sub = i * 32 + lane;
+    return sub < nsub ? ent[sub / LD] : make_int2(-1, -1);
+  };
+  auto fetch_lm = [&](const int2& ee) -> int { return (diag && ee.x >= 0) ? l0 + k.lm[ee.x] : 0; };
+  auto issue = [&](int i, const int2& ee, int l) {
+    if (ee.x >= 0) {
+      const int q = (i * 32 + lane) % LD;
+      double2* dst = ring + (i % S) * (6 * 32) + lane;
+      const double* a = k.Z + (size_t)ee.x * ZB + q * ZCOL;
 #pragma unroll
-    for (int q = 0; q < T::WD; q += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(zi + q);
-      Zi[q] = v.x;
-      Zi[q + 1] = v.y;
-    }
-    if (diag) {
+      for (int j = 0; j < 3; ++j) cp_async16(dst + j * 32, a + 2 * j);
+      if (diag) {
+        cp_async8(dst + 3 * 32, k.y + (size_t)q * k.n_lm + l);
+      } else {
+        const double* bb = k.Z + (size_t)ee.y * ZB + q * ZCOL;
 #pragma unroll
-      for (int q = 0; q < T::WD; ++q) Zj[q] = Zi[q];
-    } else {
-      const double* zj = k.Z + (size_t)ee.y * T::WD;
-#pragma unroll
-      for (int q = 0; q < T::WD; q += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(zj + q);
-        Zj[q] = v.x;
-        Zj[q + 1] = v.y;
+        for (int j = 0; j < 3; ++j) cp_async16(dst + (3 + j) * 32, bb + 2 * j);
       }
     }
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        double v = 0;
-#pragma unroll
-        for (int q = 0; q < LD; ++q) v += Zi[r * LD + q] * Zj[c * LD + q];
-        acc[r * 6 + c] += v;
-      }
-    if (diag) {
-      double y[LD];
-#pragma unroll
-      for (int q = 0; q < LD; ++q) y[q] = k.y[(size_t)q * k.n_lm + l];
-#pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        double v = 0;
-#pragma unroll
-        for (int q = 0; q < LD; ++q) v += Zi[r * LD + q] * y[q];
-        acc[36 + r] += v;
-      }
-    }
+  for (int st = 0; st < S; ++st) {
+    const int2 ee = fetch(st);
+    issue(st, ee, fetch_lm(ee));
   }
+  int2 e1 = fetch(S), e2 = fetch(S + 1);
+  int l1 = fetch_lm(e1);
+  for (int i = 0; i < nit; ++i) {
+    cp_async_wait<S - 1>();
+    if (i * 32 + lane < nsub) {
+      const double2* src = ring + (i % S) * (6 * 32) + lane;
+      double za[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double2 v = src[j * 32];
+        za[2 * j] = v.x;
+        za[2 * j + 1] = v.y;
+      }
+      if (diag) {
+        const double yq = src[3 * 32].x;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += za[r] * za[c];
+          acc[36 + r] += za[r] * yq;
+        }
+      } else {
+        double zb[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double2 v = src[(3 + j) * 32];
+          zb[2 * j] = v.x;
+          zb[2 * j + 1] = v.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[r * 6 + c] += za[r] * zb[c];
+      }
+    }
+    const int2 e_now = e1;
+    const int l_now = l1;
+    e1 = e2;
+    l1 = fetch_lm(e1);
+    e2 = fetch(i + S + 2);
+    issue(i + S, e_now, l_now);
+  }
+  cp_async_wait<0>();
 }
 
 // Reduces 64 per-lane values across the warp with 62 shuffles instead of 64 x 5: at every step a
@@ -634,12 +709,16 @@ BA_DEV void warp_transpose_reduce64(double* v, int lane) {
   }
 }
 
-__global__ void __launch_bounds__(BT) kb_schur_reduce(const __grid_constant__ LocalDev d,
+// One warp per CTA: the pairs of a window have very different list lengths (a diagonal pair lists every
+// edge of its pose, a far pair a few dozen), and warps sharing a CTA would hold its registers until the
+// longest one finishes (measured: 7 resident warps per SM instead of 12).
+__global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ LocalDev d,
                                                       const __grid_constant__ BatchDev b) {
   // pair index fastest: the warps of one window run together, so the window's Z blocks (each read by
   // every pair that contains its pose) are fetched from HBM once and then hit in L2
+  __shared__ __align__(16) double2 ring[RED_RING];
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.y, p = blockIdx.x * BW + (threadIdx.x >> 5);
+  const int w = blockIdx.y, p = blockIdx.x;
   const WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const int nf = s.nf;
@@ -653,8 +732,8 @@ __global__ void __launch_bounds__(BT) kb_schur_reduce(const __grid_constant__ Lo
   double acc[64];
 #pragma unroll
   for (int q = 0; q < 64; ++q) acc[q] = 0;
-  schur_pair_entries<0>(d.k[0], w, b.pairs + pb[0], pb[1] - pb[0], diag, lane, acc);
-  schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, lane, acc);
+  schur_pair_entries<0>(d.k[0], w, b.pairs + pb[0], pb[1] - pb[0], diag, lane, acc, ring);
+  schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, lane, acc, ring);
   warp_transpose_reduce64(acc, lane);
   if (2 * lane < 42) {
     double* out = b.hs_part + ((size_t)w * b.Pmax + p) * 42 + 2 * lane;
@@ -809,13 +888,13 @@ BA_DEV void backsub_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o,
   for (int e = ea; e < eb; ++e) {
     const int fi = b.free_idx[p0 + (k.info[e] & 0xffff)];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
-    const double* Ze = k.Z + (size_t)e * T::WD;
+    const double* Ze = k.Z + (size_t)e * ZBlk<KIND>::N;
     const double* xv = b.xp + (size_t)(f0 + fi) * 6;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       const double xr = xv[r];
 #pragma unroll
-      for (int a = 0; a < LD; ++a) v[a] -= Ze[r * LD + a] * xr;
+      for (int a = 0; a < LD; ++a) v[a] -= Ze[a * ZCOL + r] * xr;
     }
   }
   double Hup[T::HD], Lf[LD * (LD + 1) / 2], inv[LD], xl[LD];

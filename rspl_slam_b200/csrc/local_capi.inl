@@ -345,7 +345,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   // (chunk | pose | pair) index fastest, window on grid.y: the CTAs of one window run together
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
-      g_win((W + 127) / 128);
+      g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128);
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
   if (smem_solve > c->smem_optin) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "reduced system does not fit shared memory");
@@ -370,7 +370,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
     if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
-    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair, ba::BT, 0, d, b);
+    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair1, 32, 0, d, b);
     LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
     if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
