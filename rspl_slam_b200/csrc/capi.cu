@@ -97,8 +97,11 @@ struct RsplBaContext {
   std::vector<int> l_nf_begin;          // [W+1] free poses per window (prefix)
   std::vector<long long> l_pair_base;   // [W+1] capacity prefix of the pair lists
   int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
-  int l_last_path = 0;                  // 1 persistent, 2 batched (diagnostics)
+  int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve (diagnostics)
   int l_super_steps = 0;
+  // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
+  DevBuf dense_buf;
+  void* cusolver = nullptr; // cusolverDnHandle_t
 
   // ---- optional per-kernel-class timing with CUDA events on the context stream (rspl_ba_set_profiling)
   bool prof = false;
@@ -241,6 +244,8 @@ extern "C" int rspl_ba_create(int device, void* stream, RsplBaContext** out) {
   return RSPL_BA_OK;
 }
 
+static void dense_release(RsplBaContext* c); // dense_solver.inl
+
 extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   if (!c) return;
   SetDevice guard(c->device);
@@ -248,6 +253,8 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   c->frame_buf.release();
   c->local_buf.release();
   c->batch_buf.release();
+  c->dense_buf.release();
+  dense_release(c);
   c->unit_buf.release();
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
   for (auto& pe : c->prof_pool) {
@@ -725,4 +732,5 @@ extern "C" int rspl_ba_oplus(RsplBaContext* c, int kind, int32_t n, const double
   return RSPL_BA_OK;
 }
 
+#include "dense_solver.inl"
 #include "local_capi.inl"

@@ -62,20 +62,28 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   int2* pairs;    // pair entries (e_i, e_j) into the sorted edge arrays
   const long long* pair_base; // [W+1] region of each window inside `pairs`
   int* n_active;  // device counter for the host poll
+  // dense-solve path (reduced systems too large for shared memory): per window a row-major n x n
+  // matrix with the upper triangle filled (= column-major lower for cuSOLVER), rhs / solution, potrf info
+  double* dense_H;
+  const long long* dense_off; // [W] offset of the window's matrix in dense_H
+  double* dense_b;            // [6 * NF] by free-pose offset
+  int* dense_info;            // [W]
   int Cp, Cl, C;  // landmark chunks per window: points, lines, total
   int Pmax, NFmax;
 };
 
-BA_DEV void pair_decode(int p, int nf, int& fi, int& fj) {
-  int row = 0, rem = p;
-  while (rem >= nf - row) {
-    rem -= nf - row;
-    ++row;
-  }
-  fi = row;
-  fj = row + rem;
-}
 BA_DEV int pair_index(int fi, int fj, int nf) { return fi * nf - fi * (fi - 1) / 2 + (fj - fi); }
+// inverse of pair_index: closed form + fix-up (windows of the dense-solve path have ~10^6 pairs)
+BA_DEV void pair_decode(int p, int nf, int& fi, int& fj) {
+  const double t = 2.0 * nf + 1.0;
+  int row = (int)((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
+  if (row < 0) row = 0;
+  if (row > nf - 1) row = nf - 1;
+  while (row > 0 && pair_index(row, row, nf) > p) --row;
+  while (row + 1 < nf && pair_index(row + 1, row + 1, nf) <= p) ++row;
+  fi = row;
+  fj = row + (p - pair_index(row, row, nf));
+}
 
 // deterministic CTA reduction of N doubles per thread (BT threads); thread q < N ends with sum q
 template <int N>
@@ -870,6 +878,90 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     if (ok)
       for (int fi = 0; fi < nf; ++fi) sp += sc_part[fi];
     s.scale_pose = sp;
+    s.solve_ok = ok ? 1 : 0;
+  }
+}
+
+// Dense-solve path, K4 split in three: assemble -> cuSOLVER potrf / potrs (host-enqueued) -> pose update.
+// grid (Pmax, W), 64 threads: one CTA per pose pair block.
+__global__ void __launch_bounds__(64) kb_assemble_dense(const __grid_constant__ LocalDev d,
+                                                        const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, p = blockIdx.x, tid = threadIdx.x;
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  const int nf = s.nf;
+  if (p >= nf * (nf + 1) / 2) return;
+  int fi, fj;
+  pair_decode(p, nf, fi, fj);
+  const int f0 = b.nf_begin[w];
+  const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
+  if (si < 0 || sj < 0) return;
+  const int n = 6 * s.n_sys;
+  double* Hs = b.dense_H + b.dense_off[w];
+  const double* part = b.hs_part + ((size_t)w * b.Pmax + p) * 42;
+  if (tid < 36) {
+    const int r = tid / 6, c = tid % 6;
+    double v = -part[tid];
+    if (fi == fj) {
+      const int rr = r < c ? r : c, cc = r < c ? c : r;
+      v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? s.lambda : 0.0);
+    }
+    Hs[(size_t)(6 * si + r) * n + 6 * sj + c] = v;
+  } else if (tid < 42 && fi == fj) {
+    const int r = tid - 36;
+    b.dense_b[(size_t)6 * f0 + 6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - part[36 + r];
+  }
+}
+
+// pose update after the dense solve (the tail of kb_solve); one CTA per window
+__global__ void __launch_bounds__(256) kb_post_solve(const __grid_constant__ LocalDev d,
+                                                     const __grid_constant__ BatchDev b) {
+  __shared__ double red[8];
+  const int w = blockIdx.x, tid = threadIdx.x;
+  WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  const int nf = s.nf, f0 = b.nf_begin[w], p0 = d.pose_begin[w];
+  const bool ok = (s.n_sys == 0 || b.dense_info[w] == 0) && !s.prep_fail; // potrf info > 0 <=> a pivot <= 0 (§9.11)
+  const double lambda = s.lambda;
+  const double* xs = b.dense_b + (size_t)6 * f0;
+  double part = 0;
+  if (ok) {
+    for (int fi = tid; fi < nf; fi += blockDim.x) {
+      const int si = b.sys_idx[f0 + fi];
+      if (si < 0) continue;
+      const size_t gp = (size_t)(p0 + b.pose_of[f0 + fi]);
+      Pose T;
+      double x6[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        x6[q] = xs[6 * si + q];
+        b.xp[(size_t)(f0 + fi) * 6 + q] = x6[q];
+        part += x6[q] * (lambda * x6[q] + b.bp[(size_t)(f0 + fi) * 6 + q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) T.q[q] = b.P_bq[4 * gp + q] = b.P_q[4 * gp + q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) T.t[q] = b.P_bt[3 * gp + q] = b.P_t[3 * gp + q];
+      const Pose Tn = pose_oplus(T, x6);
+      double Rn[9];
+      quat_to_R(Tn.q, Rn);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) b.P_q[4 * gp + q] = Tn.q[q];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) b.P_t[3 * gp + q] = Tn.t[q];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) b.P_R[9 * gp + q] = Rn[q];
+    }
+  }
+  // fixed-order block sum of the pose part of the LM scale
+  part = warp_allreduce(part);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double sp = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sp += red[q];
+    s.scale_pose = ok ? sp : 0.0;
     s.solve_ok = ok ? 1 : 0;
   }
 }

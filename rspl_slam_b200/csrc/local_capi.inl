@@ -110,16 +110,25 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     if (npt > c->l_max_pts) c->l_max_pts = npt;
     if (nln > c->l_max_lns) c->l_max_lns = nln;
     if (ne > c->l_max_edges) c->l_max_edges = (int)ne;
-    // a landmark with k free observers yields k(k+1)/2 <= k(nf+1)/2 pair entries
-    c->l_pair_base[w + 1] = c->l_pair_base[w] + (ne * (nf + 1) + 1) / 2 + 2;
+    // a landmark with k free observers yields k(k+1)/2 <= k(nf+1)/2 pair entries; for large windows
+    // that bound is far too loose, so count sum_l deg(l)(deg(l)+1)/2 over the window's landmarks
+    long long cap = (ne * (nf + 1) + 1) / 2 + 2;
+    if (cap > (1LL << 24)) {
+      long long exact = 2;
+      std::vector<int> deg;
+      for (int k = 0; k < 2; ++k) {
+        const int l0 = kh[k].lm_begin[w], nl = kh[k].lm_begin[w + 1] - l0;
+        deg.assign(nl > 0 ? nl : 1, 0);
+        for (int cl = 0; cl < 2; ++cl)
+          for (int i = kh[k].cls_begin[cl][w]; i < kh[k].cls_begin[cl][w + 1]; ++i) deg[kh[k].cls_lm[cl][i]]++;
+        for (int l = 0; l < nl; ++l) exact += (long long)deg[l] * (deg[l] + 1) / 2;
+      }
+      if (exact < cap) cap = exact;
+    }
+    c->l_pair_base[w + 1] = c->l_pair_base[w] + cap;
   }
-  if (max_poses > 255)
-    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: %d poses in one window (limit 255)", max_poses);
-  const size_t smem = ba::local_smem_bytes(max_poses, max_free);
-  if (smem > c->smem_optin)
-    return fail(c, RSPL_BA_ERR_UNSUPPORTED,
-                "local batch: %d free poses in one window need %zu B of shared memory (limit %zu); use the global-BA path",
-                max_free, smem, c->smem_optin);
+  if (max_poses > 65535) // the packed edge record keeps the pose in 16 bits
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: %d poses in one window (limit 65535)", max_poses);
 
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
@@ -133,6 +142,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
   const size_t o_err = a.take(sizeof(int));
   const size_t o_phase = a.take(sizeof(long long) * 8 * W);
+  const size_t o_sfi = a.take(sizeof(int) * NP);
   const int slot_stride = (max_free + 3) & ~3;
   struct KOff {
     size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
@@ -213,6 +223,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.stats = (void*)(base + o_stats);
   d.err = (int*)(base + o_err);
   d.phase = (long long*)(base + o_phase);
+  d.setup_free_idx = (int*)(base + o_sfi);
   for (int k = 0; k < 2; ++k) {
     ba::KindDev& kd = d.k[k];
     const KOff& o = ko[k];
@@ -277,7 +288,8 @@ int batched_prepare(RsplBaContext* c) {
   const int C = Cp + Cl > 0 ? Cp + Cl : 1;
   const long long n_pairs = c->l_pair_base[W];
   if (n_pairs > 0x7fffffffLL) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: pair lists exceed 2^31 entries");
-  if (C > 65535 || Pmax > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: window too large for the batched path");
+  if ((long long)NFmax * (NFmax + 1) / 2 > 0x3fffffffLL)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: window too large for the batched path");
   Arena a;
   const size_t o_ws = a.take(sizeof(ba::WinState) * W);
   const size_t o_q = a.take(sizeof(double) * 4 * NP), o_t = a.take(sizeof(double) * 3 * NP);
@@ -348,8 +360,21 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128);
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
-  if (smem_solve > c->smem_optin) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "reduced system does not fit shared memory");
-  CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  // reduced systems beyond shared memory: dense matrices in HBM + cuSOLVER Cholesky (dense_solver.inl)
+  const bool dense = smem_solve > c->smem_optin;
+  DenseLayout dl;
+  std::vector<int> n_sys_host(W, 0);
+  if (dense) {
+    rc = dense_prepare(c, dl);
+    if (rc != RSPL_BA_OK) return rc;
+    c->bd.dense_H = dl.H;
+    c->bd.dense_b = dl.b;
+    c->bd.dense_info = dl.info;
+    c->bd.dense_off = dl.d_off;
+    c->l_last_path = 3;
+  } else {
+    CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  }
 #define LAUNCH(cls, kern, grid, block, shm, ...)       \
   do {                                                 \
     ProfScope ps_(c, cls);                             \
@@ -363,6 +388,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   CU_TRY(c, cudaGetLastError());
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
+  int dense_rc = RSPL_BA_OK;
   auto super_step = [&]() {
     if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
@@ -371,7 +397,16 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
     LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair1, 32, 0, d, b);
-    LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
+    if (!dense) {
+      LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
+    } else {
+      LAUNCH(PC_SOLVE, ba::kb_assemble_dense, g_pair1, 64, 0, d, b);
+      {
+        ProfScope ps_(c, PC_SOLVE);
+        dense_rc = dense_factor_solve(c, dl, n_sys_host);
+      }
+      LAUNCH(PC_SOLVE, ba::kb_post_solve, W, 256, 0, d, b);
+    }
     if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
     LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
@@ -382,7 +417,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   // which a captured graph cannot carry, so it falls back to plain launches.
   cudaGraphExec_t gexec = nullptr;
   int64_t launches_per_step = 0;
-  if (!c->prof) {
+  if (!c->prof && !dense) { // library calls of the dense path are enqueued directly
     cudaGraph_t graph = nullptr;
     const int64_t before = c->launches;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -404,6 +439,12 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   } graph_guard{gexec};
   for (int pass = 0; pass < 2; ++pass) {
     LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
+    if (dense) { // the host needs the system sizes of this pass for the library calls
+      std::vector<ba::WinState> ws(W);
+      CU_TRY(c, cudaMemcpyAsync(ws.data(), b.ws, sizeof(ba::WinState) * W, cudaMemcpyDeviceToHost, s));
+      CU_TRY(c, cudaStreamSynchronize(s));
+      for (int w = 0; w < W; ++w) n_sys_host[w] = ws[w].n_sys;
+    }
     const int worst = lo.iters[pass] * 10 + 1; // <= 10 trials per LM iteration (§9.9)
     int done_steps = 0;
     while (done_steps < worst) {
@@ -418,6 +459,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
         c->l_super_steps++;
       }
       CU_TRY(c, cudaGetLastError());
+      if (dense_rc != RSPL_BA_OK) return dense_rc;
       if (lo.iters[pass] == 0) break;
       // poll: how many windows are still iterating?
       int n_active = 0;
@@ -476,7 +518,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
     if (!strcmp(env, "persistent")) batched = false;
     else if (!strcmp(env, "batched")) batched = true;
   }
-  if (batched) return local_solve_batched(c, lo);
+  if (batched || smem > c->smem_optin || lo.max_poses > 255) return local_solve_batched(c, lo);
   c->l_last_path = 1;
   CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {

@@ -90,6 +90,7 @@ struct LocalDev {
   double* pose_tcw; // [7][n_poses] optimiser poses built by the setup kernel
   double* pose_out; // [7][n_poses]
   int slot_stride;  // >= max free poses per window
+  int* setup_free_idx; // [n_poses] window-local free index or -1 (scratch of the setup kernel)
   KindDev k[2];
   void* stats;
   int* err; // device error flag
@@ -214,14 +215,15 @@ BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_
       const bool hit = (base + lane < ne) && ((k.info[e] & 0xffff) == p);
       cnt += __popc(__ballot_sync(0xffffffffu, hit));
     }
-    if (lane == 0) s_scan[p] = cnt;
+    if (lane == 0) k.pbeg[p0 + p] = cnt; // count first, offset after the scan below (any number of poses)
   }
   __syncthreads();
   if (tid == 0) {
     int run = e0;
     for (int p = 0; p < np; ++p) {
+      const int cnt = k.pbeg[p0 + p];
       k.pbeg[p0 + p] = run;
-      run += s_scan[p];
+      run += cnt;
     }
     if (w == d.n_windows - 1) k.pbeg[d.n_poses] = k.n_edge;
   }
@@ -240,11 +242,11 @@ BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_
 }
 
 __global__ void __launch_bounds__(LOCAL_THREADS) local_setup_kernel(const __grid_constant__ LocalDev d) {
-  __shared__ int s_free_idx[256];
   __shared__ int s_scan[LOCAL_THREADS];
   const int w = blockIdx.x;
   const int tid = threadIdx.x;
   const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  int* s_free_idx = d.setup_free_idx + p0; // global scratch: windows of the dense-solve path have hundreds of poses
   if (tid == 0) {
     int nf = 0;
     for (int p = 0; p < np; ++p) s_free_idx[p] = d.pose_fixed[p0 + p] ? -1 : nf++;

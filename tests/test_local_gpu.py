@@ -26,7 +26,7 @@ ROT_TOL = 1e-5
 CHI_RTOL = 1e-4
 
 
-def _check(orc, probs, batch, res, cfg=None, same_schedule=True):
+def _check(orc, probs, batch, res, cfg=None, same_schedule=True, point_max=1e-6, line_median=1e-8):
     for w, p in enumerate(probs):
         ref = p.copy()
         st = orc.local_ba(ref, cfg)
@@ -53,7 +53,8 @@ def _check(orc, probs, batch, res, cfg=None, same_schedule=True):
         if b > a:
             dpnt = np.abs(res.point_xyz[:, a:b].T - ref.point_p).max(axis=1)
             assert (b - a < 100 or np.median(dpnt) < 1e-5) and dpnt.max() < 5e-2
-            assert np.abs(res.point_xyz[:, a:b].T - fine.point_p).max() < 1e-6
+            dfine = np.abs(res.point_xyz[:, a:b].T - fine.point_p).max(axis=1)
+            assert dfine.max() < point_max and np.quantile(dfine, 0.99) < 1e-6
         a, b = batch.line_begin[w], batch.line_begin[w + 1]
         if b > a:
             dl = np.abs(res.line_wd[:, a:b].T - ref.line_L).max(axis=1)
@@ -61,7 +62,7 @@ def _check(orc, probs, batch, res, cfg=None, same_schedule=True):
             df = np.abs(res.line_wd[:, a:b].T - fine.line_L).max(axis=1)
             # near-singular 4x4 line blocks (two views from almost the same place) amplify rounding by
             # their condition number, so single lines may differ more; the bulk must agree tightly
-            assert np.quantile(df, 0.9) < 1e-6 and (b - a < 100 or np.median(df) < 1e-8)
+            assert np.quantile(df, 0.9) < 1e-6 and (b - a < 100 or np.median(df) < line_median)
         if same_schedule:
             assert list(res.stats["iters"][w][:2]) == st["iters"][:2]
             assert list(res.stats["trials"][w][:2]) == st["trials"][:2]
@@ -155,7 +156,7 @@ def test_local_c3_large_window(gpu_ctx, orc):
     _check(orc, [p], batch, res)
 
 
-def test_local_invalid_and_unsupported_inputs(gpu_ctx):
+def test_local_invalid_and_unsupported_inputs(gpu_ctx, orc):
     batch, _ = synth.make_local_batch(4, 2, n_kf=4, n_points=50, n_lines=6)
     bad = LocalBatch(**{**batch.__dict__, "sp_point": np.full_like(batch.sp_point, 10**6)})
     with pytest.raises(capi.RsplBaError) as e:
@@ -169,7 +170,29 @@ def test_local_invalid_and_unsupported_inputs(gpu_ctx):
         with pytest.raises(capi.RsplBaError) as e:
             gpu_ctx.local_batch(dup)
         assert e.value.code == capi.RSPL_BA_ERR_UNSUPPORTED
+    # 40 keyframes: the reduced system does not fit shared memory; whichever path is selected, the call
+    # falls through to the dense reduced solve (dense_solver.inl) instead of failing
     big = synth.make_local_problem(synth.config_seed(1, 220), n_kf=40, n_points=200, n_lines=10)
-    with pytest.raises(capi.RsplBaError) as e:
-        gpu_ctx.local_batch(LocalBatch.from_problems([big]))
-    assert e.value.code == capi.RSPL_BA_ERR_UNSUPPORTED
+    bb = LocalBatch.from_problems([big])
+    _check(orc, [big], bb, gpu_ctx.local_batch(bb))
+
+
+def test_local_large_window_dense_reduced_solve(gpu_ctx, orc, local_path):
+    """Windows whose reduced camera system (6 x free poses) exceeds shared memory keep it in HBM and
+    factorise it with the dense path (dense_solver.inl) -- the single-GPU end of SURVEY 8(e) C5.
+    40 and 48 keyframes: n = 234 / 282 (shared memory holds n <= ~160)."""
+    if local_path == "persistent":
+        pytest.skip("the persistent kernel is limited to reduced systems that fit shared memory")
+    probs = [synth.make_local_problem(synth.config_seed(5, 1), n_kf=40, n_points=5000, n_lines=500, loops=1),
+             synth.make_local_problem(synth.config_seed(5, 2), n_kf=48, n_points=4000, n_lines=300)]
+    batch = LocalBatch.from_problems(probs)
+    res = gpu_ctx.local_batch(batch)
+    # (a straight 48-keyframe track constrains far points and lines along the track weakly: they amplify
+    # the rounding differences of the two solvers to micrometres; the faithful delta = 1e-9 oracle itself
+    # is 4e-6 (median) / 7e-3 (max) away from the delta = 1e-6 one on these lines)
+    _check(orc, probs, batch, res, point_max=1e-5, line_median=1e-7)
+    # batch composition does not change the result of a window (bitwise)
+    solo = gpu_ctx.local_batch(LocalBatch.from_problems(probs[1:]))
+    a = batch.pose_begin[1]
+    assert np.array_equal(solo.pose_twc, res.pose_twc[:, a:])
+    assert np.array_equal(solo.sp_inlier, res.sp_inlier[batch.stereo_pt_begin[1]:])
