@@ -194,10 +194,35 @@ int rspl_ba_sync(RsplBaContext* ctx);
 /* Per-kernel-class timing with CUDA events on the context stream (what bench.py's roofline uses).
  * Classes: 0 frame_opt, 1 local_setup, 2 local_solve (persistent), 3 init + pair lists, 4 linearize,
  * 5 pose blocks, 6 Schur prep, 7 Schur reduce, 8 reduced solve, 9 back-substitution / update /
- * evaluation, 10 LM control kernels, 11 flagging + write-back. get_profile synchronises the
- * stream, returns milliseconds and launch counts accumulated since the last call and resets them. */
+ * evaluation, 10 LM control kernels, 11 flagging + write-back, 12 collectives of the global-BA path
+ * (13-15 reserved, zero). get_profile synchronises the stream, returns milliseconds and launch counts
+ * (arrays of RSPL_BA_PROFILE_CLASSES entries) accumulated since the last call and resets them. */
+#define RSPL_BA_PROFILE_CLASSES 16
 int rspl_ba_set_profiling(RsplBaContext* ctx, int enabled);
-int rspl_ba_get_profile(RsplBaContext* ctx, double* ms12, int64_t* launches12);
+int rspl_ba_get_profile(RsplBaContext* ctx, double* ms16, int64_t* launches16);
+
+/* --- global BA: ONE problem distributed over the ranks of a communicator ----------------------
+ * Replaces nothing in the reference (its only BA is the local one, map.cc:709); it is the scale-out
+ * configuration C5 of SURVEY.md 8(e): landmarks, with all their constraints, are partitioned over the
+ * ranks (one process per GPU), poses are replicated. Every rank uploads ONE window that holds all poses
+ * (identical arrays on every rank) and its own share of the points / lines and their constraints, then
+ * calls rspl_ba_global_solve collectively. Per LM trial the ranks all-reduce (sum, fp64) the pose blocks,
+ * the rank-local pieces of the Schur complement and five scalars; the reduced camera system is
+ * factorised redundantly on every rank, so all ranks take identical LM decisions and end with
+ * identical poses. Results: poses on every rank, landmarks and inlier flags of the rank's own share.
+ * The communicator is NCCL, loaded at run time; the 128-byte id comes from rank 0
+ * (rspl_ba_comm_unique_id) and reaches the other ranks by whatever channel the host has.
+ * n_ranks == 1 needs no id and no NCCL: the collectives become device copies. */
+#define RSPL_BA_COMM_ID_BYTES 128
+int rspl_ba_comm_unique_id(void* id128);
+int rspl_ba_comm_init(RsplBaContext* ctx, int n_ranks, int rank, const void* id128);
+int rspl_ba_comm_destroy(RsplBaContext* ctx);
+int rspl_ba_comm_size(const RsplBaContext* ctx);
+int rspl_ba_comm_rank(const RsplBaContext* ctx);
+int64_t rspl_ba_collective_count(const RsplBaContext* ctx);
+int rspl_ba_global_upload(RsplBaContext* ctx, const RsplLocalBatch* shard);
+int rspl_ba_global_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
+int rspl_ba_global_download(RsplBaContext* ctx, RsplLocalBatchResult* out);
 
 /* Diagnostics: SM cycles per phase of the last local solve summed over windows. out8: 0 linearise,
  * 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky, 5 update/back-substitution/evaluation,

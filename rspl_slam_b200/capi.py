@@ -84,10 +84,22 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
     "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_local_phase_cycles",
-    "rspl_ba_set_profiling", "rspl_ba_get_profile")
+    "rspl_ba_set_profiling", "rspl_ba_get_profile",
+    "rspl_ba_comm_unique_id", "rspl_ba_comm_init", "rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank",
+    "rspl_ba_collective_count", "rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download")
 
 _lib = None
 LOCAL_BA_READY = True
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: a fresh NCCL unique id to hand to the other ranks (e.g. with torch.distributed.broadcast)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load_library().rspl_ba_comm_unique_id(buf)
+    if rc != 0:
+        raise RsplBaError(rc, "rspl_ba_comm_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 class RsplBaError(RuntimeError):
@@ -152,6 +164,20 @@ def load_library() -> C.CDLL:
     L.rspl_ba_set_profiling.restype = C.c_int
     L.rspl_ba_get_profile.argtypes = [ctx, c_f64p, C.POINTER(C.c_int64)]
     L.rspl_ba_get_profile.restype = C.c_int
+    L.rspl_ba_comm_unique_id.argtypes = [C.c_void_p]
+    L.rspl_ba_comm_unique_id.restype = C.c_int
+    L.rspl_ba_comm_init.argtypes = [ctx, C.c_int, C.c_int, C.c_void_p]
+    L.rspl_ba_comm_init.restype = C.c_int
+    for n in ("rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank"):
+        getattr(L, n).argtypes = [ctx]
+        getattr(L, n).restype = C.c_int
+    L.rspl_ba_collective_count.argtypes = [ctx]
+    L.rspl_ba_collective_count.restype = C.c_int64
+    L.rspl_ba_global_upload.argtypes = [ctx, C.POINTER(RsplLocalBatch)]
+    L.rspl_ba_global_solve.argtypes = [ctx, opt]
+    L.rspl_ba_global_download.argtypes = [ctx, C.POINTER(RsplLocalBatchResult)]
+    for n in ("rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download"):
+        getattr(L, n).restype = C.c_int
     _lib = L
     return L
 
@@ -331,16 +357,51 @@ class Context:
         self._check(self._L.rspl_ba_local_batch_download(self._ctx, C.byref(r)))
         return out
 
+    # ---- global BA: one problem, landmarks partitioned over the ranks of a communicator ----
+    def comm_init(self, n_ranks: int, rank: int, unique_id: Optional[bytes] = None):
+        """Joins the NCCL communicator of the global-BA path (`unique_id` from `comm_unique_id()` on rank 0)."""
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        self._check(self._L.rspl_ba_comm_init(self._ctx, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._check(self._L.rspl_ba_comm_destroy(self._ctx))
+
+    def comm_size(self) -> int:
+        return int(self._L.rspl_ba_comm_size(self._ctx))
+
+    def collective_count(self) -> int:
+        return int(self._L.rspl_ba_collective_count(self._ctx))
+
+    def global_upload(self, shard: LocalBatch):
+        s = self._local_struct(shard)
+        self._check(self._L.rspl_ba_global_upload(self._ctx, C.byref(s)))
+
+    def global_solve(self, opt: Optional[RsplBaOptions] = None):
+        opt = opt or make_options()
+        self._check(self._L.rspl_ba_global_solve(self._ctx, C.byref(opt)))
+
+    def global_download(self, out: LocalBatchResult) -> LocalBatchResult:
+        r = self._local_result_struct(out)
+        self._check(self._L.rspl_ba_global_download(self._ctx, C.byref(r)))
+        return out
+
+    def global_ba(self, shard: LocalBatch, opt: Optional[RsplBaOptions] = None) -> LocalBatchResult:
+        """Collective: every rank passes its shard (all poses + its landmarks) of the same problem."""
+        self.global_upload(shard)
+        self.global_solve(opt)
+        return self.global_download(self.alloc_local_result(shard))
+
     PROFILE_CLASSES = ("frame_opt", "local_setup", "local_solve_persistent", "init_pairs", "linearize", "pose_blocks",
-                       "schur_prep", "schur_reduce", "reduced_solve", "backsub_update_eval", "lm_control", "flag_writeback")
+                       "schur_prep", "schur_reduce", "reduced_solve", "backsub_update_eval", "lm_control", "flag_writeback",
+                       "collectives")
 
     def set_profiling(self, enabled: bool):
         self._check(self._L.rspl_ba_set_profiling(self._ctx, 1 if enabled else 0))
 
     def get_profile(self) -> dict:
         """{class: (milliseconds, launches)} accumulated since the last call (CUDA events on the context stream)."""
-        ms = np.zeros(12)
-        n = np.zeros(12, dtype=np.int64)
+        ms = np.zeros(16)
+        n = np.zeros(16, dtype=np.int64)
         self._check(self._L.rspl_ba_get_profile(self._ctx, _p(ms, c_f64p), n.ctypes.data_as(C.POINTER(C.c_int64))))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
 

@@ -94,6 +94,7 @@ struct RsplBaContext {
   DevBuf batch_buf;
   ba::BatchDev bd{};
   bool batch_ready = false;
+  bool batch_global = false;
   std::vector<int> l_nf_begin;          // [W+1] free poses per window (prefix)
   std::vector<long long> l_pair_base;   // [W+1] capacity prefix of the pair lists
   int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
@@ -102,6 +103,11 @@ struct RsplBaContext {
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
   DevBuf dense_buf;
   void* cusolver = nullptr; // cusolverDnHandle_t
+  // global BA: NCCL communicator (comm.inl); the uploaded window is then one shard of the problem
+  void* comm = nullptr; // ncclComm_t
+  int comm_ranks = 1, comm_rank = 0;
+  int64_t collectives = 0;
+  bool global_mode = false;
 
   // ---- optional per-kernel-class timing with CUDA events on the context stream (rspl_ba_set_profiling)
   bool prof = false;
@@ -245,6 +251,7 @@ extern "C" int rspl_ba_create(int device, void* stream, RsplBaContext** out) {
 }
 
 static void dense_release(RsplBaContext* c); // dense_solver.inl
+static void comm_release(RsplBaContext* c);  // comm.inl
 
 extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   if (!c) return;
@@ -255,6 +262,7 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   c->batch_buf.release();
   c->dense_buf.release();
   dense_release(c);
+  comm_release(c);
   c->unit_buf.release();
   for (cudaEvent_t e : c->pipe_ev) cudaEventDestroy(e);
   for (auto& pe : c->prof_pool) {
@@ -284,7 +292,7 @@ extern "C" int rspl_ba_sync(RsplBaContext* c) {
 namespace {
 enum ProfClass {
   PC_FRAME = 0, PC_LOCAL_SETUP, PC_LOCAL_PERSISTENT, PC_PAIRS, PC_LINEARIZE, PC_POSE_BLOCKS, PC_SCHUR_PREP,
-  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COUNT
+  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_COUNT
 };
 // records an event pair around one launch when profiling is on
 struct ProfScope {
@@ -314,11 +322,12 @@ extern "C" int rspl_ba_set_profiling(RsplBaContext* c, int enabled) {
   return RSPL_BA_OK;
 }
 
+static_assert(PC_COUNT <= RSPL_BA_PROFILE_CLASSES, "profile classes");
 extern "C" int rspl_ba_get_profile(RsplBaContext* c, double* ms12, int64_t* launches12) {
   if (!c || !ms12 || !launches12) return RSPL_BA_ERR_INVALID;
   SetDevice guard(c->device);
   CU_TRY(c, cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < PC_COUNT; ++i) {
+  for (int i = 0; i < RSPL_BA_PROFILE_CLASSES; ++i) {
     ms12[i] = 0;
     launches12[i] = 0;
   }
@@ -733,4 +742,5 @@ extern "C" int rspl_ba_oplus(RsplBaContext* c, int kind, int32_t n, const double
 }
 
 #include "dense_solver.inl"
+#include "comm.inl"
 #include "local_capi.inl"

@@ -55,6 +55,16 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   int* sys_idx;   // [NF] block index in the reduced system or -1
   double* Hpp;    // [NF][21]
   double* bp;     // [NF][6]
+  // Global BA (one problem, landmarks partitioned over ranks): kernels write their
+  // rank-local partial sums to the *_w buffers, the host all-reduces them into the buffers every rank
+  // reads. Without a communicator the *_w pointers alias the read buffers.
+  int global;       // 1: this batch is one shard of a distributed problem (exactly one window)
+  double* Hpp_w;    // [NF][21] followed by bp_w: one contiguous block of NF * 27 doubles
+  double* bp_w;     // [NF][6]
+  double* hs_part_w; // [W][Pmax][42] + 8 (tail[0] = landmark-Cholesky failure flag of this rank)
+  int* pact_w;      // [NP]
+  double* gs_w;     // [8] rank-local scalars: chi, nact, max diag | - | chi1, landmark scale
+  double* gs;       // [8] reduced over ranks
   double* xp;     // [NF][6] pose increments by free index
   double* hs_part; // [W][Pmax][42]
   double* part;   // [W][C][4] per-chunk partial sums
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__(128) kb_pairs_scan(const __grid_constant__ Loc
 // ------------------------------------------------------------------------------------------------
 // pass begin: active sets (§9.12), reduced-system indices
 // ------------------------------------------------------------------------------------------------
+// (active edges per pose are counted into pact_w; the owner of pact is kb_begin_pass phase 1)
 template <int KIND>
 BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k, int w) {
   const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
@@ -253,7 +264,7 @@ BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k
     for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e) {
       if (k.lvl[e]) continue;
       any = 1;
-      atomicAdd(&b.pact[p0 + (k.info[e] & 0xffff)], 1);
+      atomicAdd(&b.pact_w[p0 + (k.info[e] & 0xffff)], 1);
     }
     k.act[l] = (uint8_t)any;
     if (!any) { // kb_schur_reduce / kb_backsub read Z and y of every listed edge without testing `act`
@@ -268,14 +279,19 @@ BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k
 
 __global__ void __launch_bounds__(256) kb_begin_pass(const __grid_constant__ LocalDev d,
                                                      const __grid_constant__ BatchDev b,
-                                                     const __grid_constant__ LocalOpt o, int pass) {
+                                                     const __grid_constant__ LocalOpt o, int pass, int phase) {
+  // phase 0: count the active edges per pose (rank-local); phase 1: reduced-system indices and LM state
+  // from the (all-reduced) counts; phase 2: both, for the single-GPU paths
   const int w = blockIdx.x, tid = threadIdx.x;
   const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
-  for (int p = tid; p < np; p += blockDim.x) b.pact[p0 + p] = 0;
-  __syncthreads();
-  mark_active_b<0>(d, b, d.k[0], w);
-  mark_active_b<1>(d, b, d.k[1], w);
-  __syncthreads();
+  if (phase != 1) {
+    for (int p = tid; p < np; p += blockDim.x) b.pact_w[p0 + p] = 0;
+    __syncthreads();
+    mark_active_b<0>(d, b, d.k[0], w);
+    mark_active_b<1>(d, b, d.k[1], w);
+    __syncthreads();
+  }
+  if (phase == 0) return;
   if (tid == 0) {
     WinState& s = b.ws[w];
     const int f0 = b.nf_begin[w];
@@ -455,8 +471,8 @@ __global__ void __launch_bounds__(BT) kb_pose_blocks(const __grid_constant__ Loc
   cta_reduce<27>(acc, red);
   if (threadIdx.x < 27) {
     const double v = cta_reduce_get<27>(red, threadIdx.x);
-    if (threadIdx.x < 21) b.Hpp[(size_t)(f0 + fi) * 21 + threadIdx.x] = v;
-    else b.bp[(size_t)(f0 + fi) * 6 + threadIdx.x - 21] = v;
+    if (threadIdx.x < 21) b.Hpp_w[(size_t)(f0 + fi) * 21 + threadIdx.x] = v;
+    else b.bp_w[(size_t)(f0 + fi) * 6 + threadIdx.x - 21] = v;
   }
 }
 
@@ -470,11 +486,17 @@ __global__ void __launch_bounds__(128) kb_begin_trial(const __grid_constant__ Lo
   s.prep_fail = 0;
   if (s.stage != STAGE_NEED_LIN) return;
   double chi = 0, nact = 0, mx = 0;
-  for (int c = 0; c < b.C; ++c) {
-    const double* pp = b.part + ((size_t)w * b.C + c) * 4;
-    chi += pp[0];
-    nact += pp[1];
-    mx = fmax(mx, pp[2]);
+  if (b.global) { // sums over every rank's landmarks (kb_global_sums + all-reduce)
+    chi = b.gs[0];
+    nact = b.gs[1];
+    mx = b.gs[2];
+  } else {
+    for (int c = 0; c < b.C; ++c) {
+      const double* pp = b.part + ((size_t)w * b.C + c) * 4;
+      chi += pp[0];
+      nact += pp[1];
+      mx = fmax(mx, pp[2]);
+    }
   }
   if (nact == 0.0) { // no active edge: optimize() returns without iterating
     s.stage = STAGE_DONE;
@@ -729,6 +751,7 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   const int w = blockIdx.y, p = blockIdx.x;
   const WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
+  if (b.global && p == 0 && lane == 0) b.hs_part_w[(size_t)b.Pmax * 42] = s.prep_fail ? 1.0 : 0.0;
   const int nf = s.nf;
   if (p >= nf * (nf + 1) / 2) return;
   int fi, fj;
@@ -744,7 +767,7 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, lane, acc, ring);
   warp_transpose_reduce64(acc, lane);
   if (2 * lane < 42) {
-    double* out = b.hs_part + ((size_t)w * b.Pmax + p) * 42 + 2 * lane;
+    double* out = b.hs_part_w + ((size_t)w * b.Pmax + p) * 42 + 2 * lane;
     out[0] = acc[0];
     out[1] = acc[1];
   }
@@ -921,7 +944,8 @@ __global__ void __launch_bounds__(256) kb_post_solve(const __grid_constant__ Loc
   WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const int nf = s.nf, f0 = b.nf_begin[w], p0 = d.pose_begin[w];
-  const bool ok = (s.n_sys == 0 || b.dense_info[w] == 0) && !s.prep_fail; // potrf info > 0 <=> a pivot <= 0 (§9.11)
+  const bool prep_fail = b.global ? b.hs_part[(size_t)b.Pmax * 42] != 0.0 : s.prep_fail != 0; // any rank's landmarks
+  const bool ok = (s.n_sys == 0 || b.dense_info[w] == 0) && !prep_fail; // potrf info > 0 <=> a pivot <= 0 (§9.11)
   const double lambda = s.lambda;
   const double* xs = b.dense_b + (size_t)6 * f0;
   double part = 0;
@@ -1055,6 +1079,45 @@ __global__ void __launch_bounds__(BT) kb_backsub(const __grid_constant__ LocalDe
   }
 }
 
+// Global BA: fixed-order sum of this rank's per-chunk partials (window 0) for the all-reduce.
+// which = 0 after linearisation (chi, nact, max diagonal), 1 after back-substitution (chi1, scale).
+__global__ void __launch_bounds__(256) kb_global_sums(const __grid_constant__ BatchDev b, int which) {
+  __shared__ double red[3][8];
+  const int tid = threadIdx.x;
+  const WinState& s = b.ws[0];
+  if (which == 0 ? s.stage != STAGE_NEED_LIN : (s.stage != STAGE_NEED_TRIAL || !s.solve_ok)) return;
+  double v0 = 0, v1 = 0, mx = 0;
+  for (int c = tid; c < b.C; c += 256) {
+    const double* pp = b.part + (size_t)c * 4;
+    v0 += pp[0];
+    v1 += pp[1];
+    if (which == 0) mx = fmax(mx, pp[2]);
+  }
+  v0 = warp_allreduce(v0);
+  v1 = warp_allreduce(v1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) {
+    red[0][tid >> 5] = v0;
+    red[1][tid >> 5] = v1;
+    red[2][tid >> 5] = mx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double a0 = 0, a1 = 0, am = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a0 += red[0][q];
+      a1 += red[1][q];
+      am = fmax(am, red[2][q]);
+    }
+    double* o = b.gs_w + (which ? 4 : 0);
+    o[0] = a0;
+    o[1] = a1;
+    if (which == 0) o[2] = am;
+  }
+}
+
 // one thread per window: the Levenberg accept / reject logic (§9.9) and the window's next stage
 __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1063,7 +1126,10 @@ __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDe
   if (s.stage != STAGE_NEED_TRIAL) return;
   const bool ok = s.solve_ok;
   double chi1 = 0, scale = s.scale_pose;
-  if (ok) {
+  if (ok && b.global) {
+    chi1 = b.gs[4];
+    scale += b.gs[5];
+  } else if (ok) {
     for (int c = 0; c < b.C; ++c) {
       const double* pp = b.part + ((size_t)w * b.C + c) * 4;
       chi1 += pp[0];

@@ -279,7 +279,8 @@ namespace {
 
 // Allocates (grow-only) and wires the HBM state of the batched path for the uploaded batch.
 int batched_prepare(RsplBaContext* c) {
-  if (c->batch_ready) return RSPL_BA_OK;
+  if (c->batch_ready && c->batch_global == c->global_mode) return RSPL_BA_OK;
+  c->batch_global = c->global_mode;
   const int W = c->l_n_windows, NP = c->l_np;
   const int NF = c->l_nf_begin[W];
   const int NFmax = c->l_max_free_poses;
@@ -298,9 +299,17 @@ int batched_prepare(RsplBaContext* c) {
   const size_t o_fi = a.take(sizeof(int) * NP), o_pact = a.take(sizeof(int) * NP);
   const size_t o_nfb = a.take(sizeof(int) * (W + 1));
   const size_t o_pof = a.take(sizeof(int) * (NF + 1)), o_sys = a.take(sizeof(int) * (NF + 1));
-  const size_t o_hpp = a.take(sizeof(double) * 21 * (NF + 1)), o_bp = a.take(sizeof(double) * 6 * (NF + 1));
+  // Hpp and bp are one contiguous block of NF * 27 doubles (a single all-reduce in global mode)
+  const size_t o_hpp = a.take(sizeof(double) * 27 * (NF + 1));
   const size_t o_xp = a.take(sizeof(double) * 6 * (NF + 1));
-  const size_t o_hsp = a.take(sizeof(double) * 42 * (size_t)W * (Pmax > 0 ? Pmax : 1));
+  const size_t hs_count = 42 * (size_t)W * (Pmax > 0 ? Pmax : 1) + 8;
+  const size_t o_hsp = a.take(sizeof(double) * hs_count);
+  const bool global = c->global_mode;
+  // rank-local write buffers of the global mode (alias the read buffers otherwise)
+  const size_t o_hpp_w = global ? a.take(sizeof(double) * 27 * (NF + 1)) : o_hpp;
+  const size_t o_hsp_w = global ? a.take(sizeof(double) * hs_count) : o_hsp;
+  const size_t o_pact_w = global ? a.take(sizeof(int) * NP) : o_pact;
+  const size_t o_gs = a.take(sizeof(double) * 16);
   const size_t o_part = a.take(sizeof(double) * 4 * (size_t)W * C);
   const size_t o_pbeg = a.take(sizeof(int) * (size_t)W * (2 * Pmax + 1));
   const size_t o_pairs = a.take(sizeof(int2) * (size_t)(n_pairs + 1));
@@ -312,6 +321,7 @@ int batched_prepare(RsplBaContext* c) {
   CU_TRY(c, cudaMemcpyAsync(base + o_pbase, c->l_pair_base.data(), sizeof(long long) * (W + 1), cudaMemcpyHostToDevice,
                             c->stream));
   CU_TRY(c, cudaMemsetAsync(base + o_part, 0, sizeof(double) * 4 * (size_t)W * C, c->stream));
+  CU_TRY(c, cudaMemsetAsync(base + o_gs, 0, sizeof(double) * 16, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   ba::BatchDev& b = c->bd;
   b.ws = (ba::WinState*)(base + o_ws);
@@ -326,7 +336,14 @@ int batched_prepare(RsplBaContext* c) {
   b.pose_of = (int*)(base + o_pof);
   b.sys_idx = (int*)(base + o_sys);
   b.Hpp = (double*)(base + o_hpp);
-  b.bp = (double*)(base + o_bp);
+  b.bp = b.Hpp + (size_t)21 * NF;
+  b.global = global ? 1 : 0;
+  b.Hpp_w = (double*)(base + o_hpp_w);
+  b.bp_w = b.Hpp_w + (size_t)21 * NF;
+  b.hs_part_w = (double*)(base + o_hsp_w);
+  b.pact_w = (int*)(base + o_pact_w);
+  b.gs_w = (double*)(base + o_gs);
+  b.gs = b.gs_w + 8;
   b.xp = (double*)(base + o_xp);
   b.hs_part = (double*)(base + o_hsp);
   b.part = (double*)(base + o_part);
@@ -361,7 +378,10 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
   // reduced systems beyond shared memory: dense matrices in HBM + cuSOLVER Cholesky (dense_solver.inl)
-  const bool dense = smem_solve > c->smem_optin;
+  // (global BA always takes this route: its collectives sit between the kernels of a super-step)
+  const bool global = c->global_mode;
+  if (global && W != 1) return fail(c, RSPL_BA_ERR_INVALID, "global BA: upload exactly one window (this rank's shard)");
+  const bool dense = global || smem_solve > c->smem_optin;
   DenseLayout dl;
   std::vector<int> n_sys_host(W, 0);
   if (dense) {
@@ -388,11 +408,19 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   CU_TRY(c, cudaGetLastError());
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
-  int dense_rc = RSPL_BA_OK;
+  int dense_rc = RSPL_BA_OK, coll_rc = RSPL_BA_OK;
+  const int NF_all = c->l_nf_begin[W];
   auto super_step = [&]() {
     if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
     LAUNCH(PC_POSE_BLOCKS, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    if (global) { // pose blocks and the linearisation scalars of every rank's landmarks
+      LAUNCH(PC_CONTROL, ba::kb_global_sums, 1, 256, 0, b, 0);
+      ProfScope ps_(c, PC_COLLECTIVE);
+      if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.Hpp_w, b.Hpp, (size_t)27 * NF_all, kNcclFloat64, kNcclSum);
+      if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w, b.gs, 2, kNcclFloat64, kNcclSum);
+      if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 2, b.gs + 2, 1, kNcclFloat64, kNcclMax);
+    }
     LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
     if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
@@ -400,6 +428,11 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     if (!dense) {
       LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
     } else {
+      if (global) { // rank-local Schur complement pieces -> sum over ranks (+ the Cholesky-failure flag in the tail)
+        ProfScope ps_(c, PC_COLLECTIVE);
+        if (coll_rc == RSPL_BA_OK)
+          coll_rc = comm_all_reduce(c, b.hs_part_w, b.hs_part, (size_t)42 * b.Pmax + 8, kNcclFloat64, kNcclSum);
+      }
       LAUNCH(PC_SOLVE, ba::kb_assemble_dense, g_pair1, 64, 0, d, b);
       {
         ProfScope ps_(c, PC_SOLVE);
@@ -409,6 +442,11 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     }
     if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (global) {
+      LAUNCH(PC_CONTROL, ba::kb_global_sums, 1, 256, 0, b, 1);
+      ProfScope ps_(c, PC_COLLECTIVE);
+      if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 4, b.gs + 4, 2, kNcclFloat64, kNcclSum);
+    }
     LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
     if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
   };
@@ -438,7 +476,17 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     }
   } graph_guard{gexec};
   for (int pass = 0; pass < 2; ++pass) {
-    LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass);
+    if (global) { // a pose is in the reduced system if ANY rank holds an active edge of it
+      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 0);
+      {
+        ProfScope ps_(c, PC_COLLECTIVE);
+        coll_rc = comm_all_reduce(c, b.pact_w, b.pact, (size_t)c->l_np, kNcclInt32, kNcclSum);
+      }
+      if (coll_rc != RSPL_BA_OK) return coll_rc;
+      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 1);
+    } else {
+      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 2);
+    }
     if (dense) { // the host needs the system sizes of this pass for the library calls
       std::vector<ba::WinState> ws(W);
       CU_TRY(c, cudaMemcpyAsync(ws.data(), b.ws, sizeof(ba::WinState) * W, cudaMemcpyDeviceToHost, s));
@@ -460,6 +508,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       }
       CU_TRY(c, cudaGetLastError());
       if (dense_rc != RSPL_BA_OK) return dense_rc;
+      if (coll_rc != RSPL_BA_OK) return coll_rc;
       if (lo.iters[pass] == 0) break;
       // poll: how many windows are still iterating?
       int n_active = 0;
@@ -518,7 +567,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
     if (!strcmp(env, "persistent")) batched = false;
     else if (!strcmp(env, "batched")) batched = true;
   }
-  if (batched || smem > c->smem_optin || lo.max_poses > 255) return local_solve_batched(c, lo);
+  if (batched || c->global_mode || smem > c->smem_optin || lo.max_poses > 255) return local_solve_batched(c, lo);
   c->l_last_path = 1;
   CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
@@ -570,6 +619,24 @@ extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch* in, c
   if (rc != RSPL_BA_OK) return rc;
   rc = rspl_ba_local_batch_solve(c, opt);
   if (rc != RSPL_BA_OK) return rc;
+  return rspl_ba_local_batch_download(c, out);
+}
+
+// ---- global BA: every rank uploads ONE window holding all poses (identical on every
+// rank) and its own share of the landmarks with all their constraints; the solve is collective over the
+// context's communicator (rspl_ba_comm_init). Upload and download are the local-batch calls.
+extern "C" int rspl_ba_global_upload(RsplBaContext* c, const RsplLocalBatch* in) {
+  if (in && in->n_windows != 1) return c ? fail(c, RSPL_BA_ERR_INVALID, "global BA: exactly one window per rank") : RSPL_BA_ERR_INVALID;
+  return rspl_ba_local_batch_upload(c, in);
+}
+extern "C" int rspl_ba_global_solve(RsplBaContext* c, const RsplBaOptions* opt) {
+  if (!c) return RSPL_BA_ERR_INVALID;
+  c->global_mode = true;
+  const int rc = rspl_ba_local_batch_solve(c, opt);
+  c->global_mode = false;
+  return rc;
+}
+extern "C" int rspl_ba_global_download(RsplBaContext* c, RsplLocalBatchResult* out) {
   return rspl_ba_local_batch_download(c, out);
 }
 

@@ -396,3 +396,70 @@ def shard_range(n_units: int, rank: int, world: int) -> tuple:
     base, rem = divmod(n_units, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Global BA: landmark partition of ONE problem over ranks
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class LandmarkShard:
+    """One rank's share of a LocalProblem: all poses, a block of the points and lines with all their
+    constraints, and the index maps that scatter the rank's results back into the full problem."""
+    problem: LocalProblem
+    point_idx: np.ndarray                       # positions of the shard's points in the full problem
+    line_idx: np.ndarray
+    edge_idx: dict                              # {"mp" | "sp" | "ml" | "sl": positions in the full arrays}
+
+
+def _balanced_blocks(weights: np.ndarray, world: int) -> np.ndarray:
+    """Boundaries [world+1] of contiguous blocks with about equal total weight."""
+    n = len(weights)
+    if n == 0:
+        return np.zeros(world + 1, dtype=np.int64)
+    cum = np.cumsum(weights, dtype=np.float64)
+    targets = cum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(cum, targets, side="left") + 1
+    return np.concatenate([[0], np.minimum(cuts, n), [n]]).astype(np.int64)
+
+
+def shard_landmarks(p: LocalProblem, rank: int, world: int) -> LandmarkShard:
+    """Points and lines (each with ALL its constraints) are split into `world` contiguous blocks of
+    about equal constraint count; every rank keeps every pose. Deterministic, no communication."""
+    def block(ids, id_a, id_b):
+        pos = {int(v): i for i, v in enumerate(ids)}
+        w = np.zeros(len(ids), dtype=np.int64)
+        for arr in (id_a, id_b):
+            if len(arr):
+                np.add.at(w, np.fromiter((pos[int(v)] for v in arr), dtype=np.int64, count=len(arr)), 1)
+        cuts = _balanced_blocks(w + 1, world)  # +1: landmarks without constraints still count
+        return np.arange(cuts[rank], cuts[rank + 1], dtype=np.int64)
+
+    pt_idx = block(p.point_id, p.mp_id_point, p.sp_id_point)
+    ln_idx = block(p.line_id, p.ml_id_line, p.sl_id_line)
+    pt_ids, ln_ids = set(int(v) for v in p.point_id[pt_idx]), set(int(v) for v in p.line_id[ln_idx])
+    kw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.__dict__.items()}
+    kw["point_id"], kw["point_p"] = p.point_id[pt_idx].copy(), p.point_p[pt_idx].copy()
+    kw["line_id"], kw["line_L"] = p.line_id[ln_idx].copy(), p.line_L[ln_idx].copy()
+    kw["truth"] = {}
+    edge_idx = {}
+    for pre, lm, key, owned in (("mp", "id_point", "kp", pt_ids), ("sp", "id_point", "kp", pt_ids),
+                                ("ml", "id_line", "l2d", ln_ids), ("sl", "id_line", "l2d", ln_ids)):
+        ids = getattr(p, f"{pre}_{lm}")
+        sel = np.nonzero(np.fromiter((int(v) in owned for v in ids), dtype=bool, count=len(ids)))[0]
+        edge_idx[pre] = sel
+        for name in ("id_pose", lm, "id_cam", key, "inlier"):
+            kw[f"{pre}_{name}"] = getattr(p, f"{pre}_{name}")[sel].copy()
+    return LandmarkShard(LocalProblem(**kw).normalise(), pt_idx, ln_idx, edge_idx)
+
+
+def merge_landmark_shards(full: LocalProblem, shards: Sequence[LandmarkShard]) -> LocalProblem:
+    """Scatter the solved shards back into a copy of the full problem (poses are identical on every
+    rank; rank 0's are taken)."""
+    out = full.copy()
+    out.pose_p[:], out.pose_q[:] = shards[0].problem.pose_p, shards[0].problem.pose_q
+    for s in shards:
+        out.point_p[s.point_idx] = s.problem.point_p
+        out.line_L[s.line_idx] = s.problem.line_L
+        for pre in ("mp", "sp", "ml", "sl"):
+            getattr(out, f"{pre}_inlier")[s.edge_idx[pre]] = getattr(s.problem, f"{pre}_inlier")
+    return out
