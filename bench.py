@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — throughput of the BA hot path on B200 (metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c5] [--impl ours|reference]
 
 Workloads (BASELINE.json configs; synthetic inputs of rspl_slam_b200/synth.py, seeds of SURVEY §8d)
   c2 (default, configs[1]): batched pose-only FrameOptimization, 4096 frames x 400 stereo points
@@ -353,6 +353,152 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------
+# C5: ONE global problem, landmarks partitioned over the ranks (strong scaling; NCCL all-reduces of the
+# pose blocks, the Schur complement pieces and a few scalars per LM trial)
+# ------------------------------------------------------------------------------------------------
+def run_global(args):
+    import torch
+    import torch.distributed as dist
+    from rspl_slam_b200 import capi, synth
+    from rspl_slam_b200.problem import LocalBatch, shard_landmarks
+    from rspl_slam_b200.roofline import local_class_bytes
+
+    rank, local_rank, world = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = capi.Context(device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    opt = capi.make_options()
+    ident = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if world > 1:
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, src=0)
+    ctx.comm_init(world, rank, bytes(ident.cpu().numpy().tobytes()) if world > 1 else None)
+
+    full = synth.make_global_problem(synth.config_seed(5, 0), n_kf=args.kf, n_points=args.points, n_lines=args.lines, loops=3)
+    shard = shard_landmarks(full, rank, world)
+    batch = LocalBatch.from_problems([shard.problem])
+    pinned = _pin_batch(batch, capi)
+    out = ctx.alloc_local_result(batch, pinned=True)
+    workload = (f"C5 global BA: {args.kf} KF / {len(full.point_id)} points / {len(full.line_id)} lines / {full.n_edges} constraints, "
+                f"LM 10+5, landmarks partitioned over {world} GPU(s)")
+    total_edges = full.n_edges
+    del full
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    warm = max(args.warmup, 1)
+    ctx.global_upload(pinned)
+    launches0, coll0 = ctx.launch_count, ctx.collective_count()
+    for _ in range(warm):
+        ctx.global_solve(opt)
+    ctx.sync()
+    ctx.global_download(out)
+    stats = out.stats.copy()
+    launches_per_step = (ctx.launch_count - launches0) // warm
+    coll_per_step = (ctx.collective_count() - coll0) // warm
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t_wall0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            for i in range(args.steps):
+                flush.zero_()
+                starts[i].record(stream)
+                ctx.global_solve(opt)
+                ends[i].record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    dev_s = float(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) * 1e-3
+    # end to end: host buffers in, host buffers out
+    ctx.global_ba(pinned, opt)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.global_upload(pinned)
+        ctx.global_solve(opt)
+        ctx.global_download(out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_s, e2e_s, t_wall], dtype=torch.float64, device=dev)
+    byt = torch.tensor([float(pinned.h2d_bytes()), float(out.d2h_bytes())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(byt, op=dist.ReduceOp.SUM)
+    dev_s_max, e2e_s_max, wall_max = [float(x) for x in t.tolist()]
+    # the LM statistics are global (every rank holds the same numbers)
+    edges_lin, edges_eval = int(stats["edges_linearized"][0]), int(stats["edges_evaluated"][0])
+    lm_iters, lm_trials = int(stats["iters"][0].sum()), int(stats["trials"][0].sum())
+    if rank == 0:
+        peak, peak_src = _peaks()
+        ctx.set_profiling(True)
+    # (the profiled pass is collective too: every rank runs it, rank 0 records events)
+    ctx.global_solve(opt)
+    if rank == 0:
+        prof = ctx.get_profile()
+        ctx.set_profiling(False)
+        per_kernel = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in prof.items() if v[1]}
+        # stats count the linearised edges of ALL ranks; this rank's kernels touched its shard's share of them
+        stats_local = stats.copy()
+        stats_local["edges_linearized"] = (stats["edges_linearized"] * (batch.n_edges / max(total_edges, 1))).astype(stats["edges_linearized"].dtype)
+        cls_bytes = local_class_bytes(batch, stats_local)  # this rank's share of the contract bytes
+        groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
+                  "schur (kb_schur_prep + kb_schur_reduce + dense solve)": (("schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
+                  "backsub (kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"])}
+        best = None
+        for name, (classes, nbytes) in groups.items():
+            ms = sum(prof[c][0] for c in classes)
+            nl = sum(prof[c][1] for c in classes)
+            if nl == 0:
+                continue
+            per_kernel[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
+                                "achieved_GBs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+            if best is None or ms > best[1]:
+                best = (name, ms, nl, nbytes)
+        dom_name, dom_ms, dom_launches, alg_bytes = best
+        launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
+        line = {
+            "metric": METRIC, "value": edges_lin * args.steps / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "l2": "flushed (256 MiB write) between timed steps; inputs resident in HBM",
+                       "parallelism": f"landmark-sharded x{world}, poses replicated, {coll_per_step} NCCL all-reduces per solve, "
+                                      "replicated dense Cholesky of the reduced camera system",
+                       "timing": "CUDA events on the solver stream, max over ranks"},
+            "lm_iters_per_sec": lm_iters * args.steps / dev_s_max, "lm_trials_per_sec": lm_trials * args.steps / dev_s_max,
+            "edges_evaluated_per_sec": edges_eval * args.steps / dev_s_max, "units_per_sec": args.steps / dev_s_max,
+            "e2e": {"value": edges_lin * e2e_steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(byt[0].item()),
+                    "d2h_bytes_per_step": int(byt[1].item()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
+                    "api": "rspl_ba_global_upload / _solve / _download (pinned host buffers, all ranks)"},
+            "gpu_launches": int(launches_per_step * args.steps), "collectives_per_step": int(coll_per_step),
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": alg_bytes / max(dom_launches, 1) / launch_s / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg_bytes / max(dom_launches, 1) / launch_s / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(dom_launches, 1),
+                         "launch_ms": 1e3 * launch_s, "launches_per_step": dom_launches, "per_kernel": per_kernel,
+                         "note": "rank 0's kernels on its landmark shard; contract bytes of SURVEY 8(d)"},
+            "cpu_baseline": cpu_baseline(args), "clocks": clk.summary(), "wall_s_timed_region": wall_max,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    ctx.comm_destroy()
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
 def _traffic(workload):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
@@ -376,6 +522,13 @@ def cpu_baseline(args):
         st = orc.frame_opt_batch(probs, n_threads=1)
         dt = time.perf_counter() - t0
         sample = f"first {n} of {C2_FRAMES} C2 frames, 1 thread"
+    elif args.workload == "c5":
+        # the oracle factorises the reduced system densely in one thread: a scaled-down problem of the same generator
+        probs = [synth.make_global_problem(synth.config_seed(5, 0), n_kf=60, n_points=30000, n_lines=3000, loops=1)]
+        t0 = time.perf_counter()
+        st = orc.local_ba_batch(probs, n_threads=1)
+        dt = time.perf_counter() - t0
+        sample = "scaled-down C5 (60 KF / 30k points / 3k lines, same generator), 1 thread"
     else:
         n = 8
         probs = [synth.make_local_problem(synth.config_seed(4, i)) for i in range(n)]
@@ -394,12 +547,17 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")
+    ap.add_argument("--points", type=int, default=1_000_000, help="points of the global problem (c5)")
+    ap.add_argument("--lines", type=int, default=100_000, help="lines of the global problem (c5)")
     ap.add_argument("--frames", type=int, default=C2_FRAMES, help="frames per GPU (c2)")
     ap.add_argument("--windows", type=int, default=1024, help="windows per GPU (c4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_global(args)
     return run_ours(args)
 
 

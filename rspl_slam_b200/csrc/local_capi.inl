@@ -553,9 +553,16 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int), c->stream));
   {
     ProfScope ps(c, PC_LOCAL_SETUP);
+    for (int k = 0; k < 2; ++k)
+      if (c->ld.k[k].n_lm > 0)
+        CU_TRY(c, cudaMemsetAsync(c->ld.k[k].slot, ba::SLOT_NONE, (size_t)c->ld.k[k].n_lm * c->ld.slot_stride, c->stream));
     ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+    const dim3 g_pl(c->l_max_poses, c->l_n_windows, 2);
+    ba::setup_pose_lists<0><<<g_pl, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+    ba::setup_pose_scan<<<(2 * c->l_n_windows + 127) / 128, 128, 0, c->stream>>>(c->ld);
+    ba::setup_pose_lists<1><<<g_pl, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
   }
-  c->launches++;
+  c->launches += 4;
   CU_TRY(c, cudaGetLastError());
   // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
   // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent

@@ -116,7 +116,6 @@ BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_
   const int tid = threadIdx.x;
   const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
   const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
-  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
   // 1. degree per landmark
   for (int i = tid; i < nl; i += LOCAL_THREADS) k.cursor[l0 + i] = 0;
   __syncthreads();
@@ -173,8 +172,7 @@ BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_
       }
       k.src[a + v + 1] = key;
     }
-    uint8_t* sl = k.slot + (size_t)(l0 + i) * d.slot_stride;
-    for (int u = 0; u < d.slot_stride; ++u) sl[u] = SLOT_NONE;
+    uint8_t* sl = k.slot + (size_t)(l0 + i) * d.slot_stride; // (set to SLOT_NONE by a memset before the launch)
     for (int u = 0; u < n; ++u) {
       const int key = k.src[a + u];
       const int c = key >> 30, idx = key & 0x3fffffff;
@@ -206,39 +204,64 @@ BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_
     k.lvl[e] = 0;
   }
   __syncthreads();
-  // 6. pose-major lists: warp per pose, ballot scan over the window's sorted edges (deterministic)
-  const int lane = tid & 31, warp = tid >> 5;
-  for (int p = warp; p < np; p += LOCAL_WARPS) {
-    int cnt = 0;
-    for (int base = 0; base < ne; base += 32) {
-      const int e = e0 + base + lane;
-      const bool hit = (base + lane < ne) && ((k.info[e] & 0xffff) == p);
-      cnt += __popc(__ballot_sync(0xffffffffu, hit));
-    }
-    if (lane == 0) k.pbeg[p0 + p] = cnt; // count first, offset after the scan below (any number of poses)
+}
+
+// 6. pose-major edge lists, one CTA per (pose, window, kind): the CTA scans the window's sorted edge records
+// (each warp a contiguous slice, ballot compaction => ascending edge order, deterministic). Its own
+// launches because the work is O(poses x edges): a 2000-keyframe window would keep the single setup
+// CTA busy for seconds. MODE 0 counts into pbeg, MODE 1 fills plist (pbeg scanned in between).
+template <int MODE>
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_pose_lists(const __grid_constant__ LocalDev d) {
+  __shared__ int s_cnt[LOCAL_WARPS];
+  const int p = blockIdx.x, w = blockIdx.y;
+  const KindDev& k = d.k[blockIdx.z];
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  if (p >= np) return;
+  const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (((ne + LOCAL_WARPS - 1) / LOCAL_WARPS) + 31) & ~31; // slice per warp, multiple of 32
+  const int a = warp * per, b = a + per < ne ? a + per : ne;
+  int cnt = 0;
+  for (int base = a; base < b; base += 32) {
+    const bool hit = (base + lane < b) && ((k.info[e0 + base + lane] & 0xffff) == p);
+    cnt += __popc(__ballot_sync(0xffffffffu, hit));
   }
+  if (lane == 0) s_cnt[warp] = cnt;
   __syncthreads();
-  if (tid == 0) {
-    int run = e0;
-    for (int p = 0; p < np; ++p) {
-      const int cnt = k.pbeg[p0 + p];
-      k.pbeg[p0 + p] = run;
-      run += cnt;
+  if (MODE == 0) {
+    if (tid == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int q = 0; q < LOCAL_WARPS; ++q) tot += s_cnt[q];
+      k.pbeg[p0 + p] = tot;
     }
-    if (w == d.n_windows - 1) k.pbeg[d.n_poses] = k.n_edge;
+    return;
   }
-  __syncthreads();
-  for (int p = warp; p < np; p += LOCAL_WARPS) {
-    int out = k.pbeg[p0 + p];
-    for (int base = 0; base < ne; base += 32) {
-      const int e = e0 + base + lane;
-      const bool hit = (base + lane < ne) && ((k.info[e] & 0xffff) == p);
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) k.plist[out + __popc(m & ((1u << lane) - 1))] = e;
-      out += __popc(m);
-    }
+  int out = k.pbeg[p0 + p];
+  for (int q = 0; q < warp; ++q) out += s_cnt[q];
+  for (int base = a; base < b; base += 32) {
+    const int e = e0 + base + lane;
+    const bool hit = (base + lane < b) && ((k.info[e] & 0xffff) == p);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) k.plist[out + __popc(m & ((1u << lane) - 1))] = e;
+    out += __popc(m);
   }
-  __syncthreads();
+}
+
+// counts -> offsets, one thread per (window, kind)
+__global__ void __launch_bounds__(128) setup_pose_scan(const __grid_constant__ LocalDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * d.n_windows) return;
+  const int w = i >> 1;
+  const KindDev& k = d.k[i & 1];
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  int run = edge_base(k, w);
+  for (int p = 0; p < np; ++p) {
+    const int cnt = k.pbeg[p0 + p];
+    k.pbeg[p0 + p] = run;
+    run += cnt;
+  }
+  if (w == d.n_windows - 1) k.pbeg[d.n_poses] = k.n_edge;
 }
 
 __global__ void __launch_bounds__(LOCAL_THREADS) local_setup_kernel(const __grid_constant__ LocalDev d) {

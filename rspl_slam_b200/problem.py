@@ -426,29 +426,28 @@ def shard_landmarks(p: LocalProblem, rank: int, world: int) -> LandmarkShard:
     """Points and lines (each with ALL its constraints) are split into `world` contiguous blocks of
     about equal constraint count; every rank keeps every pose. Deterministic, no communication."""
     def block(ids, id_a, id_b):
-        pos = {int(v): i for i, v in enumerate(ids)}
-        w = np.zeros(len(ids), dtype=np.int64)
+        order = np.argsort(ids, kind="stable")
+        w = np.ones(len(ids), dtype=np.int64)  # +1: landmarks without constraints still count
+        pos_of = []
         for arr in (id_a, id_b):
-            if len(arr):
-                np.add.at(w, np.fromiter((pos[int(v)] for v in arr), dtype=np.int64, count=len(arr)), 1)
-        cuts = _balanced_blocks(w + 1, world)  # +1: landmarks without constraints still count
-        return np.arange(cuts[rank], cuts[rank + 1], dtype=np.int64)
+            pos = order[np.searchsorted(ids, arr, sorter=order)] if len(arr) else np.zeros(0, dtype=np.int64)
+            pos_of.append(pos)
+            np.add.at(w, pos, 1)
+        cuts = _balanced_blocks(w, world)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        return np.arange(lo, hi, dtype=np.int64), [np.nonzero((q >= lo) & (q < hi))[0] for q in pos_of]
 
-    pt_idx = block(p.point_id, p.mp_id_point, p.sp_id_point)
-    ln_idx = block(p.line_id, p.ml_id_line, p.sl_id_line)
-    pt_ids, ln_ids = set(int(v) for v in p.point_id[pt_idx]), set(int(v) for v in p.line_id[ln_idx])
-    kw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.__dict__.items()}
+    pt_idx, (mp_sel, sp_sel) = block(p.point_id, p.mp_id_point, p.sp_id_point)
+    ln_idx, (ml_sel, sl_sel) = block(p.line_id, p.ml_id_line, p.sl_id_line)
+    kw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in p.__dict__.items()
+          if not k.startswith(("mp_", "sp_", "ml_", "sl_", "point_", "line_"))}
     kw["point_id"], kw["point_p"] = p.point_id[pt_idx].copy(), p.point_p[pt_idx].copy()
     kw["line_id"], kw["line_L"] = p.line_id[ln_idx].copy(), p.line_L[ln_idx].copy()
     kw["truth"] = {}
-    edge_idx = {}
-    for pre, lm, key, owned in (("mp", "id_point", "kp", pt_ids), ("sp", "id_point", "kp", pt_ids),
-                                ("ml", "id_line", "l2d", ln_ids), ("sl", "id_line", "l2d", ln_ids)):
-        ids = getattr(p, f"{pre}_{lm}")
-        sel = np.nonzero(np.fromiter((int(v) in owned for v in ids), dtype=bool, count=len(ids)))[0]
-        edge_idx[pre] = sel
+    edge_idx = {"mp": mp_sel, "sp": sp_sel, "ml": ml_sel, "sl": sl_sel}
+    for pre, lm, key in (("mp", "id_point", "kp"), ("sp", "id_point", "kp"), ("ml", "id_line", "l2d"), ("sl", "id_line", "l2d")):
         for name in ("id_pose", lm, "id_cam", key, "inlier"):
-            kw[f"{pre}_{name}"] = getattr(p, f"{pre}_{name}")[sel].copy()
+            kw[f"{pre}_{name}"] = getattr(p, f"{pre}_{name}")[edge_idx[pre]].copy()
     return LandmarkShard(LocalProblem(**kw).normalise(), pt_idx, ln_idx, edge_idx)
 
 

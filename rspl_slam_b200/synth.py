@@ -109,13 +109,15 @@ def _line_oplus_batch(L: np.ndarray, v: np.ndarray) -> np.ndarray:
 def make_local_problem(seed: int, n_kf: int = 10, n_points: int = 3000, n_lines: int = 300,
                        first_kf_id: int = 0, stereo_point_frac: float = 0.85, stereo_line_frac: float = 0.70,
                        outlier_frac: float = 0.05, pixel_sigma: float = 1.0, loops: int = 0,
-                       point_cap=(2, 6), line_cap=(2, 5), extra_fixed: bool = True) -> LocalProblem:
-    """One local-BA window (config C1 with the defaults; C3: n_kf=20, n_points=10000, n_lines=1000)."""
+                       point_cap=(2, 6), line_cap=(2, 5), extra_fixed: bool = True,
+                       trajectory=None) -> LocalProblem:
+    """One local-BA window (config C1 with the defaults; C3: n_kf=20, n_points=10000, n_lines=1000).
+    ``trajectory`` = (Rwc, twc) places the window on a given path (used by make_global_problem)."""
     rng = np.random.default_rng(seed)
     cam = EUROC_CAMERA
     wh = EUROC_IMAGE_WH
     b = cam[4] / cam[0]
-    Rwc, twc = make_trajectory(rng, n_kf, loops=loops)
+    Rwc, twc = trajectory if trajectory is not None else make_trajectory(rng, n_kf, loops=loops)
     pose_id = np.arange(first_kf_id, first_kf_id + n_kf, dtype=I32)
     # fixed: KF 0 if in the window, else one extra fixed KF (map.cc:559,593) = the oldest one here
     pose_fixed = np.zeros(n_kf, dtype=U8)
@@ -249,6 +251,52 @@ def make_local_problem(seed: int, n_kf: int = 10, n_points: int = 3000, n_lines:
         sl_l2d=lm[lst], sl_inlier=one(int(lst.sum())),
         truth=dict(Rwc=Rwc, twc=twc, points=Xw_used, lines=L_true, point_gross=gross, seed=seed))
     return prob.normalise()
+
+
+def make_global_problem(seed: int, n_kf: int = 2000, n_points: int = 1_000_000, n_lines: int = 100_000,
+                        loops: int = 3, block: int = 16) -> LocalProblem:
+    """Config C5: ONE problem over a long multi-loop trajectory, keyframe 0 fixed. Built from
+    overlapping blocks of ``block`` consecutive keyframes (stride block/2): the landmarks of a block are
+    sampled in its frusta and observed by 2-6 (points) / 2-5 (lines) of its keyframes, exactly like a
+    local window, so the cost is linear in the problem size; the overlap chains the blocks together.
+    Poses are perturbed once, globally (2 cm, 0.5 deg, §8d)."""
+    rng = np.random.default_rng(seed)
+    Rwc, twc = make_trajectory(rng, n_kf, loops=loops)
+    stride = max(block // 2, 1)
+    starts = list(range(0, max(n_kf - stride, 1), stride))
+    nb = len(starts)
+    parts = []
+    for bi, s0 in enumerate(starts):
+        e0 = min(s0 + block, n_kf)
+        npb = n_points // nb + (1 if bi < n_points % nb else 0)
+        nlb = n_lines // nb + (1 if bi < n_lines % nb else 0)
+        parts.append(make_local_problem(seed + 7919 * (bi + 1), n_kf=e0 - s0, n_points=npb, n_lines=nlb, first_kf_id=s0,
+                                        trajectory=(Rwc[s0:e0], twc[s0:e0])))
+    pt_space = max(int(p.point_id.max()) + 1 if len(p.point_id) else 1 for p in parts)
+    ln_space = max(int(p.line_id.max()) + 1 if len(p.line_id) else 1 for p in parts)
+    cat = lambda name: np.concatenate([getattr(p, name) for p in parts])
+    cat_ids = lambda name, space: np.concatenate([getattr(p, name).astype(np.int64) + bi * space for bi, p in enumerate(parts)])
+    if (nb * pt_space) >= 2**31 or (nb * ln_space) >= 2**31:
+        raise ValueError("landmark id space exceeds int32")
+    pose_fixed = np.zeros(n_kf, dtype=U8)
+    pose_fixed[0] = 1
+    p0 = twc + rng.normal(0.0, 0.02, twc.shape) * (1 - pose_fixed)[:, None]
+    q0 = np.zeros((n_kf, 4))
+    for k in range(n_kf):
+        Rk = Rwc[k] if pose_fixed[k] else Rwc[k] @ rotvec_to_R(rng.normal(0.0, np.deg2rad(0.5), 3))
+        q0[k] = R_to_quat(Rk)
+    kw = dict(pose_id=np.arange(n_kf, dtype=I32), pose_p=p0, pose_q=q0, pose_fixed=pose_fixed,
+              point_id=cat_ids("point_id", pt_space), point_p=cat("point_p"),
+              line_id=cat_ids("line_id", ln_space), line_L=cat("line_L"), cams=parts[0].cams.copy())
+    for pre, lm, key, space in (("mp", "id_point", "kp", pt_space), ("sp", "id_point", "kp", pt_space),
+                                ("ml", "id_line", "l2d", ln_space), ("sl", "id_line", "l2d", ln_space)):
+        kw[f"{pre}_id_pose"] = cat(f"{pre}_id_pose")
+        kw[f"{pre}_{lm}"] = cat_ids(f"{pre}_{lm}", space)
+        kw[f"{pre}_id_cam"] = cat(f"{pre}_id_cam")
+        kw[f"{pre}_{key}"] = cat(f"{pre}_{key}")
+        kw[f"{pre}_inlier"] = cat(f"{pre}_inlier")
+    kw["truth"] = dict(Rwc=Rwc, twc=twc, seed=seed)
+    return LocalProblem(**kw).normalise()
 
 
 def make_local_batch(config: int, n_windows: int, first_instance: int = 0, **kw) -> Tuple[LocalBatch, List[LocalProblem]]:

@@ -23,20 +23,32 @@ def _problem():
     return synth.make_local_problem(synth.config_seed(5, 20), n_kf=30, n_points=3000, n_lines=300, loops=1)
 
 
-def _compare(orc, full, merged, stats):
+def _compare(orc, full, merged, stats, noise_aware=False):
+    """`noise_aware`: g2o differentiates the line edges numerically with delta = 1e-9; on a
+    long, weakly constrained chain of keyframes that noise alone moves the oracle's poses by more than
+    the 1e-5 bar (measured as the distance between the oracle runs with delta = 1e-9 and delta = 1e-6).
+    Where that happens the tolerance is widened to twice the oracle's own sensitivity -- the reference
+    result is not defined more sharply than that."""
     ref = full.copy()
     st = orc.local_ba(ref)
+    fine = full.copy()
+    st6 = orc.local_ba(fine, orc.make_config(None, numeric_delta=1e-6))
+    pos_tol = rot_tol = 1e-5
+    chi_rtol = 1e-4
+    if noise_aware:
+        pos_tol = max(pos_tol, 2 * np.linalg.norm(ref.pose_p - fine.pose_p, axis=1).max())
+        rot_tol = max(rot_tol, 2 * quat_angle(ref.pose_q, fine.pose_q).max())
+        chi_rtol = max(chi_rtol, 2 * abs(st["final_chi2"] - st6["final_chi2"]) / st["final_chi2"])
     for pre in ("mp", "sp", "ml", "sl"):
         got, exp = getattr(merged, f"{pre}_inlier"), getattr(ref, f"{pre}_inlier")
         assert np.array_equal(got, exp), f"{pre} inlier set differs at {np.nonzero(got != exp)[0][:10]}"
-    assert np.linalg.norm(merged.pose_p - ref.pose_p, axis=1).max() < 1e-5
-    assert quat_angle(merged.pose_q, ref.pose_q).max() < 1e-5
-    assert abs(stats["final_chi2"][0] - st["final_chi2"]) <= 1e-4 * st["final_chi2"]
+    assert np.linalg.norm(merged.pose_p - ref.pose_p, axis=1).max() < pos_tol
+    assert quat_angle(merged.pose_q, ref.pose_q).max() < rot_tol
+    assert abs(stats["final_chi2"][0] - st["final_chi2"]) <= chi_rtol * st["final_chi2"]
     assert list(stats["iters"][0][:2]) == st["iters"][:2] and list(stats["trials"][0][:2]) == st["trials"][:2]
     assert int(stats["edges_linearized"][0]) == st["edges_linearized"]
-    fine = full.copy()
-    orc.local_ba(fine, orc.make_config(None, numeric_delta=1e-6))
-    assert np.quantile(np.abs(merged.point_p - fine.point_p).max(axis=1), 0.99) < 1e-6
+    if len(full.point_id):
+        assert np.quantile(np.abs(merged.point_p - fine.point_p).max(axis=1), 0.99) < (1e-6 if not noise_aware else 10 * pos_tol)
 
 
 def test_global_ba_one_rank_matches_oracle(gpu_ctx, orc):
@@ -112,3 +124,23 @@ def test_global_ba_two_ranks_match_oracle(orc):
     assert np.array_equal(shards[0].problem.pose_p, shards[1].problem.pose_p)
     assert np.array_equal(shards[0].problem.pose_q, shards[1].problem.pose_q)
     _compare(orc, full, merge_landmark_shards(full, shards), out[0][2])
+
+
+def test_global_ba_on_the_c5_generator(gpu_ctx, orc):
+    """The C5 generator (overlapping keyframe blocks on a multi-loop trajectory) at test scale: 64
+    keyframes, reduced system n = 378, through the global path with a one-rank communicator. Without
+    lines every Jacobian is analytic on both sides and the result agrees to rounding; with lines the
+    comparison is limited by the noise of g2o's numeric differentiation (see _compare)."""
+    gpu_ctx.comm_init(1, 0)
+    for n_lines, noise_aware in ((0, False), (800, True)):
+        full = synth.make_global_problem(synth.config_seed(5, 40), n_kf=64, n_points=8000, n_lines=n_lines, loops=1)
+        shard = shard_landmarks(full, 0, 1)
+        batch = LocalBatch.from_problems([shard.problem])
+        res = gpu_ctx.global_ba(batch)
+        res.scatter_back(batch, [shard.problem])
+        merged = merge_landmark_shards(full, [shard])
+        _compare(orc, full, merged, res.stats, noise_aware=noise_aware)
+        if n_lines == 0:
+            ref = full.copy()
+            orc.local_ba(ref)
+            assert np.abs(merged.pose_p - ref.pose_p).max() < 1e-10
