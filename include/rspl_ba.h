@@ -194,8 +194,8 @@ int rspl_ba_sync(RsplBaContext* ctx);
 /* Per-kernel-class timing with CUDA events on the context stream (what bench.py's roofline uses).
  * Classes: 0 frame_opt, 1 local_setup, 2 local_solve (persistent), 3 init + pair lists, 4 linearize,
  * 5 pose blocks, 6 Schur prep, 7 Schur reduce, 8 reduced solve, 9 back-substitution / update /
- * evaluation, 10 LM control kernels, 11 flagging + write-back, 12 collectives of the global-BA path
- * (13-15 reserved, zero). get_profile synchronises the stream, returns milliseconds and launch counts
+ * evaluation, 10 LM control kernels, 11 flagging + write-back, 12 collectives of the global-BA path,
+ * 13 assembly of the dense reduced system + pose update (14-15 reserved, zero). get_profile synchronises the stream, returns milliseconds and launch counts
  * (arrays of RSPL_BA_PROFILE_CLASSES entries) accumulated since the last call and resets them. */
 #define RSPL_BA_PROFILE_CLASSES 16
 int rspl_ba_set_profiling(RsplBaContext* ctx, int enabled);

@@ -103,6 +103,7 @@ struct RsplBaContext {
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
   DevBuf dense_buf;
   void* cusolver = nullptr; // cusolverDnHandle_t
+  void* cublas = nullptr;   // cublasHandle_t (block-tridiagonal variant)
   // global BA: NCCL communicator (comm.inl); the uploaded window is then one shard of the problem
   void* comm = nullptr; // ncclComm_t
   int comm_ranks = 1, comm_rank = 0;
@@ -292,7 +293,7 @@ extern "C" int rspl_ba_sync(RsplBaContext* c) {
 namespace {
 enum ProfClass {
   PC_FRAME = 0, PC_LOCAL_SETUP, PC_LOCAL_PERSISTENT, PC_PAIRS, PC_LINEARIZE, PC_POSE_BLOCKS, PC_SCHUR_PREP,
-  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_COUNT
+  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_ASSEMBLE, PC_COUNT
 };
 // records an event pair around one launch when profiling is on
 struct ProfScope {

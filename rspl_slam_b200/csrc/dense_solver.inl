@@ -7,6 +7,7 @@
 // factorisation; everything around it (linearisation, Schur complement, back-substitution, LM
 // control) stays in this library's kernels. cuSOLVER is loaded with dlopen on first use, so the
 // library has no link-time dependency on it and the small-window paths never touch it.
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <dlfcn.h>
 
@@ -42,7 +43,56 @@ CusolverApi& cusolver_api() {
   return api;
 }
 
+// cuBLAS (same lazy loading) for the block-tridiagonal variant below
+struct CublasApi {
+  void* lib = nullptr;
+  decltype(&cublasCreate_v2) create = nullptr;
+  decltype(&cublasDestroy_v2) destroy = nullptr;
+  decltype(&cublasSetStream_v2) set_stream = nullptr;
+  decltype(&cublasDtrsm_v2) trsm = nullptr;
+  decltype(&cublasDsyrk_v2) syrk = nullptr;
+  decltype(&cublasDgemv_v2) gemv = nullptr;
+  decltype(&cublasDtrsv_v2) trsv = nullptr;
+  bool ok = false;
+};
+
+CublasApi& cublas_api() {
+  static CublasApi api;
+  if (api.lib) return api;
+  const char* names[] = {"libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+  for (const char* n : names) {
+    api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (api.lib) break;
+  }
+  if (!api.lib) return api;
+  api.create = (decltype(api.create))dlsym(api.lib, "cublasCreate_v2");
+  api.destroy = (decltype(api.destroy))dlsym(api.lib, "cublasDestroy_v2");
+  api.set_stream = (decltype(api.set_stream))dlsym(api.lib, "cublasSetStream_v2");
+  api.trsm = (decltype(api.trsm))dlsym(api.lib, "cublasDtrsm_v2");
+  api.syrk = (decltype(api.syrk))dlsym(api.lib, "cublasDsyrk_v2");
+  api.gemv = (decltype(api.gemv))dlsym(api.lib, "cublasDgemv_v2");
+  api.trsv = (decltype(api.trsv))dlsym(api.lib, "cublasDtrsv_v2");
+  api.ok = api.create && api.destroy && api.set_stream && api.trsm && api.syrk && api.gemv && api.trsv;
+  return api;
+}
+
+// first non-zero potrf info of the tiles -> the window's info (block-tridiagonal variant)
+__global__ void k_merge_tile_info(const int* tile_info, int n_tiles, int* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int v = 0;
+    for (int i = 0; i < n_tiles && v == 0; ++i) v = tile_info[i];
+    *out = v;
+  }
+}
+
 struct DenseLayout {
+  // Block-tridiagonal variant: when the pose pairs that share landmarks are all within `band` free-pose
+  // indices of each other (a visual-odometry chain without loop closures), the reduced system is banded;
+  // cut into tiles of >= band poses it is block-tridiagonal and its Cholesky factor has no fill outside
+  // the tiles: O(n t^2) instead of O(n^3) with library calls on t x t tiles. tile_poses[w] = 0: full dense.
+  std::vector<int> tile_poses;
+  int* tile_info = nullptr; // [max tiles]
+  int max_tiles = 0;
   std::vector<long long> off; // [W] offset of each window's matrix (doubles)
   long long total = 0;        // doubles
   int lwork = 0;
@@ -54,7 +104,7 @@ struct DenseLayout {
 };
 
 // Allocates the dense systems of the uploaded batch (grow-only) and the cuSOLVER workspace.
-int dense_prepare(RsplBaContext* c, DenseLayout& L) {
+int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band) {
   CusolverApi& api = cusolver_api();
   if (!api.ok)
     return fail(c, RSPL_BA_ERR_UNSUPPORTED,
@@ -83,12 +133,29 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L) {
   const size_t o_b = a.take(sizeof(double) * (size_t)(6 * c->l_nf_begin[W] + 1));
   const size_t o_info = a.take(sizeof(int) * 2 * W); // [W] potrf info, [W] potrs info (parameter errors only)
   const size_t o_off = a.take(sizeof(long long) * W);
+  // block-tridiagonal decision per window
+  L.tile_poses.assign(W, 0);
+  L.max_tiles = 0;
+  const bool allow_tri = !getenv("RSPL_BA_DENSE_FULL") && cublas_api().ok;
+  for (int w = 0; w < W && allow_tri; ++w) {
+    const int nf = c->l_nf_begin[w + 1] - c->l_nf_begin[w];
+    int min_tp = 64; // tiles of at least 384 unknowns: fewer, larger library calls (the chain of tiles is sequential)
+    if (const char* e = getenv("RSPL_BA_TILE_POSES")) min_tp = atoi(e) > 0 ? atoi(e) : min_tp;
+    int tp = band[w] > min_tp ? band[w] : min_tp;
+    const int tiles = (nf + tp - 1) / tp;
+    if (tiles >= 4) {
+      L.tile_poses[w] = tp;
+      if (tiles > L.max_tiles) L.max_tiles = tiles;
+    }
+  }
+  const size_t o_tinfo = a.take(sizeof(int) * (L.max_tiles + 1));
   CU_TRY(c, c->dense_buf.reserve(a.off));
   char* base = c->dense_buf.as<char>();
   L.H = (double*)(base + o_H);
   L.b = (double*)(base + o_b);
   L.info = (int*)(base + o_info);
   L.d_off = (long long*)(base + o_off);
+  L.tile_info = (int*)(base + o_tinfo);
   int lwork = 0;
   if (n_max > 0 && api.potrf_buffer(h, CUBLAS_FILL_MODE_LOWER, n_max, L.H, n_max, &lwork) != CUSOLVER_STATUS_SUCCESS)
     return fail(c, RSPL_BA_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
@@ -103,8 +170,19 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L) {
     L.b = (double*)(base + o_b);
     L.info = (int*)(base + o_info);
     L.d_off = (long long*)(base + o_off);
+    L.tile_info = (int*)(base + o_tinfo);
   }
   L.work = (double*)(base + o_work);
+  if (L.max_tiles > 0) {
+    CublasApi& bl = cublas_api();
+    if (!c->cublas) {
+      cublasHandle_t bh = nullptr;
+      if (bl.create(&bh) != CUBLAS_STATUS_SUCCESS) return fail(c, RSPL_BA_ERR_CUDA, "cublasCreate failed");
+      c->cublas = bh;
+    }
+    if (bl.set_stream((cublasHandle_t)c->cublas, c->stream) != CUBLAS_STATUS_SUCCESS)
+      return fail(c, RSPL_BA_ERR_CUDA, "cublasSetStream failed");
+  }
   CU_TRY(c, cudaMemcpyAsync(L.d_off, L.off.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(L.info, 0, sizeof(int) * 2 * W, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -120,6 +198,53 @@ int dense_factor_solve(RsplBaContext* c, const DenseLayout& L, const std::vector
     if (n == 0) continue;
     double* A = L.H + L.off[w];
     double* rhs = L.b + (size_t)6 * c->l_nf_begin[w];
+    if (L.tile_poses[w] > 0) {
+      // block-tridiagonal Cholesky; column-major lower view M(i, j) = A[j * n + i], i >= j
+      CublasApi& bl = cublas_api();
+      cublasHandle_t bh = (cublasHandle_t)c->cublas;
+      const int t = 6 * L.tile_poses[w];
+      const int T = (n + t - 1) / t;
+      const double one = 1.0, minus = -1.0;
+      auto tk = [&](int k) { return (k + 1) * t <= n ? t : n - k * t; };
+      auto M = [&](int i, int j) { return A + (size_t)j * n + i; };
+      int calls = 0;
+      for (int k = 0; k < T; ++k) {
+        const int o = k * t;
+        if (api.potrf(h, CUBLAS_FILL_MODE_LOWER, tk(k), M(o, o), n, L.work, L.lwork, L.tile_info + k) != CUSOLVER_STATUS_SUCCESS)
+          return fail(c, RSPL_BA_ERR_CUDA, "cusolverDnDpotrf (tile) failed");
+        ++calls;
+        if (k + 1 < T) {
+          const int o1 = o + t;
+          // L(k+1,k) = A(k+1,k) L(k,k)^-T ; A(k+1,k+1) -= L(k+1,k) L(k+1,k)^T
+          if (bl.trsm(bh, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, tk(k + 1), tk(k), &one,
+                      M(o, o), n, M(o1, o), n) != CUBLAS_STATUS_SUCCESS ||
+              bl.syrk(bh, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, tk(k + 1), tk(k), &minus, M(o1, o), n, &one, M(o1, o1), n) !=
+                  CUBLAS_STATUS_SUCCESS)
+            return fail(c, RSPL_BA_ERR_CUDA, "cuBLAS trsm / syrk (tile) failed");
+          calls += 2;
+        }
+      }
+      k_merge_tile_info<<<1, 32, 0, c->stream>>>(L.tile_info, T, L.info + w);
+      for (int k = 0; k < T; ++k) { // L y = b
+        const int o = k * t;
+        if (k > 0 && bl.gemv(bh, CUBLAS_OP_N, tk(k), t, &minus, M(o, o - t), n, rhs + o - t, 1, &one, rhs + o, 1) != CUBLAS_STATUS_SUCCESS)
+          return fail(c, RSPL_BA_ERR_CUDA, "cuBLAS gemv (tile) failed");
+        if (bl.trsv(bh, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, tk(k), M(o, o), n, rhs + o, 1) != CUBLAS_STATUS_SUCCESS)
+          return fail(c, RSPL_BA_ERR_CUDA, "cuBLAS trsv (tile) failed");
+        calls += 2;
+      }
+      for (int k = T - 1; k >= 0; --k) { // L^T x = y
+        const int o = k * t;
+        if (k + 1 < T &&
+            bl.gemv(bh, CUBLAS_OP_T, tk(k + 1), t, &minus, M(o + t, o), n, rhs + o + t, 1, &one, rhs + o, 1) != CUBLAS_STATUS_SUCCESS)
+          return fail(c, RSPL_BA_ERR_CUDA, "cuBLAS gemv (tile) failed");
+        if (bl.trsv(bh, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, tk(k), M(o, o), n, rhs + o, 1) != CUBLAS_STATUS_SUCCESS)
+          return fail(c, RSPL_BA_ERR_CUDA, "cuBLAS trsv (tile) failed");
+        calls += 2;
+      }
+      c->launches += calls + 1;
+      continue;
+    }
     // row-major upper triangle == column-major lower triangle
     if (api.potrf(h, CUBLAS_FILL_MODE_LOWER, n, A, n, L.work, L.lwork, L.info + w) != CUSOLVER_STATUS_SUCCESS)
       return fail(c, RSPL_BA_ERR_CUDA, "cusolverDnDpotrf failed");
@@ -137,4 +262,6 @@ int dense_factor_solve(RsplBaContext* c, const DenseLayout& L, const std::vector
 static void dense_release(RsplBaContext* c) {
   if (c->cusolver && cusolver_api().ok) cusolver_api().destroy((cusolverDnHandle_t)c->cusolver);
   c->cusolver = nullptr;
+  if (c->cublas && cublas_api().ok) cublas_api().destroy((cublasHandle_t)c->cublas);
+  c->cublas = nullptr;
 }

@@ -250,6 +250,20 @@ __global__ void __launch_bounds__(128) kb_pairs_scan(const __grid_constant__ Loc
   }
 }
 
+// largest free-pose index distance of a pose pair that shares a landmark (dense path: is the reduced
+// system banded?); grid (ceil(Pmax / 256), windows)
+__global__ void __launch_bounds__(256) kb_pair_band(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                    int* band) {
+  const int w = blockIdx.y, p = blockIdx.x * 256 + threadIdx.x;
+  const int nf = b.ws[w].nf;
+  if (p >= nf * (nf + 1) / 2) return;
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
+  if (pb[2] - pb[0] <= 0) return;
+  int fi, fj;
+  pair_decode(p, nf, fi, fj);
+  atomicMax(&band[w], fj - fi);
+}
+
 // ------------------------------------------------------------------------------------------------
 // pass begin: active sets (§9.12), reduced-system indices
 // ------------------------------------------------------------------------------------------------

@@ -385,13 +385,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   DenseLayout dl;
   std::vector<int> n_sys_host(W, 0);
   if (dense) {
-    rc = dense_prepare(c, dl);
-    if (rc != RSPL_BA_OK) return rc;
-    c->bd.dense_H = dl.H;
-    c->bd.dense_b = dl.b;
-    c->bd.dense_info = dl.info;
-    c->bd.dense_off = dl.d_off;
-    c->l_last_path = 3;
+    c->l_last_path = 3; // (buffers are set up after the pair lists: their band decides the factorisation)
   } else {
     CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
   }
@@ -406,6 +400,26 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   LAUNCH(PC_PAIRS, ba::kb_pairs_scan, g_win, 128, 0, d, b);
   LAUNCH(PC_PAIRS, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
   CU_TRY(c, cudaGetLastError());
+  if (dense) {
+    // which pose pairs share landmarks: a banded pattern allows the block-tridiagonal factorisation
+    std::vector<int> band(W, 0);
+    int* d_band = (int*)b.part; // scratch: `part` is rewritten by the first linearisation
+    CU_TRY(c, cudaMemsetAsync(d_band, 0, sizeof(int) * W, s));
+    LAUNCH(PC_PAIRS, ba::kb_pair_band, dim3((b.Pmax + 255) / 256, W), 256, 0, d, b, d_band);
+    if (global) {
+      rc = comm_all_reduce(c, d_band, d_band, (size_t)W, kNcclInt32, kNcclMax);
+      if (rc != RSPL_BA_OK) return rc;
+    }
+    CU_TRY(c, cudaMemcpyAsync(band.data(), d_band, sizeof(int) * W, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemsetAsync(d_band, 0, sizeof(int) * W, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    rc = dense_prepare(c, dl, band);
+    if (rc != RSPL_BA_OK) return rc;
+    c->bd.dense_H = dl.H;
+    c->bd.dense_b = dl.b;
+    c->bd.dense_info = dl.info;
+    c->bd.dense_off = dl.d_off;
+  }
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
   int dense_rc = RSPL_BA_OK, coll_rc = RSPL_BA_OK;
@@ -433,12 +447,12 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
         if (coll_rc == RSPL_BA_OK)
           coll_rc = comm_all_reduce(c, b.hs_part_w, b.hs_part, (size_t)42 * b.Pmax + 8, kNcclFloat64, kNcclSum);
       }
-      LAUNCH(PC_SOLVE, ba::kb_assemble_dense, g_pair1, 64, 0, d, b);
+      LAUNCH(PC_ASSEMBLE, ba::kb_assemble_dense, g_pair1, 64, 0, d, b);
       {
         ProfScope ps_(c, PC_SOLVE);
         dense_rc = dense_factor_solve(c, dl, n_sys_host);
       }
-      LAUNCH(PC_SOLVE, ba::kb_post_solve, W, 256, 0, d, b);
+      LAUNCH(PC_ASSEMBLE, ba::kb_post_solve, W, 256, 0, d, b);
     }
     if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
@@ -496,7 +510,8 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     const int worst = lo.iters[pass] * 10 + 1; // <= 10 trials per LM iteration (§9.9)
     int done_steps = 0;
     while (done_steps < worst) {
-      const int burst = done_steps == 0 ? (lo.iters[pass] < 4 ? lo.iters[pass] : 4) : 4;
+      // (a super-step of the dense path costs milliseconds: poll after every one instead of wasting factorisations)
+      const int burst = dense ? 1 : (done_steps == 0 ? (lo.iters[pass] < 4 ? lo.iters[pass] : 4) : 4);
       for (int k = 0; k < burst && done_steps < worst; ++k, ++done_steps) {
         if (gexec) {
           CU_TRY(c, cudaGraphLaunch(gexec, s));

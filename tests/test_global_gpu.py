@@ -144,3 +144,22 @@ def test_global_ba_on_the_c5_generator(gpu_ctx, orc):
             ref = full.copy()
             orc.local_ba(ref)
             assert np.abs(merged.pose_p - ref.pose_p).max() < 1e-10
+
+
+def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
+    """A 160-keyframe chain without loop closures: pose pairs share landmarks only within 15 keyframes, so
+    the reduced system (n = 954) is banded and is factorised tile by tile (dense_solver.inl). Points only:
+    all Jacobians analytic on both sides, the result must agree with the oracle to rounding, and with the
+    full dense factorisation of the same system."""
+    full = synth.make_global_problem(synth.config_seed(5, 41), n_kf=160, n_points=16000, n_lines=0, loops=2)
+    batch = LocalBatch.from_problems([full])
+    res = gpu_ctx.local_batch(batch)
+    ref = full.copy()
+    st = orc.local_ba(ref)
+    assert np.array_equal(res.sp_inlier, ref.sp_inlier) and np.array_equal(res.mp_inlier, ref.mp_inlier)
+    assert np.abs(res.pose_twc[:3].T - ref.pose_p).max() < 1e-9
+    assert list(res.stats["iters"][0][:2]) == st["iters"][:2] and list(res.stats["trials"][0][:2]) == st["trials"][:2]
+    assert abs(res.stats["final_chi2"][0] - st["final_chi2"]) <= 1e-9 * st["final_chi2"]
+    monkeypatch.setenv("RSPL_BA_DENSE_FULL", "1")
+    dense = gpu_ctx.local_batch(batch)
+    assert np.array_equal(dense.sp_inlier, res.sp_inlier) and np.abs(dense.pose_twc - res.pose_twc).max() < 1e-9
