@@ -22,6 +22,7 @@
 namespace ba {
 
 constexpr int BT = 128; // threads per CTA of the per-landmark / per-pair kernels
+constexpr int PAIRS_LM_MIN_NF = 64; // windows with more free poses build their pair lists from the landmarks
 constexpr int BW = BT / 32;
 
 enum { STAGE_NEED_LIN = 0, STAGE_NEED_TRIAL = 1, STAGE_DONE = 2 };
@@ -70,6 +71,8 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   double* part;   // [W][C][4] per-chunk partial sums
   int* pair_beg;  // [W][2*Pmax+1] entry offsets: point entries, line entries per pair
   int2* pairs;    // pair entries (e_i, e_j) into the sorted edge arrays
+  int2* pairs_tmp; // scratch of the same size (landmark-driven builder of large windows), may be null
+  int* pair_cursor; // [W][2*Pmax] scratch of that builder
   const long long* pair_base; // [W+1] region of each window inside `pairs`
   int* n_active;  // device counter for the host poll
   // dense-solve path (reduced systems too large for shared memory): per window a row-major n x n
@@ -247,6 +250,125 @@ __global__ void __launch_bounds__(128) kb_pairs_scan(const __grid_constant__ Loc
   if (run > cap) { // only possible with duplicate (pose, landmark) edges, which are rejected anyway
     atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
     for (int q = 0; q <= 2 * np_pairs; ++q) pb[q] = (int)b.pair_base[w];
+  }
+}
+
+// ---- pair lists of LARGE windows (hundreds of poses, ~10^6 pairs, most of them empty) ----------------
+// kb_pairs costs O(pairs x edges per pose); here the lists are built from the landmarks instead: a
+// landmark with k free observers contributes k(k+1)/2 entries. MODE 0 counts them per pair, MODE 1 writes
+// them behind an atomic cursor (arbitrary order), kb_pairs_sort then orders every list by its first edge
+// (= landmark order), which makes the result identical to kb_pairs' and deterministic.
+template <int KIND, int MODE>
+BA_DEV void pairs_lm_kind(const LocalDev& d, const BatchDev& b, const KindDev& k, int w, int l) {
+  const int p0 = d.pose_begin[w];
+  const int nf = b.ws[w].nf;
+  int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
+  int* cur = b.pair_cursor + (size_t)w * 2 * b.Pmax;
+  const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  for (int a = ea; a < eb; ++a) {
+    const int fa = b.free_idx[p0 + (k.info[a] & 0xffff)];
+    if (fa < 0) continue;
+    for (int c = a; c < eb; ++c) {
+      const int fc = c == a ? fa : b.free_idx[p0 + (k.info[c] & 0xffff)];
+      if (fc < 0) continue;
+      const bool swap = fc < fa;
+      const int q = 2 * pair_index(swap ? fc : fa, swap ? fa : fc, nf) + KIND;
+      if (MODE == 0) {
+        atomicAdd(&pb[q], 1);
+      } else {
+        const int pos = atomicAdd(&cur[q], 1);
+        b.pairs[pb[q] + pos] = make_int2(swap ? c : a, swap ? a : c);
+      }
+    }
+  }
+}
+
+// grid (Cp + Cl, windows), one thread per landmark
+template <int MODE>
+__global__ void __launch_bounds__(BT) kb_pairs_lm(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, c = blockIdx.x;
+  if (MODE == 1 && (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  if (c < b.Cp) {
+    const KindDev& k = d.k[0];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = c * BT + threadIdx.x;
+    if (i < nl) pairs_lm_kind<0, MODE>(d, b, k, w, l0 + i);
+  } else {
+    const KindDev& k = d.k[1];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = (c - b.Cp) * BT + threadIdx.x;
+    if (i < nl) pairs_lm_kind<1, MODE>(d, b, k, w, l0 + i);
+  }
+}
+
+// exclusive scan of one window's 2P counts by a whole CTA (1024 threads, chunks with a running total);
+// grid = windows
+__global__ void __launch_bounds__(1024) kb_pairs_scan_cta(const __grid_constant__ LocalDev d,
+                                                          const __grid_constant__ BatchDev b) {
+  __shared__ int s_warp[32];
+  __shared__ long long s_run;
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nf = b.ws[w].nf;
+  const int n = nf * (nf + 1); // 2 * pairs
+  int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
+  if (tid == 0) s_run = b.pair_base[w];
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n ? pb[i] : 0;
+    int x = v; // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const long long run = s_run;
+    const int before = (warp ? s_warp[warp - 1] : 0) + x - v;
+    if (i < n) pb[i] = (int)(run + before);
+    __syncthreads();
+    if (tid == 0) s_run = run + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    pb[n] = (int)s_run;
+    if (s_run > b.pair_base[w + 1]) atomicOr(d.err, LOCAL_ERR_DUP_EDGE); // capacity: only with duplicate edges
+  }
+}
+
+// one warp per (window, pair): order the pair's point and line lists by their first edge (rank sort
+// through pairs_tmp: the keys of a list are distinct)
+__global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * BW + (threadIdx.x >> 5);
+  const int nf = b.ws[w].nf;
+  if (p >= nf * (nf + 1) / 2 || (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
+  for (int kind = 0; kind < 2; ++kind) {
+    const int beg = pb[kind], n = pb[kind + 1] - beg;
+    if (n < 2) continue;
+    int2* seg = b.pairs + beg;
+    int2* tmp = b.pairs_tmp + beg;
+    for (int i = lane; i < n; i += 32) {
+      const int2 v = seg[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += seg[j].x < v.x ? 1 : 0;
+      tmp[rank] = v;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) seg[i] = tmp[i];
+    __syncwarp();
   }
 }
 

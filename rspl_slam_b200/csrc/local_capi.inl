@@ -313,6 +313,10 @@ int batched_prepare(RsplBaContext* c) {
   const size_t o_part = a.take(sizeof(double) * 4 * (size_t)W * C);
   const size_t o_pbeg = a.take(sizeof(int) * (size_t)W * (2 * Pmax + 1));
   const size_t o_pairs = a.take(sizeof(int2) * (size_t)(n_pairs + 1));
+  // landmark-driven pair-list builder of large windows: a second entry buffer and per-pair cursors
+  const bool big_pairs = NFmax > ba::PAIRS_LM_MIN_NF;
+  const size_t o_pairs_tmp = big_pairs ? a.take(sizeof(int2) * (size_t)(n_pairs + 1)) : 0;
+  const size_t o_cursor = big_pairs ? a.take(sizeof(int) * (size_t)W * 2 * (Pmax > 0 ? Pmax : 1)) : 0;
   const size_t o_pbase = a.take(sizeof(long long) * (W + 1));
   const size_t o_nact = a.take(sizeof(int));
   CU_TRY(c, c->batch_buf.reserve(a.off));
@@ -349,6 +353,8 @@ int batched_prepare(RsplBaContext* c) {
   b.part = (double*)(base + o_part);
   b.pair_beg = (int*)(base + o_pbeg);
   b.pairs = (int2*)(base + o_pairs);
+  b.pairs_tmp = big_pairs ? (int2*)(base + o_pairs_tmp) : nullptr;
+  b.pair_cursor = big_pairs ? (int*)(base + o_cursor) : nullptr;
   b.pair_base = (const long long*)(base + o_pbase);
   b.n_active = (int*)(base + o_nact);
   b.Cp = Cp;
@@ -396,9 +402,19 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     c->launches++;                                     \
   } while (0)
   LAUNCH(PC_PAIRS, ba::kb_init, W, ba::BT, 0, d, b, lo);
-  LAUNCH(PC_PAIRS, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
-  LAUNCH(PC_PAIRS, ba::kb_pairs_scan, g_win, 128, 0, d, b);
-  LAUNCH(PC_PAIRS, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
+  if (b.pairs_tmp) { // large windows: lists built from the landmarks, then ordered
+    const size_t n_cnt = (size_t)W * (2 * b.Pmax + 1);
+    CU_TRY(c, cudaMemsetAsync(b.pair_beg, 0, sizeof(int) * n_cnt, s));
+    CU_TRY(c, cudaMemsetAsync(b.pair_cursor, 0, sizeof(int) * (size_t)W * 2 * b.Pmax, s));
+    LAUNCH(PC_PAIRS, ba::kb_pairs_lm<0>, g_lm, ba::BT, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_scan_cta, W, 1024, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_lm<1>, g_lm, ba::BT, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_sort, g_pair, ba::BT, 0, d, b);
+  } else {
+    LAUNCH(PC_PAIRS, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_scan, g_win, 128, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
+  }
   CU_TRY(c, cudaGetLastError());
   if (dense) {
     // which pose pairs share landmarks: a banded pattern allows the block-tridiagonal factorisation
