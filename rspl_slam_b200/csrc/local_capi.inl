@@ -581,19 +581,32 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   lo.max_poses = c->l_max_poses;
   lo.max_free = c->l_max_free_poses;
   const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
+  if (c->l_n_windows > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int), c->stream));
   {
     ProfScope ps(c, PC_LOCAL_SETUP);
+    const int W = c->l_n_windows;
     for (int k = 0; k < 2; ++k)
-      if (c->ld.k[k].n_lm > 0)
+      if (c->ld.k[k].n_lm > 0) {
         CU_TRY(c, cudaMemsetAsync(c->ld.k[k].slot, ba::SLOT_NONE, (size_t)c->ld.k[k].n_lm * c->ld.slot_stride, c->stream));
-    ba::local_setup_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
-    const dim3 g_pl(c->l_max_poses, c->l_n_windows, 2);
-    ba::setup_pose_lists<0><<<g_pl, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
-    ba::setup_pose_scan<<<(2 * c->l_n_windows + 127) / 128, 128, 0, c->stream>>>(c->ld);
-    ba::setup_pose_lists<1><<<g_pl, ba::LOCAL_THREADS, 0, c->stream>>>(c->ld);
+        CU_TRY(c, cudaMemsetAsync(c->ld.k[k].cursor, 0, sizeof(int) * (size_t)c->ld.k[k].n_lm, c->stream));
+      }
+    const int T = ba::LOCAL_THREADS;
+    const int max_lm = c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns;
+    const dim3 g_e((c->l_max_edges + T - 1) / T > 0 ? (c->l_max_edges + T - 1) / T : 1, W, 2);
+    const dim3 g_l((max_lm + T - 1) / T > 0 ? (max_lm + T - 1) / T : 1, W, 2);
+    ba::setup_poses<<<W, T, 0, c->stream>>>(c->ld);
+    ba::setup_edges<0><<<g_e, T, 0, c->stream>>>(c->ld);
+    ba::setup_scan<<<dim3(W, 2), 1024, 0, c->stream>>>(c->ld);
+    ba::setup_edges<1><<<g_e, T, 0, c->stream>>>(c->ld);
+    ba::setup_landmarks<<<g_l, T, 0, c->stream>>>(c->ld);
+    ba::setup_gather<<<g_e, T, 0, c->stream>>>(c->ld);
+    const dim3 g_pl(c->l_max_poses, W, 2);
+    ba::setup_pose_lists<0><<<g_pl, T, 0, c->stream>>>(c->ld);
+    ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, c->stream>>>(c->ld);
+    ba::setup_pose_lists<1><<<g_pl, T, 0, c->stream>>>(c->ld);
   }
-  c->launches += 4;
+  c->launches += 9;
   CU_TRY(c, cudaGetLastError());
   // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
   // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent

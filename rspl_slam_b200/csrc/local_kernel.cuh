@@ -4,10 +4,11 @@
 // without kernel -> inlier flags -> write-back) without returning to the host.
 //
 // Kernels
-//   local_setup_kernel   builds, per window, the landmark-major edge order (mono edges of a landmark
+//   setup_* kernels      build, per window, the landmark-major edge order (mono edges of a landmark
 //                        first, then its stereo edges, each in the caller's order = g2o's active-edge
 //                        order restricted to the landmark), the CSR offsets, the pose-major edge lists
-//                        and the landmark x pose slot table; converts Twc -> Tcw (:42).
+//                        and the landmark x pose slot table; convert Twc -> Tcw (:42). Grids over
+//                        (chunk, window, kind), shared by both solve paths.
 //   local_solve_kernel   per LM iteration:
 //     K1 linearize_landmarks   residual, Jacobians, Huber, chi2; Hll, bl per landmark (private fp64
 //                              accumulation in g2o's edge order); W = Jp^T (rho1 Omega) Jl per edge
@@ -108,102 +109,161 @@ struct LocalOpt {
 BA_DEV int edge_base(const KindDev& k, int w) { return k.cls_begin[0][w] + k.cls_begin[1][w]; }
 
 // ------------------------------------------------------------------------------------------------
-// setup
+// setup: landmark-major sorted edge arrays, slot table, initial states. A handful of small kernels
+// over (chunk, window, kind) grids so that one huge window (global BA) is as parallel as 1024 small
+// ones. Order inside a landmark = (class, caller index) = g2o's edge order for that vertex; the
+// scatter uses integer atomics and is followed by a per-landmark sort, so the result is deterministic.
 // ------------------------------------------------------------------------------------------------
-template <int KIND>
-BA_DEV void setup_kind(const LocalDev& d, const KindDev& k, int w, const int* s_free_idx, int* s_scan) {
-  using T = KT<KIND>;
-  const int tid = threadIdx.x;
-  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
-  const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
-  // 1. degree per landmark
-  for (int i = tid; i < nl; i += LOCAL_THREADS) k.cursor[l0 + i] = 0;
-  __syncthreads();
-  for (int c = 0; c < 2; ++c) {
-    const int a = k.cls_begin[c][w], b = k.cls_begin[c][w + 1];
-    for (int i = a + tid; i < b; i += LOCAL_THREADS) atomicAdd(&k.cursor[l0 + k.cls_lm[c][i]], 1);
+// poses: Twc -> Tcw (g2o_optimization.cc:42) and the window-local free index; grid = windows
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_poses(const __grid_constant__ LocalDev d) {
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  if (tid == 0) {
+    int nf = 0;
+    for (int p = 0; p < np; ++p) d.setup_free_idx[p0 + p] = d.pose_fixed[p0 + p] ? -1 : nf++;
   }
-  __syncthreads();
-  // 2. exclusive scan -> ebeg (chunks of LOCAL_THREADS with a running total)
-  __shared__ int s_total;
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-  for (int base = 0; base < nl; base += LOCAL_THREADS) {
-    const int i = base + tid;
-    const int v = i < nl ? k.cursor[l0 + i] : 0;
-    s_scan[tid] = v;
-    __syncthreads();
-    for (int o = 1; o < LOCAL_THREADS; o <<= 1) {
-      const int t2 = tid >= o ? s_scan[tid - o] : 0;
-      __syncthreads();
-      s_scan[tid] += t2;
-      __syncthreads();
-    }
-    if (i < nl) {
-      k.ebeg[l0 + i] = e0 + s_total + s_scan[tid] - v;
-      if (v > 254) atomicOr(d.err, LOCAL_ERR_DEGREE);
-    }
-    __syncthreads();
-    if (tid == 0) s_total += s_scan[LOCAL_THREADS - 1];
-    __syncthreads();
+  for (int p = tid; p < np; p += LOCAL_THREADS) {
+    const double pp[3] = {d.pose_twc[p0 + p], d.pose_twc[d.n_poses + p0 + p], d.pose_twc[2 * d.n_poses + p0 + p]};
+    const double qq[4] = {d.pose_twc[3 * d.n_poses + p0 + p], d.pose_twc[4 * d.n_poses + p0 + p],
+                          d.pose_twc[5 * d.n_poses + p0 + p], d.pose_twc[6 * d.n_poses + p0 + p]};
+    const Pose T = pose_from_twc(pp, qq);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d.pose_tcw[(size_t)q * d.n_poses + p0 + p] = T.q[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) d.pose_tcw[(size_t)(4 + q) * d.n_poses + p0 + p] = T.t[q];
   }
-  if (tid == 0 && w == d.n_windows - 1) k.ebeg[k.n_lm] = k.n_edge;
-  for (int i = tid; i < nl; i += LOCAL_THREADS) k.cursor[l0 + i] = 0;
-  __syncthreads();
-  // 3. scatter sort keys (order inside a segment is fixed in step 4)
+}
+
+// MODE 0: degree per landmark (cursor zeroed by the host); MODE 1: scatter the sort keys behind the
+// per-landmark cursor (zeroed again by setup_scan). grid (edge chunks, windows, kinds)
+template <int MODE>
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_edges(const __grid_constant__ LocalDev d) {
+  const int w = blockIdx.y;
+  const KindDev& k = d.k[blockIdx.z];
+  const int l0 = k.lm_begin[w];
+  const int idx = blockIdx.x * LOCAL_THREADS + threadIdx.x;
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
-    const int a = k.cls_begin[c][w], b = k.cls_begin[c][w + 1];
-    for (int i = a + tid; i < b; i += LOCAL_THREADS) {
-      const int l = l0 + k.cls_lm[c][i];
+    const int i = k.cls_begin[c][w] + idx;
+    if (i >= k.cls_begin[c][w + 1]) continue;
+    const int l = l0 + k.cls_lm[c][i];
+    if (MODE == 0) {
+      atomicAdd(&k.cursor[l], 1);
+    } else {
       const int pos = k.ebeg[l] + atomicAdd(&k.cursor[l], 1);
       k.src[pos] = (c << 30) | i;
     }
   }
+}
+
+// exclusive scan of the degrees of one (window, kind) -> ebeg; grid (windows, kinds), 1024 threads
+__global__ void __launch_bounds__(1024) setup_scan(const __grid_constant__ LocalDev d) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const KindDev& k = d.k[blockIdx.y];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  if (tid == 0) s_run = edge_base(k, w);
   __syncthreads();
-  // 4. per landmark: insertion sort of its keys (class-major, caller order) + slot table
-  for (int i = tid; i < nl; i += LOCAL_THREADS) {
-    const int a = k.ebeg[l0 + i], n = k.cursor[l0 + i];
-    for (int u = 1; u < n; ++u) {
-      const int key = k.src[a + u];
-      int v = u - 1;
-      while (v >= 0 && k.src[a + v] > key) {
-        k.src[a + v + 1] = k.src[a + v];
-        --v;
-      }
-      k.src[a + v + 1] = key;
-    }
-    uint8_t* sl = k.slot + (size_t)(l0 + i) * d.slot_stride; // (set to SLOT_NONE by a memset before the launch)
-    for (int u = 0; u < n; ++u) {
-      const int key = k.src[a + u];
-      const int c = key >> 30, idx = key & 0x3fffffff;
-      const int fi = s_free_idx[k.cls_pose[c][idx]];
-      if (fi >= 0) {
-        if (sl[fi] != SLOT_NONE) atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
-        sl[fi] = (uint8_t)u;
-      }
-    }
-    // state copy
+  for (int base = 0; base < nl; base += 1024) {
+    const int i = base + tid;
+    const int v = i < nl ? k.cursor[l0 + i] : 0;
+    int x = v;
 #pragma unroll
-    for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l0 + i] = k.lm_in[(size_t)q * k.n_lm + l0 + i];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const int run = s_run;
+    if (i < nl) {
+      k.ebeg[l0 + i] = run + (warp ? s_warp[warp - 1] : 0) + x - v;
+      k.cursor[l0 + i] = 0;
+      if (v > 254) atomicOr(d.err, LOCAL_ERR_DEGREE);
+    }
+    __syncthreads();
+    if (tid == 0) s_run = run + s_warp[31];
+    __syncthreads();
   }
-  __syncthreads();
-  // 5. gather edge records into landmark-major planes
-  for (int e = e0 + tid; e < e0 + ne; e += LOCAL_THREADS) {
-    const int key = k.src[e];
+  if (tid == 0 && w == d.n_windows - 1) k.ebeg[k.n_lm] = k.n_edge;
+}
+
+// per landmark: order its keys (class-major, caller order), slot table (cleared by a memset), state copy
+template <int KIND>
+BA_DEV void setup_landmark(const LocalDev& d, const KindDev& k, int w, int l) {
+  using T = KT<KIND>;
+  const int* free_idx = d.setup_free_idx + d.pose_begin[w];
+  const int a = k.ebeg[l], n = k.cursor[l];
+  for (int u = 1; u < n; ++u) {
+    const int key = k.src[a + u];
+    int v = u - 1;
+    while (v >= 0 && k.src[a + v] > key) {
+      k.src[a + v + 1] = k.src[a + v];
+      --v;
+    }
+    k.src[a + v + 1] = key;
+  }
+  uint8_t* sl = k.slot + (size_t)l * d.slot_stride;
+  for (int u = 0; u < n; ++u) {
+    const int key = k.src[a + u];
     const int c = key >> 30, idx = key & 0x3fffffff;
-    const int cam = k.cls_cam[c] ? k.cls_cam[c][idx] : 0;
-    k.info[e] = k.cls_pose[c][idx] | (cam << 16) | (c << 30);
-    k.lm[e] = k.cls_lm[c][idx];
-    constexpr int MH = T::MD / 2 + (KIND == 0 ? 1 : 0); // mono: 2 of 3 (points), 4 of 8 (lines)
-    const int nm = c ? T::MD : (KIND == 0 ? 2 : 4);
-    (void)MH;
-#pragma unroll
-    for (int q = 0; q < T::MD; ++q)
-      k.meas[(size_t)q * k.n_edge + e] = q < nm ? k.cls_meas[c][(size_t)q * k.cls_n[c] + idx] : 0.0;
-    k.chi2[e] = 0.0;
-    k.lvl[e] = 0;
+    const int fi = free_idx[k.cls_pose[c][idx]];
+    if (fi >= 0) {
+      if (sl[fi] != SLOT_NONE) atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
+      sl[fi] = (uint8_t)u;
+    }
   }
-  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = k.lm_in[(size_t)q * k.n_lm + l];
+}
+
+// grid (landmark chunks, windows, kinds)
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_landmarks(const __grid_constant__ LocalDev d) {
+  const int w = blockIdx.y;
+  const KindDev& k = d.k[blockIdx.z];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  const int i = blockIdx.x * LOCAL_THREADS + threadIdx.x;
+  if (i >= nl) return;
+  if (blockIdx.z == 0) setup_landmark<0>(d, k, w, l0 + i);
+  else setup_landmark<1>(d, k, w, l0 + i);
+}
+
+// gather the edge records into landmark-major planes; grid (edge chunks, windows, kinds)
+template <int KIND>
+BA_DEV void setup_gather_one(const KindDev& k, int e) {
+  using T = KT<KIND>;
+  const int key = k.src[e];
+  const int c = key >> 30, idx = key & 0x3fffffff;
+  const int cam = k.cls_cam[c] ? k.cls_cam[c][idx] : 0;
+  k.info[e] = k.cls_pose[c][idx] | (cam << 16) | (c << 30);
+  k.lm[e] = k.cls_lm[c][idx];
+  const int nm = c ? T::MD : (KIND == 0 ? 2 : 4); // mono: 2 of 3 (points), 4 of 8 (lines)
+#pragma unroll
+  for (int q = 0; q < T::MD; ++q)
+    k.meas[(size_t)q * k.n_edge + e] = q < nm ? k.cls_meas[c][(size_t)q * k.cls_n[c] + idx] : 0.0;
+  k.chi2[e] = 0.0;
+  k.lvl[e] = 0;
+}
+
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_gather(const __grid_constant__ LocalDev d) {
+  const int w = blockIdx.y;
+  const KindDev& k = d.k[blockIdx.z];
+  const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
+  const int i = blockIdx.x * LOCAL_THREADS + threadIdx.x;
+  if (i >= ne) return;
+  if (blockIdx.z == 0) setup_gather_one<0>(k, e0 + i);
+  else setup_gather_one<1>(k, e0 + i);
 }
 
 // 6. pose-major edge lists, one CTA per (pose, window, kind): the CTA scans the window's sorted edge records
@@ -262,31 +322,6 @@ __global__ void __launch_bounds__(128) setup_pose_scan(const __grid_constant__ L
     run += cnt;
   }
   if (w == d.n_windows - 1) k.pbeg[d.n_poses] = k.n_edge;
-}
-
-__global__ void __launch_bounds__(LOCAL_THREADS) local_setup_kernel(const __grid_constant__ LocalDev d) {
-  __shared__ int s_scan[LOCAL_THREADS];
-  const int w = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
-  int* s_free_idx = d.setup_free_idx + p0; // global scratch: windows of the dense-solve path have hundreds of poses
-  if (tid == 0) {
-    int nf = 0;
-    for (int p = 0; p < np; ++p) s_free_idx[p] = d.pose_fixed[p0 + p] ? -1 : nf++;
-  }
-  for (int p = tid; p < np; p += LOCAL_THREADS) { // Twc -> Tcw (g2o_optimization.cc:42)
-    const double pp[3] = {d.pose_twc[p0 + p], d.pose_twc[d.n_poses + p0 + p], d.pose_twc[2 * d.n_poses + p0 + p]};
-    const double qq[4] = {d.pose_twc[3 * d.n_poses + p0 + p], d.pose_twc[4 * d.n_poses + p0 + p],
-                          d.pose_twc[5 * d.n_poses + p0 + p], d.pose_twc[6 * d.n_poses + p0 + p]};
-    const Pose T = pose_from_twc(pp, qq);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) d.pose_tcw[(size_t)q * d.n_poses + p0 + p] = T.q[q];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) d.pose_tcw[(size_t)(4 + q) * d.n_poses + p0 + p] = T.t[q];
-  }
-  __syncthreads();
-  setup_kind<0>(d, d.k[0], w, s_free_idx, s_scan);
-  setup_kind<1>(d, d.k[1], w, s_free_idx, s_scan);
 }
 
 // ------------------------------------------------------------------------------------------------
