@@ -71,6 +71,13 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   double* part;   // [W][C][4] per-chunk partial sums
   int* pair_beg;  // [W][2*Pmax+1] entry offsets: point entries, line entries per pair
   int2* pairs;    // pair entries (e_i, e_j) into the sorted edge arrays
+  // compact list of the pose pairs that can be non-zero: every diagonal pair and every pair with entries
+  // (on any rank). kb_schur_reduce / kb_solve / kb_assemble_dense run over this list, and hs_part is indexed
+  // by list position -- a 2000-keyframe window has 2.0 M pairs of which 3 % are non-empty.
+  int* ne_list;    // [W][Pmax] pair index, ascending
+  int* n_ne;       // [W]
+  int* ne_flag;    // [W][Pmax] scratch: 1 = keep
+  int* diag_pos;   // [NF] list position of the diagonal pair of a free pose
   int2* pairs_tmp; // scratch of the same size (landmark-driven builder of large windows), may be null
   int* pair_cursor; // [W][2*Pmax] scratch of that builder
   const long long* pair_base; // [W+1] region of each window inside `pairs`
@@ -370,6 +377,69 @@ __global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ Loca
     for (int i = lane; i < n; i += 32) seg[i] = tmp[i];
     __syncwarp();
   }
+}
+
+// keep-flag of every pair of a window: diagonal, or with entries; grid (ceil(Pmax / 256), windows)
+__global__ void __launch_bounds__(256) kb_pairs_flag(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= b.Pmax) return;
+  const int nf = b.ws[w].nf;
+  int keep = 0;
+  if (p < nf * (nf + 1) / 2) {
+    const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
+    int fi, fj;
+    pair_decode(p, nf, fi, fj);
+    keep = (fi == fj || pb[2] - pb[0] > 0) ? 1 : 0;
+  }
+  b.ne_flag[(size_t)w * b.Pmax + p] = keep;
+}
+
+// flags -> ascending compact list (CTA scan in chunks of 1024 with a running total); grid = windows
+__global__ void __launch_bounds__(1024) kb_pairs_compact(const __grid_constant__ LocalDev d,
+                                                         const __grid_constant__ BatchDev b) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nf = b.ws[w].nf, f0 = b.nf_begin[w];
+  const int n = nf * (nf + 1) / 2;
+  const int* flag = b.ne_flag + (size_t)w * b.Pmax;
+  int* list = b.ne_list + (size_t)w * b.Pmax;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int p = base + tid;
+    const int v = p < n ? (flag[p] ? 1 : 0) : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const int run = s_run;
+    if (v) {
+      const int pos = run + (warp ? s_warp[warp - 1] : 0) + x - 1;
+      list[pos] = p;
+      int fi, fj;
+      pair_decode(p, nf, fi, fj);
+      if (fi == fj) b.diag_pos[f0 + fi] = pos;
+    }
+    __syncthreads();
+    if (tid == 0) s_run = run + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) b.n_ne[w] = s_run;
 }
 
 // largest free-pose index distance of a pose pair that shares a landmark (dense path: is the reduced
@@ -884,12 +954,14 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   // every pair that contains its pose) are fetched from HBM once and then hit in L2
   __shared__ __align__(16) double2 ring[RED_RING];
   const int lane = threadIdx.x & 31;
-  const int w = blockIdx.y, p = blockIdx.x;
+  const int w = blockIdx.y, li = blockIdx.x; // li: position in the compact pair list
   const WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
-  if (b.global && p == 0 && lane == 0) b.hs_part_w[(size_t)b.Pmax * 42] = s.prep_fail ? 1.0 : 0.0;
+  const int n_ne = b.n_ne[w];
+  if (b.global && li == 0 && lane == 0) b.hs_part_w[(size_t)n_ne * 42] = s.prep_fail ? 1.0 : 0.0;
+  if (li >= n_ne) return;
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
   const int nf = s.nf;
-  if (p >= nf * (nf + 1) / 2) return;
   int fi, fj;
   pair_decode(p, nf, fi, fj);
   const int f0 = b.nf_begin[w];
@@ -903,7 +975,7 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   schur_pair_entries<1>(d.k[1], w, b.pairs + pb[1], pb[2] - pb[1], diag, lane, acc, ring);
   warp_transpose_reduce64(acc, lane);
   if (2 * lane < 42) {
-    double* out = b.hs_part_w + ((size_t)w * b.Pmax + p) * 42 + 2 * lane;
+    double* out = b.hs_part_w + ((size_t)w * b.Pmax + li) * 42 + 2 * lane;
     out[0] = acc[0];
     out[1] = acc[1];
   }
@@ -967,15 +1039,19 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   double* sc_part = xs + n; // [nf] pose part of the LM scale
   __shared__ int s_ok;
   const double lambda = s.lambda;
-  // assemble upper blocks
-  const int npairs = nf * (nf + 1) / 2;
-  for (int idx = tid; idx < npairs * 36; idx += blockDim.x) {
-    const int p = idx / 36, rc = idx % 36, r = rc / 6, c = rc % 6;
+  // assemble upper blocks: zero background, then the pairs of the compact list
+  for (int idx = tid; idx < n * n; idx += blockDim.x) Hs[idx] = 0.0;
+  __syncthreads();
+  const int n_ne = b.n_ne[w];
+  const int* list = b.ne_list + (size_t)w * b.Pmax;
+  for (int idx = tid; idx < n_ne * 36; idx += blockDim.x) {
+    const int li = idx / 36, rc = idx % 36, r = rc / 6, c = rc % 6;
+    const int p = list[li];
     int fi, fj;
     pair_decode(p, nf, fi, fj);
     const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
     if (si < 0 || sj < 0) continue;
-    double v = -b.hs_part[((size_t)w * b.Pmax + p) * 42 + rc];
+    double v = -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
     if (fi == fj) {
       const int rr = r < c ? r : c, cc = r < c ? c : r;
       v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? lambda : 0.0);
@@ -986,8 +1062,8 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     const int fi = idx / 6, r = idx % 6;
     const int si = b.sys_idx[f0 + fi];
     if (si < 0) continue;
-    const int p = pair_index(fi, fi, nf);
-    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + p) * 42 + 36 + r];
+    const int li = b.diag_pos[f0 + fi];
+    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r];
   }
   __syncthreads();
   __shared__ int s_chol;
@@ -1042,22 +1118,22 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
 }
 
 // Dense-solve path, K4 split in three: assemble -> cuSOLVER potrf / potrs (host-enqueued) -> pose update.
-// grid (Pmax, W), 64 threads: one CTA per pose pair block.
+// grid (longest compact pair list, W), 64 threads: one CTA per pose pair block.
 __global__ void __launch_bounds__(64) kb_assemble_dense(const __grid_constant__ LocalDev d,
                                                         const __grid_constant__ BatchDev b) {
-  const int w = blockIdx.y, p = blockIdx.x, tid = threadIdx.x;
+  const int w = blockIdx.y, li = blockIdx.x, tid = threadIdx.x; // li: position in the compact pair list
   const WinState& s = b.ws[w];
-  if (s.stage != STAGE_NEED_TRIAL) return;
+  if (s.stage != STAGE_NEED_TRIAL || li >= b.n_ne[w]) return;
   const int nf = s.nf;
-  if (p >= nf * (nf + 1) / 2) return;
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
   int fi, fj;
   pair_decode(p, nf, fi, fj);
   const int f0 = b.nf_begin[w];
   const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
   if (si < 0 || sj < 0) return;
   const int n = 6 * s.n_sys;
-  double* Hs = b.dense_H + b.dense_off[w];
-  const double* part = b.hs_part + ((size_t)w * b.Pmax + p) * 42;
+  double* Hs = b.dense_H + b.dense_off[w]; // (zeroed by the host before this launch: pairs off the list are zero blocks)
+  const double* part = b.hs_part + ((size_t)w * b.Pmax + li) * 42;
   if (tid < 36) {
     const int r = tid / 6, c = tid % 6;
     double v = -part[tid];
@@ -1080,7 +1156,7 @@ __global__ void __launch_bounds__(256) kb_post_solve(const __grid_constant__ Loc
   WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const int nf = s.nf, f0 = b.nf_begin[w], p0 = d.pose_begin[w];
-  const bool prep_fail = b.global ? b.hs_part[(size_t)b.Pmax * 42] != 0.0 : s.prep_fail != 0; // any rank's landmarks
+  const bool prep_fail = b.global ? b.hs_part[(size_t)b.n_ne[w] * 42] != 0.0 : s.prep_fail != 0; // any rank's landmarks
   const bool ok = (s.n_sys == 0 || b.dense_info[w] == 0) && !prep_fail; // potrf info > 0 <=> a pivot <= 0 (§9.11)
   const double lambda = s.lambda;
   const double* xs = b.dense_b + (size_t)6 * f0;

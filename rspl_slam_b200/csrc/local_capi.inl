@@ -315,6 +315,10 @@ int batched_prepare(RsplBaContext* c) {
   const size_t o_pairs = a.take(sizeof(int2) * (size_t)(n_pairs + 1));
   // landmark-driven pair-list builder of large windows: a second entry buffer and per-pair cursors
   const bool big_pairs = NFmax > ba::PAIRS_LM_MIN_NF;
+  const size_t o_ne_list = a.take(sizeof(int) * (size_t)W * (Pmax > 0 ? Pmax : 1));
+  const size_t o_ne_flag = a.take(sizeof(int) * (size_t)W * (Pmax > 0 ? Pmax : 1));
+  const size_t o_n_ne = a.take(sizeof(int) * W);
+  const size_t o_diag_pos = a.take(sizeof(int) * (NF + 1));
   const size_t o_pairs_tmp = big_pairs ? a.take(sizeof(int2) * (size_t)(n_pairs + 1)) : 0;
   const size_t o_cursor = big_pairs ? a.take(sizeof(int) * (size_t)W * 2 * (Pmax > 0 ? Pmax : 1)) : 0;
   const size_t o_pbase = a.take(sizeof(long long) * (W + 1));
@@ -353,6 +357,10 @@ int batched_prepare(RsplBaContext* c) {
   b.part = (double*)(base + o_part);
   b.pair_beg = (int*)(base + o_pbeg);
   b.pairs = (int2*)(base + o_pairs);
+  b.ne_list = (int*)(base + o_ne_list);
+  b.ne_flag = (int*)(base + o_ne_flag);
+  b.n_ne = (int*)(base + o_n_ne);
+  b.diag_pos = (int*)(base + o_diag_pos);
   b.pairs_tmp = big_pairs ? (int2*)(base + o_pairs_tmp) : nullptr;
   b.pair_cursor = big_pairs ? (int*)(base + o_cursor) : nullptr;
   b.pair_base = (const long long*)(base + o_pbase);
@@ -416,6 +424,19 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     LAUNCH(PC_PAIRS, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
   }
   CU_TRY(c, cudaGetLastError());
+  // compact list of the pairs that can be non-zero (union over the ranks in global mode)
+  LAUNCH(PC_PAIRS, ba::kb_pairs_flag, dim3((b.Pmax + 255) / 256, W), 256, 0, d, b);
+  if (global) {
+    rc = comm_all_reduce(c, b.ne_flag, b.ne_flag, (size_t)b.Pmax, kNcclInt32, kNcclMax);
+    if (rc != RSPL_BA_OK) return rc;
+  }
+  LAUNCH(PC_PAIRS, ba::kb_pairs_compact, W, 1024, 0, d, b);
+  std::vector<int> n_ne_host(W, 0);
+  CU_TRY(c, cudaMemcpyAsync(n_ne_host.data(), b.n_ne, sizeof(int) * W, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  int n_ne_max = 1;
+  for (int w = 0; w < W; ++w) n_ne_max = n_ne_host[w] > n_ne_max ? n_ne_host[w] : n_ne_max;
+  const dim3 g_ne(n_ne_max, W);
   if (dense) {
     // which pose pairs share landmarks: a banded pattern allows the block-tridiagonal factorisation
     std::vector<int> band(W, 0);
@@ -454,16 +475,20 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
     if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
-    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_pair1, 32, 0, d, b);
+    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
     if (!dense) {
       LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
     } else {
       if (global) { // rank-local Schur complement pieces -> sum over ranks (+ the Cholesky-failure flag in the tail)
         ProfScope ps_(c, PC_COLLECTIVE);
         if (coll_rc == RSPL_BA_OK)
-          coll_rc = comm_all_reduce(c, b.hs_part_w, b.hs_part, (size_t)42 * b.Pmax + 8, kNcclFloat64, kNcclSum);
+          coll_rc = comm_all_reduce(c, b.hs_part_w, b.hs_part, (size_t)42 * n_ne_host[0] + 1, kNcclFloat64, kNcclSum);
       }
-      LAUNCH(PC_ASSEMBLE, ba::kb_assemble_dense, g_pair1, 64, 0, d, b);
+      {
+        ProfScope ps_(c, PC_ASSEMBLE);
+        if (cudaMemsetAsync(dl.H, 0, sizeof(double) * (size_t)dl.total, s) != cudaSuccess) dense_rc = RSPL_BA_ERR_CUDA;
+      }
+      LAUNCH(PC_ASSEMBLE, ba::kb_assemble_dense, g_ne, 64, 0, d, b);
       {
         ProfScope ps_(c, PC_SOLVE);
         dense_rc = dense_factor_solve(c, dl, n_sys_host);
