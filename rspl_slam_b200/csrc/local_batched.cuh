@@ -459,61 +459,64 @@ __global__ void __launch_bounds__(256) kb_pair_band(const __grid_constant__ Loca
 // ------------------------------------------------------------------------------------------------
 // pass begin: active sets (§9.12), reduced-system indices
 // ------------------------------------------------------------------------------------------------
-// (active edges per pose are counted into pact_w; the owner of pact is kb_begin_pass phase 1)
+// Active edges per pose are counted into pact_w (zeroed by the host), one thread per landmark;
+// grid (Cp + Cl, windows). Inactive landmarks get their Z blocks and y zeroed: kb_schur_reduce and
+// kb_backsub read them for every listed edge without testing `act`.
 template <int KIND>
-BA_DEV void mark_active_b(const LocalDev& d, const BatchDev& b, const KindDev& k, int w) {
-  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+BA_DEV void mark_active_one(const LocalDev& d, const BatchDev& b, const KindDev& k, int w, int l) {
   const int p0 = d.pose_begin[w];
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-    const int l = l0 + i;
-    int any = 0;
-    for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e) {
-      if (k.lvl[e]) continue;
-      any = 1;
-      atomicAdd(&b.pact_w[p0 + (k.info[e] & 0xffff)], 1);
-    }
-    k.act[l] = (uint8_t)any;
-    if (!any) { // kb_schur_reduce / kb_backsub read Z and y of every listed edge without testing `act`
-      for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e)
+  int any = 0;
+  for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e) {
+    if (k.lvl[e]) continue;
+    any = 1;
+    atomicAdd(&b.pact_w[p0 + (k.info[e] & 0xffff)], 1);
+  }
+  k.act[l] = (uint8_t)any;
+  if (!any) {
+    for (int e = k.ebeg[l]; e < k.ebeg[l + 1]; ++e)
 #pragma unroll
-        for (int q = 0; q < ZBlk<KIND>::N; ++q) k.Z[(size_t)e * ZBlk<KIND>::N + q] = 0.0;
+      for (int q = 0; q < ZBlk<KIND>::N; ++q) k.Z[(size_t)e * ZBlk<KIND>::N + q] = 0.0;
 #pragma unroll
-      for (int q = 0; q < KT<KIND>::LD; ++q) k.y[(size_t)q * k.n_lm + l] = 0.0;
-    }
+    for (int q = 0; q < KT<KIND>::LD; ++q) k.y[(size_t)q * k.n_lm + l] = 0.0;
   }
 }
 
-__global__ void __launch_bounds__(256) kb_begin_pass(const __grid_constant__ LocalDev d,
+__global__ void __launch_bounds__(BT) kb_mark_active(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, c = blockIdx.x;
+  if (c < b.Cp) {
+    const KindDev& k = d.k[0];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = c * BT + threadIdx.x;
+    if (i < nl) mark_active_one<0>(d, b, k, w, l0 + i);
+  } else {
+    const KindDev& k = d.k[1];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = (c - b.Cp) * BT + threadIdx.x;
+    if (i < nl) mark_active_one<1>(d, b, k, w, l0 + i);
+  }
+}
+
+// reduced-system indices and LM state of the pass from the (all-reduced, in global mode) counts; one thread per window
+__global__ void __launch_bounds__(128) kb_begin_pass(const __grid_constant__ LocalDev d,
                                                      const __grid_constant__ BatchDev b,
-                                                     const __grid_constant__ LocalOpt o, int pass, int phase) {
-  // phase 0: count the active edges per pose (rank-local); phase 1: reduced-system indices and LM state
-  // from the (all-reduced) counts; phase 2: both, for the single-GPU paths
-  const int w = blockIdx.x, tid = threadIdx.x;
-  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
-  if (phase != 1) {
-    for (int p = tid; p < np; p += blockDim.x) b.pact_w[p0 + p] = 0;
-    __syncthreads();
-    mark_active_b<0>(d, b, d.k[0], w);
-    mark_active_b<1>(d, b, d.k[1], w);
-    __syncthreads();
-  }
-  if (phase == 0) return;
-  if (tid == 0) {
-    WinState& s = b.ws[w];
-    const int f0 = b.nf_begin[w];
-    int nsys = 0;
-    for (int fi = 0; fi < s.nf; ++fi) b.sys_idx[f0 + fi] = b.pact[p0 + b.pose_of[f0 + fi]] > 0 ? nsys++ : -1;
-    s.n_sys = nsys;
-    s.pass = pass;
-    s.it = 0;
-    s.qmax = 0;
-    s.lambda = 0;
-    s.ni = 2;
-    s.robust = pass == 0 ? 1 : 0;
-    s.iters = o.iters[pass];
-    s.restore = 0;
-    s.stage = s.iters > 0 ? STAGE_NEED_LIN : STAGE_DONE;
-  }
+                                                     const __grid_constant__ LocalOpt o, int pass) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.n_windows) return;
+  const int p0 = d.pose_begin[w];
+  WinState& s = b.ws[w];
+  const int f0 = b.nf_begin[w];
+  int nsys = 0;
+  for (int fi = 0; fi < s.nf; ++fi) b.sys_idx[f0 + fi] = b.pact[p0 + b.pose_of[f0 + fi]] > 0 ? nsys++ : -1;
+  s.n_sys = nsys;
+  s.pass = pass;
+  s.it = 0;
+  s.qmax = 0;
+  s.lambda = 0;
+  s.ni = 2;
+  s.robust = pass == 0 ? 1 : 0;
+  s.iters = o.iters[pass];
+  s.restore = 0;
+  s.stage = s.iters > 0 ? STAGE_NEED_LIN : STAGE_DONE;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -531,17 +531,17 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     }
   } graph_guard{gexec};
   for (int pass = 0; pass < 2; ++pass) {
-    if (global) { // a pose is in the reduced system if ANY rank holds an active edge of it
-      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 0);
+    // active-edge counts per pose; in global mode a pose is in the reduced system if ANY rank holds an active edge of it
+    CU_TRY(c, cudaMemsetAsync(b.pact_w, 0, sizeof(int) * (size_t)c->l_np, s));
+    if (b.C) LAUNCH(PC_CONTROL, ba::kb_mark_active, g_lm, ba::BT, 0, d, b);
+    if (global) {
       {
         ProfScope ps_(c, PC_COLLECTIVE);
         coll_rc = comm_all_reduce(c, b.pact_w, b.pact, (size_t)c->l_np, kNcclInt32, kNcclSum);
       }
       if (coll_rc != RSPL_BA_OK) return coll_rc;
-      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 1);
-    } else {
-      LAUNCH(PC_CONTROL, ba::kb_begin_pass, W, 256, 0, d, b, lo, pass, 2);
     }
+    LAUNCH(PC_CONTROL, ba::kb_begin_pass, g_win, 128, 0, d, b, lo, pass);
     if (dense) { // the host needs the system sizes of this pass for the library calls
       std::vector<ba::WinState> ws(W);
       CU_TRY(c, cudaMemcpyAsync(ws.data(), b.ws, sizeof(ba::WinState) * W, cudaMemcpyDeviceToHost, s));
