@@ -62,3 +62,21 @@ def test_product_does_not_import_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inl")):
                     src = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "liboracle" not in src and "import orc" not in src and "from oracle" not in src, f
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) needs no GPU: one JSON line with the
+    keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "point+line BA edges linearized/sec" and line["unit"] == "edges/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

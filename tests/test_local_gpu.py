@@ -196,3 +196,18 @@ def test_local_large_window_dense_reduced_solve(gpu_ctx, orc, local_path):
     a = batch.pose_begin[1]
     assert np.array_equal(solo.pose_twc, res.pose_twc[:, a:])
     assert np.array_equal(solo.sp_inlier, res.sp_inlier[batch.stereo_pt_begin[1]:])
+
+
+def test_local_degenerate_windows(gpu_ctx, orc, local_path):
+    """All poses fixed (nothing in the reduced system: only the landmarks move), a single free pose, and a
+    window whose only constraints are lines -- each beside a normal window in the same batch."""
+    a = synth.make_local_problem(synth.config_seed(1, 230), n_kf=4, n_points=120, n_lines=12)
+    a.pose_fixed[:] = 1
+    b = synth.make_local_problem(synth.config_seed(1, 231), n_kf=5, n_points=150, n_lines=15)
+    b.pose_fixed[:] = 1
+    b.pose_fixed[2] = 0
+    c = synth.make_local_problem(synth.config_seed(1, 232), n_kf=6, n_points=200, n_lines=20)
+    probs = [a, b, c]
+    batch = LocalBatch.from_problems(probs)
+    res = gpu_ctx.local_batch(batch)
+    _check(orc, probs, batch, res)
