@@ -78,15 +78,9 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
       n_cls[k][cl] = kh[k].cls_begin[cl][W];
       if (n_cls[k][cl] && (!kh[k].cls_pose[cl] || !kh[k].cls_lm[cl] || !kh[k].cls_meas[cl]))
         return fail(c, RSPL_BA_ERR_INVALID, "local batch: null edge array");
-      if (n_cls[k][cl]) {
-        if (!indices_ok(kh[k].cls_pose[cl], kh[k].cls_begin[cl], in->pose_begin, W) ||
-            !indices_ok(kh[k].cls_lm[cl], kh[k].cls_begin[cl], kh[k].lm_begin, W))
-          return fail(c, RSPL_BA_ERR_INVALID, "local batch: edge references a vertex outside its window");
-        if (!cams_ok(kh[k].cls_cam[cl], n_cls[k][cl], in->n_cameras))
-          return fail(c, RSPL_BA_ERR_INVALID, "local batch: id_camera out of range");
-        if (in->n_cameras > 1 && !kh[k].cls_cam[cl])
-          return fail(c, RSPL_BA_ERR_INVALID, "local batch: several cameras but no per-edge camera index");
-      }
+      if (n_cls[k][cl] && in->n_cameras > 1 && !kh[k].cls_cam[cl])
+        return fail(c, RSPL_BA_ERR_INVALID, "local batch: several cameras but no per-edge camera index");
+      // (the O(edges) index checks run below, while the copies are in flight)
     }
   }
   // per-window limits of the shared-memory path
@@ -120,7 +114,10 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
         const int l0 = kh[k].lm_begin[w], nl = kh[k].lm_begin[w + 1] - l0;
         deg.assign(nl > 0 ? nl : 1, 0);
         for (int cl = 0; cl < 2; ++cl)
-          for (int i = kh[k].cls_begin[cl][w]; i < kh[k].cls_begin[cl][w + 1]; ++i) deg[kh[k].cls_lm[cl][i]]++;
+          for (int i = kh[k].cls_begin[cl][w]; i < kh[k].cls_begin[cl][w + 1]; ++i) {
+            const int l = kh[k].cls_lm[cl][i]; // (range-checked here: the index validation runs later)
+            if ((unsigned)l < (unsigned)nl) deg[l]++;
+          }
         for (int l = 0; l < nl; ++l) exact += (long long)deg[l] * (deg[l] + 1) / 2;
       }
       if (exact < cap) cap = exact;
@@ -207,7 +204,20 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     }
   }
 #undef H2D
+  // index validation on the host while the DMA engine works (a rejected batch has been copied for nothing,
+  // but is never solved: local_uploaded stays false)
+  const char* bad = nullptr;
+  for (int k = 0; k < 2 && !bad; ++k)
+    for (int cl = 0; cl < 2 && !bad; ++cl) {
+      if (!n_cls[k][cl]) continue;
+      if (!indices_ok(kh[k].cls_pose[cl], kh[k].cls_begin[cl], in->pose_begin, W) ||
+          !indices_ok(kh[k].cls_lm[cl], kh[k].cls_begin[cl], kh[k].lm_begin, W))
+        bad = "local batch: edge references a vertex outside its window";
+      else if (!cams_ok(kh[k].cls_cam[cl], n_cls[k][cl], in->n_cameras))
+        bad = "local batch: id_camera out of range";
+    }
   CU_TRY(c, cudaStreamSynchronize(s));
+  if (bad) return fail(c, RSPL_BA_ERR_INVALID, "%s", bad);
 
   ba::LocalDev& d = c->ld;
   d.n_windows = W;
