@@ -143,7 +143,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const int slot_stride = (max_free + 3) & ~3;
   struct KOff {
     size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
-    size_t meas, info, lm, src, chi2, lvl, Wb, Zb, ebeg, cursor, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
+    size_t meas, info, lm, src, chi2, lvl, Wb, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
   } ko[2];
   for (int k = 0; k < 2; ++k) {
     const int LD = k ? 4 : 3, SD = k ? 6 : 3, MD = k ? 8 : 3, HD = k ? 10 : 6, WD = 6 * LD;
@@ -169,6 +169,8 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     o.Zb = a.take(sizeof(double) * WD * ne);
     o.ebeg = a.take(sizeof(int) * (nl + 1));
     o.cursor = a.take(sizeof(int) * nl);
+    o.newidx = a.take(sizeof(int) * nl);
+    o.orig = a.take(sizeof(int) * nl);
     o.x = a.take(sizeof(double) * SD * nl);
     o.xb = a.take(sizeof(double) * SD * nl);
     o.H = a.take(sizeof(double) * HD * nl);
@@ -260,6 +262,8 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     kd.Z = (double*)(base + o.Zb);
     kd.ebeg = (int*)(base + o.ebeg);
     kd.cursor = (int*)(base + o.cursor);
+    kd.newidx = (int*)(base + o.newidx);
+    kd.orig = (int*)(base + o.orig);
     kd.x = (double*)(base + o.x);
     kd.xb = (double*)(base + o.xb);
     kd.H = (double*)(base + o.H);
@@ -632,6 +636,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
     const dim3 g_l((max_lm + T - 1) / T > 0 ? (max_lm + T - 1) / T : 1, W, 2);
     ba::setup_poses<<<W, T, 0, c->stream>>>(c->ld);
     ba::setup_edges<0><<<g_e, T, 0, c->stream>>>(c->ld);
+    ba::setup_order<<<dim3(W, 2), T, 0, c->stream>>>(c->ld);
     ba::setup_scan<<<dim3(W, 2), 1024, 0, c->stream>>>(c->ld);
     ba::setup_edges<1><<<g_e, T, 0, c->stream>>>(c->ld);
     ba::setup_landmarks<<<g_l, T, 0, c->stream>>>(c->ld);
@@ -641,7 +646,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
     ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, c->stream>>>(c->ld);
     ba::setup_pose_lists<1><<<g_pl, T, 0, c->stream>>>(c->ld);
   }
-  c->launches += 9;
+  c->launches += 10;
   CU_TRY(c, cudaGetLastError());
   // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
   // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent

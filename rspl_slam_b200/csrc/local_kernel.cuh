@@ -69,6 +69,11 @@ struct KindDev {
   double* Z;     // [n_edge][WD]
   int* ebeg;     // [n_lm + 1] offsets into the sorted edge arrays
   int* cursor;   // [n_lm] scratch
+  // Internal landmark numbering: inside a window the landmarks are ordered by DESCENDING degree (stable), so the
+  // 32 landmarks a warp of the thread-per-landmark kernels works on have (almost) the same number of edges and
+  // its lanes run the same trip count. newidx / orig map the caller's window-local index to the internal one and back.
+  int* newidx;   // [n_lm] caller index -> internal index (window-local), stored at lm_begin[w] + caller index
+  int* orig;     // [n_lm] internal index -> caller index
   double* x;     // [SD][n_lm] state
   double* xb;    // [SD][n_lm] LM backup
   double* H;     // [HD][n_lm] upper triangle of Hll
@@ -146,13 +151,61 @@ __global__ void __launch_bounds__(LOCAL_THREADS) setup_edges(const __grid_consta
   for (int c = 0; c < 2; ++c) {
     const int i = k.cls_begin[c][w] + idx;
     if (i >= k.cls_begin[c][w + 1]) continue;
-    const int l = l0 + k.cls_lm[c][i];
     if (MODE == 0) {
-      atomicAdd(&k.cursor[l], 1);
+      atomicAdd(&k.cursor[l0 + k.cls_lm[c][i]], 1); // by caller index
     } else {
+      const int l = l0 + k.newidx[l0 + k.cls_lm[c][i]]; // internal index
       const int pos = k.ebeg[l] + atomicAdd(&k.cursor[l], 1);
       k.src[pos] = (c << 30) | i;
     }
+  }
+}
+
+// internal landmark order of one (window, kind): stable counting sort by descending degree. Degrees come in
+// `cursor` (caller index); they leave in `ebeg` (internal index) for setup_scan. grid (windows, kinds), 256 threads
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_order(const __grid_constant__ LocalDev d) {
+  __shared__ int s_start[256]; // first internal index of a degree bucket, advanced chunk by chunk
+  __shared__ int s_deg[LOCAL_THREADS];
+  const int w = blockIdx.x, tid = threadIdx.x;
+  const KindDev& k = d.k[blockIdx.y];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  s_start[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nl; i += LOCAL_THREADS) {
+    const int dg = k.cursor[l0 + i];
+    atomicAdd(&s_start[dg < 255 ? dg : 255], 1); // histogram (integer: deterministic)
+  }
+  __syncthreads();
+  if (tid == 0) { // bucket starts, largest degree first
+    int run = 0;
+    for (int b = 255; b >= 0; --b) {
+      const int cnt = s_start[b];
+      s_start[b] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+  for (int base = 0; base < nl; base += LOCAL_THREADS) {
+    const int i = base + tid;
+    const int dg = i < nl ? k.cursor[l0 + i] : -1;
+    const int bk = dg < 255 ? dg : 255;
+    s_deg[tid] = dg < 0 ? -1 : bk;
+    __syncthreads();
+    int rank = 0, total = 0;
+    if (dg >= 0) {
+      for (int t2 = 0; t2 < LOCAL_THREADS; ++t2) {
+        const int same = s_deg[t2] == bk ? 1 : 0;
+        total += same;
+        rank += t2 < tid ? same : 0;
+      }
+      const int pos = s_start[bk] + rank;
+      k.newidx[l0 + i] = pos;
+      k.orig[l0 + pos] = i;
+      k.ebeg[l0 + pos] = dg;
+    }
+    __syncthreads();
+    if (dg >= 0 && rank == total - 1) s_start[bk] += total; // the last landmark of the bucket in this chunk advances it
+    __syncthreads();
   }
 }
 
@@ -167,7 +220,7 @@ __global__ void __launch_bounds__(1024) setup_scan(const __grid_constant__ Local
   __syncthreads();
   for (int base = 0; base < nl; base += 1024) {
     const int i = base + tid;
-    const int v = i < nl ? k.cursor[l0 + i] : 0;
+    const int v = i < nl ? k.ebeg[l0 + i] : 0; // degree by internal index (setup_order), scanned in place
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -224,8 +277,9 @@ BA_DEV void setup_landmark(const LocalDev& d, const KindDev& k, int w, int l) {
       sl[fi] = (uint8_t)u;
     }
   }
+  const int lo = k.lm_begin[w] + k.orig[l]; // the caller's landmark
 #pragma unroll
-  for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = k.lm_in[(size_t)q * k.n_lm + l];
+  for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = k.lm_in[(size_t)q * k.n_lm + lo];
 }
 
 // grid (landmark chunks, windows, kinds)
@@ -241,13 +295,13 @@ __global__ void __launch_bounds__(LOCAL_THREADS) setup_landmarks(const __grid_co
 
 // gather the edge records into landmark-major planes; grid (edge chunks, windows, kinds)
 template <int KIND>
-BA_DEV void setup_gather_one(const KindDev& k, int e) {
+BA_DEV void setup_gather_one(const KindDev& k, int l0, int e) {
   using T = KT<KIND>;
   const int key = k.src[e];
   const int c = key >> 30, idx = key & 0x3fffffff;
   const int cam = k.cls_cam[c] ? k.cls_cam[c][idx] : 0;
   k.info[e] = k.cls_pose[c][idx] | (cam << 16) | (c << 30);
-  k.lm[e] = k.cls_lm[c][idx];
+  k.lm[e] = k.newidx[l0 + k.cls_lm[c][idx]];
   const int nm = c ? T::MD : (KIND == 0 ? 2 : 4); // mono: 2 of 3 (points), 4 of 8 (lines)
 #pragma unroll
   for (int q = 0; q < T::MD; ++q)
@@ -262,8 +316,9 @@ __global__ void __launch_bounds__(LOCAL_THREADS) setup_gather(const __grid_const
   const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
   const int i = blockIdx.x * LOCAL_THREADS + threadIdx.x;
   if (i >= ne) return;
-  if (blockIdx.z == 0) setup_gather_one<0>(k, e0 + i);
-  else setup_gather_one<1>(k, e0 + i);
+  const int l0 = k.lm_begin[w];
+  if (blockIdx.z == 0) setup_gather_one<0>(k, l0, e0 + i);
+  else setup_gather_one<1>(k, l0, e0 + i);
 }
 
 // 6. pose-major edge lists, one CTA per (pose, window, kind): the CTA scans the window's sorted edge records
@@ -1051,7 +1106,7 @@ BA_DEV void write_landmarks(const KindDev& k, int w) {
   const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
   for (int i = threadIdx.x; i < nl; i += LOCAL_THREADS)
 #pragma unroll
-    for (int q = 0; q < T::SD; ++q) k.lm_out[(size_t)q * k.n_lm + l0 + i] = k.x[(size_t)q * k.n_lm + l0 + i];
+    for (int q = 0; q < T::SD; ++q) k.lm_out[(size_t)q * k.n_lm + l0 + k.orig[l0 + i]] = k.x[(size_t)q * k.n_lm + l0 + i];
 }
 
 // One LM pass = SparseOptimizer::initializeOptimization(0) + optimize(iters) (§9.9, §9.12)
