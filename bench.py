@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — throughput of the BA hot path on B200 (metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2p|c4|c5] [--impl ours|reference]
 
 Workloads (BASELINE.json configs; synthetic inputs of rspl_slam_b200/synth.py, seeds of SURVEY §8d)
   c2 (default, configs[1]): batched pose-only FrameOptimization, 4096 frames x 400 stereo points
@@ -39,7 +39,16 @@ UNIT = "edges/s"
 # SURVEY §8(d) contract figures (algorithmic bytes)
 BYTES_POSE_ONLY_STEREO = 60  # per stereo edge per evaluation: 24 meas + 24 Xw + 4 flag + 8 chi2
 BYTES_POSE_ONLY_MONO = 52
-C2_FRAMES, C2_POINTS = 4096, 400
+BYTES_POSE_ONLY_STEREO_LINE = 124  # 64 meas + 48 world line + 4 flag + 8 chi2 (same accounting, line extension)
+BYTES_POSE_ONLY_MONO_LINE = 92
+C2_FRAMES, C2_POINTS, C2_LINES = 4096, 400, 60
+
+
+def _c2_lines(args):
+    """BASELINE configs[1] names 400 stereo points + 60 lines per frame. The reference's FrameOptimization takes no
+    lines (g2o_optimization.cc:284-285), so `c2p` (points only) is its parity path and `c2` adds the 60 lines as
+    constraints on fixed lines (SURVEY 8a note / 8d)."""
+    return 0 if args.workload == "c2p" else args.frame_lines
 
 
 def _peaks():
@@ -117,10 +126,11 @@ def run_reference(args):
     from rspl_slam_b200 import synth
     threads = orc.max_threads()
     t_all, edges_all, iters_all = [], 0, 0
-    if args.workload == "c2":
+    if args.workload in ("c2", "c2p"):
+        nl = _c2_lines(args)
         sample = min(C2_FRAMES, max(threads * 24, 64))
-        desc = f"{sample} of {C2_FRAMES} frames per step (400 stereo pts, 4x10 LM), {threads} threads, one frame per thread"
-        base = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS) for i in range(sample)]
+        desc = f"{sample} of {C2_FRAMES} frames per step (400 stereo pts + {nl} lines, 4x10 LM), {threads} threads, one frame per thread"
+        base = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS, n_lines=nl) for i in range(sample)]
         for step in range(args.warmup + args.steps):
             probs = [p.copy() for p in base]
             t0 = time.perf_counter()
@@ -130,7 +140,7 @@ def run_reference(args):
                 t_all.append(dt)
                 edges_all += sum(s["edges_linearized"] for s in st)
                 iters_all += sum(sum(s["iters"]) for s in st)
-        workload = f"C2 batched pose-only FrameOptimization ({C2_FRAMES} frames x {C2_POINTS} stereo pts per GPU)"
+        workload = f"C2 batched pose-only FrameOptimization ({C2_FRAMES} frames x ({C2_POINTS} stereo pts + {nl} lines) per GPU)"
     elif args.workload == "c5":
         # one problem: the oracle is single-threaded per problem and factorises densely, so the bounded sample is a
         # scaled-down problem of the same generator
@@ -210,14 +220,17 @@ def run_ours(args):
     opt = capi.make_options()
 
     # ---- inputs: this rank's shard of independent units (weak scaling: fixed work per GPU)
-    if args.workload == "c2":
+    if args.workload in ("c2", "c2p"):
         n_units = args.frames
-        batch = synth.make_frame_batch(2, n_units, first_instance=rank * n_units, n_points=C2_POINTS)
+        nl = _c2_lines(args)
+        batch = synth.make_frame_batch(2, n_units, first_instance=rank * n_units, n_points=C2_POINTS, n_lines=nl)
         upload, solve = ctx.frame_batch_upload, ctx.frame_batch_solve
         out = ctx.alloc_frame_result(batch, pinned=True)
         download = lambda: ctx.frame_batch_download(out)
         oneshot = lambda b: ctx.frame_batch(b, opt, out)
-        workload = f"C2 batched pose-only FrameOptimization ({n_units} frames x {C2_POINTS} stereo pts per GPU, Huber + 4 rounds x LM10)"
+        workload = (f"C2 batched pose-only FrameOptimization ({n_units} frames x ({C2_POINTS} stereo pts + {nl} lines) per GPU, "
+                    "Huber + 4 rounds x LM10" + ("; lines = constraints on fixed 3-D lines, an extension: the reference's "
+                    "FrameOptimization takes none" if nl else "; points only = the reference's FrameOptimization") + ")")
         kernel = "ba::frame_opt_kernel"
     else:
         n_units = args.windows
@@ -228,11 +241,16 @@ def run_ours(args):
         oneshot = lambda b: ctx.local_batch(b, opt, out)
         workload = f"C4 batched LocalmapOptimization ({n_units} windows of 10 KF/3k pts/300 lines per GPU, LM 10+5)"
         kernel = "ba::local_ba_kernel"
-    if args.workload == "c2" and len(batch.cameras) == 1:
+    is_c2 = args.workload in ("c2", "c2p")
+    if is_c2 and len(batch.cameras) == 1:
         # one camera and all ->inlier flags true are the ABI defaults: pass NULL instead of copying 8 MB of zeros / ones
         batch.mono_cam = batch.stereo_cam = None
         if batch.mono_inlier.all() and batch.stereo_inlier.all():
             batch.mono_inlier = batch.stereo_inlier = None
+        if batch.mline_begin is not None:
+            batch.mline_cam = batch.sline_cam = None
+            if batch.mline_inlier.all() and batch.sline_inlier.all():
+                batch.mline_inlier = batch.sline_inlier = None
     pinned = _pin_batch(batch, capi)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -309,10 +327,13 @@ def run_ours(args):
         ctx.set_profiling(False)
         per_kernel = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
                       for k, v in prof.items() if v[1]}
-        if args.workload == "c2":
-            n_st, n_mo = int(batch.stereo_begin[-1]), int(batch.mono_begin[-1])
-            frac_st = n_st / max(n_st + n_mo, 1)
-            alg_bytes = edges_eval * (BYTES_POSE_ONLY_STEREO * frac_st + BYTES_POSE_ONLY_MONO * (1 - frac_st))
+        if is_c2:
+            cnt = {BYTES_POSE_ONLY_STEREO: int(batch.stereo_begin[-1]), BYTES_POSE_ONLY_MONO: int(batch.mono_begin[-1])}
+            if batch.mline_begin is not None:
+                cnt[BYTES_POSE_ONLY_STEREO_LINE] = int(batch.sline_begin[-1])
+                cnt[BYTES_POSE_ONLY_MONO_LINE] = int(batch.mline_begin[-1])
+            # evaluations are spread over the edge classes in proportion to their counts
+            alg_bytes = edges_eval * sum(bts * n for bts, n in cnt.items()) / max(sum(cnt.values()), 1)
             dom_ms = prof["frame_opt"][0] / prof_steps
             dom_launches = prof["frame_opt"][1] / prof_steps
             dom_name = kernel
@@ -350,7 +371,7 @@ def run_ours(args):
             "units_per_sec": n_units * world * args.steps / dev_s_max,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes()),
                     "d2h_bytes_per_step": int(out.d2h_bytes()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
-                    "api": "rspl_ba_%s_batch (pinned host buffers in, pinned host buffers out)" % ("frame" if args.workload == "c2" else "local")},
+                    "api": "rspl_ba_%s_batch (pinned host buffers in, pinned host buffers out)" % ("frame" if is_c2 else "local")},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic(args.workload), "peak_source": peak_src,
@@ -531,13 +552,13 @@ def cpu_baseline(args):
     reference's call pattern are single-threaded)."""
     from oracle import orc
     from rspl_slam_b200 import synth
-    if args.workload == "c2":
-        n = 1024
-        probs = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS) for i in range(n)]
+    if args.workload in ("c2", "c2p"):
+        n = 1024 if args.workload == "c2p" else 256  # (g2o differentiates line edges numerically: ~6x the work per frame)
+        probs = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS, n_lines=_c2_lines(args)) for i in range(n)]
         t0 = time.perf_counter()
         st = orc.frame_opt_batch(probs, n_threads=1)
         dt = time.perf_counter() - t0
-        sample = f"first {n} of {C2_FRAMES} C2 frames, 1 thread"
+        sample = f"first {n} of {C2_FRAMES} C2 frames ({C2_POINTS} stereo pts + {_c2_lines(args)} lines), 1 thread"
     elif args.workload == "c5":
         # the oracle factorises the reduced system densely in one thread: a scaled-down problem of the same generator
         probs = [synth.make_global_problem(synth.config_seed(5, 0), n_kf=60, n_points=30000, n_lines=3000, loops=1)]
@@ -563,7 +584,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2p", "c4", "c5"],
+                    help="c2: pose-only frames, 400 stereo points + 60 lines (BASELINE configs[1]); c2p: points only (the reference's path)")
+    ap.add_argument("--frame-lines", type=int, default=C2_LINES, help="lines per frame (c2)")
     ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")
     ap.add_argument("--points", type=int, default=1_000_000, help="points of the global problem (c5)")
     ap.add_argument("--lines", type=int, default=100_000, help="lines of the global problem (c5)")

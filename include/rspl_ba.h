@@ -95,6 +95,22 @@ typedef struct RsplFrameBatch {
   const double* stereo_xw;      /* [3][n_stereo] */
   const int32_t* stereo_cam;    /* [n_stereo] or NULL */
   const uint8_t* stereo_inlier; /* [n_stereo] or NULL */
+  /* Optional extension, NOT in the reference (its FrameOptimization takes no line containers and leaves
+   * deltaMonoLine / deltaStereoLine unused, g2o_optimization.cc:284-285): constraints of a frame on FIXED
+   * 3-D lines, i.e. EdgeSE3ProjectLine / EdgeStereoSE3ProjectLine (edge_project_line.cc:21-42,
+   * edge_project_stereo_line.cc:22-51) with the VertexLine3D held fixed. Information 0.1 I and Huber
+   * delta = (float)sqrt(threshold) as in LocalmapOptimization (:128-169); classified per round like the
+   * point edges ((float)chi2 > thr_mono_line / thr_stereo_line). All NULL / absent: the reference's case. */
+  const int32_t* mono_line_begin;    /* [n_frames+1] or NULL */
+  const int32_t* stereo_line_begin;  /* [n_frames+1] or NULL (both or neither) */
+  const double* mono_line_lw;        /* [6][n_ml] world line g2o::Line3D [w, d], copied into the edge */
+  const double* mono_line_meas;      /* [4][n_ml] x1,y1,x2,y2 (left) */
+  const int32_t* mono_line_cam;      /* [n_ml] or NULL */
+  const uint8_t* mono_line_inlier;   /* [n_ml] or NULL (all 1) */
+  const double* stereo_line_lw;      /* [6][n_sl] */
+  const double* stereo_line_meas;    /* [8][n_sl] left x1,y1,x2,y2, right x1,y1,x2,y2 */
+  const int32_t* stereo_line_cam;    /* [n_sl] or NULL */
+  const uint8_t* stereo_line_inlier; /* [n_sl] or NULL */
 } RsplFrameBatch;
 
 typedef struct RsplFrameBatchResult {
@@ -103,6 +119,8 @@ typedef struct RsplFrameBatchResult {
   uint8_t* stereo_inlier;  /* [n_stereo] */
   int32_t* num_inliers;    /* [n_frames] FrameOptimization's return value, or NULL */
   RsplBaStats* stats;      /* [n_frames] or NULL */
+  uint8_t* mono_line_inlier;   /* [n_ml] (line extension; may be NULL when the batch has no lines) */
+  uint8_t* stereo_line_inlier; /* [n_sl] */
 } RsplFrameBatchResult;
 
 /* ---------------------------------------------------------------------------------------------

@@ -1251,6 +1251,7 @@ extern "C" int orc_frame_opt(OrcFrameProblem* P, const OrcConfig* cfg, OrcStats*
   Graph& G = tls_graph();
   G.stats = stats;
   G.bf_float = cfg->stereo_bf_float != 0;
+  G.num_delta = cfg->numeric_delta > 0 ? cfg->numeric_delta : 1e-9;
   std::map<int, int> point_of;
   for (int i = 0; i < P->n_points; ++i) point_of[P->point_id[i]] = i;
   Vertex v;
@@ -1294,6 +1295,60 @@ extern "C" int orc_frame_opt(OrcFrameProblem* P, const OrcConfig* cfg, OrcStats*
     std::memset(e.err, 0, sizeof(e.err));
     G.E.push_back(e);
   }
+  // ---- extension (see oracle.h): edges to fixed line vertices, set up like :128-169
+  std::map<int, int> line_of;
+  for (int i = 0; i < P->n_lines; ++i) {
+    Vertex vl;
+    vl.kind = V_LINE;
+    vl.id = 1 + i;
+    vl.fixed = true;
+    vl.marginalized = true;
+    for (int k = 0; k < 6; ++k) vl.est[k] = P->line_L[6 * i + k];
+    line_of[P->line_id[i]] = (int)G.V.size();
+    G.V.push_back(vl);
+  }
+  const float deltaMonoLine = std::sqrt(cfg->mono_line);     // :284
+  const float deltaStereoLine = std::sqrt(cfg->stereo_line); // :285
+  const size_t e_mline0 = G.E.size();
+  for (int i = 0; i < P->n_mono_ln; ++i) {
+    Edge e;
+    e.type = E_MONO_LN;
+    auto pl = line_of.find(P->ml_id_line[i]);
+    if (pl == line_of.end() || P->ml_id_cam[i] < 0 || P->ml_id_cam[i] >= P->n_cams) return -2;
+    e.v_lm = pl->second;
+    e.v_pose = 0;
+    for (int k = 0; k < 4; ++k) e.meas[k] = P->ml_l2d[4 * i + k];
+    e.info = 0.1;
+    e.dim = 2;
+    e.delta = deltaMonoLine;
+    set_cam(e, &P->cams[5 * P->ml_id_cam[i]]);
+    e.Kv[0] = -e.fy * e.cx;
+    e.Kv[1] = -e.fx * e.cy;
+    e.Kv[2] = e.fx * e.fy;
+    e.b = 0;
+    std::memset(e.err, 0, sizeof(e.err));
+    G.E.push_back(e);
+  }
+  const size_t e_sline0 = G.E.size();
+  for (int i = 0; i < P->n_stereo_ln; ++i) {
+    Edge e;
+    e.type = E_STEREO_LN;
+    auto pl = line_of.find(P->sl_id_line[i]);
+    if (pl == line_of.end() || P->sl_id_cam[i] < 0 || P->sl_id_cam[i] >= P->n_cams) return -2;
+    e.v_lm = pl->second;
+    e.v_pose = 0;
+    for (int k = 0; k < 8; ++k) e.meas[k] = P->sl_l2d[8 * i + k];
+    e.info = 0.1;
+    e.dim = 4;
+    e.delta = deltaStereoLine;
+    set_cam(e, &P->cams[5 * P->sl_id_cam[i]]);
+    e.Kv[0] = -e.fy * e.cx;
+    e.Kv[1] = -e.fx * e.cy;
+    e.Kv[2] = e.fx * e.fy;
+    e.b = e.bf / e.fx;
+    std::memset(e.err, 0, sizeof(e.err));
+    G.E.push_back(e);
+  }
   int num_outlier = 0;
   double chi = 0;
   for (int iter = 0; iter < cfg->rounds; ++iter) { // :339
@@ -1329,6 +1384,34 @@ extern "C" int orc_frame_opt(OrcFrameProblem* P, const OrcConfig* cfg, OrcStats*
       }
       if (iter == 2) e.robust = false;
     }
+    for (int i = 0; i < P->n_mono_ln; ++i) { // extension: same classification for the line edges
+      Edge& e = G.E[e_mline0 + i];
+      if (!P->ml_inlier[i]) G.compute_error(e);
+      const float chi2 = (float)e.chi2();
+      if (chi2 > cfg->mono_line) {
+        P->ml_inlier[i] = 0;
+        e.level = 1;
+        num_outlier++;
+      } else {
+        P->ml_inlier[i] = 1;
+        e.level = 0;
+      }
+      if (iter == 2) e.robust = false;
+    }
+    for (int i = 0; i < P->n_stereo_ln; ++i) {
+      Edge& e = G.E[e_sline0 + i];
+      if (!P->sl_inlier[i]) G.compute_error(e);
+      const float chi2 = (float)e.chi2();
+      if (chi2 > cfg->stereo_line) {
+        P->sl_inlier[i] = 0;
+        e.level = 1;
+        num_outlier++;
+      } else {
+        P->sl_inlier[i] = 1;
+        e.level = 0;
+      }
+      if (iter == 2) e.robust = false;
+    }
     if (G.E.size() < 10) break; // :387 (total, not active, edges)
   }
   if (stats) stats->final_chi2 = chi;
@@ -1338,7 +1421,7 @@ extern "C" int orc_frame_opt(OrcFrameProblem* P, const OrcConfig* cfg, OrcStats*
   P->pose_q[1] = Twc.r.y;
   P->pose_q[2] = Twc.r.z;
   P->pose_q[3] = Twc.r.w;
-  return P->n_mono_pt + P->n_stereo_pt - num_outlier; // :396
+  return P->n_mono_pt + P->n_stereo_pt + P->n_mono_ln + P->n_stereo_ln - num_outlier; // :396 (+ extension edges)
 }
 
 extern "C" int orc_max_threads(void) {

@@ -114,6 +114,22 @@ typedef struct OrcFrameProblem {
   const int32_t *sp_id_point, *sp_id_cam;
   const double* sp_kp;
   uint8_t* sp_inlier;
+  /* Extension, NOT in the reference (its FrameOptimization takes no line containers and leaves
+   * deltaMonoLine / deltaStereoLine unused, g2o_optimization.cc:284-285): constraints of the frame on
+   * FIXED 3-D lines, i.e. EdgeSE3ProjectLine / EdgeStereoSE3ProjectLine whose VertexLine3D is fixed
+   * (SURVEY 8a note). Set-up as in LocalmapOptimization (:128-169): information 0.1 I, Huber delta =
+   * (float)sqrt(threshold); classified per round like the point edges ((float)chi2 > threshold). */
+  int32_t n_lines;
+  const int32_t* line_id;
+  const double* line_L; /* [n][6] */
+  int32_t n_mono_ln;
+  const int32_t *ml_id_line, *ml_id_cam;
+  const double* ml_l2d; /* [n][4] */
+  uint8_t* ml_inlier;
+  int32_t n_stereo_ln;
+  const int32_t *sl_id_line, *sl_id_cam;
+  const double* sl_l2d; /* [n][8] */
+  uint8_t* sl_inlier;
 } OrcFrameProblem;
 
 /* LocalmapOptimization (g2o_optimization.cc:21-252). Returns 0, or <0 on malformed input. */

@@ -62,6 +62,10 @@ class OrcFrameProblem(C.Structure):
         ("n_cams", C.c_int32), ("cams", c_f64p),
         ("n_mono_pt", C.c_int32), ("mp_id_point", c_i32p), ("mp_id_cam", c_i32p), ("mp_kp", c_f64p), ("mp_inlier", c_u8p),
         ("n_stereo_pt", C.c_int32), ("sp_id_point", c_i32p), ("sp_id_cam", c_i32p), ("sp_kp", c_f64p), ("sp_inlier", c_u8p),
+        # extension: constraints on fixed lines (oracle.h)
+        ("n_lines", C.c_int32), ("line_id", c_i32p), ("line_L", c_f64p),
+        ("n_mono_ln", C.c_int32), ("ml_id_line", c_i32p), ("ml_id_cam", c_i32p), ("ml_l2d", c_f64p), ("ml_inlier", c_u8p),
+        ("n_stereo_ln", C.c_int32), ("sl_id_line", c_i32p), ("sl_id_cam", c_i32p), ("sl_l2d", c_f64p), ("sl_inlier", c_u8p),
     ]
 
 
@@ -134,7 +138,10 @@ def _frame_struct(p) -> OrcFrameProblem:
         _p(p.pose_p, c_f64p), _p(p.pose_q, c_f64p), len(p.point_id), _p(p.point_id, c_i32p), _p(p.point_p, c_f64p),
         len(p.cams), _p(p.cams, c_f64p),
         len(p.mp_id_point), _p(p.mp_id_point, c_i32p), _p(p.mp_id_cam, c_i32p), _p(p.mp_kp, c_f64p), _p(p.mp_inlier, c_u8p),
-        len(p.sp_id_point), _p(p.sp_id_point, c_i32p), _p(p.sp_id_cam, c_i32p), _p(p.sp_kp, c_f64p), _p(p.sp_inlier, c_u8p))
+        len(p.sp_id_point), _p(p.sp_id_point, c_i32p), _p(p.sp_id_cam, c_i32p), _p(p.sp_kp, c_f64p), _p(p.sp_inlier, c_u8p),
+        len(p.line_id), _p(p.line_id, c_i32p), _p(p.line_L, c_f64p),
+        len(p.ml_id_line), _p(p.ml_id_line, c_i32p), _p(p.ml_id_cam, c_i32p), _p(p.ml_l2d, c_f64p), _p(p.ml_inlier, c_u8p),
+        len(p.sl_id_line), _p(p.sl_id_line, c_i32p), _p(p.sl_id_cam, c_i32p), _p(p.sl_l2d, c_f64p), _p(p.sl_inlier, c_u8p))
 
 
 def _stats_dict(s: OrcStats, trace_buf=None) -> dict:

@@ -50,12 +50,17 @@ class RsplFrameBatch(C.Structure):
     _fields_ = [("n_frames", C.c_int32), ("n_cameras", C.c_int32), ("cameras", c_f64p), ("pose_twc", c_f64p),
                 ("mono_begin", c_i32p), ("stereo_begin", c_i32p),
                 ("mono_meas", c_f64p), ("mono_xw", c_f64p), ("mono_cam", c_i32p), ("mono_inlier", c_u8p),
-                ("stereo_meas", c_f64p), ("stereo_xw", c_f64p), ("stereo_cam", c_i32p), ("stereo_inlier", c_u8p)]
+                ("stereo_meas", c_f64p), ("stereo_xw", c_f64p), ("stereo_cam", c_i32p), ("stereo_inlier", c_u8p),
+                # line extension (all NULL: the reference's case)
+                ("mono_line_begin", c_i32p), ("stereo_line_begin", c_i32p),
+                ("mono_line_lw", c_f64p), ("mono_line_meas", c_f64p), ("mono_line_cam", c_i32p), ("mono_line_inlier", c_u8p),
+                ("stereo_line_lw", c_f64p), ("stereo_line_meas", c_f64p), ("stereo_line_cam", c_i32p),
+                ("stereo_line_inlier", c_u8p)]
 
 
 class RsplFrameBatchResult(C.Structure):
     _fields_ = [("pose_twc", c_f64p), ("mono_inlier", c_u8p), ("stereo_inlier", c_u8p), ("num_inliers", c_i32p),
-                ("stats", C.POINTER(RsplBaStats))]
+                ("stats", C.POINTER(RsplBaStats)), ("mono_line_inlier", c_u8p), ("stereo_line_inlier", c_u8p)]
 
 
 class RsplLocalBatch(C.Structure):
@@ -269,7 +274,10 @@ class Context:
             b.n_frames, len(b.cameras), _p(b.cameras, c_f64p), _p(b.pose_twc, c_f64p),
             _p(b.mono_begin, c_i32p), _p(b.stereo_begin, c_i32p),
             _p(b.mono_meas, c_f64p), _p(b.mono_xw, c_f64p), _p(b.mono_cam, c_i32p), _p(b.mono_inlier, c_u8p),
-            _p(b.stereo_meas, c_f64p), _p(b.stereo_xw, c_f64p), _p(b.stereo_cam, c_i32p), _p(b.stereo_inlier, c_u8p))
+            _p(b.stereo_meas, c_f64p), _p(b.stereo_xw, c_f64p), _p(b.stereo_cam, c_i32p), _p(b.stereo_inlier, c_u8p),
+            _p(b.mline_begin, c_i32p), _p(b.sline_begin, c_i32p),
+            _p(b.mline_lw, c_f64p), _p(b.mline_meas, c_f64p), _p(b.mline_cam, c_i32p), _p(b.mline_inlier, c_u8p),
+            _p(b.sline_lw, c_f64p), _p(b.sline_meas, c_f64p), _p(b.sline_cam, c_i32p), _p(b.sline_inlier, c_u8p))
 
     @staticmethod
     def alloc_frame_result(b: FrameBatch, pinned: bool = False) -> FrameBatchResult:
@@ -277,12 +285,15 @@ class Context:
         return FrameBatchResult(
             pose_twc=mk((7, b.n_frames), np.float64), mono_inlier=mk((int(b.mono_begin[-1]),), np.uint8),
             stereo_inlier=mk((int(b.stereo_begin[-1]),), np.uint8), num_inliers=mk((b.n_frames,), np.int32),
-            stats=mk((b.n_frames,), STATS_DTYPE))
+            stats=mk((b.n_frames,), STATS_DTYPE),
+            mline_inlier=mk((int(b.mline_begin[-1]),), np.uint8) if b.mline_begin is not None else None,
+            sline_inlier=mk((int(b.sline_begin[-1]),), np.uint8) if b.sline_begin is not None else None)
 
     @staticmethod
     def _frame_result_struct(r: FrameBatchResult) -> RsplFrameBatchResult:
         return RsplFrameBatchResult(_p(r.pose_twc, c_f64p), _p(r.mono_inlier, c_u8p), _p(r.stereo_inlier, c_u8p),
-                                    _p(r.num_inliers, c_i32p), C.cast(r.stats.ctypes.data, C.POINTER(RsplBaStats)))
+                                    _p(r.num_inliers, c_i32p), C.cast(r.stats.ctypes.data, C.POINTER(RsplBaStats)),
+                                    _p(r.mline_inlier, c_u8p), _p(r.sline_inlier, c_u8p))
 
     def frame_batch(self, b: FrameBatch, opt: Optional[RsplBaOptions] = None,
                     out: Optional[FrameBatchResult] = None) -> FrameBatchResult:

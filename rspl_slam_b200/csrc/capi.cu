@@ -79,6 +79,8 @@ struct RsplBaContext {
   int f_n_frames = 0, f_n_mono = 0, f_n_stereo = 0;
   ba::Cam f_cam0{};
   std::vector<int32_t> f_mb, f_sb; // host copies of the frame edge offsets
+  std::vector<int32_t> f_mlb, f_slb; // ... and of the line-extension offsets (zeros when absent)
+  int f_n_mline = 0, f_n_sline = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined one-shot call
   cudaStream_t s_cmp[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk kernels may overlap each other
   std::vector<cudaEvent_t> pipe_ev;
@@ -186,6 +188,10 @@ ba::FrameOpt make_frame_opt(const RsplBaOptions& o) {
   f.thr_stereo = o.thr_stereo_point;
   f.delta_mono = (double)(float)sqrt(o.thr_mono_point);     // const float deltaMonoPoint = sqrt(cfg.mono_point) (:282)
   f.delta_stereo = (double)(float)sqrt(o.thr_stereo_point); // (:283)
+  f.thr_mline = o.thr_mono_line;
+  f.thr_sline = o.thr_stereo_line;
+  f.delta_mline = (double)(float)sqrt(o.thr_mono_line);   // deltaMonoLine (:284, unused by the reference)
+  f.delta_sline = (double)(float)sqrt(o.thr_stereo_line); // deltaStereoLine (:285)
   f.rounds = o.frame_rounds;
   f.iters = o.frame_iters;
   return f;
@@ -364,6 +370,8 @@ namespace {
 
 struct FrameOffsets {
   size_t cam, pose, mb, sb, mm, mx, mc, mi, sm, sx, sc, si, op, omi, osi, ml, sl, ni, st;
+  // line extension
+  size_t lmb, lsb, lml, lmm, lmc, lmi, lsl, lsm, lsc, lsi, olmi, olsi, lmlv, lslv;
 };
 
 // validates the batch, sizes the device arena and wires the kernel argument block (no copies yet)
@@ -384,6 +392,22 @@ int frame_prepare(RsplBaContext* c, const RsplFrameBatch* in, FrameOffsets& o) {
     return fail(c, RSPL_BA_ERR_INVALID, "frame batch: id_camera out of range");
   if (in->n_cameras > 1 && ((nm && !in->mono_cam) || (ns && !in->stereo_cam)))
     return fail(c, RSPL_BA_ERR_INVALID, "frame batch: several cameras but no per-edge camera index");
+  // line extension: both offset arrays or neither
+  int nml = 0, nsl = 0;
+  if (in->mono_line_begin || in->stereo_line_begin) {
+    if (!in->mono_line_begin || !in->stereo_line_begin || !offsets_ok(in->mono_line_begin, F) ||
+        !offsets_ok(in->stereo_line_begin, F))
+      return fail(c, RSPL_BA_ERR_INVALID, "frame batch: bad line offsets");
+    nml = in->mono_line_begin[F];
+    nsl = in->stereo_line_begin[F];
+    if ((nml && (!in->mono_line_lw || !in->mono_line_meas)) || (nsl && (!in->stereo_line_lw || !in->stereo_line_meas)))
+      return fail(c, RSPL_BA_ERR_INVALID, "frame batch: null line arrays");
+    if (!cams_ok(in->mono_line_cam, nml, in->n_cameras) || !cams_ok(in->stereo_line_cam, nsl, in->n_cameras))
+      return fail(c, RSPL_BA_ERR_INVALID, "frame batch: id_camera out of range");
+    if (in->n_cameras > 1 && ((nml && !in->mono_line_cam) || (nsl && !in->stereo_line_cam)))
+      return fail(c, RSPL_BA_ERR_INVALID, "frame batch: several cameras but no per-edge camera index");
+  }
+  const bool has_lines = nml + nsl > 0;
   Arena a;
   o.cam = a.take(sizeof(double) * 5 * in->n_cameras);
   o.pose = a.take(sizeof(double) * 7 * F);
@@ -404,6 +428,22 @@ int frame_prepare(RsplBaContext* c, const RsplFrameBatch* in, FrameOffsets& o) {
   o.sl = a.take(ns);
   o.ni = a.take(sizeof(int) * F);
   o.st = a.take(sizeof(ba::DevStats) * F);
+  if (has_lines) {
+    o.lmb = a.take(sizeof(int) * (F + 1));
+    o.lsb = a.take(sizeof(int) * (F + 1));
+    o.lml = a.take(sizeof(double) * 6 * nml);
+    o.lmm = a.take(sizeof(double) * 4 * nml);
+    o.lmc = a.take(sizeof(int) * nml);
+    o.lmi = a.take(nml);
+    o.lsl = a.take(sizeof(double) * 6 * nsl);
+    o.lsm = a.take(sizeof(double) * 8 * nsl);
+    o.lsc = a.take(sizeof(int) * nsl);
+    o.lsi = a.take(nsl);
+    o.olmi = a.take(nml);
+    o.olsi = a.take(nsl);
+    o.lmlv = a.take(nml);
+    o.lslv = a.take(nsl);
+  }
   CU_TRY(c, c->frame_buf.reserve(a.off));
   char* base = c->frame_buf.as<char>();
   ba::FrameDev& d = c->fd;
@@ -430,6 +470,32 @@ int frame_prepare(RsplBaContext* c, const RsplFrameBatch* in, FrameOffsets& o) {
   d.stereo_lvl = (uint8_t*)(base + o.sl);
   d.num_inliers = (int*)(base + o.ni);
   d.stats = (void*)(base + o.st);
+  d.n_mline = nml;
+  d.n_sline = nsl;
+  if (has_lines) {
+    d.mline_begin = (const int*)(base + o.lmb);
+    d.sline_begin = (const int*)(base + o.lsb);
+    d.mline_lw = (const double*)(base + o.lml);
+    d.mline_meas = (const double*)(base + o.lmm);
+    d.mline_cam = in->mono_line_cam ? (const int*)(base + o.lmc) : nullptr;
+    d.mline_inl_in = in->mono_line_inlier ? (const uint8_t*)(base + o.lmi) : nullptr;
+    d.sline_lw = (const double*)(base + o.lsl);
+    d.sline_meas = (const double*)(base + o.lsm);
+    d.sline_cam = in->stereo_line_cam ? (const int*)(base + o.lsc) : nullptr;
+    d.sline_inl_in = in->stereo_line_inlier ? (const uint8_t*)(base + o.lsi) : nullptr;
+    d.mline_inl = (uint8_t*)(base + o.olmi);
+    d.sline_inl = (uint8_t*)(base + o.olsi);
+    d.mline_lvl = (uint8_t*)(base + o.lmlv);
+    d.sline_lvl = (uint8_t*)(base + o.lslv);
+  } else {
+    d.mline_begin = d.sline_begin = nullptr;
+    d.mline_lw = d.mline_meas = d.sline_lw = d.sline_meas = nullptr;
+    d.mline_cam = d.sline_cam = nullptr;
+    d.mline_inl_in = d.sline_inl_in = nullptr;
+    d.mline_inl = d.sline_inl = d.mline_lvl = d.sline_lvl = nullptr;
+  }
+  c->f_n_mline = nml;
+  c->f_n_sline = nsl;
   c->f_cam0 = ba::Cam{in->cameras[0], in->cameras[1], in->cameras[2], in->cameras[3], in->cameras[4]};
   c->f_n_frames = F;
   c->f_n_mono = nm;
@@ -462,6 +528,23 @@ int frame_copy_in(RsplBaContext* c, const RsplFrameBatch* in, const FrameOffsets
   for (int k = 0; k < 3; ++k) H2D(o.sx + sizeof(double) * ((size_t)k * ns + s0), in->stereo_xw + (size_t)k * ns + s0, sizeof(double) * (s1 - s0));
   if (in->stereo_cam) H2D(o.sc + sizeof(int) * s0, in->stereo_cam + s0, sizeof(int) * (s1 - s0));
   if (in->stereo_inlier) H2D(o.si + s0, in->stereo_inlier + s0, s1 - s0);
+  if (c->f_n_mline + c->f_n_sline > 0) {
+    const int nml = c->f_n_mline, nsl = c->f_n_sline;
+    if (header) {
+      H2D(o.lmb, in->mono_line_begin, sizeof(int) * (F + 1));
+      H2D(o.lsb, in->stereo_line_begin, sizeof(int) * (F + 1));
+    }
+    const size_t a0 = in->mono_line_begin[f0], a1 = in->mono_line_begin[f1];
+    const size_t b0 = in->stereo_line_begin[f0], b1 = in->stereo_line_begin[f1];
+    for (int k = 0; k < 6; ++k) H2D(o.lml + sizeof(double) * ((size_t)k * nml + a0), in->mono_line_lw + (size_t)k * nml + a0, sizeof(double) * (a1 - a0));
+    for (int k = 0; k < 4; ++k) H2D(o.lmm + sizeof(double) * ((size_t)k * nml + a0), in->mono_line_meas + (size_t)k * nml + a0, sizeof(double) * (a1 - a0));
+    if (in->mono_line_cam) H2D(o.lmc + sizeof(int) * a0, in->mono_line_cam + a0, sizeof(int) * (a1 - a0));
+    if (in->mono_line_inlier) H2D(o.lmi + a0, in->mono_line_inlier + a0, a1 - a0);
+    for (int k = 0; k < 6; ++k) H2D(o.lsl + sizeof(double) * ((size_t)k * nsl + b0), in->stereo_line_lw + (size_t)k * nsl + b0, sizeof(double) * (b1 - b0));
+    for (int k = 0; k < 8; ++k) H2D(o.lsm + sizeof(double) * ((size_t)k * nsl + b0), in->stereo_line_meas + (size_t)k * nsl + b0, sizeof(double) * (b1 - b0));
+    if (in->stereo_line_cam) H2D(o.lsc + sizeof(int) * b0, in->stereo_line_cam + b0, sizeof(int) * (b1 - b0));
+    if (in->stereo_line_inlier) H2D(o.lsi + b0, in->stereo_line_inlier + b0, b1 - b0);
+  }
 #undef H2D
   return RSPL_BA_OK;
 }
@@ -473,11 +556,15 @@ int frame_launch(RsplBaContext* c, const RsplBaOptions* opt, int f0, int f1, cud
   fo.frame0 = f0;
   fo.frame1 = f1;
   const int grid = (f1 - f0 + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
-  const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr);
+  const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr &&
+                                                   c->fd.mline_cam == nullptr && c->fd.sline_cam == nullptr);
   {
     ProfScope ps(c, PC_FRAME);
-    if (single_cam) ba::frame_opt_kernel<true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-    else ba::frame_opt_kernel<false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    const bool lines = c->f_n_mline + c->f_n_sline > 0;
+    if (single_cam && !lines) ba::frame_opt_kernel<true, false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    else if (!lines) ba::frame_opt_kernel<false, false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    else if (single_cam) ba::frame_opt_kernel<true, true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    else ba::frame_opt_kernel<false, true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
   }
   c->launches++;
   CU_TRY(c, cudaGetLastError());
@@ -495,12 +582,28 @@ int frame_copy_out(RsplBaContext* c, RsplFrameBatchResult* out, const int32_t* m
                               sizeof(double) * (f1 - f0), cudaMemcpyDeviceToHost, s));
   if (m1 > m0) CU_TRY(c, cudaMemcpyAsync(out->mono_inlier + m0, d.mono_inl + m0, m1 - m0, cudaMemcpyDeviceToHost, s));
   if (s1 > s0) CU_TRY(c, cudaMemcpyAsync(out->stereo_inlier + s0, d.stereo_inl + s0, s1 - s0, cudaMemcpyDeviceToHost, s));
+  if (c->f_n_mline + c->f_n_sline > 0) {
+    const size_t a0 = c->f_mlb[f0], a1 = c->f_mlb[f1], b0 = c->f_slb[f0], b1 = c->f_slb[f1];
+    if (a1 > a0) CU_TRY(c, cudaMemcpyAsync(out->mono_line_inlier + a0, d.mline_inl + a0, a1 - a0, cudaMemcpyDeviceToHost, s));
+    if (b1 > b0) CU_TRY(c, cudaMemcpyAsync(out->stereo_line_inlier + b0, d.sline_inl + b0, b1 - b0, cudaMemcpyDeviceToHost, s));
+  }
   if (out->num_inliers)
     CU_TRY(c, cudaMemcpyAsync(out->num_inliers + f0, d.num_inliers + f0, sizeof(int) * (f1 - f0), cudaMemcpyDeviceToHost, s));
   if (out->stats)
     CU_TRY(c, cudaMemcpyAsync(out->stats + f0, (const RsplBaStats*)d.stats + f0, sizeof(RsplBaStats) * (f1 - f0),
                               cudaMemcpyDeviceToHost, s));
   return RSPL_BA_OK;
+}
+
+void frame_keep_line_offsets(RsplBaContext* c, const RsplFrameBatch* in) {
+  const int F = c->f_n_frames;
+  if (c->f_n_mline + c->f_n_sline > 0) {
+    c->f_mlb.assign(in->mono_line_begin, in->mono_line_begin + F + 1);
+    c->f_slb.assign(in->stereo_line_begin, in->stereo_line_begin + F + 1);
+  } else {
+    c->f_mlb.assign(F + 1, 0);
+    c->f_slb.assign(F + 1, 0);
+  }
 }
 
 int ensure_pipeline(RsplBaContext* c, int n_chunks) {
@@ -531,6 +634,7 @@ extern "C" int rspl_ba_frame_batch_upload(RsplBaContext* c, const RsplFrameBatch
     CU_TRY(c, cudaStreamSynchronize(c->stream)); // caller buffers may be reused after return
     c->f_mb.assign(in->mono_begin, in->mono_begin + c->f_n_frames + 1);
     c->f_sb.assign(in->stereo_begin, in->stereo_begin + c->f_n_frames + 1);
+    frame_keep_line_offsets(c, in);
   }
   c->frame_uploaded = true;
   return RSPL_BA_OK;
@@ -553,7 +657,8 @@ extern "C" int rspl_ba_frame_batch_download(RsplBaContext* c, RsplFrameBatchResu
   if (!c->frame_solved) return fail(c, RSPL_BA_ERR_STATE, "frame_batch_download before solve");
   const int F = c->f_n_frames, nm = c->f_n_mono, ns = c->f_n_stereo;
   if (F == 0) return RSPL_BA_OK;
-  if (!out->pose_twc || (nm && !out->mono_inlier) || (ns && !out->stereo_inlier))
+  if (!out->pose_twc || (nm && !out->mono_inlier) || (ns && !out->stereo_inlier) ||
+      (c->f_n_mline && !out->mono_line_inlier) || (c->f_n_sline && !out->stereo_line_inlier))
     return fail(c, RSPL_BA_ERR_INVALID, "frame result: null output arrays");
   SetDevice guard(c->device);
   int rc = frame_copy_out(c, out, c->f_mb.data(), c->f_sb.data(), 0, F, c->stream);
@@ -579,10 +684,12 @@ extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, c
   const int F = c->f_n_frames;
   c->frame_uploaded = c->frame_solved = true;
   if (F == 0) return RSPL_BA_OK;
-  if (!out->pose_twc || (c->f_n_mono && !out->mono_inlier) || (c->f_n_stereo && !out->stereo_inlier))
+  if (!out->pose_twc || (c->f_n_mono && !out->mono_inlier) || (c->f_n_stereo && !out->stereo_inlier) ||
+      (c->f_n_mline && !out->mono_line_inlier) || (c->f_n_sline && !out->stereo_line_inlier))
     return fail(c, RSPL_BA_ERR_INVALID, "frame result: null output arrays");
   c->f_mb.assign(in->mono_begin, in->mono_begin + F + 1);
   c->f_sb.assign(in->stereo_begin, in->stereo_begin + F + 1);
+  frame_keep_line_offsets(c, in);
   int n_chunks = F / 512;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > 4) n_chunks = 4;

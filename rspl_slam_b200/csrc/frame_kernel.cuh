@@ -34,6 +34,22 @@ struct FrameDev {
   const double* stereo_xw;    // [3][n_stereo]
   const int* stereo_cam;
   const uint8_t* stereo_inl_in;
+  // line extension (constraints on fixed lines; absent in the reference): n_mline + n_sline == 0 when unused
+  const int* mline_begin;     // [F+1]
+  const int* sline_begin;     // [F+1]
+  int n_mline, n_sline;
+  const double* mline_lw;     // [6][n_mline]
+  const double* mline_meas;   // [4][n_mline]
+  const int* mline_cam;       // may be null
+  const uint8_t* mline_inl_in;
+  const double* sline_lw;     // [6][n_sline]
+  const double* sline_meas;   // [8][n_sline]
+  const int* sline_cam;
+  const uint8_t* sline_inl_in;
+  uint8_t* mline_inl;
+  uint8_t* sline_inl;
+  uint8_t* mline_lvl;
+  uint8_t* sline_lvl;
   // outputs / work
   double* out_pose_twc;       // [7][F]
   uint8_t* mono_inl;          // [n_mono]   current ->inlier flag (level = !inlier after round 0)
@@ -47,6 +63,7 @@ struct FrameDev {
 struct FrameOpt {
   double thr_mono, thr_stereo;
   double delta_mono, delta_stereo; // (float)sqrt(thr) widened
+  double thr_mline, thr_sline, delta_mline, delta_sline; // line extension
   int rounds, iters;
   Cam cam0;                        // camera 0, read straight from the constant bank when SINGLE_CAM
   int frame0, frame1;              // frame range of this launch (chunks of a pipelined batch)
@@ -63,6 +80,9 @@ struct DevStats { // layout == RsplBaStats
 
 #ifndef FRAME_MIN_BLOCKS
 #define FRAME_MIN_BLOCKS 4 // 128 registers: best of {3, 4, 5} measured on B200 (profiles/README.md)
+#endif
+#ifndef FRAME_LINES_MIN_BLOCKS
+#define FRAME_LINES_MIN_BLOCKS 4 // instantiation with the line extension: 2 / 3 / 4 CTAs per SM measured 4.61 / 4.33 / 4.28 ms (C2 with 60 lines)
 #endif
 constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
 constexpr int FRAME_WARPS = FRAME_THREADS / 32;
@@ -150,6 +170,60 @@ BA_DEV void accumulate_pose_only(const double* J, const double* r, double w, dou
     acc[up6(3, 3)] += wc[3] * c[3];
     acc[up6(3, 5)] += wc[3] * c[5];
     acc[up6(5, 5)] += wc[5] * c[5];
+  }
+}
+
+// H += wo J^T J ; b -= wo J^T r for a dense ROWS x 6 Jacobian (line edges)
+template <int ROWS>
+BA_DEV void accumulate_pose_dense(const double* J, const double* r, double wo, double* acc) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double g = 0;
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) g += J[q * 6 + i] * r[q];
+    acc[21 + i] -= wo * g;
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      double h = 0;
+#pragma unroll
+      for (int q = 0; q < ROWS; ++q) h += J[q * 6 + i] * J[q * 6 + j];
+      acc[up6(i, j)] += wo * h;
+    }
+  }
+}
+
+// line edges of a frame (extension): information 0.1 I (g2o_optimization.cc:133,154), line vertex fixed
+template <bool LINEARIZE, bool SINGLE_CAM, bool STEREO>
+BA_DEV void line_pass(const FrameDev& d, const FrameOpt& o, int e0, int e1, const double* R, const double* t, bool robust,
+                      int lane, double* acc) {
+  constexpr int ROWS = STEREO ? 4 : 2, MD = STEREO ? 8 : 4;
+  const int n = STEREO ? d.n_sline : d.n_mline;
+  const double* lw = STEREO ? d.sline_lw : d.mline_lw;
+  const double* ms = STEREO ? d.sline_meas : d.mline_meas;
+  const uint8_t* lvl = STEREO ? d.sline_lvl : d.mline_lvl;
+  const int* cams = STEREO ? d.sline_cam : d.mline_cam;
+  const double delta = STEREO ? o.delta_sline : o.delta_mline;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    if (lvl[e]) continue;
+    Cam camv;
+    if (!SINGLE_CAM) load_cam(d.cameras, cams[e], camv);
+    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
+    double L[6], m[MD], r[4];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) L[q] = lw[(size_t)q * n + e];
+#pragma unroll
+    for (int q = 0; q < MD; ++q) m[q] = ms[(size_t)q * n + e];
+    double Jp[24], Jl[16];
+    if (LINEARIZE) line_linearize<STEREO>(cam, R, t, L, m, r, Jp, Jl);
+    else line_residual<STEREO>(cam, R, t, L, m, r);
+    double chi2 = 0;
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) chi2 += r[q] * r[q];
+    chi2 *= 0.1;
+    double w = 1.0;
+    const double rho0 = robust ? huber(chi2, delta, w) : chi2;
+    acc[NACC - 1] += rho0;
+    if (LINEARIZE) accumulate_pose_dense<ROWS>(Jp, r, 0.1 * w, acc);
   }
 }
 
@@ -262,9 +336,11 @@ BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
 
 // One warp per frame: every lane carries the same pose / LM scalars (computed redundantly, so no
 // broadcast and no block barrier is ever needed); lanes stride over the frame's edges.
-template <bool SINGLE_CAM>
-__global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_kernel(const __grid_constant__ FrameDev d,
-                                                                      const __grid_constant__ FrameOpt o) {
+// HAS_LINES: the batch carries the line extension (the point-only instantiation is the reference's path and
+// keeps its register budget).
+template <bool SINGLE_CAM, bool HAS_LINES>
+__global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLOCKS : FRAME_MIN_BLOCKS)
+    frame_opt_kernel(const __grid_constant__ FrameDev d, const __grid_constant__ FrameOpt o) {
   __shared__ WarpState wstate[FRAME_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int f = o.frame0 + blockIdx.x * FRAME_WARPS + warp;
@@ -272,7 +348,9 @@ __global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_ker
   WarpState& ws = wstate[warp];
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];
-  const int n_edges = (m1 - m0) + (s1 - s0);
+  const int ml0 = HAS_LINES ? d.mline_begin[f] : 0, ml1 = HAS_LINES ? d.mline_begin[f + 1] : 0;
+  const int sl0 = HAS_LINES ? d.sline_begin[f] : 0, sl1 = HAS_LINES ? d.sline_begin[f + 1] : 0;
+  const int n_edges = (m1 - m0) + (s1 - s0) + (ml1 - ml0) + (sl1 - sl0);
 
   // ---- setup: pose (g2o_optimization.cc:271), flags, levels
   PoseRt T; // optimiser pose Tcw as rotation matrix + translation (quaternion only at the boundary)
@@ -303,6 +381,16 @@ __global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_ker
     d.stereo_lvl[e] = 0;
     d.stereo_inl[e] = d.stereo_inl_in ? d.stereo_inl_in[e] : 1;
   }
+  if (HAS_LINES) {
+    for (int e = ml0 + lane; e < ml1; e += 32) {
+      d.mline_lvl[e] = 0;
+      d.mline_inl[e] = d.mline_inl_in ? d.mline_inl_in[e] : 1;
+    }
+    for (int e = sl0 + lane; e < sl1; e += 32) {
+      d.sline_lvl[e] = 0;
+      d.sline_inl[e] = d.sline_inl_in ? d.sline_inl_in[e] : 1;
+    }
+  }
   __syncwarp();
 
   bool robust = true;
@@ -321,6 +409,10 @@ __global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_ker
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
           edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
+          if (HAS_LINES) {
+            line_pass<true, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, acc);
+            line_pass<true, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, acc);
+          }
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
@@ -379,6 +471,10 @@ __global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_ker
             double a2[NACC];
             a2[NACC - 1] = 0;
             edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
+            if (HAS_LINES) {
+              line_pass<false, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, a2);
+              line_pass<false, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, a2);
+            }
             tempChi = warp_allreduce(a2[NACC - 1]);
           }
           if (lane == 0) {
@@ -456,6 +552,46 @@ __global__ void __launch_bounds__(FRAME_THREADS, FRAME_MIN_BLOCKS) frame_opt_ker
       d.stereo_inl[e] = out ? 0 : 1;
       d.stereo_lvl[e] = out ? 1 : 0;
       my_out += out;
+    }
+    if (HAS_LINES) { // same classification for the line edges (extension)
+      for (int e = ml0 + lane; e < ml1; e += 32) {
+        Cam camv;
+        if (!SINGLE_CAM) load_cam(d.cameras, d.mline_cam[e], camv);
+        const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
+        double L[6], m[4], r[2];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) L[q] = d.mline_lw[(size_t)q * d.n_mline + e];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = d.mline_meas[(size_t)q * d.n_mline + e];
+        const bool recompute = !d.mline_inl[e];
+        const bool was_active = !d.mline_lvl[e] && n_active > 0;
+        if (recompute || !was_active) line_residual<false>(cam, T.R, T.t, L, m, r);
+        else line_residual<false>(cam, Re, te, L, m, r);
+        const float chi2 = (float)(0.1 * (r[0] * r[0] + r[1] * r[1]));
+        const bool out = (double)chi2 > o.thr_mline;
+        d.mline_inl[e] = out ? 0 : 1;
+        d.mline_lvl[e] = out ? 1 : 0;
+        my_out += out;
+      }
+      for (int e = sl0 + lane; e < sl1; e += 32) {
+        Cam camv;
+        if (!SINGLE_CAM) load_cam(d.cameras, d.sline_cam[e], camv);
+        const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
+        double L[6], m[8], r[4];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) L[q] = d.sline_lw[(size_t)q * d.n_sline + e];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = d.sline_meas[(size_t)q * d.n_sline + e];
+        const bool recompute = !d.sline_inl[e];
+        const bool was_active = !d.sline_lvl[e] && n_active > 0;
+        if (recompute || !was_active) line_residual<true>(cam, T.R, T.t, L, m, r);
+        else line_residual<true>(cam, Re, te, L, m, r);
+        const float chi2 = (float)(0.1 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]));
+        const bool out = (double)chi2 > o.thr_sline;
+        d.sline_inl[e] = out ? 0 : 1;
+        d.sline_lvl[e] = out ? 1 : 0;
+        my_out += out;
+      }
     }
     num_outlier = __reduce_add_sync(0xffffffffu, my_out);
     n_active = n_edges - num_outlier;

@@ -17,7 +17,7 @@ into the reference-style containers the way the shim mutates the caller's maps i
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -130,6 +130,18 @@ class FrameProblem:
     sp_kp: np.ndarray        # (n,3)
     sp_inlier: np.ndarray
     truth: dict = field(default_factory=dict)
+    # Extension (not in the reference, whose FrameOptimization takes no lines, g2o_optimization.cc:284-285):
+    # constraints of the frame on FIXED 3-D lines (SURVEY §8a note); empty by default.
+    line_id: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=I32))
+    line_L: np.ndarray = field(default_factory=lambda: np.zeros((0, 6)))
+    ml_id_line: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=I32))
+    ml_id_cam: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=I32))
+    ml_l2d: np.ndarray = field(default_factory=lambda: np.zeros((0, 4)))
+    ml_inlier: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=U8))
+    sl_id_line: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=I32))
+    sl_id_cam: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=I32))
+    sl_l2d: np.ndarray = field(default_factory=lambda: np.zeros((0, 8)))
+    sl_inlier: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=U8))
 
     def normalise(self) -> "FrameProblem":
         self.pose_p, self.pose_q = _f(self.pose_p, (3,)), _f(self.pose_q, (4,))
@@ -139,7 +151,16 @@ class FrameProblem:
         self.sp_id_point, self.sp_id_cam = _i(self.sp_id_point), _i(self.sp_id_cam)
         self.mp_kp, self.sp_kp = _f(self.mp_kp, (-1, 2)), _f(self.sp_kp, (-1, 3))
         self.mp_inlier, self.sp_inlier = _u(self.mp_inlier), _u(self.sp_inlier)
+        self.line_id, self.line_L = _i(self.line_id), _f(self.line_L, (-1, 6))
+        self.ml_id_line, self.ml_id_cam, self.sl_id_line, self.sl_id_cam = (_i(self.ml_id_line), _i(self.ml_id_cam),
+                                                                            _i(self.sl_id_line), _i(self.sl_id_cam))
+        self.ml_l2d, self.sl_l2d = _f(self.ml_l2d, (-1, 4)), _f(self.sl_l2d, (-1, 8))
+        self.ml_inlier, self.sl_inlier = _u(self.ml_inlier), _u(self.sl_inlier)
         return self
+
+    @property
+    def n_edges(self) -> int:
+        return len(self.mp_id_point) + len(self.sp_id_point) + len(self.ml_id_line) + len(self.sl_id_line)
 
     def copy(self) -> "FrameProblem":
         kw = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()}
@@ -178,14 +199,35 @@ class FrameBatch:
     stereo_xw: np.ndarray     # (3,Ns)
     stereo_cam: np.ndarray    # (Ns,)
     stereo_inlier: np.ndarray  # (Ns,)
+    # line extension (None: the batch has no line constraints, the reference's case)
+    mline_begin: Optional[np.ndarray] = None   # (F+1,)
+    sline_begin: Optional[np.ndarray] = None
+    mline_lw: Optional[np.ndarray] = None      # (6,Nml) fixed world line [w, d] copied into the edge
+    mline_meas: Optional[np.ndarray] = None    # (4,Nml)
+    mline_cam: Optional[np.ndarray] = None
+    mline_inlier: Optional[np.ndarray] = None
+    sline_lw: Optional[np.ndarray] = None      # (6,Nsl)
+    sline_meas: Optional[np.ndarray] = None    # (8,Nsl)
+    sline_cam: Optional[np.ndarray] = None
+    sline_inlier: Optional[np.ndarray] = None
+
+    _LINE_FIELDS = ("mline_begin", "sline_begin", "mline_lw", "mline_meas", "mline_cam", "mline_inlier",
+                    "sline_lw", "sline_meas", "sline_cam", "sline_inlier")
 
     @property
     def n_frames(self) -> int:
         return self.pose_twc.shape[1]
 
     @property
+    def has_lines(self) -> bool:
+        return self.mline_begin is not None and (int(self.mline_begin[-1]) + int(self.sline_begin[-1])) > 0
+
+    @property
     def n_edges(self) -> int:
-        return int(self.mono_begin[-1]) + int(self.stereo_begin[-1])
+        n = int(self.mono_begin[-1]) + int(self.stereo_begin[-1])
+        if self.mline_begin is not None:
+            n += int(self.mline_begin[-1]) + int(self.sline_begin[-1])
+        return n
 
     @staticmethod
     def from_problems(probs: List[FrameProblem]) -> "FrameBatch":
@@ -202,7 +244,22 @@ class FrameBatch:
             mxw.append(p.point_p[order][_local_index(ids_sorted, p.mp_id_point, "point")])
             sxw.append(p.point_p[order][_local_index(ids_sorted, p.sp_id_point, "point")])
         cat = lambda xs, d: (np.concatenate(xs, axis=0) if xs else np.zeros((0, d)))
+        lines = {}
+        if any(len(p.ml_id_line) + len(p.sl_id_line) for p in probs):
+            mlw, slw = [], []
+            for p in probs:
+                order = np.argsort(p.line_id, kind="stable")
+                ids_sorted = p.line_id[order]
+                mlw.append(p.line_L[order][_local_index(ids_sorted, p.ml_id_line, "line")])
+                slw.append(p.line_L[order][_local_index(ids_sorted, p.sl_id_line, "line")])
+            lines = dict(
+                mline_begin=_offsets([len(p.ml_id_line) for p in probs]), sline_begin=_offsets([len(p.sl_id_line) for p in probs]),
+                mline_lw=_f(cat(mlw, 6).T), mline_meas=_f(cat([p.ml_l2d for p in probs], 4).T),
+                mline_cam=_i(np.concatenate([p.ml_id_cam for p in probs])), mline_inlier=_u(np.concatenate([p.ml_inlier for p in probs])),
+                sline_lw=_f(cat(slw, 6).T), sline_meas=_f(cat([p.sl_l2d for p in probs], 8).T),
+                sline_cam=_i(np.concatenate([p.sl_id_cam for p in probs])), sline_inlier=_u(np.concatenate([p.sl_inlier for p in probs])))
         return FrameBatch(
+            **lines,
             cameras=_f(cams), pose_twc=_f(pose), mono_begin=mb, stereo_begin=sb,
             mono_meas=_f(cat([p.mp_kp for p in probs], 2).T), mono_xw=_f(cat(mxw, 3).T),
             mono_cam=_i(np.concatenate([p.mp_id_cam for p in probs])),
@@ -223,7 +280,22 @@ class FrameBatch:
             mp_id_point=np.arange(nm, dtype=I32), mp_id_cam=self.mono_cam[m0:m1].copy(),
             mp_kp=self.mono_meas[:, m0:m1].T.copy(), mp_inlier=self.mono_inlier[m0:m1].copy(),
             sp_id_point=np.arange(nm, nm + ns, dtype=I32), sp_id_cam=self.stereo_cam[s0:s1].copy(),
-            sp_kp=self.stereo_meas[:, s0:s1].T.copy(), sp_inlier=self.stereo_inlier[s0:s1].copy()).normalise()
+            sp_kp=self.stereo_meas[:, s0:s1].T.copy(), sp_inlier=self.stereo_inlier[s0:s1].copy(),
+            **self._frame_lines(f)).normalise()
+
+    def _frame_lines(self, f: int) -> dict:
+        if self.mline_begin is None:
+            return {}
+        a0, a1 = int(self.mline_begin[f]), int(self.mline_begin[f + 1])
+        b0, b1 = int(self.sline_begin[f]), int(self.sline_begin[f + 1])
+        na, nb = a1 - a0, b1 - b0
+        return dict(
+            line_id=np.arange(na + nb, dtype=I32),
+            line_L=np.concatenate([self.mline_lw[:, a0:a1].T, self.sline_lw[:, b0:b1].T], axis=0),
+            ml_id_line=np.arange(na, dtype=I32), ml_id_cam=self.mline_cam[a0:a1].copy(),
+            ml_l2d=self.mline_meas[:, a0:a1].T.copy(), ml_inlier=self.mline_inlier[a0:a1].copy(),
+            sl_id_line=np.arange(na, na + nb, dtype=I32), sl_id_cam=self.sline_cam[b0:b1].copy(),
+            sl_l2d=self.sline_meas[:, b0:b1].T.copy(), sl_inlier=self.sline_inlier[b0:b1].copy())
 
     def slice(self, f0: int, f1: int) -> "FrameBatch":
         """Frames [f0, f1) as an independent batch (how a rank takes its shard)."""
@@ -235,12 +307,26 @@ class FrameBatch:
             mono_meas=_f(self.mono_meas[:, m0:m1]), mono_xw=_f(self.mono_xw[:, m0:m1]),
             mono_cam=_i(self.mono_cam[m0:m1]), mono_inlier=_u(self.mono_inlier[m0:m1]),
             stereo_meas=_f(self.stereo_meas[:, s0:s1]), stereo_xw=_f(self.stereo_xw[:, s0:s1]),
-            stereo_cam=_i(self.stereo_cam[s0:s1]), stereo_inlier=_u(self.stereo_inlier[s0:s1]))
+            stereo_cam=_i(self.stereo_cam[s0:s1]), stereo_inlier=_u(self.stereo_inlier[s0:s1]),
+            **self._slice_lines(f0, f1))
+
+    def _slice_lines(self, f0: int, f1: int) -> dict:
+        if self.mline_begin is None:
+            return {}
+        a0, a1 = int(self.mline_begin[f0]), int(self.mline_begin[f1])
+        b0, b1 = int(self.sline_begin[f0]), int(self.sline_begin[f1])
+        return dict(
+            mline_begin=_i(self.mline_begin[f0:f1 + 1] - a0), sline_begin=_i(self.sline_begin[f0:f1 + 1] - b0),
+            mline_lw=_f(self.mline_lw[:, a0:a1]), mline_meas=_f(self.mline_meas[:, a0:a1]),
+            mline_cam=_i(self.mline_cam[a0:a1]), mline_inlier=_u(self.mline_inlier[a0:a1]),
+            sline_lw=_f(self.sline_lw[:, b0:b1]), sline_meas=_f(self.sline_meas[:, b0:b1]),
+            sline_cam=_i(self.sline_cam[b0:b1]), sline_inlier=_u(self.sline_inlier[b0:b1]))
 
     def h2d_bytes(self) -> int:
         return sum(int(getattr(self, k).nbytes) for k in (
             "cameras", "pose_twc", "mono_begin", "stereo_begin", "mono_meas", "mono_xw", "mono_cam",
-            "mono_inlier", "stereo_meas", "stereo_xw", "stereo_cam", "stereo_inlier") if getattr(self, k) is not None)
+            "mono_inlier", "stereo_meas", "stereo_xw", "stereo_cam", "stereo_inlier") + self._LINE_FIELDS
+            if getattr(self, k) is not None)
 
 
 @dataclass
@@ -250,10 +336,12 @@ class FrameBatchResult:
     stereo_inlier: np.ndarray
     num_inliers: np.ndarray    # (F,)
     stats: np.ndarray          # structured (F,)
+    mline_inlier: Optional[np.ndarray] = None  # line extension
+    sline_inlier: Optional[np.ndarray] = None
 
     def d2h_bytes(self) -> int:
-        return sum(int(getattr(self, k).nbytes) for k in ("pose_twc", "mono_inlier", "stereo_inlier",
-                                                          "num_inliers", "stats"))
+        return sum(int(getattr(self, k).nbytes) for k in ("pose_twc", "mono_inlier", "stereo_inlier", "num_inliers", "stats",
+                                                          "mline_inlier", "sline_inlier") if getattr(self, k) is not None)
 
 
 _EDGE_CLASSES = (("mp", "point", 2, "kp"), ("sp", "point", 3, "kp"), ("ml", "line", 4, "l2d"), ("sl", "line", 8, "l2d"))

@@ -326,14 +326,73 @@ def _frame_arrays(seed: int, n_points: int, stereo_frac: float, outlier_frac: fl
     return Rwc, twc, R0, t0, Xw, m, stereo, gross
 
 
+def _frame_line_arrays(seed: int, Rwc: np.ndarray, twc: np.ndarray, n_lines: int, stereo_frac: float = 0.7,
+                       outlier_frac: float = 0.05, pixel_sigma: float = 1.0):
+    """Fixed world lines seen by the frame (the "+60 lines" of config C2, an extension of the reference's
+    pose-only path): segments of 0.5-3 m in front of the camera, g2o::Line3D [w, d] in world coordinates,
+    measurements = endpoints slid +-10 % along the segment, projected into the left and right image, + noise.
+    Own random stream, so the point data of the frame does not depend on n_lines."""
+    rng = np.random.default_rng(seed ^ 0x11E5)
+    cam, wh = EUROC_CAMERA, EUROC_IMAGE_WH
+    b = cam[4] / cam[0]
+
+    def proj(Pc, shift):
+        x = Pc[:, 0] - shift
+        return np.stack([cam[0] * x / Pc[:, 2] + cam[2], cam[1] * Pc[:, 1] / Pc[:, 2] + cam[3]], axis=1)
+
+    def inside(uv, z):
+        return (z > 0.5) & (uv[:, 0] >= 0) & (uv[:, 0] < wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < wh[1])
+
+    P1 = np.zeros((0, 3))
+    P2 = np.zeros((0, 3))
+    while len(P1) < n_lines:
+        nc = max(4 * n_lines, 32)
+        u, v, z = rng.uniform(40, wh[0] - 40, nc), rng.uniform(40, wh[1] - 40, nc), rng.uniform(1.5, 8.0, nc)
+        a = np.stack([(u - cam[2]) / cam[0] * z, (v - cam[3]) / cam[1] * z, z], axis=1)
+        d = rng.normal(size=(nc, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        e = a + d * rng.uniform(0.5, 3.0, nc)[:, None]
+        ok = np.ones(nc, dtype=bool)
+        for s_ in (-0.1, 0.0, 1.0, 1.1):
+            Q = a + s_ * (e - a)
+            for shift in (0.0, b):
+                ok &= inside(proj(Q, shift), Q[:, 2])
+        P1, P2 = np.concatenate([P1, a[ok]]), np.concatenate([P2, e[ok]])
+    P1, P2 = P1[:n_lines], P2[:n_lines]
+    slide = np.stack([rng.uniform(-0.1, 0.1, (n_lines, 2)), 1.0 + rng.uniform(-0.1, 0.1, (n_lines, 2))], axis=2)  # (n, L/R, end)
+    meas = np.zeros((n_lines, 8))
+    for side, shift in ((0, 0.0), (1, b)):
+        for end in (0, 1):
+            Q = P1 + slide[:, side, end][:, None] * (P2 - P1)
+            meas[:, 4 * side + 2 * end:4 * side + 2 * end + 2] = proj(Q, shift)
+    meas += rng.normal(0.0, pixel_sigma, meas.shape)
+    gross = rng.random(n_lines) < outlier_frac
+    meas[gross] += rng.uniform(-40.0, 40.0, (int(gross.sum()), 8))
+    stereo = rng.random(n_lines) < stereo_frac
+    P1w, P2w = P1 @ Rwc.T + twc, P2 @ Rwc.T + twc
+    Lw = line_from_cartesian(P1w, P2w - P1w) if n_lines else np.zeros((0, 6))
+    return Lw, meas, stereo, gross
+
+
 def make_frame_problem(seed: int, n_points: int = 400, stereo_frac: float = 1.0, outlier_frac: float = 0.05,
-                       pixel_sigma: float = 1.0) -> FrameProblem:
-    """One pose-only frame (config C2: 400 stereo points)."""
+                       pixel_sigma: float = 1.0, n_lines: int = 0) -> FrameProblem:
+    """One pose-only frame (config C2: 400 stereo points; n_lines = 60 adds the line extension)."""
     Rwc, twc, R0, t0, Xw, m, stereo, gross = _frame_arrays(seed, n_points, stereo_frac, outlier_frac, pixel_sigma)
     rng = np.random.default_rng(seed ^ 0x5EED)
     ids = _ids_with_gaps(rng, n_points, start=100)
     mo = ~stereo
+    lines = {}
+    if n_lines > 0:
+        Lw, lm, lst, _ = _frame_line_arrays(seed, Rwc, twc, n_lines, outlier_frac=outlier_frac, pixel_sigma=pixel_sigma)
+        lid = np.arange(7, 7 + 3 * n_lines, 3, dtype=I32)
+        lmo = ~lst
+        lines = dict(line_id=lid, line_L=Lw,
+                     ml_id_line=lid[lmo], ml_id_cam=np.zeros(int(lmo.sum()), dtype=I32), ml_l2d=lm[lmo, :4],
+                     ml_inlier=np.ones(int(lmo.sum()), dtype=U8),
+                     sl_id_line=lid[lst], sl_id_cam=np.zeros(int(lst.sum()), dtype=I32), sl_l2d=lm[lst],
+                     sl_inlier=np.ones(int(lst.sum()), dtype=U8))
     return FrameProblem(
+        **lines,
         pose_p=t0, pose_q=R_to_quat(R0), point_id=ids, point_p=Xw, cams=EUROC_CAMERA[None, :].copy(),
         mp_id_point=ids[mo], mp_id_cam=np.zeros(int(mo.sum()), dtype=I32), mp_kp=m[mo, :2],
         mp_inlier=np.ones(int(mo.sum()), dtype=U8),
@@ -343,14 +402,25 @@ def make_frame_problem(seed: int, n_points: int = 400, stereo_frac: float = 1.0,
 
 
 def make_frame_batch(config: int, n_frames: int, first_instance: int = 0, n_points: int = 400,
-                     stereo_frac: float = 1.0, outlier_frac: float = 0.05, pixel_sigma: float = 1.0) -> FrameBatch:
+                     stereo_frac: float = 1.0, outlier_frac: float = 0.05, pixel_sigma: float = 1.0,
+                     n_lines: int = 0) -> FrameBatch:
     """n_frames independent pose-only frames as one flat batch (same per-frame content as
-    ``make_frame_problem(config_seed(config, first_instance + f))``)."""
+    ``make_frame_problem(config_seed(config, first_instance + f), n_lines=n_lines)``)."""
     pose = np.zeros((7, n_frames))
     mm, mx, sm, sx, mb, sb = [], [], [], [], [0], [0]
+    lml, lmm, lsl, lsm, lmb, lsb = [], [], [], [], [0], [0]
     for f in range(n_frames):
-        _, _, R0, t0, Xw, m, stereo, _ = _frame_arrays(config_seed(config, first_instance + f), n_points,
-                                                       stereo_frac, outlier_frac, pixel_sigma)
+        Rwc, twc, R0, t0, Xw, m, stereo, _ = _frame_arrays(config_seed(config, first_instance + f), n_points,
+                                                           stereo_frac, outlier_frac, pixel_sigma)
+        if n_lines > 0:
+            Lw, lm, lst, _ = _frame_line_arrays(config_seed(config, first_instance + f), Rwc, twc, n_lines,
+                                                outlier_frac=outlier_frac, pixel_sigma=pixel_sigma)
+            lml.append(Lw[~lst])
+            lmm.append(lm[~lst, :4])
+            lsl.append(Lw[lst])
+            lsm.append(lm[lst])
+            lmb.append(lmb[-1] + int((~lst).sum()))
+            lsb.append(lsb[-1] + int(lst.sum()))
         pose[:3, f] = t0
         pose[3:, f] = R_to_quat(R0)
         mo = ~stereo
@@ -367,4 +437,9 @@ def make_frame_batch(config: int, n_frames: int, first_instance: int = 0, n_poin
         mono_begin=np.asarray(mb, dtype=I32), stereo_begin=np.asarray(sb, dtype=I32),
         mono_meas=c(mm, 2), mono_xw=c(mx, 3), mono_cam=np.zeros(nm, dtype=I32), mono_inlier=np.ones(nm, dtype=U8),
         stereo_meas=c(sm, 3), stereo_xw=c(sx, 3), stereo_cam=np.zeros(ns, dtype=I32),
-        stereo_inlier=np.ones(ns, dtype=U8))
+        stereo_inlier=np.ones(ns, dtype=U8),
+        **(dict(mline_begin=np.asarray(lmb, dtype=I32), sline_begin=np.asarray(lsb, dtype=I32),
+                mline_lw=c(lml, 6), mline_meas=c(lmm, 4), mline_cam=np.zeros(lmb[-1], dtype=I32),
+                mline_inlier=np.ones(lmb[-1], dtype=U8),
+                sline_lw=c(lsl, 6), sline_meas=c(lsm, 8), sline_cam=np.zeros(lsb[-1], dtype=I32),
+                sline_inlier=np.ones(lsb[-1], dtype=U8)) if n_lines > 0 else {}))

@@ -39,8 +39,9 @@ def test_struct_layouts_match_header(lib):
     from rspl_slam_b200 import capi
     assert ctypes.sizeof(capi.RsplBaStats) == 64 and capi.STATS_DTYPE.itemsize == 64
     assert ctypes.sizeof(capi.RsplBaOptions) == 56
-    # pointer-heavy structs: 2 ints + 12 pointers / 2 ints + 28 pointers
-    assert ctypes.sizeof(capi.RsplFrameBatch) == 8 + 12 * 8
+    # pointer-heavy structs: 2 ints + 12 (+ 10 of the line extension) pointers / 2 ints + 28 pointers
+    assert ctypes.sizeof(capi.RsplFrameBatch) == 8 + 22 * 8
+    assert ctypes.sizeof(capi.RsplFrameBatchResult) == 7 * 8
     assert ctypes.sizeof(capi.RsplLocalBatch) == 8 + 28 * 8
 
 

@@ -24,6 +24,11 @@ def _check_against_oracle(orc, probs, batch, res, cfg=None):
         s0, s1 = batch.stereo_begin[f], batch.stereo_begin[f + 1]
         assert np.array_equal(q.mp_inlier, res.mono_inlier[m0:m1]), f"frame {f}: mono inlier set differs"
         assert np.array_equal(q.sp_inlier, res.stereo_inlier[s0:s1]), f"frame {f}: stereo inlier set differs"
+        if batch.mline_begin is not None:
+            a0, a1 = batch.mline_begin[f], batch.mline_begin[f + 1]
+            b0, b1 = batch.sline_begin[f], batch.sline_begin[f + 1]
+            assert np.array_equal(q.ml_inlier, res.mline_inlier[a0:a1]), f"frame {f}: mono line inlier set differs"
+            assert np.array_equal(q.sl_inlier, res.sline_inlier[b0:b1]), f"frame {f}: stereo line inlier set differs"
         assert int(res.num_inliers[f]) == st["ret"]
         assert np.linalg.norm(q.pose_p - res.pose_twc[:3, f]) < POS_TOL
         assert quat_angle(q.pose_q, res.pose_twc[3:, f]) < ROT_TOL
@@ -149,3 +154,44 @@ def test_invalid_inputs_are_rejected(gpu_ctx):
     with pytest.raises(capi.RsplBaError) as e:
         capi.Context(device=0).frame_batch_solve()
     assert e.value.code == capi.RSPL_BA_ERR_STATE
+
+
+def test_frame_batch_with_line_extension(gpu_ctx, orc):
+    """BASELINE config C2 in full: 400 stereo points + 60 lines per frame. The reference's FrameOptimization
+    takes no lines (g2o_optimization.cc:284-285); the extension treats them as EdgeSE3ProjectLine /
+    EdgeStereoSE3ProjectLine with the line vertex fixed (SURVEY 8a note), and the oracle does the same with
+    g2o's numeric pose Jacobians. Also ragged / mono-only / line-only frames, and pipelined chunks."""
+    probs = [synth.make_frame_problem(synth.config_seed(2, 300 + i), n_lines=60) for i in range(24)]
+    probs.append(synth.make_frame_problem(synth.config_seed(2, 330), n_points=40, n_lines=7))
+    probs.append(synth.make_frame_problem(synth.config_seed(2, 331), n_points=12, n_lines=25, stereo_frac=0.4))
+    only_lines = synth.make_frame_problem(synth.config_seed(2, 332), n_points=4, n_lines=30)
+    for k in ("mp_id_point", "mp_id_cam", "mp_inlier", "sp_id_point", "sp_id_cam", "sp_inlier"):
+        setattr(only_lines, k, getattr(only_lines, k)[:0])
+    only_lines.mp_kp, only_lines.sp_kp = only_lines.mp_kp[:0], only_lines.sp_kp[:0]
+    probs.append(only_lines)
+    probs.append(synth.make_frame_problem(synth.config_seed(2, 333)))  # a frame without lines in a batch with lines
+    batch = FrameBatch.from_problems(probs)
+    assert batch.has_lines
+    res = gpu_ctx.frame_batch(batch)
+    _check_against_oracle(orc, probs, batch, res)
+    # upload / solve / download path gives the same bits as the one-shot call
+    gpu_ctx.frame_batch_upload(batch)
+    gpu_ctx.frame_batch_solve()
+    res2 = gpu_ctx.frame_batch_download(gpu_ctx.alloc_frame_result(batch))
+    assert np.array_equal(res.pose_twc, res2.pose_twc) and np.array_equal(res.sline_inlier, res2.sline_inlier)
+    # a frame's result does not depend on the batch around it
+    solo = gpu_ctx.frame_batch(batch.slice(3, 4))
+    assert np.array_equal(solo.pose_twc[:, 0], res.pose_twc[:, 3])
+
+
+def test_frame_batch_lines_large_pipelined(gpu_ctx, orc):
+    """2048 frames with lines go through the chunked H2D / compute / D2H pipeline of the one-shot call."""
+    batch = synth.make_frame_batch(2, 2048, first_instance=5000, n_points=60, n_lines=12)
+    res = gpu_ctx.frame_batch(batch)
+    for f in (0, 511, 512, 1300, 2047):
+        p = batch.frame_problem(f)
+        st = orc.frame_opt(p)
+        assert int(res.num_inliers[f]) == st["ret"]
+        assert np.linalg.norm(p.pose_p - res.pose_twc[:3, f]) < POS_TOL
+        b0, b1 = batch.sline_begin[f], batch.sline_begin[f + 1]
+        assert np.array_equal(p.sl_inlier, res.sline_inlier[b0:b1])
