@@ -339,10 +339,11 @@ BA_DEV void line_image_residual(const Cam& cam, const double* wv, const double* 
   const double kv0 = -cam.fy * cam.cx, kv1 = -cam.fx * cam.cy, kv2 = cam.fx * cam.fy;
   const double l0 = cam.fy * wv[0], l1 = cam.fx * wv[1];
   const double l2 = kv0 * wv[0] + kv1 * wv[1] + kv2 * wv[2];
-  const double n = sqrt(l0 * l0 + l1 * l1);
-  const double inv = 1.0 / n;
-  e[0] = (m[0] * l0 + m[1] * l1 + l2) / n;
-  e[1] = (m[2] * l0 + m[3] * l1 + l2) / n;
+  // 1 / |l_xy| with one rsqrt instead of a square root and three divisions (differs from the divisions of
+  // edge_project_line.cc:32-33 by rounding only)
+  const double inv = rsqrt(l0 * l0 + l1 * l1);
+  e[0] = (m[0] * l0 + m[1] * l1 + l2) * inv;
+  e[1] = (m[2] * l0 + m[3] * l1 + l2) * inv;
   if (WITH_G) {
     const double n0 = l0 * inv, n1 = l1 * inv;
 #pragma unroll
