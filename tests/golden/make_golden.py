@@ -34,7 +34,12 @@ FRAME_CASES = {
     "frame_a": dict(seed=synth.config_seed(2, 9000), n_points=120),
     "frame_b": dict(seed=synth.config_seed(2, 9001), n_points=60, stereo_frac=0.6),
     "frame_c": dict(seed=synth.config_seed(2, 9002), n_points=8),
+    # line extension of the pose-only path (constraints on fixed lines; absent in the reference)
+    "frame_d_lines": dict(seed=synth.config_seed(2, 9003), n_points=100, n_lines=24),
+    "frame_e_lines": dict(seed=synth.config_seed(2, 9004), n_points=30, n_lines=40, stereo_frac=0.5),
 }
+FRAME_LINE_FIELDS = ["line_id", "line_L", "ml_id_line", "ml_id_cam", "ml_l2d", "ml_inlier", "sl_id_line", "sl_id_cam", "sl_l2d",
+                     "sl_inlier"]
 
 
 def main():
@@ -53,9 +58,10 @@ def main():
         p = synth.make_frame_problem(**kw)
         q = p.copy()
         st = orc.frame_opt(q, trace=True)
+        fields = FRAME_FIELDS + (FRAME_LINE_FIELDS if kw.get("n_lines") else [])
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"),
-            **{"in_" + f: getattr(p, f) for f in FRAME_FIELDS}, **{"out_" + f: getattr(q, f) for f in FRAME_FIELDS},
+            **{"in_" + f: getattr(p, f) for f in fields}, **{"out_" + f: getattr(q, f) for f in fields},
             iters=np.asarray(st["iters"]), trials=np.asarray(st["trials"]), final_chi2=st["final_chi2"], ret=st["ret"],
             edges_linearized=st["edges_linearized"])
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
