@@ -662,7 +662,7 @@ BA_DEV void pose_block_kind(const LocalDev& d, const BatchDev& b, const LocalOpt
   }
 }
 
-__global__ void __launch_bounds__(BT) kb_pose_blocks(const __grid_constant__ LocalDev d,
+__global__ void __launch_bounds__(BT, 4) kb_pose_blocks(const __grid_constant__ LocalDev d,
                                                      const __grid_constant__ BatchDev b,
                                                      const __grid_constant__ LocalOpt o) {
   __shared__ double red[BW * 27];
@@ -1219,13 +1219,19 @@ BA_DEV void backsub_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o,
   for (int e = ea; e < eb; ++e) {
     const int fi = b.free_idx[p0 + (k.info[e] & 0xffff)];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
-    const double* Ze = k.Z + (size_t)e * ZBlk<KIND>::N;
+    // (the block is read with 16-byte loads: this kernel is bound by L1 wavefronts, one per line an instruction touches)
+    const double2* Ze2 = reinterpret_cast<const double2*>(k.Z + (size_t)e * ZBlk<KIND>::N);
     const double* xv = b.xp + (size_t)(f0 + fi) * 6;
+    double xr[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const double xr = xv[r];
+    for (int r = 0; r < 6; ++r) xr[r] = xv[r];
 #pragma unroll
-      for (int a = 0; a < LD; ++a) v[a] -= Ze[a * ZCOL + r] * xr;
+    for (int a = 0; a < LD; ++a) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double2 z = Ze2[a * 3 + j];
+        v[a] -= z.x * xr[2 * j] + z.y * xr[2 * j + 1];
+      }
     }
   }
   double Hup[T::HD], Lf[LD * (LD + 1) / 2], inv[LD], xl[LD];
