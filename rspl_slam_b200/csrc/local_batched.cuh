@@ -587,7 +587,7 @@ BA_DEV void linearize_one(const LocalDev& d, const BatchDev& b, const LocalOpt& 
 // grid (chunks of this kind, windows): the chunk index is the fastest-varying block index so the
 // CTAs of one window run together and share its poses / edges in L1 / L2
 template <int KIND>
-__global__ void __launch_bounds__(BT) kb_linearize(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+__global__ void __launch_bounds__(BT, KIND == 0 ? 5 : 2) kb_linearize(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
                                                    const __grid_constant__ LocalOpt o) {
   __shared__ double red[BW * 3];
   const int w = blockIdx.y;
