@@ -209,3 +209,25 @@ def test_local_ba_rejects_missing_ids(orc):
     p.sp_id_point[0] = 10**6
     with pytest.raises(RuntimeError):
         orc.local_ba(p)
+
+
+def test_pose_only_line_extension_recovers_the_true_pose(orc):
+    """Known answer for the extension of the pose-only path (constraints on fixed lines; absent in the reference):
+    with noise-free measurements every line residual vanishes at the true pose, so the optimisation started from a
+    perturbed pose must return to it, lines alone and lines + points, and flag nothing as an outlier."""
+    import numpy as np
+    from rspl_slam_b200 import synth
+    from rspl_slam_b200.geometry import quat_angle, R_to_quat
+
+    for n_points in (4, 60):
+        p = synth.make_frame_problem(synth.config_seed(2, 9100 + n_points), n_points=n_points, n_lines=40, outlier_frac=0.0,
+                                     pixel_sigma=0.0)
+        if n_points == 4:  # lines only
+            for k in ("mp_id_point", "mp_id_cam", "mp_inlier", "sp_id_point", "sp_id_cam", "sp_inlier"):
+                setattr(p, k, getattr(p, k)[:0])
+            p.mp_kp, p.sp_kp = p.mp_kp[:0], p.sp_kp[:0]
+        st = orc.frame_opt(p)
+        assert st["ret"] == p.n_edges and p.ml_inlier.all() and p.sl_inlier.all()
+        assert np.linalg.norm(p.pose_p - p.truth["twc"]) < 1e-6
+        assert quat_angle(p.pose_q, R_to_quat(p.truth["Rwc"])) < 1e-6
+        assert st["final_chi2"] < 1e-6
