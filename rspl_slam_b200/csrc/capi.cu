@@ -691,8 +691,10 @@ extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, c
   c->f_sb.assign(in->stereo_begin, in->stereo_begin + F + 1);
   frame_keep_line_offsets(c, in);
   int n_chunks = F / 512;
+  int max_chunks = 4;
+  if (const char* e = getenv("RSPL_BA_FRAME_CHUNKS")) max_chunks = atoi(e) > 0 ? atoi(e) : max_chunks;
   if (n_chunks < 1) n_chunks = 1;
-  if (n_chunks > 4) n_chunks = 4;
+  if (n_chunks > max_chunks) n_chunks = max_chunks;
   rc = ensure_pipeline(c, n_chunks + 1);
   if (rc != RSPL_BA_OK) return rc;
   // everything queued earlier on the context stream completes first
