@@ -295,21 +295,26 @@ def local_ba(p, thr=(50.0, 75.0, 50.0, 75.0), iters=(10, 5)):
     return trace
 
 
-def frame_opt(p, thr=(50.0, 75.0), rounds=4, iters=10):
-    """FrameOptimization on a rspl_slam_b200.problem.FrameProblem, IN PLACE. Returns (ret, trace)."""
+def frame_opt(p, thr=(50.0, 75.0, 50.0, 75.0), rounds=4, iters=10):
+    """FrameOptimization on a rspl_slam_b200.problem.FrameProblem, IN PLACE. Returns (ret, trace).
+    Line constraints on fixed lines (the extension of oracle.h; none in the reference) are edges whose
+    landmark is a constant, like the world point of the pose-only point edges."""
     P = Problem()
     T0 = _T_from_twc(p.pose_p, p.pose_q)
     P.poses, P.pose_fixed = [T0], [False]
     xw = {int(i): p.point_p[k] for k, i in enumerate(p.point_id)}
     mono = [_mk_edge("mo", 0, -1, m, p.cams[0], thr[0], Xw=xw[int(i)]) for i, m in zip(p.mp_id_point, p.mp_kp)]
     stereo = [_mk_edge("so", 0, -1, m, p.cams[0], thr[1], Xw=xw[int(i)]) for i, m in zip(p.sp_id_point, p.sp_kp)]
-    P.edges = mono + stereo
+    lw = {int(i): p.line_L[k] for k, i in enumerate(p.line_id)}
+    mline = [_mk_edge("ml", 0, -1, m, p.cams[0], thr[2], Xw=lw[int(i)]) for i, m in zip(p.ml_id_line, p.ml_l2d)]
+    sline = [_mk_edge("sl", 0, -1, m, p.cams[0], thr[3], Xw=lw[int(i)]) for i, m in zip(p.sl_id_line, p.sl_l2d)]
+    P.edges = mono + stereo + mline + sline
     trace, n_out = [], 0
     for rnd in range(rounds):
         P.poses[0] = (T0[0].copy(), T0[1].copy())
         P.optimize(iters, 0, trace)
         n_out = 0
-        for es, inl in ((mono, p.mp_inlier), (stereo, p.sp_inlier)):
+        for es, inl in ((mono, p.mp_inlier), (stereo, p.sp_inlier), (mline, p.ml_inlier), (sline, p.sl_inlier)):
             for k, e in enumerate(es):
                 if not inl[k]:
                     e.err = e.residual(P.poses[0], e.Xw)

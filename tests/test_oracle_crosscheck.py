@@ -38,7 +38,9 @@ def test_local_ba_two_restatements_agree(orc, inst, kw):
 
 
 @pytest.mark.parametrize("inst,kw", [(0, dict(n_points=60)), (1, dict(n_points=40, stereo_frac=0.5)),
-                                      (2, dict(n_points=7)), (3, dict(n_points=80, outlier_frac=0.2))])
+                                      (2, dict(n_points=7)), (3, dict(n_points=80, outlier_frac=0.2)),
+                                      # the line extension of the pose-only path (constraints on fixed lines)
+                                      (4, dict(n_points=50, n_lines=20)), (5, dict(n_points=6, n_lines=30, outlier_frac=0.15))])
 def test_frame_optimization_two_restatements_agree(orc, inst, kw):
     p = synth.make_frame_problem(synth.config_seed(2, 7000 + inst), **kw)
     a, b = p.copy(), p.copy()
@@ -46,6 +48,7 @@ def test_frame_optimization_two_restatements_agree(orc, inst, kw):
     ret, tr = np_oracle.frame_opt(b)
     assert ret == st["ret"]
     assert np.array_equal(a.sp_inlier, b.sp_inlier) and np.array_equal(a.mp_inlier, b.mp_inlier)
+    assert np.array_equal(a.sl_inlier, b.sl_inlier) and np.array_equal(a.ml_inlier, b.ml_inlier)
     assert np.linalg.norm(a.pose_p - b.pose_p) < 1e-7 and quat_angle(a.pose_q, b.pose_q) < 1e-7
     # until the iteration has converged to rounding noise both restatements take the same decisions
     for r, t in list(zip(st["trace"], tr))[:3]:
