@@ -832,7 +832,10 @@ __global__ void __launch_bounds__(BT) kb_schur_prep(const __grid_constant__ Loca
 // lane-private ring of RED_STAGES stages (the 227 KB of shared memory hold the in-flight data instead of
 // registers), entry records are fetched one further iteration ahead, and a lane only ever reads what it
 // copied itself, so no barrier is needed.
-constexpr int RED_STAGES = 4;
+#ifndef RED_STAGES_N
+#define RED_STAGES_N 4
+#endif
+constexpr int RED_STAGES = RED_STAGES_N;
 constexpr int RED_RING = RED_STAGES * 6 * 32; // double2 per warp: [stage][piece][lane], conflict-free both ways
 
 BA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
