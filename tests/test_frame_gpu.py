@@ -154,6 +154,19 @@ def test_invalid_inputs_are_rejected(gpu_ctx):
     with pytest.raises(capi.RsplBaError) as e:
         capi.Context(device=0).frame_batch_solve()
     assert e.value.code == capi.RSPL_BA_ERR_STATE
+    # line extension: offsets must come in pairs and be monotone, arrays must be present, cameras in range
+    lb = synth.make_frame_batch(2, 4, first_instance=810, n_points=20, n_lines=6)
+    for patch in (dict(sline_begin=None), dict(mline_begin=lb.mline_begin[::-1].copy()), dict(sline_lw=None),
+                  dict(mline_cam=np.full_like(lb.mline_cam, 7))):
+        bad = FrameBatch(**{**lb.__dict__, **patch})
+        with pytest.raises(capi.RsplBaError) as e:
+            gpu_ctx.frame_batch(bad, out=gpu_ctx.alloc_frame_result(lb))
+        assert e.value.code == capi.RSPL_BA_ERR_INVALID, patch
+    res = gpu_ctx.alloc_frame_result(lb)
+    res.sline_inlier = None  # result buffers of the line edges are mandatory when the batch has lines
+    with pytest.raises(capi.RsplBaError) as e:
+        gpu_ctx.frame_batch(lb, out=res)
+    assert e.value.code == capi.RSPL_BA_ERR_INVALID
 
 
 def test_frame_batch_with_line_extension(gpu_ctx, orc):
