@@ -38,6 +38,7 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <vector>
 
 #include "../rspl_ba.h"
@@ -259,10 +260,45 @@ int LocalmapOptimizationImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPoints
 // ------------------------------------------------------------------------------------------------
 // FrameOptimization: returns the reference's int (number of inliers) through *num_inliers
 // ------------------------------------------------------------------------------------------------
+namespace detail {
+// stand-ins for "no line containers" (the reference's FrameOptimization has none)
+struct NoLineConstraint {
+  int id_line = 0, id_camera = 0;
+  bool inlier = true;
+  double line_2d(int) const { return 0.0; }
+};
+struct NoLine {
+  double line_3d(int) const { return 0.0; }
+};
+} // namespace detail
+
+// FrameOptimization plus constraints on FIXED map lines (extension: the reference's FrameOptimization takes
+// no line containers, g2o_optimization.h:20-22). `lines` is the reference's MapOfLine3d, the constraint
+// vectors its VectorOfMonoLineConstraints / VectorOfStereoLineConstraints (types.h:124-174); their
+// id_pose is ignored (there is one pose), ->inlier is read and written like the point constraints'.
+template <class MapOfPosesT, class MapOfPointsT, class MapOfLinesT, class CameraListT, class MonoPtT, class StereoPtT,
+          class MonoLnT, class StereoLnT, class CfgT>
+int FrameOptimizationWithLinesImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPointsT& points, MapOfLinesT& lines,
+                                   CameraListT& camera_list, MonoPtT& mono_point_constraints,
+                                   StereoPtT& stereo_point_constraints, MonoLnT& mono_line_constraints,
+                                   StereoLnT& stereo_line_constraints, const CfgT& cfg, int* num_inliers);
+
 template <class MapOfPosesT, class MapOfPointsT, class CameraListT, class MonoPtT, class StereoPtT, class CfgT>
 int FrameOptimizationImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPointsT& points, CameraListT& camera_list,
                           MonoPtT& mono_point_constraints, StereoPtT& stereo_point_constraints, const CfgT& cfg,
                           int* num_inliers) {
+  std::map<int, detail::NoLine> no_lines;
+  std::vector<std::shared_ptr<detail::NoLineConstraint>> no_ml, no_sl;
+  return FrameOptimizationWithLinesImpl(ctx, poses, points, no_lines, camera_list, mono_point_constraints,
+                                        stereo_point_constraints, no_ml, no_sl, cfg, num_inliers);
+}
+
+template <class MapOfPosesT, class MapOfPointsT, class MapOfLinesT, class CameraListT, class MonoPtT, class StereoPtT,
+          class MonoLnT, class StereoLnT, class CfgT>
+int FrameOptimizationWithLinesImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPointsT& points, MapOfLinesT& lines,
+                                   CameraListT& camera_list, MonoPtT& mono_point_constraints,
+                                   StereoPtT& stereo_point_constraints, MonoLnT& mono_line_constraints,
+                                   StereoLnT& stereo_line_constraints, const CfgT& cfg, int* num_inliers) {
   if (num_inliers) *num_inliers = 0;
   if (!ctx) return RSPL_BA_ERR_CUDA;
   if (poses.size() != 1) return RSPL_BA_ERR_INVALID; // assert(poses.size() == 1), g2o_optimization.cc:259
@@ -291,6 +327,30 @@ int FrameOptimizationImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPointsT& 
     s_cam[i] = c->id_camera;
     s_inl[i] = c->inlier ? 1 : 0;
   }
+  // line constraints (empty in the reference's path): the fixed world line is copied into the edge
+  const size_t nml = mono_line_constraints.size(), nsl = stereo_line_constraints.size();
+  std::vector<double> ml_lw(6 * nml), ml_meas(4 * nml), sl_lw(6 * nsl), sl_meas(8 * nsl);
+  std::vector<int32_t> ml_cam(nml), sl_cam(nsl);
+  std::vector<uint8_t> ml_inl(nml + 1), sl_inl(nsl + 1);
+  for (size_t i = 0; i < nml; ++i) {
+    const auto& c = mono_line_constraints[i];
+    auto it = lines.find(c->id_line);
+    if (it == lines.end()) return RSPL_BA_ERR_INVALID;
+    for (int k = 0; k < 6; ++k) ml_lw[k * nml + i] = it->second.line_3d(k);
+    for (int k = 0; k < 4; ++k) ml_meas[k * nml + i] = c->line_2d(k);
+    ml_cam[i] = c->id_camera;
+    ml_inl[i] = c->inlier ? 1 : 0;
+  }
+  for (size_t i = 0; i < nsl; ++i) {
+    const auto& c = stereo_line_constraints[i];
+    auto it = lines.find(c->id_line);
+    if (it == lines.end()) return RSPL_BA_ERR_INVALID;
+    for (int k = 0; k < 6; ++k) sl_lw[k * nsl + i] = it->second.line_3d(k);
+    for (int k = 0; k < 8; ++k) sl_meas[k * nsl + i] = c->line_2d(k);
+    sl_cam[i] = c->id_camera;
+    sl_inl[i] = c->inlier ? 1 : 0;
+  }
+  const int32_t mline_begin[2] = {0, (int32_t)nml}, sline_begin[2] = {0, (int32_t)nsl};
   const int32_t mono_begin[2] = {0, (int32_t)nm}, stereo_begin[2] = {0, (int32_t)ns};
   RsplFrameBatch in{};
   in.n_frames = 1;
@@ -307,19 +367,35 @@ int FrameOptimizationImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPointsT& 
   in.stereo_xw = s_xw.data();
   in.stereo_cam = s_cam.data();
   in.stereo_inlier = s_inl.data();
+  if (nml + nsl > 0) {
+    in.mono_line_begin = mline_begin;
+    in.stereo_line_begin = sline_begin;
+    in.mono_line_lw = ml_lw.data();
+    in.mono_line_meas = ml_meas.data();
+    in.mono_line_cam = ml_cam.data();
+    in.mono_line_inlier = ml_inl.data();
+    in.stereo_line_lw = sl_lw.data();
+    in.stereo_line_meas = sl_meas.data();
+    in.stereo_line_cam = sl_cam.data();
+    in.stereo_line_inlier = sl_inl.data();
+  }
   double o_pose[7];
   int32_t n_inl = 0;
-  std::vector<uint8_t> o_m(nm + 1), o_s(ns + 1);
+  std::vector<uint8_t> o_m(nm + 1), o_s(ns + 1), o_ml(nml + 1), o_sl(nsl + 1);
   RsplFrameBatchResult out{};
   out.pose_twc = o_pose;
   out.mono_inlier = o_m.data();
   out.stereo_inlier = o_s.data();
+  out.mono_line_inlier = o_ml.data();
+  out.stereo_line_inlier = o_sl.data();
   out.num_inliers = &n_inl;
   const RsplBaOptions opt = detail::make_options(cfg);
   const int rc = rspl_ba_frame_batch(ctx, &in, &opt, &out);
   if (rc != RSPL_BA_OK) return rc;
   for (size_t i = 0; i < nm; ++i) mono_point_constraints[i]->inlier = o_m[i] != 0;
   for (size_t i = 0; i < ns; ++i) stereo_point_constraints[i]->inlier = o_s[i] != 0;
+  for (size_t i = 0; i < nml; ++i) mono_line_constraints[i]->inlier = o_ml[i] != 0;
+  for (size_t i = 0; i < nsl; ++i) stereo_line_constraints[i]->inlier = o_sl[i] != 0;
   for (int k = 0; k < 3; ++k) pose.p(k) = o_pose[k]; // :391-393
   pose.q.x() = o_pose[3];
   pose.q.y() = o_pose[4];

@@ -87,8 +87,12 @@ int main(int argc, char** argv) {
   double ret = 0;
   if (kind == 0) {
     LocalmapOptimization(poses, points, lines, cams, mp, sp, ml, sl, cfg);
-  } else {
+  } else if (kind == 1) {
     ret = FrameOptimization(poses, points, cams, mp, sp, cfg);
+  } else { // kind 2: pose-only with constraints on fixed lines (the extension; no reference signature)
+    int n = 0;
+    (void)rspl_ba::FrameOptimizationWithLinesImpl(rspl_ba::thread_context(), poses, points, lines, cams, mp, sp, ml, sl, cfg, &n);
+    ret = n;
   }
   std::vector<double> out;
   out.push_back(ret);

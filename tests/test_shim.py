@@ -27,8 +27,9 @@ def driver(tmp_path_factory):
 
 def _dump(kind, p, path, cfg=(50.0, 75.0, 50.0, 75.0)):
     local = kind == 0
-    v = [kind, len(p.pose_id) if local else 1, len(p.point_id), len(p.line_id) if local else 0,
-         len(p.mp_id_point), len(p.sp_id_point), len(p.ml_id_pose) if local else 0, len(p.sl_id_pose) if local else 0]
+    with_lines = kind in (0, 2)
+    v = [kind, len(p.pose_id) if local else 1, len(p.point_id), len(p.line_id) if with_lines else 0,
+         len(p.mp_id_point), len(p.sp_id_point), len(p.ml_id_line) if with_lines else 0, len(p.sl_id_line) if with_lines else 0]
     v += list(cfg) + list(p.cams[0])
     if local:
         for i in range(len(p.pose_id)):
@@ -37,7 +38,7 @@ def _dump(kind, p, path, cfg=(50.0, 75.0, 50.0, 75.0)):
         v += [7, 0, *p.pose_p, *p.pose_q]
     for i in range(len(p.point_id)):
         v += [p.point_id[i], *p.point_p[i]]
-    if local:
+    if with_lines:
         for i in range(len(p.line_id)):
             v += [p.line_id[i], *p.line_L[i]]
     pose_of = (lambda a, i: a[i]) if local else (lambda a, i: 7)
@@ -45,11 +46,11 @@ def _dump(kind, p, path, cfg=(50.0, 75.0, 50.0, 75.0)):
         v += [pose_of(getattr(p, "mp_id_pose", None), i), p.mp_id_point[i], p.mp_inlier[i], *p.mp_kp[i]]
     for i in range(len(p.sp_id_point)):
         v += [pose_of(getattr(p, "sp_id_pose", None), i), p.sp_id_point[i], p.sp_inlier[i], *p.sp_kp[i]]
-    if local:
-        for i in range(len(p.ml_id_pose)):
-            v += [p.ml_id_pose[i], p.ml_id_line[i], p.ml_inlier[i], *p.ml_l2d[i]]
-        for i in range(len(p.sl_id_pose)):
-            v += [p.sl_id_pose[i], p.sl_id_line[i], p.sl_inlier[i], *p.sl_l2d[i]]
+    if with_lines:
+        for i in range(len(p.ml_id_line)):
+            v += [p.ml_id_pose[i] if local else 7, p.ml_id_line[i], p.ml_inlier[i], *p.ml_l2d[i]]
+        for i in range(len(p.sl_id_line)):
+            v += [p.sl_id_pose[i] if local else 7, p.sl_id_line[i], p.sl_inlier[i], *p.sl_l2d[i]]
     np.asarray(v, dtype=np.float64).tofile(path)
 
 
@@ -101,3 +102,25 @@ def test_shim_frame_equals_direct_cabi(driver, gpu_ctx, tmp_path):
     nm = len(p.mp_inlier)
     assert np.array_equal(out[k:k + nm].astype(np.uint8), res.mono_inlier)
     assert np.array_equal(out[k + nm:].astype(np.uint8), res.stereo_inlier)
+
+
+@pytest.mark.gpu
+def test_shim_frame_with_lines_equals_direct_cabi(driver, gpu_ctx, tmp_path):
+    """The shim's extension entry point (FrameOptimizationWithLinesImpl: the reference's line containers next to
+    its FrameOptimization arguments) gives the bits of the direct C-ABI call."""
+    from rspl_slam_b200.problem import FrameBatch
+    p = synth.make_frame_problem(synth.config_seed(2, 401), n_points=120, stereo_frac=0.8, n_lines=30)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    _dump(2, p, fin)
+    subprocess.run([driver, fin, fout], check=True)
+    out = np.fromfile(fout, dtype=np.float64)
+    batch = FrameBatch.from_problems([p])
+    res = gpu_ctx.frame_batch(batch)
+    assert int(out[0]) == int(res.num_inliers[0])
+    assert np.array_equal(out[1:8].view(np.uint64), np.ascontiguousarray(res.pose_twc[:, 0]).view(np.uint64))
+    k = 8 + 3 * len(p.point_id) + 6 * len(p.line_id)
+    nm, ns, nml = len(p.mp_inlier), len(p.sp_inlier), len(p.ml_inlier)
+    assert np.array_equal(out[k:k + nm].astype(np.uint8), res.mono_inlier)
+    assert np.array_equal(out[k + nm:k + nm + ns].astype(np.uint8), res.stereo_inlier)
+    assert np.array_equal(out[k + nm + ns:k + nm + ns + nml].astype(np.uint8), res.mline_inlier)
+    assert np.array_equal(out[k + nm + ns + nml:].astype(np.uint8), res.sline_inlier)
