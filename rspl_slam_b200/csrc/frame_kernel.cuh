@@ -227,6 +227,88 @@ BA_DEV void line_pass(const FrameDev& d, const FrameOpt& o, int e0, int e1, cons
   }
 }
 
+// Line edges, one lane per residual ROW: a frame has few line edges (60 in config C2) of very different cost (2 or 4
+// rows), so a lane per edge leaves most of the warp idle (one pass over 20 mono + two over 40 stereo edges). Here
+// the item space is 4 rows x (mono + stereo edges) -- rows 2, 3 of a mono edge are empty -- so 32 lanes take 8 whole
+// edges per step; the chi2 of an edge (needed by its Huber weight) is a 2-step shuffle sum over its 4 lanes. The
+// camera-frame line is recomputed by each of the 4 lanes (27 FMAs) instead of shared.
+template <bool LINEARIZE, bool SINGLE_CAM>
+BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml1, int sl0, int sl1, const double* R,
+                           const double* t, bool robust, int lane, double* acc) {
+  const int nm = ml1 - ml0, n_items = 4 * (nm + (sl1 - sl0));
+  for (int base = 0; base < n_items; base += 32) { // uniform trip count: the shuffles below need the whole warp
+    const int item = base + lane;
+    const bool valid = item < n_items;
+    const int ei = valid ? item >> 2 : 0, row = item & 3;
+    const bool st = ei >= nm;
+    const int e = st ? sl0 + (ei - nm) : ml0 + ei;
+    const bool act = valid && (st || row < 2) && !(st ? d.sline_lvl[e] : d.mline_lvl[e]);
+    double r = 0.0, J[6] = {0, 0, 0, 0, 0, 0};
+    if (act) {
+      Cam camv;
+      if (!SINGLE_CAM) load_cam(d.cameras, st ? d.sline_cam[e] : d.mline_cam[e], camv);
+      const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
+      const int stride = st ? d.n_sline : d.n_mline;
+      const double* lw = st ? d.sline_lw : d.mline_lw;
+      const double* ms = st ? d.sline_meas : d.mline_meas;
+      double L[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) L[q] = lw[(size_t)q * stride + e];
+      const int mq = 4 * (row >> 1) + 2 * (row & 1); // endpoint (x, y) of this row: left 1, left 2, right 1, right 2
+      const double mx = ms[(size_t)mq * stride + e], my = ms[(size_t)(mq + 1) * stride + e];
+      LineCam lc;
+      line_to_camera(R, t, L, lc);
+      const double b = cam.bf / cam.fx;
+      const bool right = row >= 2;
+      const double wv[3] = {lc.wc[0], right ? lc.wc[1] + b * lc.dc[2] : lc.wc[1], right ? lc.wc[2] - b * lc.dc[1] : lc.wc[2]};
+      const double kv0 = -cam.fy * cam.cx, kv1 = -cam.fx * cam.cy, kv2 = cam.fx * cam.fy;
+      const double l0 = cam.fy * wv[0], l1 = cam.fx * wv[1], l2 = kv0 * wv[0] + kv1 * wv[1] + kv2 * wv[2];
+      const double inv = rsqrt(l0 * l0 + l1 * l1);
+      r = (mx * l0 + my * l1 + l2) * inv;
+      if (LINEARIZE) {
+        const double n0 = l0 * inv, n1 = l1 * inv;
+        const double a0 = (mx - r * n0) * inv, a1 = (my - r * n1) * inv, a2 = inv;
+        const double g[3] = {a0 * cam.fy + a2 * kv0, a1 * cam.fx + a2 * kv1, a2 * kv2};
+        double a[3], c[3];
+        cross3(lc.wc, g, a);
+        cross3(lc.dc, g, c);
+        if (right) {
+          const double h[3] = {0.0, -b * g[2], b * g[1]};
+          double e2[3];
+          cross3(lc.dc, h, e2);
+          a[0] += e2[0];
+          a[1] += e2[1];
+          a[2] += e2[2];
+        }
+        J[0] = a[0];
+        J[1] = a[1];
+        J[2] = a[2];
+        J[3] = c[0];
+        J[4] = c[1];
+        J[5] = c[2];
+      }
+    }
+    double c2 = r * r;
+    c2 += __shfl_xor_sync(0xffffffffu, c2, 1);
+    c2 += __shfl_xor_sync(0xffffffffu, c2, 2);
+    c2 *= 0.1;
+    double w = 1.0;
+    const double rho0 = robust ? huber(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
+    if (act) {
+      if (row == 0) acc[NACC - 1] += rho0;
+      if (LINEARIZE) {
+        const double wo = 0.1 * w;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          acc[21 + i] -= wo * J[i] * r;
+#pragma unroll
+          for (int j = i; j < 6; ++j) acc[up6(i, j)] += wo * J[i] * J[j];
+        }
+      }
+    }
+  }
+}
+
 // fixed-order butterfly: every lane ends with the same bitwise-deterministic sum
 BA_DEV double warp_allreduce(double v) {
 #pragma unroll
@@ -410,8 +492,12 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
           edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
           if (HAS_LINES) {
+#ifdef RSPL_BA_LINE_PER_EDGE
             line_pass<true, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, acc);
             line_pass<true, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, acc);
+#else
+            line_pass_rows<true, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, acc);
+#endif
           }
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
@@ -472,8 +558,12 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
             a2[NACC - 1] = 0;
             edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
             if (HAS_LINES) {
+#ifdef RSPL_BA_LINE_PER_EDGE
               line_pass<false, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, a2);
               line_pass<false, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, a2);
+#else
+              line_pass_rows<false, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, a2);
+#endif
             }
             tempChi = warp_allreduce(a2[NACC - 1]);
           }
