@@ -100,6 +100,8 @@ struct RsplBaContext {
   std::vector<int> l_nf_begin;          // [W+1] free poses per window (prefix)
   std::vector<long long> l_pair_base;   // [W+1] capacity prefix of the pair lists
   int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
+  cudaStream_t s_aux = nullptr;           // the line kernels of a super-step run beside the point kernels
+  cudaEvent_t fork_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve (diagnostics)
   int l_super_steps = 0;
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
@@ -278,6 +280,9 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
   }
+  if (c->s_aux) cudaStreamDestroy(c->s_aux);
+  for (int i = 0; i < 6; ++i)
+    if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   for (int i = 0; i < 4; ++i)
     if (c->s_cmp[i]) cudaStreamDestroy(c->s_cmp[i]);

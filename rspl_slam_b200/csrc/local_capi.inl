@@ -475,10 +475,37 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   // one super-step = a fixed sequence of launches with constant arguments
   int dense_rc = RSPL_BA_OK, coll_rc = RSPL_BA_OK;
   const int NF_all = c->l_nf_begin[W];
+  // The line kernels (few landmarks, 190-200 registers, ~10 % resident warps) run on a second stream beside the
+  // point kernels of the same phase; fork / join events become graph dependencies under capture. Not when
+  // profiling (event pairs are recorded on the main stream) and not on the dense path.
+  const bool fork_lines = !c->prof && !dense && b.Cp && b.Cl;
+  if (fork_lines && !c->s_aux) {
+    CU_TRY(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s_ln = fork_lines ? c->s_aux : s;
+  auto fork = [&](int k) {
+    if (!fork_lines) return;
+    cudaEventRecord(c->fork_ev[2 * k], s);
+    cudaStreamWaitEvent(s_ln, c->fork_ev[2 * k], 0);
+  };
+  auto join = [&](int k) {
+    if (!fork_lines) return;
+    cudaEventRecord(c->fork_ev[2 * k + 1], s_ln);
+    cudaStreamWaitEvent(s, c->fork_ev[2 * k + 1], 0);
+  };
+#define LAUNCH_LN(cls, kern, grid, block, shm, ...)    \
+  do {                                                 \
+    ProfScope ps_(c, cls);                             \
+    kern<<<grid, block, shm, s_ln>>>(__VA_ARGS__);     \
+    c->launches++;                                     \
+  } while (0)
   auto super_step = [&]() {
+    fork(0);
     if (b.Cp) LAUNCH(PC_LINEARIZE, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
-    if (b.Cl) LAUNCH(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH_LN(PC_LINEARIZE, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
     LAUNCH(PC_POSE_BLOCKS, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    join(0);
     if (global) { // pose blocks and the linearisation scalars of every rank's landmarks
       LAUNCH(PC_CONTROL, ba::kb_global_sums, 1, 256, 0, b, 0);
       ProfScope ps_(c, PC_COLLECTIVE);
@@ -487,8 +514,10 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 2, b.gs + 2, 1, kNcclFloat64, kNcclMax);
     }
     LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
+    fork(1);
     if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
-    if (b.Cl) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH_LN(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+    join(1);
     LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
     if (!dense) {
       LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
@@ -509,8 +538,10 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       }
       LAUNCH(PC_ASSEMBLE, ba::kb_post_solve, W, 256, 0, d, b);
     }
+    fork(2);
     if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
-    if (b.Cl) LAUNCH(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (b.Cl) LAUNCH_LN(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    join(2);
     if (global) {
       LAUNCH(PC_CONTROL, ba::kb_global_sums, 1, 256, 0, b, 1);
       ProfScope ps_(c, PC_COLLECTIVE);
@@ -593,6 +624,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   LAUNCH(PC_FLAG_WRITEBACK, ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
   LAUNCH(PC_FLAG_WRITEBACK, ba::kb_writeback, W, 256, 0, d, b);
 #undef LAUNCH
+#undef LAUNCH_LN
   CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;
 }
