@@ -82,7 +82,7 @@ struct DevStats { // layout == RsplBaStats
 #define FRAME_MIN_BLOCKS 4 // 128 registers: best of {3, 4, 5} measured on B200 (profiles/README.md)
 #endif
 #ifndef FRAME_LINES_MIN_BLOCKS
-#define FRAME_LINES_MIN_BLOCKS 4 // instantiation with the line extension: 2 / 3 / 4 CTAs per SM measured 4.61 / 4.33 / 4.28 ms (C2 with 60 lines)
+#define FRAME_LINES_MIN_BLOCKS 4 // instantiation with the line extension: 3 / 4 / 5 CTAs per SM measured 4.03 / 3.60 / 5.34 ms (C2 with 60 lines)
 #endif
 constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
 constexpr int FRAME_WARPS = FRAME_THREADS / 32;
