@@ -341,7 +341,7 @@ def run_ours(args):
             from rspl_slam_b200.roofline import local_class_bytes
             cls_bytes = local_class_bytes(batch, stats)  # bytes per step of the linearise / Schur / back-sub classes
             groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
-                      "schur (kb_schur_prep + kb_schur_reduce + kb_solve)": (("schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
+                      "schur (kt_schur_tile | kb_schur_prep + kb_schur_reduce, + kb_solve)": (("schur_tile", "schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
                       "backsub (kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"]),
                       "persistent (local_solve_kernel)": (("local_solve_persistent",), sum(cls_bytes.values()))}
             best = None

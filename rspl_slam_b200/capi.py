@@ -404,7 +404,7 @@ class Context:
 
     PROFILE_CLASSES = ("frame_opt", "local_setup", "local_solve_persistent", "init_pairs", "linearize", "pose_blocks",
                        "schur_prep", "schur_reduce", "reduced_solve", "backsub_update_eval", "lm_control", "flag_writeback",
-                       "collectives", "dense_assemble")
+                       "collectives", "dense_assemble", "schur_tile")
 
     def set_profiling(self, enabled: bool):
         self._check(self._L.rspl_ba_set_profiling(self._ctx, 1 if enabled else 0))

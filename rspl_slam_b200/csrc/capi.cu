@@ -19,6 +19,7 @@
 #include "frame_kernel.cuh"
 #include "local_kernel.cuh"
 #include "local_batched.cuh"
+#include "local_tiled.cuh"
 
 static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
 
@@ -102,7 +103,11 @@ struct RsplBaContext {
   int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
   cudaStream_t s_aux = nullptr;           // the line kernels of a super-step run beside the point kernels
   cudaEvent_t fork_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve (diagnostics)
+  // tiled Schur path (local_tiled.cuh)
+  DevBuf tile_buf;
+  ba::TileDev td{};
+  std::vector<long long> l_cost[2];     // [W] shared-memory cost of a window's points / lines (tile sizing)
+  int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve, 4 batched + tiled Schur (diagnostics)
   int l_super_steps = 0;
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
   DevBuf dense_buf;
@@ -271,6 +276,7 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   c->frame_buf.release();
   c->local_buf.release();
   c->batch_buf.release();
+  c->tile_buf.release();
   c->dense_buf.release();
   dense_release(c);
   comm_release(c);
@@ -306,7 +312,7 @@ extern "C" int rspl_ba_sync(RsplBaContext* c) {
 namespace {
 enum ProfClass {
   PC_FRAME = 0, PC_LOCAL_SETUP, PC_LOCAL_PERSISTENT, PC_PAIRS, PC_LINEARIZE, PC_POSE_BLOCKS, PC_SCHUR_PREP,
-  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_ASSEMBLE, PC_COUNT
+  PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_ASSEMBLE, PC_SCHUR_TILE, PC_COUNT
 };
 // records an event pair around one launch when profiling is on
 struct ProfScope {

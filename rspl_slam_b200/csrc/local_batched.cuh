@@ -1031,8 +1031,35 @@ BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, int n, in
   }
 }
 
+// Tables of the tiled Schur path (local_tiled.cuh): landmark tiles sized by shared memory, their slices of the
+// pair lists, the per-tile partial reduced systems.
+struct TileDev {
+  int Q;           // tile quantile in bytes of shared memory
+  int Tcap;        // tiles per (window, kind) <= Tcap
+  int Tp, Tl;      // grid widths: max tiles of points / lines over the windows
+  int* tile_lm;    // [(w*2+kind)*(Tcap+1) + t] first landmark (batch-global index) of tile t; entry ntile = end
+  int* ntile;      // [w*2+kind]
+  int* tpb;        // [((w*2+kind)*(Tcap+1) + t)*Pmax + li] first entry of tile t in the kind-list of compact pair li
+  int* order;      // [w*Pmax + o] compact pair position, longest list first
+  double* hs_tile; // [((w*(Tp+Tl) + tt)*Pmax + li)*42], tt = t (points) or Tp + t (lines)
+  double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)
+};
+
+// sum of the per-tile partial reduced systems of a window (tile order: points then lines => deterministic)
+BA_DEV double tile_sum(const BatchDev& b, const TileDev& td, int w, int li, int el) {
+  double v = 0.0;
+  const int ntp = td.ntile[w * 2], ntl = td.ntile[w * 2 + 1];
+  const double* base = td.hs_tile + (size_t)w * (td.Tp + td.Tl) * b.Pmax * 42 + (size_t)li * 42 + el;
+  const size_t stride = (size_t)b.Pmax * 42;
+  for (int t = 0; t < ntp; ++t) v += base[t * stride];
+  for (int t = 0; t < ntl; ++t) v += base[(td.Tp + t) * stride];
+  return v;
+}
+
 // K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory
-__global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+template <bool TILED>
+__global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                const __grid_constant__ TileDev td) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = blockIdx.x, tid = threadIdx.x;
   WinState& s = b.ws[w];
@@ -1057,7 +1084,7 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     pair_decode(p, nf, fi, fj);
     const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
     if (si < 0 || sj < 0) continue;
-    double v = -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
+    double v = TILED ? -tile_sum(b, td, w, li, rc) : -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
     if (fi == fj) {
       const int rr = r < c ? r : c, cc = r < c ? c : r;
       v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? lambda : 0.0);
@@ -1069,7 +1096,8 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     const int si = b.sys_idx[f0 + fi];
     if (si < 0) continue;
     const int li = b.diag_pos[f0 + fi];
-    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r];
+    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] -
+                     (TILED ? tile_sum(b, td, w, li, 36 + r) : b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r]);
   }
   __syncthreads();
   __shared__ int s_chol;
@@ -1100,6 +1128,10 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
         for (int q = 0; q < 4; ++q) T.q[q] = b.P_bq[4 * gp + q] = b.P_q[4 * gp + q];
 #pragma unroll
         for (int q = 0; q < 3; ++q) T.t[q] = b.P_bt[3 * gp + q] = b.P_t[3 * gp + q];
+        if (TILED) {
+#pragma unroll
+          for (int q = 0; q < 9; ++q) td.P_bR[9 * gp + q] = b.P_R[9 * gp + q];
+        }
         const Pose Tn = pose_oplus(T, x6);
         double Rn[9];
         quat_to_R(Tn.q, Rn);

@@ -89,6 +89,8 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   c->l_nf_begin.assign(W + 1, 0);
   c->l_pair_base.assign(W + 1, 0);
   c->l_max_pts = c->l_max_lns = c->l_max_edges = 0;
+  c->l_cost[0].assign(W, 0);
+  c->l_cost[1].assign(W, 0);
   for (int w = 0; w < W; ++w) {
     const int a = in->pose_begin[w], b = in->pose_begin[w + 1];
     int nf = 0;
@@ -101,6 +103,12 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
                          (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]) +
                          (in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) +
                          (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]);
+    c->l_cost[0][w] = (long long)ba::TileCost<0>::A * npt +
+                      (long long)ba::TileCost<0>::B * ((in->mono_pt_begin[w + 1] - in->mono_pt_begin[w]) +
+                                                       (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]));
+    c->l_cost[1][w] = (long long)ba::TileCost<1>::A * nln +
+                      (long long)ba::TileCost<1>::B * ((in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) +
+                                                       (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]));
     if (npt > c->l_max_pts) c->l_max_pts = npt;
     if (nln > c->l_max_lns) c->l_max_lns = nln;
     if (ne > c->l_max_edges) c->l_max_edges = (int)ne;
@@ -137,7 +145,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const size_t o_tcw = a.take(sizeof(double) * 7 * NP);
   const size_t o_pout = a.take(sizeof(double) * 7 * NP);
   const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
-  const size_t o_err = a.take(sizeof(int));
+  const size_t o_err = a.take(sizeof(int) * 4); // error flag, max degree of points / lines
   const size_t o_phase = a.take(sizeof(long long) * 8 * W);
   const size_t o_sfi = a.take(sizeof(int) * NP);
   const int slot_stride = (max_free + 3) & ~3;
@@ -234,6 +242,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.slot_stride = slot_stride;
   d.stats = (void*)(base + o_stats);
   d.err = (int*)(base + o_err);
+  d.maxdeg = d.err + 1;
   d.phase = (long long*)(base + o_phase);
   d.setup_free_idx = (int*)(base + o_sfi);
   for (int k = 0; k < 2; ++k) {
@@ -388,6 +397,56 @@ int batched_prepare(RsplBaContext* c) {
   return RSPL_BA_OK;
 }
 
+// Tables of the tiled Schur path (local_tiled.cuh): tile size, tile counts, device arrays. maxdeg = largest landmark
+// degree per kind (read back from the setup kernels); smem_tile = dynamic shared memory of kt_schur_tile per kind.
+int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
+  const int W = c->l_n_windows;
+  const int cost_a[2] = {ba::TileCost<0>::A, ba::TileCost<1>::A}, cost_b[2] = {ba::TileCost<0>::B, ba::TileCost<1>::B};
+  long long total = 0;
+  for (int k = 0; k < 2; ++k)
+    for (int w = 0; w < W; ++w) total += c->l_cost[k][w];
+  // default: two CTAs per SM; small batches (single windows) get smaller tiles so that they spread over the SMs
+  long long Q = 100 << 10;
+  if (const char* e = getenv("RSPL_BA_TILE_Q")) Q = atoll(e) > 4096 ? atoll(e) : Q;
+  else
+    while (Q > (12 << 10) && total / Q < 2LL * c->num_sms) Q >>= 1;
+  for (int k = 0; k < 2; ++k) {
+    const long long room = (long long)c->smem_optin - cost_a[k] - (long long)cost_b[k] * maxdeg[k] - 64;
+    if (room < 4096) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: landmark degree %d too large for the tiled Schur path", maxdeg[k]);
+    if (Q > room) Q = room;
+  }
+  int T[2] = {0, 0};
+  for (int k = 0; k < 2; ++k)
+    for (int w = 0; w < W; ++w) {
+      const int nt = (int)((c->l_cost[k][w] + Q - 1) / Q);
+      if (nt > T[k]) T[k] = nt;
+    }
+  const int Tcap = T[0] > T[1] ? (T[0] > 0 ? T[0] : 1) : (T[1] > 0 ? T[1] : 1);
+  const int Pmax = c->bd.Pmax;
+  Arena a;
+  const size_t o_tlm = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1));
+  const size_t o_nt = a.take(sizeof(int) * (size_t)W * 2);
+  const size_t o_tpb = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1) * Pmax);
+  const size_t o_ord = a.take(sizeof(int) * (size_t)W * Pmax);
+  const size_t o_hs = a.take(sizeof(double) * (size_t)W * (T[0] + T[1] > 0 ? T[0] + T[1] : 1) * Pmax * 42);
+  const size_t o_bR = a.take(sizeof(double) * 9 * (size_t)c->l_np);
+  CU_TRY(c, c->tile_buf.reserve(a.off));
+  char* base = c->tile_buf.as<char>();
+  ba::TileDev& td = c->td;
+  td.Q = (int)Q;
+  td.Tcap = Tcap;
+  td.Tp = T[0];
+  td.Tl = T[1];
+  td.tile_lm = (int*)(base + o_tlm);
+  td.ntile = (int*)(base + o_nt);
+  td.tpb = (int*)(base + o_tpb);
+  td.order = (int*)(base + o_ord);
+  td.hs_tile = (double*)(base + o_hs);
+  td.P_bR = (double*)(base + o_bR);
+  for (int k = 0; k < 2; ++k) smem_tile[k] = (size_t)(Q + cost_a[k] + (long long)cost_b[k] * maxdeg[k] + 32);
+  return RSPL_BA_OK;
+}
+
 // The batched LocalmapOptimization: fixed kernel sequence per super-step, per-window LM state
 // machines on the device, host polls the number of still-iterating windows.
 int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
@@ -415,7 +474,8 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   if (dense) {
     c->l_last_path = 3; // (buffers are set up after the pair lists: their band decides the factorisation)
   } else {
-    CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
   }
 #define LAUNCH(cls, kern, grid, block, shm, ...)       \
   do {                                                 \
@@ -446,8 +506,15 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   }
   LAUNCH(PC_PAIRS, ba::kb_pairs_compact, W, 1024, 0, d, b);
   std::vector<int> n_ne_host(W, 0);
+  int setup_flags[4] = {0, 0, 0, 0}; // error flag, max degree of points / lines
   CU_TRY(c, cudaMemcpyAsync(n_ne_host.data(), b.n_ne, sizeof(int) * W, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(setup_flags, d.err, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
   CU_TRY(c, cudaStreamSynchronize(s));
+  // g2o accepts what the slot table cannot hold; say so before iterating on a truncated table
+  if (setup_flags[0] & ba::LOCAL_ERR_DUP_EDGE)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: two constraints join the same (pose, landmark) pair");
+  if (setup_flags[0] & ba::LOCAL_ERR_DEGREE)
+    return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: a landmark has more than 254 observations");
   int n_ne_max = 1;
   for (int w = 0; w < W; ++w) n_ne_max = n_ne_host[w] > n_ne_max ? n_ne_host[w] : n_ne_max;
   const dim3 g_ne(n_ne_max, W);
@@ -471,6 +538,23 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     c->bd.dense_info = dl.info;
     c->bd.dense_off = dl.d_off;
   }
+  // Schur elimination: per-tile fused kernel (local_tiled.cuh) unless the reduced system goes to HBM (dense / global)
+  bool tiled = !dense;
+  if (const char* env = getenv("RSPL_BA_SCHUR"))
+    if (!strcmp(env, "legacy")) tiled = false;
+  const ba::TileDev& td = c->td;
+  size_t smem_tile[2] = {0, 0};
+  if (tiled) {
+    rc = tiles_prepare(c, setup_flags + 1, smem_tile);
+    if (rc != RSPL_BA_OK) return rc;
+    c->l_last_path = 4;
+    LAUNCH(PC_PAIRS, ba::kt_tiles_lm, dim3((td.Tcap + 1 + 127) / 128, W, 2), 128, 0, d, td);
+    LAUNCH(PC_PAIRS, ba::kt_tiles_pairs, dim3(((size_t)b.Pmax * (td.Tcap + 1) + 255) / 256, W, 2), 256, 0, d, b, td);
+    LAUNCH(PC_PAIRS, ba::kt_order, (W + 3) / 4, 128, 0, d, b, td);
+    CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[0]));
+    CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[1]));
+  }
+  const dim3 g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
   int dense_rc = RSPL_BA_OK, coll_rc = RSPL_BA_OK;
@@ -515,12 +599,19 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     }
     LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
     fork(1);
-    if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
-    if (b.Cl) LAUNCH_LN(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (tiled) {
+      if (b.Cp && td.Tp) LAUNCH(PC_SCHUR_TILE, ba::kt_schur_tile<0>, g_tp, ba::TILE_THREADS, smem_tile[0], d, b, lo, td);
+      if (b.Cl && td.Tl) LAUNCH_LN(PC_SCHUR_TILE, ba::kt_schur_tile<1>, g_tl, ba::TILE_THREADS, smem_tile[1], d, b, lo, td);
+    } else {
+      if (b.Cp) LAUNCH(PC_SCHUR_PREP, ba::kb_schur_prep<0>, g_pt, ba::BT, 0, d, b, lo);
+      if (b.Cl) LAUNCH_LN(PC_SCHUR_PREP, ba::kb_schur_prep<1>, g_ln, ba::BT, 0, d, b, lo);
+    }
     join(1);
-    LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
-    if (!dense) {
-      LAUNCH(PC_SOLVE, ba::kb_solve, W, 256, smem_solve, d, b);
+    if (!tiled) LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
+    if (tiled) {
+      LAUNCH(PC_SOLVE, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
+    } else if (!dense) {
+      LAUNCH(PC_SOLVE, ba::kb_solve<false>, W, 256, smem_solve, d, b, td);
     } else {
       if (global) { // rank-local Schur complement pieces -> sum over ranks (+ the Cholesky-failure flag in the tail)
         ProfScope ps_(c, PC_COLLECTIVE);
@@ -539,8 +630,13 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       LAUNCH(PC_ASSEMBLE, ba::kb_post_solve, W, 256, 0, d, b);
     }
     fork(2);
-    if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
-    if (b.Cl) LAUNCH_LN(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    if (tiled) {
+      if (b.Cp) LAUNCH(PC_BACKSUB, ba::kt_backsub_rc<0>, g_pt, ba::BT, 0, d, b, lo, td);
+      if (b.Cl) LAUNCH_LN(PC_BACKSUB, ba::kt_backsub_rc<1>, g_ln, ba::BT, 0, d, b, lo, td);
+    } else {
+      if (b.Cp) LAUNCH(PC_BACKSUB, ba::kb_backsub<0>, g_pt, ba::BT, 0, d, b, lo);
+      if (b.Cl) LAUNCH_LN(PC_BACKSUB, ba::kb_backsub<1>, g_ln, ba::BT, 0, d, b, lo);
+    }
     join(2);
     if (global) {
       LAUNCH(PC_CONTROL, ba::kb_global_sums, 1, 256, 0, b, 1);
@@ -653,7 +749,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   lo.max_free = c->l_max_free_poses;
   const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
   if (c->l_n_windows > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
-  CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int), c->stream));
+  CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int) * 4, c->stream));
   {
     ProfScope ps(c, PC_LOCAL_SETUP);
     const int W = c->l_n_windows;

@@ -100,6 +100,7 @@ struct LocalDev {
   KindDev k[2];
   void* stats;
   int* err; // device error flag
+  int* maxdeg; // [2] largest landmark degree of the batch per kind (setup_scan)
   long long* phase; // [n_windows][8] cycles per phase (diagnostics), may be null
 };
 
@@ -244,6 +245,10 @@ __global__ void __launch_bounds__(1024) setup_scan(const __grid_constant__ Local
       k.ebeg[l0 + i] = run + (warp ? s_warp[warp - 1] : 0) + x - v;
       k.cursor[l0 + i] = 0;
       if (v > 254) atomicOr(d.err, LOCAL_ERR_DEGREE);
+    }
+    {
+      const int mv = __reduce_max_sync(0xffffffffu, v);
+      if (lane == 0 && mv > 0) atomicMax(&d.maxdeg[blockIdx.y], mv);
     }
     __syncthreads();
     if (tid == 0) s_run = run + s_warp[31];

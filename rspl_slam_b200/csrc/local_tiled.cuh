@@ -1,0 +1,437 @@
+// local_tiled.cuh — Schur elimination of the landmarks WITHOUT a round trip of Z = W L^-T through HBM.
+//
+// The batched path of local_batched.cuh wrote one 144/192-byte Z block per edge (kb_schur_prep), gathered every
+// block ~5 times from L2 (kb_schur_reduce: one warp per pose pair) and once more in kb_backsub: L2-request bound
+// at 0.14 of the HBM contract roofline. Here the landmarks of a window are cut into TILES sized by shared memory,
+// and one CTA per tile does both halves of g2o's Schur step (BlockSolver::solve):
+//   phase 1a  thread per landmark : L = chol(Hll + lambda), y = L^-1 bl                  -> shared memory
+//   phase 1b  thread per EDGE     : W = Jp^T (rho1 Omega) Jl from the 40-byte edge record, Z = W L^-T -> shared memory
+//   phase 2   8 lanes per pose pair: sum over the tile's entries of that pair's list of Z_i Z_j^T (and Z_i y on
+//             the diagonal); a lane owns one landmark-coordinate column of one entry per iteration (a rank-1
+//             update of 36 + 6 private accumulators), a fixed 3-step transpose reduction sums the 8 lanes
+// and writes the tile's partial reduced system hs_tile[window][tile][pair][42]. kb_solve adds the tiles in tile
+// order. Back-substitution (kb_backsub_rc) no longer reads Z either: it recomputes W^T xp from the edge record at
+// the pre-update state, xl = (Hll + lambda)^-1 (bl - sum W^T xp). Every sum has a fixed owner and order: results
+// stay bitwise reproducible and independent of the batch composition.
+//
+// Tiles are defined by quantiles of the cumulative shared-memory cost A * (landmarks before l) + B * (edges
+// before l) along the window's internal landmark order, so a tile never exceeds Q + A + B * max degree bytes.
+#pragma once
+
+#include "local_batched.cuh"
+
+namespace ba {
+
+template <int KIND>
+struct TileCost {
+  // per landmark: L (packed lower) + 1/diag + y; per edge: the Z block + a 16-bit tile-local landmark index
+  static constexpr int LN = KT<KIND>::LD * (KT<KIND>::LD + 1) / 2 + 2 * KT<KIND>::LD; // doubles: 12 (points), 18 (lines)
+  static constexpr int A = LN * 8;
+  static constexpr int B = ZBlk<KIND>::N * 8 + 2;
+};
+BA_DEV int tile_cost_a(int kind) { return kind ? TileCost<1>::A : TileCost<0>::A; }
+BA_DEV int tile_cost_b(int kind) { return kind ? TileCost<1>::B : TileCost<0>::B; }
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_GROUPS = TILE_THREADS / 8;
+
+
+// ---- setup -------------------------------------------------------------------------------------
+// tile boundaries by binary search on the (strictly increasing) cumulative cost; grid (ceil((Tcap+1)/128), W, 2)
+__global__ void __launch_bounds__(128) kt_tiles_lm(const __grid_constant__ LocalDev d, const __grid_constant__ TileDev td) {
+  const int w = blockIdx.y, kind = blockIdx.z;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const KindDev& k = d.k[kind];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
+  const long long A = tile_cost_a(kind), B = tile_cost_b(kind);
+  const long long total = A * nl + B * ne;
+  const int nt = (int)((total + td.Q - 1) / td.Q);
+  if (t == 0) td.ntile[w * 2 + kind] = nt;
+  if (t > nt || t > td.Tcap) return;
+  // first landmark i in [0, nl] with cost(i) >= t * Q  (cost(nl) = total)
+  const long long target = (long long)t * td.Q;
+  int lo = 0, hi = nl;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const long long c = A * mid + B * (k.ebeg[l0 + mid] - e0);
+    if (c >= target) hi = mid;
+    else lo = mid + 1;
+  }
+  td.tile_lm[(size_t)(w * 2 + kind) * (td.Tcap + 1) + t] = l0 + (t == nt ? nl : lo);
+}
+
+// per (window, kind, tile, compact pair): first entry of the pair's list whose first edge lies in the tile or later.
+// grid (ceil(Pmax * (Tcap+1) / 256), W, 2)
+__global__ void __launch_bounds__(256) kt_tiles_pairs(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                      const __grid_constant__ TileDev td) {
+  const int w = blockIdx.y, kind = blockIdx.z;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int li = idx % b.Pmax, t = idx / b.Pmax;
+  const int nt = td.ntile[w * 2 + kind];
+  if (t > nt || t > td.Tcap || li >= b.n_ne[w]) return;
+  const KindDev& k = d.k[kind];
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p + kind;
+  int lo = pb[0], hi = pb[1];
+  if (t == nt) {
+    lo = hi;
+  } else {
+    const int l = td.tile_lm[(size_t)(w * 2 + kind) * (td.Tcap + 1) + t];
+    const int efirst = k.ebeg[l];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (b.pairs[mid].x >= efirst) hi = mid;
+      else lo = mid + 1;
+    }
+  }
+  td.tpb[((size_t)(w * 2 + kind) * (td.Tcap + 1) + t) * b.Pmax + li] = lo;
+}
+
+// processing order of the compact pairs of a window: longest list first (stable rank sort), so that the four
+// 8-lane groups of a warp work on lists of similar length; one warp per window, grid ceil(W / 4), 128 threads
+__global__ void __launch_bounds__(128) kt_order(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                const __grid_constant__ TileDev td) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= d.n_windows) return;
+  const int n = b.n_ne[w];
+  const int* list = b.ne_list + (size_t)w * b.Pmax;
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
+  for (int i = lane; i < n; i += 32) {
+    const int len = pb[2 * list[i] + 2] - pb[2 * list[i]];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const int lj = pb[2 * list[j] + 2] - pb[2 * list[j]];
+      rank += (lj > len || (lj == len && j < i)) ? 1 : 0;
+    }
+    td.order[(size_t)w * b.Pmax + rank] = i;
+  }
+}
+
+// ---- the fused Schur tile kernel ---------------------------------------------------------------
+// sums 48 per-lane values over the 8 lanes of a group (xor 4, 2, 1): lane8 ends with elements 6*lane8 .. 6*lane8+5
+BA_DEV void group8_transpose_reduce48(double* v, int lane8) {
+#pragma unroll
+  for (int off = 4, n = 48; off >= 1; off >>= 1, n >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane8 & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+#ifndef TILE_MIN_CTAS
+#define TILE_MIN_CTAS 2
+#endif
+
+template <int KIND>
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
+    kt_schur_tile(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b, const __grid_constant__ LocalOpt o,
+                  const __grid_constant__ TileDev td) {
+  using T = KT<KIND>;
+  constexpr int LD = T::LD, ZN = ZBlk<KIND>::N, LN = TileCost<KIND>::LN, NTRI = LD * (LD + 1) / 2;
+  extern __shared__ __align__(16) unsigned char tile_smem[];
+  const int w = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  if (t >= td.ntile[w * 2 + KIND]) return;
+  const KindDev& k = d.k[KIND];
+  const int* tl = td.tile_lm + (size_t)(w * 2 + KIND) * (td.Tcap + 1) + t;
+  const int la = tl[0], lb = tl[1];
+  const int ea = k.ebeg[la], eb = k.ebeg[lb];
+  const int nl = lb - la, ne = eb - ea;
+  double* Zs = reinterpret_cast<double*>(tile_smem);               // [ne][ZN], column-major blocks (ZCOL)
+  double* Ls = Zs + (size_t)ne * ZN;                                // [nl][LN]: L packed, inv, y
+  unsigned short* elm = reinterpret_cast<unsigned short*>(Ls + (size_t)nl * LN); // [ne] tile-local landmark of an edge
+  const int p0 = d.pose_begin[w], f0 = b.nf_begin[w], l0 = k.lm_begin[w];
+  const double lambda = s.lambda;
+  const bool robust = s.robust;
+
+  // ---- phase 1a: landmark factors
+  int fail = 0;
+  for (int i = tid; i < nl; i += TILE_THREADS) {
+    const int l = la + i;
+    double* Lm = Ls + (size_t)i * LN;
+    if (!k.act[l]) {
+#pragma unroll
+      for (int q = 0; q < LN; ++q) Lm[q] = 0.0;
+      continue;
+    }
+    double Hup[T::HD], Lf[NTRI], inv[LD];
+#pragma unroll
+    for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+    if (!small_chol<LD>(Hup, lambda, Lf, inv)) fail = 1;
+    double y[LD];
+#pragma unroll
+    for (int a = 0; a < LD; ++a) {
+      double v = k.b[(size_t)a * k.n_lm + l];
+#pragma unroll
+      for (int p = 0; p < a; ++p) v -= Lf[a * (a + 1) / 2 + p] * y[p];
+      y[a] = v * inv[a];
+    }
+#pragma unroll
+    for (int q = 0; q < NTRI; ++q) Lm[q] = Lf[q];
+#pragma unroll
+    for (int q = 0; q < LD; ++q) {
+      Lm[NTRI + q] = inv[q];
+      Lm[NTRI + LD + q] = y[q];
+    }
+  }
+  if (fail) atomicOr(&s.prep_fail, 1);
+  __syncthreads();
+
+  // ---- phase 1b: Z blocks, one thread per edge
+  for (int j = tid; j < ne; j += TILE_THREADS) {
+    const int e = ea + j;
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const int li = l0 + k.lm[e] - la; // tile-local landmark
+    elm[j] = (unsigned short)li;
+    double2* Zj = reinterpret_cast<double2*>(Zs + (size_t)j * ZN);
+    const int fi = b.free_idx[p0 + p];
+    if (fi < 0 || b.sys_idx[f0 + fi] < 0 || k.lvl[e]) { // fixed pose / excluded edge (level 1): no contribution
+#pragma unroll
+      for (int q = 0; q < ZN / 2; ++q) Zj[q] = make_double2(0.0, 0.0);
+      continue;
+    }
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double X[T::SD], m[T::MD], r[4], Jp[24], Jl[16];
+    load_lm<KIND>(k, la + li, X);
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, true>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, m, r, Jp, Jl);
+    double wgt = 1.0;
+    if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
+    const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+    const double* Lm = Ls + (size_t)li * LN;
+    double Lf[NTRI], inv[LD];
+#pragma unroll
+    for (int q = 0; q < NTRI; ++q) Lf[q] = Lm[q];
+#pragma unroll
+    for (int q = 0; q < LD; ++q) inv[q] = Lm[NTRI + q];
+    double z[6][LD];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = 0; c < LD; ++c) {
+        double h = 0;
+#pragma unroll
+        for (int rr = 0; rr < T::ROWS; ++rr) h += Jp[rr * 6 + a] * Jl[rr * LD + c];
+        double v = wo * h;
+#pragma unroll
+        for (int pp = 0; pp < c; ++pp) v -= Lf[c * (c + 1) / 2 + pp] * z[a][pp];
+        z[a][c] = v * inv[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < LD; ++c) {
+      Zj[c * 3 + 0] = make_double2(z[0][c], z[1][c]);
+      Zj[c * 3 + 1] = make_double2(z[2][c], z[3][c]);
+      Zj[c * 3 + 2] = make_double2(z[4][c], z[5][c]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: pair products over the tile's entries, 8 lanes per pose pair
+  const int lane = tid & 31, lane8 = tid & 7, warp = tid >> 5, g4 = (tid >> 3) & 3;
+  const int n_ne = b.n_ne[w];
+  const int nquads = (n_ne + 3) >> 2;
+  const int* ord = td.order + (size_t)w * b.Pmax;
+  const int* tp0 = td.tpb + ((size_t)(w * 2 + KIND) * (td.Tcap + 1) + t) * b.Pmax;
+  const int* tp1 = tp0 + b.Pmax;
+  const int tt = KIND ? td.Tp + t : t;
+  double* out_base = td.hs_tile + ((size_t)w * (td.Tp + td.Tl) + tt) * b.Pmax * 42;
+  (void)lane;
+  for (int quad = warp; quad < nquads; quad += TILE_THREADS / 32) {
+    const int oi = quad * 4 + g4;
+    const bool have = oi < n_ne;
+    int li = 0, beg = 0, ncol = 0;
+    bool diag = false;
+    if (have) {
+      li = ord[oi];
+      const int p = b.ne_list[(size_t)w * b.Pmax + li];
+      int fi, fj;
+      pair_decode(p, s.nf, fi, fj);
+      diag = fi == fj;
+      beg = tp0[li];
+      ncol = (tp1[li] - beg) * LD;
+    }
+    double acc[48];
+#pragma unroll
+    for (int q = 0; q < 48; ++q) acc[q] = 0.0;
+    int2 ee = make_int2(0, 0);
+    if (lane8 < ncol) ee = b.pairs[beg + lane8 / LD];
+    for (int c = lane8; c < ncol; c += 8) {
+      const int2 cur = ee;
+      const int cn = c + 8;
+      if (cn < ncol) ee = b.pairs[beg + cn / LD]; // next entry record while this one is processed
+      const int q = c % LD;
+      const int ji = cur.x - ea;
+      const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)ji * ZN + q * ZCOL);
+      double za[6];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const double2 v = a2[u];
+        za[2 * u] = v.x;
+        za[2 * u + 1] = v.y;
+      }
+      if (diag) {
+        const double yq = Ls[(size_t)elm[ji] * LN + NTRI + LD + q];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r * 6 + cc] += za[r] * za[cc];
+          acc[36 + r] += za[r] * yq;
+        }
+      } else {
+        const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)(cur.y - ea) * ZN + q * ZCOL);
+        double zb[6];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const double2 v = b2[u];
+          zb[2 * u] = v.x;
+          zb[2 * u + 1] = v.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) acc[r * 6 + cc] += za[r] * zb[cc];
+      }
+    }
+    __syncwarp();
+    group8_transpose_reduce48(acc, lane8);
+    if (have && lane8 < 7) {
+      double2* out = reinterpret_cast<double2*>(out_base + (size_t)li * 42 + 6 * lane8);
+      out[0] = make_double2(acc[0], acc[1]);
+      out[1] = make_double2(acc[2], acc[3]);
+      out[2] = make_double2(acc[4], acc[5]);
+    }
+  }
+}
+
+// ---- back-substitution without Z: xl = (Hll + lambda)^-1 (bl - sum_e W_e^T xp), W_e^T xp = wo Jl^T (Jp xp) recomputed
+// from the edge record at the pre-update state (pose backups P_bR / P_bt; the landmark itself is updated here).
+template <int KIND>
+BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& td, const LocalOpt& o, const KindDev& k, int w,
+                           int l, double lambda, bool robust, double& chi_part, double& scale_part) {
+  using T = KT<KIND>;
+  constexpr int LD = T::LD;
+  const int p0 = d.pose_begin[w], f0 = b.nf_begin[w];
+  double X[T::SD];
+  load_lm<KIND>(k, l, X);
+  double u[LD];
+#pragma unroll
+  for (int a = 0; a < LD; ++a) u[a] = 0.0;
+  const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  for (int e = ea; e < eb; ++e) {
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const int fi = b.free_idx[p0 + p];
+    if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double m[T::MD], r[4], Jp[24], Jl[16];
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, true>(cam, o.bf_float, stereo, td.P_bR + 9 * (size_t)(p0 + p), b.P_bt + 3 * (size_t)(p0 + p), X, m, r, Jp, Jl);
+    double wgt = 1.0;
+    if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
+    const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+    const double* xv = b.xp + (size_t)(f0 + fi) * 6;
+    double g[T::ROWS];
+#pragma unroll
+    for (int rr = 0; rr < T::ROWS; ++rr) {
+      double acc = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc += Jp[rr * 6 + a] * xv[a];
+      g[rr] = wo * acc;
+    }
+#pragma unroll
+    for (int a = 0; a < LD; ++a) {
+      double acc = 0;
+#pragma unroll
+      for (int rr = 0; rr < T::ROWS; ++rr) acc += Jl[rr * LD + a] * g[rr];
+      u[a] += acc;
+    }
+  }
+  double Hup[T::HD], Lf[LD * (LD + 1) / 2], inv[LD], v[LD], xl[LD];
+#pragma unroll
+  for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+  small_chol<LD>(Hup, lambda, Lf, inv);
+  double bl[LD];
+#pragma unroll
+  for (int a = 0; a < LD; ++a) { // L v = bl - u
+    bl[a] = k.b[(size_t)a * k.n_lm + l];
+    double t2 = bl[a] - u[a];
+#pragma unroll
+    for (int p = 0; p < a; ++p) t2 -= Lf[a * (a + 1) / 2 + p] * v[p];
+    v[a] = t2 * inv[a];
+  }
+#pragma unroll
+  for (int a = LD - 1; a >= 0; --a) { // L^T xl = v
+    double t2 = v[a];
+#pragma unroll
+    for (int p = a + 1; p < LD; ++p) t2 -= Lf[p * (p + 1) / 2 + a] * xl[p];
+    xl[a] = t2 * inv[a];
+  }
+#pragma unroll
+  for (int a = 0; a < LD; ++a) scale_part += xl[a] * (lambda * xl[a] + bl[a]);
+  double Xn[T::SD];
+#pragma unroll
+  for (int q = 0; q < T::SD; ++q) k.xb[(size_t)q * k.n_lm + l] = X[q];
+  if (KIND == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) Xn[q] = X[q] + xl[q];
+  } else {
+    line_oplus(X, xl, Xn);
+  }
+#pragma unroll
+  for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = Xn[q];
+  for (int e = ea; e < eb; ++e) {
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
+    const int p = info & 0xffff;
+    const bool stereo = (info >> 30) & 1;
+    Cam cam;
+    load_cam(d.cameras, (info >> 16) & 0xff, cam);
+    double m[T::MD], r[4];
+    load_edge<KIND>(k, e, m);
+    eval_edge<KIND, false>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), Xn, m, r,
+                           nullptr, nullptr);
+    const double c2 = edge_chi2<KIND>(r);
+    k.chi2[e] = c2;
+    double wgt;
+    chi_part += robust ? huber(c2, o.delta[2 * KIND + (stereo ? 1 : 0)], wgt) : c2;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BT) kt_backsub_rc(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                    const __grid_constant__ LocalOpt o, const __grid_constant__ TileDev td) {
+  __shared__ double red[BW * 2];
+  const int w = blockIdx.y;
+  const int c = blockIdx.x + (KIND ? b.Cp : 0);
+  const WinState& s = b.ws[w];
+  if (s.stage != STAGE_NEED_TRIAL || !s.solve_ok) return;
+  double v[2] = {0, 0}; // chi1, scale
+  {
+    const KindDev& k = d.k[KIND];
+    const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+    const int i = blockIdx.x * BT + threadIdx.x;
+    if (i < nl && k.act[l0 + i]) backsub_rc_one<KIND>(d, b, td, o, k, w, l0 + i, s.lambda, s.robust, v[0], v[1]);
+  }
+  cta_reduce<2>(v, red);
+  if (threadIdx.x == 0) {
+    double* pp = b.part + ((size_t)w * b.C + c) * 4;
+    pp[0] = cta_reduce_get<2>(red, 0);
+    pp[1] = cta_reduce_get<2>(red, 1);
+  }
+}
+
+} // namespace ba
