@@ -1,29 +1,37 @@
 #!/usr/bin/env python
 """bench.py — throughput of the BA hot path on B200 (metric of BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2p|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|c2|c2p|c4|c1|c3|frame1|c5] [--impl ours|reference]
 
-Workloads (BASELINE.json configs; synthetic inputs of rspl_slam_b200/synth.py, seeds of SURVEY §8d)
-  c2 (default, configs[1]): batched pose-only FrameOptimization, 4096 frames x 400 stereo points
-                            per GPU, Huber + 4 rounds x LM(10)
-  c4 (configs[3])         : batched LocalmapOptimization, windows of 10 KF / 3k points / 300 lines,
-                            LM 10 + 5, `--windows` per GPU (default 1024)
+ONE JSON line. With `--workload all` (default) the headline keys are C2 (BASELINE configs[1], the configuration
+the metric is quoted on) and `workloads` holds one sub-object per further configuration, each with its own
+`value`, `ms_per_step`, `e2e`, `roofline`, `cpu_baseline`:
+  c2     configs[1]: batched pose-only FrameOptimization, 4096 frames x (400 stereo points + 60 lines) per GPU,
+         Huber + 4 rounds x LM(10). The 60 lines are an extension (constraints on fixed lines, SURVEY 8a note).
+  c2p    the same, points only = the reference's own FrameOptimization (g2o_optimization.cc:256-397)
+  c4     configs[3]: 1024 LocalmapOptimization windows (10 KF / 3k points / 300 lines) per GPU, LM 10 + 5
+  c1     configs[0]: ONE such window (the reference's call pattern, map.cc:709-710): latency
+  c3     configs[2]: one 20-KF / 10k-point / 1k-line window: latency
+  frame1 one FrameOptimization call on one frame (map_builder.cc:583-584): latency
+  c5     configs[4]: one global BA, 2000 KF / 1M points / 100k lines, landmarks partitioned over the ranks, NCCL
+         all-reduces from the library's own communicator (strong scaling); at N >= 2 a `parity_check` on a
+         test-scale problem (poses bit-identical on all ranks, and equal to the un-sharded solve within tolerance)
 A "step" is one pass of the hot path (the whole on-device LM schedule) over one batch.
-
-  value  : edges linearised / s, inputs resident in HBM, CUDA events on the solver's stream,
-           L2 flushed between steps, max over ranks (units of all ranks / slowest rank's time)
+  value  : edges linearised / s, inputs resident in HBM, CUDA events on the solver's stream, L2 flushed between
+           steps, max over ranks (units of all ranks / slowest rank's time)
   e2e    : same metric through the C-ABI call with pinned HOST buffers (H2D + solve + D2H timed)
   roofline / cpu_baseline: see DESIGN.md §Measurement
-Multi-GPU: one process per GPU (torchrun), independent units sharded by rank, NO data-path
-collective -> "scaling": "weak" (per-GPU work fixed).
-`--impl reference` times the CPU oracle (the g2o-equivalent restatement of the reference's own
-path; g2o itself cannot be built here) on all host threads, rank 0 only.
+Multi-GPU: one process per GPU (torchrun). C2 / C4: independent units sharded by rank, no data-path collective
+("weak"); C5: one problem, "strong". c1 / c3 / frame1 do not shard (replicas only): N = 1 runs only.
+`--impl reference` times the CPU oracle (the g2o-equivalent restatement of the reference's own path; g2o itself
+cannot be built here) on all host threads, rank 0 only, for the same workloads.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -42,13 +50,30 @@ BYTES_POSE_ONLY_MONO = 52
 BYTES_POSE_ONLY_STEREO_LINE = 124  # 64 meas + 48 world line + 4 flag + 8 chi2 (same accounting, line extension)
 BYTES_POSE_ONLY_MONO_LINE = 92
 C2_FRAMES, C2_POINTS, C2_LINES = 4096, 400, 60
+ALL_N1 = ["c2", "c2p", "c4", "c1", "c3", "frame1", "c5"]
+ALL_MULTI = ["c2", "c2p", "c4", "c5"]
 
 
-def _c2_lines(args):
-    """BASELINE configs[1] names 400 stereo points + 60 lines per frame. The reference's FrameOptimization takes no
-    lines (g2o_optimization.cc:284-285), so `c2p` (points only) is its parity path and `c2` adds the 60 lines as
-    constraints on fixed lines (SURVEY 8a note / 8d)."""
-    return 0 if args.workload == "c2p" else args.frame_lines
+def workload_name(key, args):
+    """config.workload — the same string in both arms."""
+    if key == "c2":
+        return (f"C2 batched pose-only FrameOptimization: {args.frames} frames x ({C2_POINTS} stereo points + "
+                f"{args.frame_lines} lines) per GPU, Huber + 4 rounds x LM10")
+    if key == "c2p":
+        return (f"C2p batched pose-only FrameOptimization, points only (the reference's own path): {args.frames} frames x "
+                f"{C2_POINTS} stereo points per GPU, Huber + 4 rounds x LM10")
+    if key == "c4":
+        return f"C4 batched LocalmapOptimization: {args.windows} windows of 10 KF / 3k points / 300 lines per GPU, LM 10+5"
+    if key == "c1":
+        return "C1 one LocalmapOptimization window: 10 KF / 3k points / 300 lines, LM 10+5 (latency)"
+    if key == "c3":
+        return "C3 one LocalmapOptimization window: 20 KF / 10k points / 1k lines, LM 10+5 (latency)"
+    if key == "frame1":
+        return f"one FrameOptimization call: 1 frame x {C2_POINTS} stereo points, Huber + 4 rounds x LM10 (latency)"
+    if key == "c5":
+        return (f"C5 global BA: {args.kf} KF / {args.points} points / {args.lines} lines on a 3-loop trajectory, LM 10+5, "
+                "landmarks partitioned over the GPUs")
+    raise ValueError(key)
 
 
 def _peaks():
@@ -59,6 +84,17 @@ def _peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _fp64_peak():
+    """FP64 FMA peak measured by profiles/scripts/fp64_peak.py on this pool's B200 (committed), else the vendor figure."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["fp64_tflops"]), "measured (profiles/fp64_peak.json)"
+        except Exception:
+            pass
+    return 37.0, "vendor figure (not measured)"
 
 
 class ClockSampler:
@@ -115,73 +151,91 @@ def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def _local_kw(key):
+    return dict(n_kf=20, n_points=10000, n_lines=1000) if key == "c3" else {}
+
+
 # ------------------------------------------------------------------------------------------------
-# reference arm: the CPU oracle on the host cores (rank 0 only)
+# CPU oracle legs (reference arm and cpu_baseline): bounded samples of the same workloads
 # ------------------------------------------------------------------------------------------------
+def _oracle_sample(key, args, threads, budget):
+    """Returns (problems, runner, description): a bounded sample of workload `key` for `threads` oracle threads,
+    sized for roughly `budget` seconds of CPU work."""
+    from oracle import orc
+    from rspl_slam_b200 import synth
+    if key in ("c2", "c2p", "frame1"):
+        nl = args.frame_lines if key == "c2" else 0
+        per_frame = 0.12 if nl else 0.02  # s per frame per thread (g2o differentiates line edges numerically)
+        n = 1 if key == "frame1" else int(min(args.frames, max(threads, budget * threads / per_frame)))
+        probs = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS, n_lines=nl) for i in range(n)]
+        desc = (f"{n} of {args.frames} frames per step ({C2_POINTS} stereo pts + {nl} lines, 4x10 LM), {threads} thread(s), "
+                "one frame per thread")
+        return probs, (lambda ps: orc.frame_opt_batch(ps, n_threads=threads)), desc
+    if key in ("c4", "c1", "c3"):
+        cfg = {"c4": 4, "c1": 1, "c3": 3}[key]
+        n = 1 if key != "c4" else int(min(args.windows, max(threads, budget * threads / 0.35)))
+        probs = [synth.make_local_problem(synth.config_seed(cfg, i), **_local_kw(key)) for i in range(n)]
+        desc = (f"{n} of {args.windows} windows per step, {threads} thread(s), one window per thread" if key == "c4"
+                else "the whole window, 1 thread (one problem)")
+        return probs, (lambda ps: orc.local_ba_batch(ps, n_threads=threads if key == "c4" else 1)), desc
+    if key == "c5":
+        # one problem: the oracle is single-threaded per problem and factorises densely, so the bounded sample is a
+        # scaled-down problem of the same generator
+        probs = [synth.make_global_problem(synth.config_seed(5, 0), n_kf=60, n_points=30000, n_lines=3000, loops=1)]
+        return probs, (lambda ps: orc.local_ba_batch(ps, n_threads=1)), \
+            "scaled-down C5 (60 KF / 30k points / 3k lines, same generator), 1 thread (one problem)"
+    raise ValueError(key)
+
+
+def cpu_baseline(key, args, budget=6.0):
+    """The oracle timed on this box's host cores on a bounded sample (1 thread: default g2o and the reference's
+    call pattern are single-threaded)."""
+    probs, runner, desc = _oracle_sample(key, args, 1, budget)
+    t0 = time.perf_counter()
+    st = runner(probs)
+    dt = time.perf_counter() - t0
+    edges = sum(s["edges_linearized"] for s in st)
+    return {"value": edges / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc, "seconds": dt,
+            "lm_iters_per_sec": sum(sum(s["iters"]) for s in st) / dt}
+
+
+def reference_one(key, args, steps, warmup, budget):
+    from oracle import orc
+    threads = orc.max_threads()
+    use = threads if key in ("c2", "c2p", "c4") else 1
+    base, runner, desc = _oracle_sample(key, args, use, budget)
+    t_all, edges_all, iters_all = [], 0, 0
+    for step in range(warmup + steps):
+        probs = [p.copy() for p in base]
+        t0 = time.perf_counter()
+        st = runner(probs)
+        dt = time.perf_counter() - t0
+        if step >= warmup:
+            t_all.append(dt)
+            edges_all += sum(s["edges_linearized"] for s in st)
+            iters_all += sum(sum(s["iters"]) for s in st)
+    total = float(sum(t_all))
+    value = edges_all / total
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * total / max(len(t_all), 1), "higher_is_better": True,
+        "scaling": "strong" if key == "c5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(key, args),
+                   "reference_impl": "CPU oracle (g2o-equivalent restatement; g2o/Eigen not installable here)"},
+        "lm_iters_per_sec": iters_all / total,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
 def run_reference(args):
     rank, _, world = _dist_env()
     if rank != 0:
         return 0
-    from oracle import orc
-    from rspl_slam_b200 import synth
-    threads = orc.max_threads()
-    t_all, edges_all, iters_all = [], 0, 0
-    if args.workload in ("c2", "c2p"):
-        nl = _c2_lines(args)
-        sample = min(C2_FRAMES, max(threads * 24, 64))
-        desc = f"{sample} of {C2_FRAMES} frames per step (400 stereo pts + {nl} lines, 4x10 LM), {threads} threads, one frame per thread"
-        base = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS, n_lines=nl) for i in range(sample)]
-        for step in range(args.warmup + args.steps):
-            probs = [p.copy() for p in base]
-            t0 = time.perf_counter()
-            st = orc.frame_opt_batch(probs, n_threads=threads)
-            dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                t_all.append(dt)
-                edges_all += sum(s["edges_linearized"] for s in st)
-                iters_all += sum(sum(s["iters"]) for s in st)
-        workload = f"C2 batched pose-only FrameOptimization ({C2_FRAMES} frames x ({C2_POINTS} stereo pts + {nl} lines) per GPU)"
-    elif args.workload == "c5":
-        # one problem: the oracle is single-threaded per problem and factorises densely, so the bounded sample is a
-        # scaled-down problem of the same generator
-        desc = "scaled-down C5 (60 KF / 30k points / 3k lines, same generator) per step, 1 thread (one problem)"
-        threads = 1
-        base = [synth.make_global_problem(synth.config_seed(5, 0), n_kf=60, n_points=30000, n_lines=3000, loops=1)]
-        for step in range(args.warmup + args.steps):
-            probs = [p.copy() for p in base]
-            t0 = time.perf_counter()
-            st = orc.local_ba_batch(probs, n_threads=1)
-            dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                t_all.append(dt)
-                edges_all += sum(s["edges_linearized"] for s in st)
-                iters_all += sum(sum(s["iters"]) for s in st)
-        workload = f"C5 global BA ({args.kf} KF / {args.points} points / {args.lines} lines)"
-    else:
-        sample = max(threads, 8)
-        desc = f"{sample} of {args.windows} windows per step (10 KF/3k pts/300 lines, LM 10+5), {threads} threads"
-        base = [synth.make_local_problem(synth.config_seed(4, i)) for i in range(sample)]
-        for step in range(args.warmup + args.steps):
-            probs = [p.copy() for p in base]
-            t0 = time.perf_counter()
-            st = orc.local_ba_batch(probs, n_threads=threads)
-            dt = time.perf_counter() - t0
-            if step >= args.warmup:
-                t_all.append(dt)
-                edges_all += sum(s["edges_linearized"] for s in st)
-                iters_all += sum(sum(s["iters"]) for s in st)
-        workload = f"C4 batched LocalmapOptimization ({args.windows} windows per GPU)"
-    total = float(sum(t_all))
-    value = edges_all / total
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(len(t_all), 1), "higher_is_better": True,
-        "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "reference_impl": "CPU oracle (g2o-equivalent restatement; g2o/Eigen not installable here)"},
-        "lm_iters_per_sec": iters_all / total,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    keys = (ALL_N1 if args.gpus <= 1 else ALL_MULTI) if args.workload == "all" else [args.workload]
+    line = reference_one(keys[0], args, args.steps, args.warmup, budget=2.0)
+    if len(keys) > 1:
+        line["workloads"] = {k: reference_one(k, args, max(1, min(args.steps, 2)), 1, budget=1.5) for k in keys[1:]}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -202,92 +256,148 @@ def _pin_batch(batch, capi):
     return type(batch)(**kw)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from rspl_slam_b200 import capi, synth
+def _traffic(key):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", f"traffic_{key}.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["dram_bytes_per_launch"])
+        except Exception:
+            return None
+    return None
 
-    rank, local_rank, world = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
 
-    ctx = capi.Context(device=local_rank)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    opt = capi.make_options()
+class Env:
+    """Process-wide state shared by the workloads of one run."""
 
-    # ---- inputs: this rank's shard of independent units (weak scaling: fixed work per GPU)
-    if args.workload in ("c2", "c2p"):
-        n_units = args.frames
-        nl = _c2_lines(args)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from rspl_slam_b200 import capi
+        self.torch, self.dist, self.capi, self.args = torch, dist, capi, args
+        self.rank, self.local_rank, self.world = _dist_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = capi.Context(device=self.local_rank)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        self.opt = capi.make_options()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.peak, self.peak_src = _peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce(self, vals, op):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t.tolist()]
+
+    def timed_steps(self, solve, steps):
+        """`steps` solves on the solver stream, an L2 flush before each, CUDA events around each; returns
+        (device seconds, wall seconds of the region, clock summary)."""
+        torch = self.torch
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()
+        with ClockSampler(self.local_rank) as clk:
+            t0 = time.perf_counter()
+            with torch.cuda.stream(self.stream):
+                for i in range(steps):
+                    self.flush.zero_()  # evict L2 between timed steps (not timed)
+                    starts[i].record(self.stream)
+                    solve()
+                    ends[i].record(self.stream)
+            self.barrier()
+            wall = time.perf_counter() - t0
+        dev_s = float(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) * 1e-3
+        return dev_s, wall, clk.summary()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+        self.ctx.close()
+
+
+def _local_roofline(env, batch, stats, prof, prof_steps, key):
+    from rspl_slam_b200.roofline import local_class_bytes
+    per_kernel = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps} for k, v in prof.items() if v[1]}
+    cls_bytes = local_class_bytes(batch, stats)  # bytes per step of the linearise / Schur / back-sub classes
+    groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
+              "schur (kt_schur_tile | kb_schur_prep + kb_schur_reduce, + reduced solve)":
+                  (("schur_tile", "schur_prep", "schur_reduce", "reduced_solve", "dense_assemble"), cls_bytes["schur"]),
+              "backsub (kt_backsub_rc | kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"])}
+    best = None
+    for name, (classes, nbytes) in groups.items():
+        ms = sum(prof[c][0] for c in classes if c in prof) / prof_steps
+        nl = sum(prof[c][1] for c in classes if c in prof) / prof_steps
+        if nl == 0:
+            continue
+        per_kernel[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
+                            "achieved_GBs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / env.peak}
+        if best is None or ms > best[1]:
+            best = (name, ms, nl, nbytes)
+    dom_name, dom_ms, dom_launches, alg_bytes = best
+    launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
+    alg_per_launch = alg_bytes / max(dom_launches, 1)
+    achieved = alg_per_launch / launch_s / 1e9
+    return {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": env.peak, "unit": "GB/s", "frac": achieved / env.peak,
+            "traffic": _traffic(key), "peak_source": env.peak_src, "algorithmic_bytes_per_launch": alg_per_launch,
+            "launch_ms": 1e3 * launch_s, "launches_per_step": dom_launches, "per_kernel": per_kernel,
+            "note": "achieved = SURVEY 8(d) contract bytes (materialised-W formulation) of the slowest kernel class / its CUDA-event "
+                    "time; the kernels recompute instead of materialising, so real DRAM traffic (`traffic`) is lower, see DESIGN.md"}
+
+
+def bench_units(env, key, steps, warmup, with_cpu):
+    """c2 / c2p / frame1 (frames) and c4 / c1 / c3 (local windows): independent units, this rank's shard."""
+    from rspl_slam_b200 import synth
+    args, ctx, capi, opt = env.args, env.ctx, env.capi, env.opt
+    rank, world = env.rank, env.world
+    is_frame = key in ("c2", "c2p", "frame1")
+    if is_frame:
+        n_units = 1 if key == "frame1" else args.frames
+        nl = args.frame_lines if key == "c2" else 0
         batch = synth.make_frame_batch(2, n_units, first_instance=rank * n_units, n_points=C2_POINTS, n_lines=nl)
         upload, solve = ctx.frame_batch_upload, ctx.frame_batch_solve
         out = ctx.alloc_frame_result(batch, pinned=True)
         download = lambda: ctx.frame_batch_download(out)
         oneshot = lambda b: ctx.frame_batch(b, opt, out)
-        workload = (f"C2 batched pose-only FrameOptimization ({n_units} frames x ({C2_POINTS} stereo pts + {nl} lines) per GPU, "
-                    "Huber + 4 rounds x LM10" + ("; lines = constraints on fixed 3-D lines, an extension: the reference's "
-                    "FrameOptimization takes none" if nl else "; points only = the reference's FrameOptimization") + ")")
-        kernel = "ba::frame_opt_kernel"
+        if len(batch.cameras) == 1:
+            # one camera and all ->inlier flags true are the ABI defaults: pass NULL instead of copying zeros / ones
+            batch.mono_cam = batch.stereo_cam = None
+            if batch.mono_inlier.all() and batch.stereo_inlier.all():
+                batch.mono_inlier = batch.stereo_inlier = None
+            if batch.mline_begin is not None:
+                batch.mline_cam = batch.sline_cam = None
+                if batch.mline_inlier.all() and batch.sline_inlier.all():
+                    batch.mline_inlier = batch.sline_inlier = None
     else:
-        n_units = args.windows
-        batch, _ = synth.make_local_batch(4, n_units, first_instance=rank * n_units)
+        n_units = args.windows if key == "c4" else 1
+        cfg = {"c4": 4, "c1": 1, "c3": 3}[key]
+        batch, _ = synth.make_local_batch(cfg, n_units, first_instance=rank * n_units, **_local_kw(key))
         upload, solve = ctx.local_batch_upload, ctx.local_batch_solve
         out = ctx.alloc_local_result(batch, pinned=True)
         download = lambda: ctx.local_batch_download(out)
         oneshot = lambda b: ctx.local_batch(b, opt, out)
-        workload = f"C4 batched LocalmapOptimization ({n_units} windows of 10 KF/3k pts/300 lines per GPU, LM 10+5)"
-        kernel = "ba::local_ba_kernel"
-    is_c2 = args.workload in ("c2", "c2p")
-    if is_c2 and len(batch.cameras) == 1:
-        # one camera and all ->inlier flags true are the ABI defaults: pass NULL instead of copying 8 MB of zeros / ones
-        batch.mono_cam = batch.stereo_cam = None
-        if batch.mono_inlier.all() and batch.stereo_inlier.all():
-            batch.mono_inlier = batch.stereo_inlier = None
-        if batch.mline_begin is not None:
-            batch.mline_cam = batch.sline_cam = None
-            if batch.mline_inlier.all() and batch.sline_inlier.all():
-                batch.mline_inlier = batch.sline_inlier = None
     pinned = _pin_batch(batch, capi)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
 
     # ---- resident-input timing
     upload(pinned)
     launches0 = ctx.launch_count
-    for _ in range(max(args.warmup, 3)):
+    warm = max(warmup, 3)
+    for _ in range(warm):
         solve(opt)
     ctx.sync()
     download()
     stats = out.stats.copy()
-    warm_launches = ctx.launch_count - launches0
-    launches_per_step = warm_launches // max(args.warmup, 3)
-
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            for i in range(args.steps):
-                flush.zero_()  # evict L2 between timed steps (not timed)
-                starts[i].record(stream)
-                solve(opt)
-                ends[i].record(stream)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    dev_s = float(sum(step_ms)) * 1e-3
-    gpu_launches = launches_per_step * args.steps
-
+    launches_per_step = (ctx.launch_count - launches0) // warm
+    dev_s, wall, clocks = env.timed_steps(lambda: solve(opt), steps)
     edges_lin = int(stats["edges_linearized"].sum())
     edges_eval = int(stats["edges_evaluated"].sum())
     lm_iters = int(stats["iters"].sum())
@@ -296,145 +406,169 @@ def run_ours(args):
     # ---- end to end through the C-ABI with pinned host buffers
     for _ in range(2):
         oneshot(pinned)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    env.barrier()
+    e2e_steps = max(3, min(steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         oneshot(pinned)
-    barrier()
+    env.barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---- max over ranks
-    t = torch.tensor([dev_s, e2e_s, t_wall], dtype=torch.float64, device=dev)
-    tot = torch.tensor([edges_lin, lm_iters, edges_eval, lm_trials], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_s_max, e2e_s_max, wall_max = [float(x) for x in t.tolist()]
-    edges_lin_all, lm_iters_all, edges_eval_all, lm_trials_all = [float(x) for x in tot.tolist()]
+    dev_s_max, e2e_s_max, wall_max = env.reduce([dev_s, e2e_s, wall], "MAX")
+    edges_lin_all, lm_iters_all, edges_eval_all, lm_trials_all = env.reduce([edges_lin, lm_iters, edges_eval, lm_trials], "SUM")
 
-    if rank == 0:
-        value = edges_lin_all * args.steps / dev_s_max
-        e2e_value = edges_lin_all * e2e_steps / e2e_s_max
-        peak, peak_src = _peaks()
-        # roofline of the dominant kernel class: algorithmic bytes / CUDA-event time of
-        # that class, measured in a separate profiled pass (event pairs around every launch)
-        prof_steps = max(1, min(args.steps, 5))
-        ctx.set_profiling(True)
-        for _ in range(prof_steps):
-            solve(opt)
-        prof = ctx.get_profile()
-        ctx.set_profiling(False)
-        per_kernel = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] / prof_steps}
-                      for k, v in prof.items() if v[1]}
-        if is_c2:
-            cnt = {BYTES_POSE_ONLY_STEREO: int(batch.stereo_begin[-1]), BYTES_POSE_ONLY_MONO: int(batch.mono_begin[-1])}
-            if batch.mline_begin is not None:
-                cnt[BYTES_POSE_ONLY_STEREO_LINE] = int(batch.sline_begin[-1])
-                cnt[BYTES_POSE_ONLY_MONO_LINE] = int(batch.mline_begin[-1])
-            # evaluations are spread over the edge classes in proportion to their counts
-            alg_bytes = edges_eval * sum(bts * n for bts, n in cnt.items()) / max(sum(cnt.values()), 1)
-            dom_ms = prof["frame_opt"][0] / prof_steps
-            dom_launches = prof["frame_opt"][1] / prof_steps
-            dom_name = kernel
-        else:
-            from rspl_slam_b200.roofline import local_class_bytes
-            cls_bytes = local_class_bytes(batch, stats)  # bytes per step of the linearise / Schur / back-sub classes
-            groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
-                      "schur (kt_schur_tile | kb_schur_prep + kb_schur_reduce, + kb_solve)": (("schur_tile", "schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
-                      "backsub (kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"]),
-                      "persistent (local_solve_kernel)": (("local_solve_persistent",), sum(cls_bytes.values()))}
-            best = None
-            for name, (classes, nbytes) in groups.items():
-                ms = sum(prof[c][0] for c in classes) / prof_steps
-                nl = sum(prof[c][1] for c in classes) / prof_steps
-                if nl == 0:
-                    continue
-                per_kernel[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
-                                    "achieved_GBs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
-                if best is None or ms > best[1]:
-                    best = (name, ms, nl, nbytes)
-            dom_name, dom_ms, dom_launches, alg_bytes = best
+    # roofline of the dominant kernel class: algorithmic bytes / CUDA-event time of that class,
+    # measured in a separate profiled pass (event pairs around every launch); rank 0's kernels
+    prof_steps = max(1, min(steps, 5))
+    ctx.set_profiling(True)
+    for _ in range(prof_steps):
+        solve(opt)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    if rank != 0:
+        return None
+    if is_frame:
+        cnt = {BYTES_POSE_ONLY_STEREO: int(batch.stereo_begin[-1]), BYTES_POSE_ONLY_MONO: int(batch.mono_begin[-1])}
+        if batch.mline_begin is not None:
+            cnt[BYTES_POSE_ONLY_STEREO_LINE] = int(batch.sline_begin[-1])
+            cnt[BYTES_POSE_ONLY_MONO_LINE] = int(batch.mline_begin[-1])
+        # evaluations are spread over the edge classes in proportion to their counts
+        alg_bytes = edges_eval * sum(bts * n for bts, n in cnt.items()) / max(sum(cnt.values()), 1)
+        dom_ms = prof["frame_opt"][0] / prof_steps
+        dom_launches = prof["frame_opt"][1] / prof_steps
         launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
-        alg_per_launch = alg_bytes / max(dom_launches, 1)
-        achieved = alg_per_launch / launch_s / 1e9
-        cpu = cpu_baseline(args)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "l2": "flushed (256 MiB write) between timed steps; inputs resident in HBM",
-                       "parallelism": f"dp{world} (independent units, no collective)", "timing": "CUDA events on the solver stream, max over ranks"},
-            "lm_iters_per_sec": lm_iters_all * args.steps / dev_s_max,
-            "lm_trials_per_sec": lm_trials_all * args.steps / dev_s_max,
-            "edges_evaluated_per_sec": edges_eval_all * args.steps / dev_s_max,
-            "units_per_sec": n_units * world * args.steps / dev_s_max,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes()),
-                    "d2h_bytes_per_step": int(out.d2h_bytes()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
-                    "api": "rspl_ba_%s_batch (pinned host buffers in, pinned host buffers out)" % ("frame" if is_c2 else "local")},
-            "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": _traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_per_launch, "launch_ms": 1e3 * launch_s,
-                         "launches_per_step": dom_launches, "per_kernel": per_kernel,
-                         "note": "achieved = SURVEY 8(d) contract bytes (materialised-W formulation) / CUDA-event time of the kernel class; "
-                                 "the kernels recompute instead of materialising, so real DRAM traffic (`traffic`) is lower, see DESIGN.md"},
-            "cpu_baseline": cpu,
-            "clocks": clk.summary(),
-            "wall_s_timed_region": wall_max,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    ctx.close()
-    return 0
+        achieved = alg_bytes / max(dom_launches, 1) / launch_s / 1e9
+        fp64_peak, fp64_src = _fp64_peak()
+        roof = {"bound": "hbm", "kernel": "ba::frame_opt_kernel", "achieved": achieved, "peak": env.peak, "unit": "GB/s",
+                "frac": achieved / env.peak, "traffic": _traffic(key), "peak_source": env.peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / max(dom_launches, 1), "launch_ms": 1e3 * launch_s,
+                "launches_per_step": dom_launches,
+                "fp64": {"peak_tflops": fp64_peak, "peak_source": fp64_src,
+                         "note": "the kernel is FP64-issue bound (real DRAM traffic = `traffic`); its FP64 pipe utilisation is in the "
+                                 "ncu summary under profiles/"},
+                "note": "achieved = SURVEY 8(d) contract bytes (every LM pass streams the edge records) / CUDA-event time; the kernel "
+                        "keeps the frame's edges on chip, so real DRAM traffic (`traffic`) is ~1 % of that, see DESIGN.md"}
+    else:
+        roof = _local_roofline(env, batch, stats, prof, prof_steps, key)
+    res = {
+        "metric": METRIC, "value": edges_lin_all * steps / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * dev_s_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(key, args), "l2": "flushed (256 MiB write) between timed steps; inputs resident in HBM",
+                   "parallelism": f"dp{world} (independent units, no collective)",
+                   "timing": "CUDA events on the solver stream, max over ranks"},
+        "lm_iters_per_sec": lm_iters_all * steps / dev_s_max,
+        "lm_trials_per_sec": lm_trials_all * steps / dev_s_max,
+        "edges_evaluated_per_sec": edges_eval_all * steps / dev_s_max,
+        "units_per_sec": n_units * world * steps / dev_s_max,
+        "e2e": {"value": edges_lin_all * e2e_steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes()),
+                "d2h_bytes_per_step": int(out.d2h_bytes()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
+                "api": "rspl_ba_%s_batch (pinned host buffers in, pinned host buffers out)" % ("frame" if is_frame else "local")},
+        "gpu_launches": int(launches_per_step * steps),
+        "roofline": roof,
+        "clocks": clocks,
+        "wall_s_timed_region": wall_max,
+    }
+    if key in ("c1", "c3", "frame1"):
+        res["shim_latency"] = shim_latency(key)
+    if with_cpu:
+        res["cpu_baseline"] = cpu_baseline(key, args)
+    return res
+
+
+def shim_latency(key, reps=20):
+    """Latency of ONE call through the reference signatures (include/rspl_ba/g2o_optimization_shim.hpp): container
+    flattening + H2D + solve + D2H + scatter, measured by tests/shim/shim_driver.cpp in a subprocess."""
+    try:
+        import tempfile
+        from rspl_slam_b200 import synth
+        sys.path.insert(0, os.path.join(ROOT, "tests", "shim"))
+        from shim_dump import dump_problem
+        tmp = tempfile.mkdtemp(prefix="rspl_shim_")
+        exe = os.path.join(tmp, "shim_driver")
+        env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+        subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT}/include", f"-I{ROOT}/tests/shim", f"{ROOT}/tests/shim/shim_driver.cpp",
+                        "-o", exe, f"-L{ROOT}/rspl_slam_b200", "-lrspl_ba", f"-Wl,-rpath,{ROOT}/rspl_slam_b200"], check=True, env=env,
+                       capture_output=True)
+        fin, fout = os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")
+        if key == "frame1":
+            dump_problem(1, synth.make_frame_problem(synth.config_seed(2, 0), n_points=C2_POINTS), fin)
+            entry = "FrameOptimization"
+        else:
+            cfg = {"c1": 1, "c3": 3}[key]
+            dump_problem(0, synth.make_local_problem(synth.config_seed(cfg, 0), **_local_kw(key)), fin)
+            entry = "LocalmapOptimization"
+        r = subprocess.run([exe, fin, fout, str(reps)], check=True, capture_output=True, text=True, env=env, timeout=300)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        d["entry_point"] = entry + " (reference signature, host containers in / out)"
+        return d
+    except Exception as e:  # the latency leg must not take the bench line down
+        return {"error": repr(e)[:300]}
 
 
 # ------------------------------------------------------------------------------------------------
 # C5: ONE global problem, landmarks partitioned over the ranks (strong scaling; NCCL all-reduces of the
 # pose blocks, the Schur complement pieces and a few scalars per LM trial, SURVEY 8e)
 # ------------------------------------------------------------------------------------------------
-def run_global(args):
-    import torch
-    import torch.distributed as dist
-    from rspl_slam_b200 import capi, synth
-    from rspl_slam_b200.problem import LocalBatch, shard_landmarks
-    from rspl_slam_b200.roofline import local_class_bytes
-
-    rank, local_rank, world = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    ctx = capi.Context(device=local_rank)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    opt = capi.make_options()
-    ident = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
-    if world > 1:
-        if rank == 0:
+def _comm_init(env, ctx):
+    torch, dist, capi = env.torch, env.dist, env.capi
+    ident = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8, device=env.dev)
+    if env.world > 1:
+        if env.rank == 0:
             ident.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(ident, src=0)
-    ctx.comm_init(world, rank, bytes(ident.cpu().numpy().tobytes()) if world > 1 else None)
+    ctx.comm_init(env.world, env.rank, bytes(ident.cpu().numpy().tobytes()) if env.world > 1 else None)
 
+
+def global_parity_check(env):
+    """N >= 2: a test-scale global problem solved over all ranks; poses must be bit-identical on every rank and agree
+    with the un-sharded solve (one-rank communicator on rank 0) within the parity tolerances."""
+    from rspl_slam_b200 import synth
+    from rspl_slam_b200.geometry import quat_angle
+    from rspl_slam_b200.problem import LocalBatch, shard_landmarks
+    torch, dist = env.torch, env.dist
+    full = synth.make_global_problem(synth.config_seed(5, 77), n_kf=48, n_points=12000, n_lines=1200, loops=1)
+    shard = shard_landmarks(full, env.rank, env.world)
+    res = env.ctx.global_ba(LocalBatch.from_problems([shard.problem]), env.opt)
+    poses = torch.from_numpy(np.ascontiguousarray(res.pose_twc)).to(env.dev)
+    gathered = [torch.empty_like(poses) for _ in range(env.world)]
+    dist.all_gather(gathered, poses)
+    out = None
+    if env.rank == 0:
+        bit_identical = all(bool(torch.equal(g.view(torch.int64), gathered[0].view(torch.int64))) for g in gathered)
+        solo = env.capi.Context(device=env.local_rank)
+        solo.comm_init(1, 0, None)
+        ref = solo.global_ba(LocalBatch.from_problems([full]), env.opt)
+        solo.comm_destroy()
+        solo.close()
+        dp = float(np.abs(res.pose_twc[:3] - ref.pose_twc[:3]).max())
+        dr = float(max(quat_angle(res.pose_twc[3:, i], ref.pose_twc[3:, i]) for i in range(res.pose_twc.shape[1])))
+        out = {"problem": "48 KF / 12k points / 1.2k lines (C5 generator)", "ranks": env.world,
+               "poses_bit_identical_across_ranks": bool(bit_identical),
+               "max_pose_diff_vs_one_rank_m": dp, "max_rot_diff_vs_one_rank_rad": dr,
+               "within_tolerance": bool(dp < 1e-5 and dr < 1e-5),
+               "iters_equal": bool(np.array_equal(res.stats["iters"], ref.stats["iters"]))}
+    env.barrier()
+    return out
+
+
+def bench_global(env, steps, warmup, with_cpu):
+    from rspl_slam_b200 import synth
+    from rspl_slam_b200.problem import LocalBatch, shard_landmarks
+    args, ctx, capi, opt = env.args, env.ctx, env.capi, env.opt
+    rank, world = env.rank, env.world
+    _comm_init(env, ctx)
+    parity = global_parity_check(env) if world > 1 else None
     full = synth.make_global_problem(synth.config_seed(5, 0), n_kf=args.kf, n_points=args.points, n_lines=args.lines, loops=3)
     shard = shard_landmarks(full, rank, world)
     batch = LocalBatch.from_problems([shard.problem])
     pinned = _pin_batch(batch, capi)
     out = ctx.alloc_local_result(batch, pinned=True)
-    workload = (f"C5 global BA: {args.kf} KF / {len(full.point_id)} points / {len(full.line_id)} lines / {full.n_edges} constraints, "
-                f"LM 10+5, landmarks partitioned over {world} GPU(s)")
     total_edges = full.n_edges
+    n_pts, n_lns = len(full.point_id), len(full.line_id)
     del full
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    warm = max(args.warmup, 1)
+    warm = max(warmup, 1)
     ctx.global_upload(pinned)
     launches0, coll0 = ctx.launch_count, ctx.collective_count()
     for _ in range(warm):
@@ -444,138 +578,99 @@ def run_global(args):
     stats = out.stats.copy()
     launches_per_step = (ctx.launch_count - launches0) // warm
     coll_per_step = (ctx.collective_count() - coll0) // warm
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            for i in range(args.steps):
-                flush.zero_()
-                starts[i].record(stream)
-                ctx.global_solve(opt)
-                ends[i].record(stream)
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    dev_s = float(sum(s.elapsed_time(e) for s, e in zip(starts, ends))) * 1e-3
+    dev_s, wall, clocks = env.timed_steps(lambda: ctx.global_solve(opt), steps)
     # end to end: host buffers in, host buffers out
     ctx.global_ba(pinned, opt)
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    env.barrier()
+    e2e_steps = max(1, min(steps, 3))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.global_upload(pinned)
         ctx.global_solve(opt)
         ctx.global_download(out)
-    barrier()
+    env.barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([dev_s, e2e_s, t_wall], dtype=torch.float64, device=dev)
-    byt = torch.tensor([float(pinned.h2d_bytes()), float(out.d2h_bytes())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(byt, op=dist.ReduceOp.SUM)
-    dev_s_max, e2e_s_max, wall_max = [float(x) for x in t.tolist()]
+    dev_s_max, e2e_s_max, wall_max = env.reduce([dev_s, e2e_s, wall], "MAX")
+    h2d, d2h = env.reduce([float(pinned.h2d_bytes()), float(out.d2h_bytes())], "SUM")
     # the LM statistics are global (every rank holds the same numbers)
     edges_lin, edges_eval = int(stats["edges_linearized"][0]), int(stats["edges_evaluated"][0])
     lm_iters, lm_trials = int(stats["iters"][0].sum()), int(stats["trials"][0].sum())
-    if rank == 0:
-        peak, peak_src = _peaks()
-        ctx.set_profiling(True)
-    # (the profiled pass is collective too: every rank runs it, rank 0 records events)
+    # (the profiled pass is collective too: every rank runs it, rank 0 reports)
+    ctx.set_profiling(True)
     ctx.global_solve(opt)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    res = None
     if rank == 0:
-        prof = ctx.get_profile()
-        ctx.set_profiling(False)
-        per_kernel = {k: {"ms_per_step": v[0], "launches_per_step": v[1]} for k, v in prof.items() if v[1]}
         # stats count the linearised edges of ALL ranks; this rank's kernels touched its shard's share of them
         stats_local = stats.copy()
-        stats_local["edges_linearized"] = (stats["edges_linearized"] * (batch.n_edges / max(total_edges, 1))).astype(stats["edges_linearized"].dtype)
-        cls_bytes = local_class_bytes(batch, stats_local)  # this rank's share of the contract bytes
-        groups = {"linearize (kb_linearize + kb_pose_blocks)": (("linearize", "pose_blocks"), cls_bytes["linearize"]),
-                  "schur (kb_schur_prep + kb_schur_reduce + dense solve)": (("schur_prep", "schur_reduce", "reduced_solve"), cls_bytes["schur"]),
-                  "backsub (kb_backsub)": (("backsub_update_eval",), cls_bytes["backsub"])}
-        best = None
-        for name, (classes, nbytes) in groups.items():
-            ms = sum(prof[c][0] for c in classes)
-            nl = sum(prof[c][1] for c in classes)
-            if nl == 0:
-                continue
-            per_kernel[name] = {"ms_per_step": ms, "algorithmic_bytes_per_step": nbytes,
-                                "achieved_GBs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
-            if best is None or ms > best[1]:
-                best = (name, ms, nl, nbytes)
-        dom_name, dom_ms, dom_launches, alg_bytes = best
-        launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
-        line = {
-            "metric": METRIC, "value": edges_lin * args.steps / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "strong",
+        stats_local["edges_linearized"] = (stats["edges_linearized"] * (batch.n_edges / max(total_edges, 1))).astype(
+            stats["edges_linearized"].dtype)
+        roof = _local_roofline(env, batch, stats_local, prof, 1, "c5")
+        roof["note"] = "rank 0's kernels on its landmark shard; contract bytes of SURVEY 8(d)"
+        res = {
+            "metric": METRIC, "value": edges_lin * steps / dev_s_max, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dev_s_max / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "l2": "flushed (256 MiB write) between timed steps; inputs resident in HBM",
-                       "parallelism": f"landmark-sharded x{world}, poses replicated, {coll_per_step} NCCL all-reduces per solve, "
-                                      "replicated dense Cholesky of the reduced camera system",
+            "config": {"workload": workload_name("c5", args),
+                       "l2": "flushed (256 MiB write) between timed steps; inputs resident in HBM",
+                       "problem": f"{n_pts} points / {n_lns} lines / {total_edges} constraints",
+                       "parallelism": f"landmark-sharded x{world}, poses replicated, {coll_per_step} all-reduces per solve from the "
+                                      "library's own NCCL communicator (rspl_ba_comm_init)",
                        "timing": "CUDA events on the solver stream, max over ranks"},
-            "lm_iters_per_sec": lm_iters * args.steps / dev_s_max, "lm_trials_per_sec": lm_trials * args.steps / dev_s_max,
-            "edges_evaluated_per_sec": edges_eval * args.steps / dev_s_max, "units_per_sec": args.steps / dev_s_max,
-            "e2e": {"value": edges_lin * e2e_steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(byt[0].item()),
-                    "d2h_bytes_per_step": int(byt[1].item()), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
+            "lm_iters_per_sec": lm_iters * steps / dev_s_max, "lm_trials_per_sec": lm_trials * steps / dev_s_max,
+            "edges_evaluated_per_sec": edges_eval * steps / dev_s_max, "units_per_sec": steps / dev_s_max,
+            "e2e": {"value": edges_lin * e2e_steps / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s_max / e2e_steps,
                     "api": "rspl_ba_global_upload / _solve / _download (pinned host buffers, all ranks)"},
-            "gpu_launches": int(launches_per_step * args.steps), "collectives_per_step": int(coll_per_step),
-            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": alg_bytes / max(dom_launches, 1) / launch_s / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": alg_bytes / max(dom_launches, 1) / launch_s / 1e9 / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(dom_launches, 1),
-                         "launch_ms": 1e3 * launch_s, "launches_per_step": dom_launches, "per_kernel": per_kernel,
-                         "note": "rank 0's kernels on its landmark shard; contract bytes of SURVEY 8(d)"},
-            "cpu_baseline": cpu_baseline(args), "clocks": clk.summary(), "wall_s_timed_region": wall_max,
+            "gpu_launches": int(launches_per_step * steps), "collectives_per_step": int(coll_per_step),
+            "comm": {"library": "NCCL via rspl_ba_comm_init (dlopen)", "ranks": world, "all_reduces_per_solve": int(coll_per_step),
+                     "ms_per_solve_rank0": prof.get("collectives", (0.0, 0))[0]},
+            "roofline": roof, "clocks": clocks, "wall_s_timed_region": wall_max,
         }
-        print(json.dumps(line), flush=True)
-    barrier()
+        if parity is not None:
+            res["parity_check"] = parity
+        if with_cpu:
+            res["cpu_baseline"] = cpu_baseline("c5", args)
+    env.barrier()
     ctx.comm_destroy()
-    if world > 1:
-        dist.destroy_process_group()
-    ctx.close()
+    return res
+
+
+def sub_steps(key, args):
+    """(steps, warmup) of a sub-workload of the default run, bounded so that the whole run ends within minutes."""
+    if key == "c2p":
+        return max(3, min(args.steps, 20)), 3
+    if key == "c4":
+        return max(2, min(args.steps, 5)), 3
+    if key in ("c1", "c3", "frame1"):
+        return max(5, min(args.steps, 30)), 3
+    if key == "c5":
+        return max(1, min(args.steps, 3)), 1
+    return args.steps, args.warmup
+
+
+def run_ours(args):
+    env = Env(args)
+    multi = env.world > 1
+    keys = (ALL_MULTI if multi else ALL_N1) if args.workload == "all" else [args.workload]
+    if multi:
+        keys = [k for k in keys if k not in ("c1", "c3", "frame1")] or keys  # single units do not shard (replicas only)
+    results = {}
+    for i, key in enumerate(keys):
+        steps, warmup = (args.steps, args.warmup) if i == 0 else sub_steps(key, args)
+        with_cpu = not multi  # the CPU baseline is reported on rank 0 at N = 1 only
+        t0 = time.perf_counter()
+        results[key] = bench_global(env, steps, warmup, with_cpu) if key == "c5" else bench_units(env, key, steps, warmup, with_cpu)
+        if env.rank == 0 and results[key] is not None:
+            results[key]["bench_wall_s"] = time.perf_counter() - t0
+    if env.rank == 0:
+        line = dict(results[keys[0]])
+        if len(keys) > 1:
+            line["workloads"] = {k: results[k] for k in keys[1:]}
+        print(json.dumps(line), flush=True)
+    env.close()
     return 0
-
-
-def _traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", f"traffic_{workload}.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["dram_bytes_per_launch"])
-        except Exception:
-            return None
-    return None
-
-
-def cpu_baseline(args):
-    """The oracle timed on this box's host cores on a bounded sample (1 thread: default g2o and the
-    reference's call pattern are single-threaded)."""
-    from oracle import orc
-    from rspl_slam_b200 import synth
-    if args.workload in ("c2", "c2p"):
-        n = 1024 if args.workload == "c2p" else 256  # (g2o differentiates line edges numerically: ~6x the work per frame)
-        probs = [synth.make_frame_problem(synth.config_seed(2, i), n_points=C2_POINTS, n_lines=_c2_lines(args)) for i in range(n)]
-        t0 = time.perf_counter()
-        st = orc.frame_opt_batch(probs, n_threads=1)
-        dt = time.perf_counter() - t0
-        sample = f"first {n} of {C2_FRAMES} C2 frames ({C2_POINTS} stereo pts + {_c2_lines(args)} lines), 1 thread"
-    elif args.workload == "c5":
-        # the oracle factorises the reduced system densely in one thread: a scaled-down problem of the same generator
-        probs = [synth.make_global_problem(synth.config_seed(5, 0), n_kf=60, n_points=30000, n_lines=3000, loops=1)]
-        t0 = time.perf_counter()
-        st = orc.local_ba_batch(probs, n_threads=1)
-        dt = time.perf_counter() - t0
-        sample = "scaled-down C5 (60 KF / 30k points / 3k lines, same generator), 1 thread"
-    else:
-        n = 8
-        probs = [synth.make_local_problem(synth.config_seed(4, i)) for i in range(n)]
-        t0 = time.perf_counter()
-        st = orc.local_ba_batch(probs, n_threads=1)
-        dt = time.perf_counter() - t0
-        sample = f"first {n} C4 windows, 1 thread"
-    edges = sum(s["edges_linearized"] for s in st)
-    return {"value": edges / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-            "seconds": dt, "lm_iters_per_sec": sum(sum(s["iters"]) for s in st) / dt}
 
 
 def main():
@@ -584,8 +679,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2p", "c4", "c5"],
-                    help="c2: pose-only frames, 400 stereo points + 60 lines (BASELINE configs[1]); c2p: points only (the reference's path)")
+    ap.add_argument("--workload", default="all", choices=["all", "c2", "c2p", "c4", "c1", "c3", "frame1", "c5"],
+                    help="all: C2 headline + every other configuration as `workloads` sub-objects")
     ap.add_argument("--frame-lines", type=int, default=C2_LINES, help="lines per frame (c2)")
     ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")
     ap.add_argument("--points", type=int, default=1_000_000, help="points of the global problem (c5)")
@@ -595,8 +690,6 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "c5":
-        return run_global(args)
     return run_ours(args)
 
 

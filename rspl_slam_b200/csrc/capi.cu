@@ -106,7 +106,8 @@ struct RsplBaContext {
   // tiled Schur path (local_tiled.cuh)
   DevBuf tile_buf;
   ba::TileDev td{};
-  std::vector<long long> l_cost[2];     // [W] shared-memory cost of a window's points / lines (tile sizing)
+  std::vector<long long> l_cost[2];     // [W] edges of a window's points / lines (tile sizing)
+  std::vector<long long> l_cost_nl[2];  // [W] landmarks of each kind
   int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve, 4 batched + tiled Schur (diagnostics)
   int l_super_steps = 0;
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily

@@ -1039,7 +1039,11 @@ struct TileDev {
   int Tp, Tl;      // grid widths: max tiles of points / lines over the windows
   int* tile_lm;    // [(w*2+kind)*(Tcap+1) + t] first landmark (batch-global index) of tile t; entry ntile = end
   int* ntile;      // [w*2+kind]
+  int cost_b[2];   // shared-memory bytes per edge (Z block, landmark index, its share of the staged pair entries)
   int* tpb;        // [((w*2+kind)*(Tcap+1) + t)*Pmax + li] first entry of tile t in the kind-list of compact pair li
+  int* tso;        // [((w*2+kind)*Tcap + t)*(Pmax+1) + li] offset of pair li inside the tile's entry block; [n_ne] = total
+  int* tent_base;  // [(w*2+kind)*Tcap + t] position of the tile's entry block in tent
+  ushort2* tent;   // tile-major copy of the pair entries, edge indices relative to the tile's first edge
   int* order;      // [w*Pmax + o] compact pair position, longest list first
   double* hs_tile; // [((w*(Tp+Tl) + tt)*Pmax + li)*42], tt = t (points) or Tp + t (lines)
   double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)

@@ -91,6 +91,8 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   c->l_max_pts = c->l_max_lns = c->l_max_edges = 0;
   c->l_cost[0].assign(W, 0);
   c->l_cost[1].assign(W, 0);
+  c->l_cost_nl[0].assign(W, 0);
+  c->l_cost_nl[1].assign(W, 0);
   for (int w = 0; w < W; ++w) {
     const int a = in->pose_begin[w], b = in->pose_begin[w + 1];
     int nf = 0;
@@ -103,12 +105,10 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
                          (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]) +
                          (in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) +
                          (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]);
-    c->l_cost[0][w] = (long long)ba::TileCost<0>::A * npt +
-                      (long long)ba::TileCost<0>::B * ((in->mono_pt_begin[w + 1] - in->mono_pt_begin[w]) +
-                                                       (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]));
-    c->l_cost[1][w] = (long long)ba::TileCost<1>::A * nln +
-                      (long long)ba::TileCost<1>::B * ((in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) +
-                                                       (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]));
+    c->l_cost[0][w] = (long long)(in->mono_pt_begin[w + 1] - in->mono_pt_begin[w]) + (in->stereo_pt_begin[w + 1] - in->stereo_pt_begin[w]);
+    c->l_cost[1][w] = (long long)(in->mono_ln_begin[w + 1] - in->mono_ln_begin[w]) + (in->stereo_ln_begin[w + 1] - in->stereo_ln_begin[w]);
+    c->l_cost_nl[0][w] = npt;
+    c->l_cost_nl[1][w] = nln;
     if (npt > c->l_max_pts) c->l_max_pts = npt;
     if (nln > c->l_max_lns) c->l_max_lns = nln;
     if (ne > c->l_max_edges) c->l_max_edges = (int)ne;
@@ -401,30 +401,38 @@ int batched_prepare(RsplBaContext* c) {
 // degree per kind (read back from the setup kernels); smem_tile = dynamic shared memory of kt_schur_tile per kind.
 int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   const int W = c->l_n_windows;
-  const int cost_a[2] = {ba::TileCost<0>::A, ba::TileCost<1>::A}, cost_b[2] = {ba::TileCost<0>::B, ba::TileCost<1>::B};
+  // shared-memory cost of a window's landmarks of one kind: A per landmark, B per edge; the staged pair entries add
+  // 2 (maxdeg + 1) bytes per edge to the compile-time per-edge cost
+  const int cost_a[2] = {ba::TileCost<0>::A, ba::TileCost<1>::A};
+  const int cost_b[2] = {ba::TileCost<0>::B + 2 * (maxdeg[0] + 1), ba::TileCost<1>::B + 2 * (maxdeg[1] + 1)};
+  const int Pmax = c->bd.Pmax;
+  const long long fixed = (long long)(Pmax + 1) * 4 + 64;
+  auto cost = [&](int k, int w) { return c->l_cost_nl[k][w] * cost_a[k] + c->l_cost[k][w] * cost_b[k]; };
   long long total = 0;
   for (int k = 0; k < 2; ++k)
-    for (int w = 0; w < W; ++w) total += c->l_cost[k][w];
+    for (int w = 0; w < W; ++w) total += cost(k, w);
   // default: two CTAs per SM; small batches (single windows) get smaller tiles so that they spread over the SMs
   long long Q = 100 << 10;
   if (const char* e = getenv("RSPL_BA_TILE_Q")) Q = atoll(e) > 4096 ? atoll(e) : Q;
   else
     while (Q > (12 << 10) && total / Q < 2LL * c->num_sms) Q >>= 1;
   for (int k = 0; k < 2; ++k) {
-    const long long room = (long long)c->smem_optin - cost_a[k] - (long long)cost_b[k] * maxdeg[k] - 64;
+    const long long room = (long long)c->smem_optin - cost_a[k] - (long long)cost_b[k] * maxdeg[k] - fixed;
     if (room < 4096) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: landmark degree %d too large for the tiled Schur path", maxdeg[k]);
     if (Q > room) Q = room;
   }
   int T[2] = {0, 0};
   for (int k = 0; k < 2; ++k)
     for (int w = 0; w < W; ++w) {
-      const int nt = (int)((c->l_cost[k][w] + Q - 1) / Q);
+      const int nt = (int)((cost(k, w) + Q - 1) / Q);
       if (nt > T[k]) T[k] = nt;
     }
   const int Tcap = T[0] > T[1] ? (T[0] > 0 ? T[0] : 1) : (T[1] > 0 ? T[1] : 1);
-  const int Pmax = c->bd.Pmax;
   Arena a;
   const size_t o_tlm = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1));
+  const size_t o_tso = a.take(sizeof(int) * (size_t)W * 2 * Tcap * (Pmax + 1));
+  const size_t o_tb = a.take(sizeof(int) * (size_t)W * 2 * Tcap);
+  const size_t o_tent = a.take(sizeof(ushort2) * (size_t)(c->l_pair_base[W] + 1));
   const size_t o_nt = a.take(sizeof(int) * (size_t)W * 2);
   const size_t o_tpb = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1) * Pmax);
   const size_t o_ord = a.take(sizeof(int) * (size_t)W * Pmax);
@@ -440,10 +448,15 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   td.tile_lm = (int*)(base + o_tlm);
   td.ntile = (int*)(base + o_nt);
   td.tpb = (int*)(base + o_tpb);
+  td.tso = (int*)(base + o_tso);
+  td.tent_base = (int*)(base + o_tb);
+  td.tent = (ushort2*)(base + o_tent);
+  td.cost_b[0] = cost_b[0];
+  td.cost_b[1] = cost_b[1];
   td.order = (int*)(base + o_ord);
   td.hs_tile = (double*)(base + o_hs);
   td.P_bR = (double*)(base + o_bR);
-  for (int k = 0; k < 2; ++k) smem_tile[k] = (size_t)(Q + cost_a[k] + (long long)cost_b[k] * maxdeg[k] + 32);
+  for (int k = 0; k < 2; ++k) smem_tile[k] = (size_t)(Q + cost_a[k] + (long long)cost_b[k] * maxdeg[k] + fixed);
   return RSPL_BA_OK;
 }
 
@@ -550,6 +563,9 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     c->l_last_path = 4;
     LAUNCH(PC_PAIRS, ba::kt_tiles_lm, dim3((td.Tcap + 1 + 127) / 128, W, 2), 128, 0, d, td);
     LAUNCH(PC_PAIRS, ba::kt_tiles_pairs, dim3(((size_t)b.Pmax * (td.Tcap + 1) + 255) / 256, W, 2), 256, 0, d, b, td);
+    LAUNCH(PC_PAIRS, ba::kt_tiles_scan, dim3(td.Tcap, W, 2), 32, 0, d, b, td);
+    LAUNCH(PC_PAIRS, ba::kt_tiles_base, (W + 127) / 128, 128, 0, d, b, td);
+    LAUNCH(PC_PAIRS, ba::kt_tiles_fill, dim3(((size_t)b.Pmax * td.Tcap + 255) / 256, W, 2), 256, 0, d, b, td);
     LAUNCH(PC_PAIRS, ba::kt_order, (W + 3) / 4, 128, 0, d, b, td);
     CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[0]));
     CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[1]));

@@ -24,13 +24,13 @@ namespace ba {
 
 template <int KIND>
 struct TileCost {
-  // per landmark: L (packed lower) + 1/diag + y; per edge: the Z block + a 16-bit tile-local landmark index
+  // per landmark: L (packed lower) + 1/diag + y; per edge: the Z block + a 16-bit tile-local landmark index (+ at
+  // run time 4 bytes per staged pair entry: a landmark of degree k has at most k(k+1)/2 entries, (k+1)/2 per edge)
   static constexpr int LN = KT<KIND>::LD * (KT<KIND>::LD + 1) / 2 + 2 * KT<KIND>::LD; // doubles: 12 (points), 18 (lines)
   static constexpr int A = LN * 8;
   static constexpr int B = ZBlk<KIND>::N * 8 + 2;
 };
 BA_DEV int tile_cost_a(int kind) { return kind ? TileCost<1>::A : TileCost<0>::A; }
-BA_DEV int tile_cost_b(int kind) { return kind ? TileCost<1>::B : TileCost<0>::B; }
 
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_GROUPS = TILE_THREADS / 8;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) kt_tiles_lm(const __grid_constant__ Local
   const KindDev& k = d.k[kind];
   const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
   const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
-  const long long A = tile_cost_a(kind), B = tile_cost_b(kind);
+  const long long A = tile_cost_a(kind), B = td.cost_b[kind];
   const long long total = A * nl + B * ne;
   const int nt = (int)((total + td.Q - 1) / td.Q);
   if (t == 0) td.ntile[w * 2 + kind] = nt;
@@ -86,6 +86,74 @@ __global__ void __launch_bounds__(256) kt_tiles_pairs(const __grid_constant__ Lo
     }
   }
   td.tpb[((size_t)(w * 2 + kind) * (td.Tcap + 1) + t) * b.Pmax + li] = lo;
+}
+
+// offsets of the pairs inside a tile's entry block (exclusive scan over the compact pairs); one warp per
+// (tile, window, kind); the total is parked in tent_base for kt_tiles_base. grid (Tcap, W, 2), 32 threads
+__global__ void __launch_bounds__(32) kt_tiles_scan(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                    const __grid_constant__ TileDev td) {
+  const int t = blockIdx.x, w = blockIdx.y, kind = blockIdx.z, lane = threadIdx.x;
+  const size_t wk = (size_t)(w * 2 + kind);
+  if (t >= td.ntile[wk]) {
+    if (lane == 0) td.tent_base[wk * td.Tcap + t] = 0;
+    return;
+  }
+  const int n = b.n_ne[w];
+  const int* tp0 = td.tpb + (wk * (td.Tcap + 1) + t) * b.Pmax;
+  const int* tp1 = tp0 + b.Pmax;
+  int* so = td.tso + (wk * td.Tcap + t) * (b.Pmax + 1);
+  int run = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int li = base + lane;
+    const int v = li < n ? tp1[li] - tp0[li] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (li < n) so[li] = run + x - v;
+    run += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) {
+    so[n] = run;
+    td.tent_base[wk * td.Tcap + t] = run;
+  }
+}
+
+// totals -> positions of the tiles' entry blocks inside the window's region of tent; one thread per window
+__global__ void __launch_bounds__(128) kt_tiles_base(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                     const __grid_constant__ TileDev td) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.n_windows) return;
+  int run = (int)b.pair_base[w];
+  for (int kind = 0; kind < 2; ++kind)
+    for (int t = 0; t < td.Tcap; ++t) {
+      int* p = td.tent_base + (size_t)(w * 2 + kind) * td.Tcap + t;
+      const int c = *p;
+      *p = run;
+      run += c;
+    }
+}
+
+// tile-major entry blocks: thread per (pair, tile, window, kind) copies its slice with tile-local edge indices;
+// grid (ceil(Pmax * Tcap / 256), W, 2)
+__global__ void __launch_bounds__(256) kt_tiles_fill(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                     const __grid_constant__ TileDev td) {
+  const int w = blockIdx.y, kind = blockIdx.z;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int li = idx % b.Pmax, t = idx / b.Pmax;
+  const size_t wk = (size_t)(w * 2 + kind);
+  if (t >= td.ntile[wk] || li >= b.n_ne[w]) return;
+  const KindDev& k = d.k[kind];
+  const int ea = k.ebeg[td.tile_lm[wk * (td.Tcap + 1) + t]];
+  const int* tp0 = td.tpb + (wk * (td.Tcap + 1) + t) * b.Pmax;
+  const int beg = tp0[li], end = tp0[b.Pmax + li];
+  ushort2* dst = td.tent + td.tent_base[wk * td.Tcap + t] + td.tso[(wk * td.Tcap + t) * (b.Pmax + 1) + li];
+  for (int i = beg; i < end; ++i) {
+    const int2 e = b.pairs[i];
+    dst[i - beg] = make_ushort2((unsigned short)(e.x - ea), (unsigned short)(e.y - ea));
+  }
 }
 
 // processing order of the compact pairs of a window: longest list first (stable rank sort), so that the four
@@ -146,7 +214,18 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   const int nl = lb - la, ne = eb - ea;
   double* Zs = reinterpret_cast<double*>(tile_smem);               // [ne][ZN], column-major blocks (ZCOL)
   double* Ls = Zs + (size_t)ne * ZN;                                // [nl][LN]: L packed, inv, y
-  unsigned short* elm = reinterpret_cast<unsigned short*>(Ls + (size_t)nl * LN); // [ne] tile-local landmark of an edge
+  const int n_ne = b.n_ne[w];
+  const size_t tile_id = (size_t)(w * 2 + KIND) * td.Tcap + t;
+  const int* tso_g = td.tso + tile_id * (b.Pmax + 1);
+  const int n_ent = tso_g[n_ne];
+  ushort2* ent = reinterpret_cast<ushort2*>(Ls + (size_t)nl * LN);                  // [n_ent] staged pair entries
+  int* tso = reinterpret_cast<int*>(ent + n_ent);                                     // [n_ne + 1]
+  unsigned short* elm = reinterpret_cast<unsigned short*>(tso + n_ne + 1);            // [ne] tile-local landmark of an edge
+  { // stage the tile's pair entries and their per-pair offsets (one contiguous block each)
+    const ushort2* src = td.tent + td.tent_base[tile_id];
+    for (int i = tid; i < n_ent; i += TILE_THREADS) ent[i] = src[i];
+    for (int i = tid; i <= n_ne; i += TILE_THREADS) tso[i] = tso_g[i];
+  }
   const int p0 = d.pose_begin[w], f0 = b.nf_begin[w], l0 = k.lm_begin[w];
   const double lambda = s.lambda;
   const bool robust = s.robust;
@@ -238,15 +317,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   __syncthreads();
 
   // ---- phase 2: pair products over the tile's entries, 8 lanes per pose pair
-  const int lane = tid & 31, lane8 = tid & 7, warp = tid >> 5, g4 = (tid >> 3) & 3;
-  const int n_ne = b.n_ne[w];
+  const int lane8 = tid & 7, warp = tid >> 5, g4 = (tid >> 3) & 3;
   const int nquads = (n_ne + 3) >> 2;
   const int* ord = td.order + (size_t)w * b.Pmax;
-  const int* tp0 = td.tpb + ((size_t)(w * 2 + KIND) * (td.Tcap + 1) + t) * b.Pmax;
-  const int* tp1 = tp0 + b.Pmax;
   const int tt = KIND ? td.Tp + t : t;
   double* out_base = td.hs_tile + ((size_t)w * (td.Tp + td.Tl) + tt) * b.Pmax * 42;
-  (void)lane;
   for (int quad = warp; quad < nquads; quad += TILE_THREADS / 32) {
     const int oi = quad * 4 + g4;
     const bool have = oi < n_ne;
@@ -258,20 +333,16 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
       int fi, fj;
       pair_decode(p, s.nf, fi, fj);
       diag = fi == fj;
-      beg = tp0[li];
-      ncol = (tp1[li] - beg) * LD;
+      beg = tso[li];
+      ncol = (tso[li + 1] - beg) * LD;
     }
     double acc[48];
 #pragma unroll
     for (int q = 0; q < 48; ++q) acc[q] = 0.0;
-    int2 ee = make_int2(0, 0);
-    if (lane8 < ncol) ee = b.pairs[beg + lane8 / LD];
     for (int c = lane8; c < ncol; c += 8) {
-      const int2 cur = ee;
-      const int cn = c + 8;
-      if (cn < ncol) ee = b.pairs[beg + cn / LD]; // next entry record while this one is processed
+      const ushort2 cur = ent[beg + c / LD];
       const int q = c % LD;
-      const int ji = cur.x - ea;
+      const int ji = cur.x;
       const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)ji * ZN + q * ZCOL);
       double za[6];
 #pragma unroll
@@ -289,7 +360,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
           acc[36 + r] += za[r] * yq;
         }
       } else {
-        const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)(cur.y - ea) * ZN + q * ZCOL);
+        const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)cur.y * ZN + q * ZCOL);
         double zb[6];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {

@@ -1,6 +1,10 @@
 // shim_driver.cpp — calls the reference-signature LocalmapOptimization / FrameOptimization provided
 // by include/rspl_ba/g2o_optimization_shim.hpp on a problem read from a flat float64 file and writes
 // the mutated containers back. TEST INFRASTRUCTURE (see tests/test_shim.py).
+// With a third argument N it also times N further calls on fresh copies of the containers (bench.py's
+// single-call latency through the reference signatures) and prints {"median_us", "min_us"} to stdout.
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -85,15 +89,45 @@ int main(int argc, char** argv) {
     sl.push_back(c);
   }
   double ret = 0;
-  if (kind == 0) {
-    LocalmapOptimization(poses, points, lines, cams, mp, sp, ml, sl, cfg);
-  } else if (kind == 1) {
-    ret = FrameOptimization(poses, points, cams, mp, sp, cfg);
-  } else { // kind 2: pose-only with constraints on fixed lines (the extension; no reference signature)
-    int n = 0;
-    (void)rspl_ba::FrameOptimizationWithLinesImpl(rspl_ba::thread_context(), poses, points, lines, cams, mp, sp, ml, sl, cfg, &n);
-    ret = n;
+  auto call = [&](MapOfPoses& P, MapOfPoints3d& X, MapOfLine3d& L, VectorOfMonoPointConstraints& a,
+                  VectorOfStereoPointConstraints& b, VectorOfMonoLineConstraints& c, VectorOfStereoLineConstraints& e) {
+    double r = 0;
+    if (kind == 0) {
+      LocalmapOptimization(P, X, L, cams, a, b, c, e, cfg);
+    } else if (kind == 1) {
+      r = FrameOptimization(P, X, cams, a, b, cfg);
+    } else { // kind 2: pose-only with constraints on fixed lines (the extension; no reference signature)
+      int n = 0;
+      (void)rspl_ba::FrameOptimizationWithLinesImpl(rspl_ba::thread_context(), P, X, L, cams, a, b, c, e, cfg, &n);
+      r = n;
+    }
+    return r;
+  };
+  const int reps = argc > 3 ? atoi(argv[3]) : 0;
+  if (reps > 0) { // latency of one call through the reference signature (containers copied outside the timed region)
+    auto deep = [](const auto& v) {
+      typename std::decay<decltype(v)>::type o;
+      for (auto& p : v) o.push_back(std::make_shared<typename std::decay<decltype(*p)>::type>(*p));
+      return o;
+    };
+    std::vector<double> us;
+    for (int i = 0; i < reps + 3; ++i) {
+      MapOfPoses P = poses;
+      MapOfPoints3d X = points;
+      MapOfLine3d L = lines;
+      auto a = deep(mp);
+      auto b = deep(sp);
+      auto c = deep(ml);
+      auto e = deep(sl);
+      const auto t0 = std::chrono::steady_clock::now();
+      call(P, X, L, a, b, c, e);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (i >= 3) us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+    }
+    std::sort(us.begin(), us.end());
+    printf("{\"median_us\": %.2f, \"min_us\": %.2f, \"reps\": %d}\n", us[us.size() / 2], us[0], reps);
   }
+  ret = call(poses, points, lines, mp, sp, ml, sl);
   std::vector<double> out;
   out.push_back(ret);
   for (auto& kv : poses) {
