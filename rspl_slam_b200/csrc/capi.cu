@@ -108,6 +108,18 @@ struct RsplBaContext {
   ba::TileDev td{};
   std::vector<long long> l_cost[2];     // [W] edges of a window's points / lines (tile sizing)
   std::vector<long long> l_cost_nl[2];  // [W] landmarks of each kind
+  // whole-schedule CUDA graphs of the local solve (setup -> LM passes as conditional WHILE nodes -> flags), keyed by
+  // the kernel argument blocks: a call whose shapes and buffers match an earlier one only launches the cached graph
+  struct LocalGraph {
+    std::vector<unsigned char> key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t stamp = 0;
+    int launches_fixed = 0, launches_step = 0;
+  };
+  std::vector<LocalGraph> graph_cache;
+  uint64_t graph_stamp = 0;
+  cudaStream_t s_body = nullptr;          // origin stream of the loop-body capture
+  int l_graph_launches_step = 0;          // kernels per super-step of the last graph launch (0: not a graph launch)
   int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve, 4 batched + tiled Schur (diagnostics)
   int l_super_steps = 0;
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
@@ -287,6 +299,9 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
     cudaEventDestroy(pe.a);
     cudaEventDestroy(pe.b);
   }
+  for (auto& g : c->graph_cache)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (c->s_body) cudaStreamDestroy(c->s_body);
   if (c->s_aux) cudaStreamDestroy(c->s_aux);
   for (int i = 0; i < 6; ++i)
     if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);

@@ -406,7 +406,7 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   const int cost_a[2] = {ba::TileCost<0>::A, ba::TileCost<1>::A};
   const int cost_b[2] = {ba::TileCost<0>::B + 2 * (maxdeg[0] + 1), ba::TileCost<1>::B + 2 * (maxdeg[1] + 1)};
   const int Pmax = c->bd.Pmax;
-  const long long fixed = (long long)(Pmax + 1) * 4 + 64;
+  const long long fixed = (long long)ba::tile_fixed_bytes(Pmax, c->l_max_poses, c->ld.n_cameras);
   auto cost = [&](int k, int w) { return c->l_cost_nl[k][w] * cost_a[k] + c->l_cost[k][w] * cost_b[k]; };
   long long total = 0;
   for (int k = 0; k < 2; ++k)
@@ -432,7 +432,7 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   const size_t o_tlm = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1));
   const size_t o_tso = a.take(sizeof(int) * (size_t)W * 2 * Tcap * (Pmax + 1));
   const size_t o_tb = a.take(sizeof(int) * (size_t)W * 2 * Tcap);
-  const size_t o_tent = a.take(sizeof(ushort2) * (size_t)(c->l_pair_base[W] + 1));
+  const size_t o_tent = a.take(sizeof(ushort2) * (size_t)(c->l_pair_base[W] + 8LL * Tcap * W + 8));
   const size_t o_nt = a.take(sizeof(int) * (size_t)W * 2);
   const size_t o_tpb = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1) * Pmax);
   const size_t o_ord = a.take(sizeof(int) * (size_t)W * Pmax);
@@ -457,6 +457,266 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   td.hs_tile = (double*)(base + o_hs);
   td.P_bR = (double*)(base + o_bR);
   for (int k = 0; k < 2; ++k) smem_tile[k] = (size_t)(Q + cost_a[k] + (long long)cost_b[k] * maxdeg[k] + fixed);
+  return RSPL_BA_OK;
+}
+
+// grids of the setup kernels (shared by the graph path and the host-driven path)
+void enqueue_local_setup(RsplBaContext* c, cudaStream_t s) {
+  const int W = c->l_n_windows;
+  cudaMemsetAsync(c->ld.err, 0, sizeof(int) * 4, s);
+  for (int k = 0; k < 2; ++k)
+    if (c->ld.k[k].n_lm > 0) {
+      cudaMemsetAsync(c->ld.k[k].slot, ba::SLOT_NONE, (size_t)c->ld.k[k].n_lm * c->ld.slot_stride, s);
+      cudaMemsetAsync(c->ld.k[k].cursor, 0, sizeof(int) * (size_t)c->ld.k[k].n_lm, s);
+    }
+  const int T = ba::LOCAL_THREADS;
+  const int max_lm = c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns;
+  const dim3 g_e((c->l_max_edges + T - 1) / T > 0 ? (c->l_max_edges + T - 1) / T : 1, W, 2);
+  const dim3 g_l((max_lm + T - 1) / T > 0 ? (max_lm + T - 1) / T : 1, W, 2);
+  ba::setup_poses<<<W, T, 0, s>>>(c->ld);
+  ba::setup_edges<0><<<g_e, T, 0, s>>>(c->ld);
+  ba::setup_order<<<dim3(W, 2), T, 0, s>>>(c->ld);
+  ba::setup_scan<<<dim3(W, 2), 1024, 0, s>>>(c->ld);
+  ba::setup_edges<1><<<g_e, T, 0, s>>>(c->ld);
+  ba::setup_landmarks<<<g_l, T, 0, s>>>(c->ld);
+  ba::setup_gather<<<g_e, T, 0, s>>>(c->ld);
+  const dim3 g_pl(c->l_max_poses, W, 2);
+  ba::setup_pose_lists<0><<<g_pl, T, 0, s>>>(c->ld);
+  ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, s>>>(c->ld);
+  ba::setup_pose_lists<1><<<g_pl, T, 0, s>>>(c->ld);
+  c->launches += 10;
+}
+
+// ---- the whole LocalmapOptimization schedule as ONE CUDA graph ----------------------------------
+// setup kernels -> pair lists -> tile tables -> [pass 1: WHILE(any window iterating) { super-step }] -> flagging ->
+// [pass 2: WHILE { super-step }] -> final flags -> write-back. The loop conditions are set on the device (kt_cond,
+// cudaGraphSetConditional), so the host neither polls nor synchronises; the instantiated graph is cached in the
+// context under the byte image of every kernel argument block, so a call with the same shapes and buffers is a
+// single cudaGraphLaunch. Used whenever the reduced systems fit shared memory (no cuSOLVER, no NCCL in the loop)
+// and profiling is off.
+struct LocalGraphKey {
+  ba::LocalDev d;
+  ba::BatchDev b;
+  ba::TileDev td;
+  ba::LocalOpt lo;
+  int W, max_pts, max_lns, max_edges, max_poses;
+  unsigned long long smem_solve, smem_tile[2];
+};
+
+int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_solve, const size_t smem_tile[2],
+                        RsplBaContext::LocalGraph& out) {
+  const ba::LocalDev& d = c->ld;
+  const ba::BatchDev& b = c->bd;
+  const ba::TileDev& td = c->td;
+  const int W = c->l_n_windows;
+  cudaStream_t s = c->stream;
+  if (!c->s_body) CU_TRY(c, cudaStreamCreateWithFlags(&c->s_body, cudaStreamNonBlocking));
+  if (!c->s_aux) {
+    CU_TRY(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+    for (int i = 0; i < 6; ++i) CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
+  }
+  const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
+      g_win((W + 127) / 128), g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
+  const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
+  const bool fork_lines = b.Cp && b.Cl;
+  int n_launch = 0;
+#define GK(stream, kern, grid, block, shm, ...)      \
+  do {                                               \
+    kern<<<grid, block, shm, stream>>>(__VA_ARGS__); \
+    ++n_launch;                                      \
+  } while (0)
+  // one super-step on (sm, sl): the line kernels of a phase run beside the point kernels (fork / join events
+  // become graph dependencies)
+  auto super_step = [&](cudaStream_t sm, cudaStream_t sl) {
+    auto fork = [&](int k) {
+      if (!fork_lines) return;
+      cudaEventRecord(c->fork_ev[2 * k], sm);
+      cudaStreamWaitEvent(sl, c->fork_ev[2 * k], 0);
+    };
+    auto join = [&](int k) {
+      if (!fork_lines) return;
+      cudaEventRecord(c->fork_ev[2 * k + 1], sl);
+      cudaStreamWaitEvent(sm, c->fork_ev[2 * k + 1], 0);
+    };
+    cudaStream_t sline = fork_lines ? sl : sm;
+    fork(0);
+    if (b.Cp) GK(sm, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
+    if (b.Cl) GK(sline, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
+    GK(sm, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    join(0);
+    GK(sm, ba::kb_begin_trial, g_win, 128, 0, d, b);
+    fork(1);
+    if (b.Cp && td.Tp) GK(sm, ba::kt_schur_tile<0>, g_tp, ba::TILE_THREADS, smem_tile[0], d, b, lo, td);
+    if (b.Cl && td.Tl) GK(sline, ba::kt_schur_tile<1>, g_tl, ba::TILE_THREADS, smem_tile[1], d, b, lo, td);
+    join(1);
+    GK(sm, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
+    fork(2);
+    if (b.Cp) GK(sm, ba::kt_backsub_rc<0>, g_pt, ba::BT, 0, d, b, lo, td);
+    if (b.Cl) GK(sline, ba::kt_backsub_rc<1>, g_ln, ba::BT, 0, d, b, lo, td);
+    join(2);
+    GK(sm, ba::kb_decide, g_win, 128, 0, d, b);
+    if (b.C) GK(sm, ba::kb_restore, g_lm, ba::BT, 0, d, b);
+  };
+  cudaGraph_t graph = nullptr;
+  bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  int launches_step = 0;
+  if (ok) {
+    const int64_t l0 = c->launches;
+    enqueue_local_setup(c, s);
+    n_launch += (int)(c->launches - l0);
+    c->launches = l0;
+    cudaMemsetAsync(b.n_active, 0, sizeof(int), s);
+    GK(s, ba::kb_init, W, ba::BT, 0, d, b, lo);
+    GK(s, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
+    GK(s, ba::kb_pairs_scan, g_win, 128, 0, d, b);
+    GK(s, ba::kb_pairs<1>, g_pair, ba::BT, 0, d, b);
+    GK(s, ba::kb_pairs_flag, dim3((b.Pmax + 255) / 256, W), 256, 0, d, b);
+    GK(s, ba::kb_pairs_compact, W, 1024, 0, d, b);
+    GK(s, ba::kt_tiles_lm, dim3((td.Tcap + 1 + 127) / 128, W, 2), 128, 0, d, td);
+    GK(s, ba::kt_tiles_pairs, dim3(((size_t)b.Pmax * (td.Tcap + 1) + 255) / 256, W, 2), 256, 0, d, b, td);
+    GK(s, ba::kt_tiles_scan, dim3(td.Tcap, W, 2), 32, 0, d, b, td);
+    GK(s, ba::kt_tiles_base, (W + 127) / 128, 128, 0, d, b, td);
+    GK(s, ba::kt_tiles_fill, dim3(((size_t)b.Pmax * td.Tcap + 255) / 256, W, 2), 256, 0, d, b, td);
+    GK(s, ba::kt_order, (W + 3) / 4, 128, 0, d, b, td);
+    for (int pass = 0; pass < 2 && ok; ++pass) {
+      cudaMemsetAsync(b.pact_w, 0, sizeof(int) * (size_t)c->l_np, s);
+      if (b.C) GK(s, ba::kb_mark_active, g_lm, ba::BT, 0, d, b);
+      GK(s, ba::kb_begin_pass, g_win, 128, 0, d, b, lo, pass);
+      // WHILE node: created by hand behind the nodes captured so far, its body captured from s_body
+      cudaStreamCaptureStatus st;
+      cudaGraph_t g = nullptr;
+      const cudaGraphNode_t* deps = nullptr;
+      size_t ndeps = 0;
+      cudaGraphConditionalHandle h;
+      ok = cudaStreamGetCaptureInfo(s, &st, nullptr, &g, &deps, &ndeps) == cudaSuccess && g &&
+           cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+      if (!ok) break;
+      GK(s, ba::kt_cond, 1, 256, 0, d, b, h, 0);
+      ok = cudaStreamGetCaptureInfo(s, &st, nullptr, &g, &deps, &ndeps) == cudaSuccess;
+      if (!ok) break;
+      cudaGraphNodeParams np = {};
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = h;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      ok = cudaGraphAddNode(&node, g, deps, ndeps, &np) == cudaSuccess;
+      if (!ok) break;
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      ok = cudaStreamUpdateCaptureDependencies(s, &node, 1, cudaStreamSetCaptureDependencies) == cudaSuccess &&
+           cudaStreamBeginCaptureToGraph(c->s_body, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (!ok) break;
+      const int before = n_launch;
+      super_step(c->s_body, c->s_aux);
+      GK(c->s_body, ba::kt_cond, 1, 256, 0, d, b, h, 1);
+      launches_step = n_launch - before;
+      n_launch = before;
+      ok = cudaStreamEndCapture(c->s_body, nullptr) == cudaSuccess;
+      if (!ok) break;
+      if (pass == 0) GK(s, ba::kb_flag<false>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+    }
+    if (ok) {
+      GK(s, ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
+      GK(s, ba::kb_writeback, W, 256, 0, d, b);
+    }
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    ok = ok && e == cudaSuccess && graph;
+  }
+#undef GK
+  if (!ok) {
+    if (graph) cudaGraphDestroy(graph);
+    // leave no stream in capture mode behind
+    cudaStreamCaptureStatus st;
+    if (cudaStreamIsCapturing(c->s_body, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+      cudaGraph_t dump = nullptr;
+      cudaStreamEndCapture(c->s_body, &dump);
+    }
+    if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+      cudaGraph_t dump = nullptr;
+      cudaStreamEndCapture(s, &dump);
+      if (dump) cudaGraphDestroy(dump);
+    }
+    cudaGetLastError();
+    return RSPL_BA_ERR_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess || !exec) {
+    cudaGetLastError();
+    return RSPL_BA_ERR_CUDA;
+  }
+  out.exec = exec;
+  out.launches_fixed = n_launch;
+  out.launches_step = launches_step;
+  return RSPL_BA_OK;
+}
+
+// returns RSPL_BA_OK when the solve was enqueued as a graph, RSPL_BA_ERR_STATE when this batch does not qualify
+// (the caller then takes the host-driven path), another code on failure
+int local_solve_graph(RsplBaContext* c, const ba::LocalOpt& lo) {
+  if (c->prof || c->global_mode) return RSPL_BA_ERR_STATE;
+  if (const char* env = getenv("RSPL_BA_GRAPH"))
+    if (!strcmp(env, "off")) return RSPL_BA_ERR_STATE;
+  if (const char* env = getenv("RSPL_BA_SCHUR"))
+    if (!strcmp(env, "legacy")) return RSPL_BA_ERR_STATE;
+  int rc = batched_prepare(c);
+  if (rc != RSPL_BA_OK) return rc;
+  const ba::BatchDev& b = c->bd;
+  const int W = c->l_n_windows;
+  if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
+  const int n_max = 6 * b.NFmax;
+  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
+  if (smem_solve > c->smem_optin || b.pairs_tmp) return RSPL_BA_ERR_STATE; // dense reduced system: host-driven path
+  // one constraint per (pose, landmark) pair => a landmark's degree is bounded by the poses of its window
+  const int deg_bound = c->l_max_poses < 254 ? c->l_max_poses : 254;
+  const int maxdeg[2] = {deg_bound, deg_bound};
+  size_t smem_tile[2];
+  rc = tiles_prepare(c, maxdeg, smem_tile);
+  if (rc != RSPL_BA_OK) return rc;
+  CU_TRY(c, cudaFuncSetAttribute(ba::kb_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+  CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[0]));
+  CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[1]));
+  LocalGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.d = c->ld;
+  key.b = c->bd;
+  key.td = c->td;
+  key.lo = lo;
+  key.W = W;
+  key.max_pts = c->l_max_pts;
+  key.max_lns = c->l_max_lns;
+  key.max_edges = c->l_max_edges;
+  key.max_poses = c->l_max_poses;
+  key.smem_solve = smem_solve;
+  key.smem_tile[0] = smem_tile[0];
+  key.smem_tile[1] = smem_tile[1];
+  RsplBaContext::LocalGraph* hit = nullptr;
+  for (auto& g : c->graph_cache)
+    if (g.exec && g.key.size() == sizeof(key) && !memcmp(g.key.data(), &key, sizeof(key))) hit = &g;
+  if (!hit) {
+    RsplBaContext::LocalGraph fresh;
+    rc = capture_local_graph(c, lo, smem_solve, smem_tile, fresh);
+    if (rc != RSPL_BA_OK) return fail(c, rc, "local batch: CUDA graph capture of the LM schedule failed");
+    fresh.key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+    if (c->graph_cache.size() < 8) {
+      c->graph_cache.push_back(fresh);
+      hit = &c->graph_cache.back();
+    } else { // replace the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < c->graph_cache.size(); ++i)
+        if (c->graph_cache[i].stamp < c->graph_cache[lru].stamp) lru = i;
+      if (c->graph_cache[lru].exec) cudaGraphExecDestroy(c->graph_cache[lru].exec);
+      c->graph_cache[lru] = fresh;
+      hit = &c->graph_cache[lru];
+    }
+  }
+  hit->stamp = ++c->graph_stamp;
+  CU_TRY(c, cudaGraphLaunch(hit->exec, c->stream));
+  c->launches += hit->launches_fixed;
+  c->l_graph_launches_step = hit->launches_step; // (x super-steps: added at download, from the device counter)
+  c->l_last_path = 4;
+  c->l_super_steps = 0;
   return RSPL_BA_OK;
 }
 
@@ -752,7 +1012,7 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   if (c->l_n_windows == 0) return RSPL_BA_OK;
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
-  ba::LocalOpt lo;
+  ba::LocalOpt lo{};
   lo.thr[0] = opt->thr_mono_point;
   lo.thr[1] = opt->thr_stereo_point;
   lo.thr[2] = opt->thr_mono_line;
@@ -765,32 +1025,15 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   lo.max_free = c->l_max_free_poses;
   const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
   if (c->l_n_windows > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
-  CU_TRY(c, cudaMemsetAsync(c->ld.err, 0, sizeof(int) * 4, c->stream));
+  c->l_graph_launches_step = 0;
+  {
+    const int grc = local_solve_graph(c, lo);
+    if (grc != RSPL_BA_ERR_STATE) return grc;
+  }
   {
     ProfScope ps(c, PC_LOCAL_SETUP);
-    const int W = c->l_n_windows;
-    for (int k = 0; k < 2; ++k)
-      if (c->ld.k[k].n_lm > 0) {
-        CU_TRY(c, cudaMemsetAsync(c->ld.k[k].slot, ba::SLOT_NONE, (size_t)c->ld.k[k].n_lm * c->ld.slot_stride, c->stream));
-        CU_TRY(c, cudaMemsetAsync(c->ld.k[k].cursor, 0, sizeof(int) * (size_t)c->ld.k[k].n_lm, c->stream));
-      }
-    const int T = ba::LOCAL_THREADS;
-    const int max_lm = c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns;
-    const dim3 g_e((c->l_max_edges + T - 1) / T > 0 ? (c->l_max_edges + T - 1) / T : 1, W, 2);
-    const dim3 g_l((max_lm + T - 1) / T > 0 ? (max_lm + T - 1) / T : 1, W, 2);
-    ba::setup_poses<<<W, T, 0, c->stream>>>(c->ld);
-    ba::setup_edges<0><<<g_e, T, 0, c->stream>>>(c->ld);
-    ba::setup_order<<<dim3(W, 2), T, 0, c->stream>>>(c->ld);
-    ba::setup_scan<<<dim3(W, 2), 1024, 0, c->stream>>>(c->ld);
-    ba::setup_edges<1><<<g_e, T, 0, c->stream>>>(c->ld);
-    ba::setup_landmarks<<<g_l, T, 0, c->stream>>>(c->ld);
-    ba::setup_gather<<<g_e, T, 0, c->stream>>>(c->ld);
-    const dim3 g_pl(c->l_max_poses, W, 2);
-    ba::setup_pose_lists<0><<<g_pl, T, 0, c->stream>>>(c->ld);
-    ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, c->stream>>>(c->ld);
-    ba::setup_pose_lists<1><<<g_pl, T, 0, c->stream>>>(c->ld);
+    enqueue_local_setup(c, c->stream);
   }
-  c->launches += 10;
   CU_TRY(c, cudaGetLastError());
   // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
   // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent
@@ -825,12 +1068,13 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
     return fail(c, RSPL_BA_ERR_INVALID, "local result: null output arrays");
   SetDevice guard(c->device);
   cudaStream_t s = c->stream;
-  int err = 0;
+  int err = 0, steps = 0;
 #define D2H(dst, src, bytes)                                                                        \
   do {                                                                                              \
     if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); \
   } while (0)
   D2H(&err, d.err, sizeof(int));
+  if (c->l_graph_launches_step) D2H(&steps, c->bd.n_active, sizeof(int));
   D2H(out->pose_twc, d.pose_out, sizeof(double) * 7 * c->l_np);
   D2H(out->point_xyz, d.k[0].lm_out, sizeof(double) * 3 * c->l_npt);
   D2H(out->line_wd, d.k[1].lm_out, sizeof(double) * 6 * c->l_nln);
@@ -841,6 +1085,11 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
   if (out->stats) D2H(out->stats, d.stats, sizeof(RsplBaStats) * c->l_n_windows);
 #undef D2H
   CU_TRY(c, cudaStreamSynchronize(s));
+  if (c->l_graph_launches_step) { // the graph's super-steps ran without the host counting them
+    c->launches += (int64_t)steps * c->l_graph_launches_step;
+    c->l_super_steps = steps;
+    c->l_graph_launches_step = 0;
+  }
   if (err & ba::LOCAL_ERR_DUP_EDGE)
     return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: two constraints join the same (pose, landmark) pair");
   if (err & ba::LOCAL_ERR_DEGREE)

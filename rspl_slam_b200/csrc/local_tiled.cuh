@@ -24,9 +24,9 @@ namespace ba {
 
 template <int KIND>
 struct TileCost {
-  // per landmark: L (packed lower) + 1/diag + y; per edge: the Z block + a 16-bit tile-local landmark index (+ at
+  // per landmark: L (packed lower) + 1/diag + y + the landmark state; per edge: the Z block + a 16-bit tile-local landmark index (+ at
   // run time 4 bytes per staged pair entry: a landmark of degree k has at most k(k+1)/2 entries, (k+1)/2 per edge)
-  static constexpr int LN = KT<KIND>::LD * (KT<KIND>::LD + 1) / 2 + 2 * KT<KIND>::LD; // doubles: 12 (points), 18 (lines)
+  static constexpr int LN = KT<KIND>::LD * (KT<KIND>::LD + 1) / 2 + 2 * KT<KIND>::LD + KT<KIND>::SD; // doubles: 15 (points), 24 (lines)
   static constexpr int A = LN * 8;
   static constexpr int B = ZBlk<KIND>::N * 8 + 2;
 };
@@ -126,11 +126,14 @@ __global__ void __launch_bounds__(128) kt_tiles_base(const __grid_constant__ Loc
                                                      const __grid_constant__ TileDev td) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.n_windows) return;
-  int run = (int)b.pair_base[w];
+  // (every block starts on a multiple of 4 entries = 16 bytes: the region of window w is shifted by the slack of the
+  // windows before it)
+  int run = (int)b.pair_base[w] + 8 * td.Tcap * w;
   for (int kind = 0; kind < 2; ++kind)
     for (int t = 0; t < td.Tcap; ++t) {
       int* p = td.tent_base + (size_t)(w * 2 + kind) * td.Tcap + t;
       const int c = *p;
+      run = (run + 3) & ~3;
       *p = run;
       run += c;
     }
@@ -172,7 +175,9 @@ __global__ void __launch_bounds__(128) kt_order(const __grid_constant__ LocalDev
       const int lj = pb[2 * list[j] + 2] - pb[2 * list[j]];
       rank += (lj > len || (lj == len && j < i)) ? 1 : 0;
     }
-    td.order[(size_t)w * b.Pmax + rank] = i;
+    int fi, fj;
+    pair_decode(list[i], b.ws[w].nf, fi, fj);
+    td.order[(size_t)w * b.Pmax + rank] = i | (fi == fj ? 1 << 30 : 0);
   }
 }
 
@@ -196,58 +201,127 @@ BA_DEV void group8_transpose_reduce48(double* v, int lane8) {
 #define TILE_MIN_CTAS 2
 #endif
 
+// shared-memory bytes of a tile that do not depend on its landmarks: per-pair offsets and processing order, the
+// window's pose table (R, t, in-system flag) and the cameras
+__host__ __device__ inline size_t tile_fixed_bytes(int Pmax, int max_poses, int n_cameras) {
+  return (size_t)(2 * Pmax + 2) * 4 + (size_t)max_poses * 13 * 8 + (size_t)n_cameras * 5 * 8 + 64;
+}
+
+// The kernel is written so that every global load depends on nothing but the block and thread indices: the
+// window's small tables, the tile's pair entries, the landmark blocks and the first batch of edge records are all
+// requested up front (one exposed memory latency), the next batch of edge records is requested before the
+// current one is processed, and the three compute phases read shared memory only.
 template <int KIND>
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     kt_schur_tile(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b, const __grid_constant__ LocalOpt o,
                   const __grid_constant__ TileDev td) {
   using T = KT<KIND>;
-  constexpr int LD = T::LD, ZN = ZBlk<KIND>::N, LN = TileCost<KIND>::LN, NTRI = LD * (LD + 1) / 2;
+  constexpr int LD = T::LD, SD = T::SD, MD = T::MD, ZN = ZBlk<KIND>::N, NTRI = LD * (LD + 1) / 2;
+  constexpr int LN = TileCost<KIND>::LN; // L packed, 1/diag, y, X
+  constexpr int OFF_INV = NTRI, OFF_Y = NTRI + LD, OFF_X = NTRI + 2 * LD;
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int w = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
   WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   if (t >= td.ntile[w * 2 + KIND]) return;
   const KindDev& k = d.k[KIND];
+  const size_t tile_id = (size_t)(w * 2 + KIND) * td.Tcap + t;
   const int* tl = td.tile_lm + (size_t)(w * 2 + KIND) * (td.Tcap + 1) + t;
   const int la = tl[0], lb = tl[1];
-  const int ea = k.ebeg[la], eb = k.ebeg[lb];
-  const int nl = lb - la, ne = eb - ea;
-  double* Zs = reinterpret_cast<double*>(tile_smem);               // [ne][ZN], column-major blocks (ZCOL)
-  double* Ls = Zs + (size_t)ne * ZN;                                // [nl][LN]: L packed, inv, y
   const int n_ne = b.n_ne[w];
-  const size_t tile_id = (size_t)(w * 2 + KIND) * td.Tcap + t;
   const int* tso_g = td.tso + tile_id * (b.Pmax + 1);
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0, f0 = b.nf_begin[w], l0 = k.lm_begin[w];
+  const int ea = k.ebeg[la], eb = k.ebeg[lb];
   const int n_ent = tso_g[n_ne];
-  ushort2* ent = reinterpret_cast<ushort2*>(Ls + (size_t)nl * LN);                  // [n_ent] staged pair entries
-  int* tso = reinterpret_cast<int*>(ent + n_ent);                                     // [n_ne + 1]
-  unsigned short* elm = reinterpret_cast<unsigned short*>(tso + n_ne + 1);            // [ne] tile-local landmark of an edge
-  { // stage the tile's pair entries and their per-pair offsets (one contiguous block each)
-    const ushort2* src = td.tent + td.tent_base[tile_id];
-    for (int i = tid; i < n_ent; i += TILE_THREADS) ent[i] = src[i];
-    for (int i = tid; i <= n_ne; i += TILE_THREADS) tso[i] = tso_g[i];
-  }
-  const int p0 = d.pose_begin[w], f0 = b.nf_begin[w], l0 = k.lm_begin[w];
+  const int nl = lb - la, ne = eb - ea;
+  const int n_ent4 = (n_ent + 3) >> 2;
+  // ---- shared-memory layout
+  double* Zs = reinterpret_cast<double*>(tile_smem);                       // [ne][ZN], column-major blocks (ZCOL)
+  double* Ls = Zs + (size_t)ne * ZN;                                        // [nl][LN]
+  double* Ps = Ls + (size_t)nl * LN;                                        // [np][13]: R, t, in-system flag
+  double* Cs = Ps + (size_t)np * 13;                                        // [n_cameras][5]
+  uint4* ent4 = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(Cs + (size_t)d.n_cameras * 5) + 15) & ~(uintptr_t)15);
+  const ushort2* ent = reinterpret_cast<const ushort2*>(ent4);             // [n_ent] staged pair entries
+  int* tso = reinterpret_cast<int*>(ent4 + n_ent4);                         // [n_ne + 1]
+  int* ords = tso + n_ne + 1;                                               // [n_ne] processing order | diag << 30
+  unsigned short* elm = reinterpret_cast<unsigned short*>(ords + n_ne);     // [ne] tile-local landmark of an edge
   const double lambda = s.lambda;
   const bool robust = s.robust;
 
-  // ---- phase 1a: landmark factors
+  // ---- first batch of edge records (registers), requested before anything else is waited for
+  struct Rec {
+    int info, lm;
+    unsigned char lvl;
+    double m[MD];
+  };
+  auto load_rec = [&](int j, Rec& r) {
+    const int e = ea + j;
+    r.info = k.info[e];
+    r.lm = k.lm[e];
+    r.lvl = k.lvl[e];
+#pragma unroll
+    for (int q = 0; q < MD; ++q) r.m[q] = k.meas[(size_t)q * k.n_edge + e];
+  };
+  Rec cur;
+  if (tid < ne) load_rec(tid, cur);
+
+  // ---- stage the window tables and the tile's pair entries
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(td.tent + td.tent_base[tile_id]);
+    uint4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = tid + u * TILE_THREADS;
+      if (i < n_ent4) v[u] = src[i];
+    }
+    for (int i = tid + 3 * TILE_THREADS; i < n_ent4; i += TILE_THREADS) ent4[i] = src[i];
+    for (int i = tid; i <= n_ne; i += TILE_THREADS) tso[i] = tso_g[i];
+    for (int i = tid; i < n_ne; i += TILE_THREADS) ords[i] = td.order[(size_t)w * b.Pmax + i];
+    for (int i = tid; i < np * 13; i += TILE_THREADS) {
+      const int p = i / 13, q = i - p * 13;
+      double v2;
+      if (q < 9) v2 = b.P_R[9 * (size_t)(p0 + p) + q];
+      else if (q < 12) v2 = b.P_t[3 * (size_t)(p0 + p) + q - 9];
+      else {
+        const int fi = b.free_idx[p0 + p];
+        v2 = (fi >= 0 && b.sys_idx[f0 + fi] >= 0) ? 1.0 : 0.0;
+      }
+      Ps[i] = v2;
+    }
+    for (int i = tid; i < d.n_cameras * 5; i += TILE_THREADS) Cs[i] = d.cameras[i];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = tid + u * TILE_THREADS;
+      if (i < n_ent4) ent4[i] = v[u];
+    }
+  }
+
+  // ---- phase 1a: landmark factors (and the landmark state, for phase 1b)
   int fail = 0;
   for (int i = tid; i < nl; i += TILE_THREADS) {
     const int l = la + i;
     double* Lm = Ls + (size_t)i * LN;
-    if (!k.act[l]) {
-#pragma unroll
-      for (int q = 0; q < LN; ++q) Lm[q] = 0.0;
-      continue;
-    }
-    double Hup[T::HD], Lf[NTRI], inv[LD];
+    double Hup[T::HD], bl[LD], X[SD];
+    const bool act = k.act[l];
 #pragma unroll
     for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+#pragma unroll
+    for (int q = 0; q < LD; ++q) bl[q] = k.b[(size_t)q * k.n_lm + l];
+#pragma unroll
+    for (int q = 0; q < SD; ++q) X[q] = k.x[(size_t)q * k.n_lm + l];
+#pragma unroll
+    for (int q = 0; q < SD; ++q) Lm[OFF_X + q] = X[q];
+    if (!act) { // every edge of an inactive landmark is excluded (level 1): its Z blocks are zero
+#pragma unroll
+      for (int q = 0; q < OFF_X; ++q) Lm[q] = 0.0;
+      continue;
+    }
+    double Lf[NTRI], inv[LD];
     if (!small_chol<LD>(Hup, lambda, Lf, inv)) fail = 1;
     double y[LD];
 #pragma unroll
     for (int a = 0; a < LD; ++a) {
-      double v = k.b[(size_t)a * k.n_lm + l];
+      double v = bl[a];
 #pragma unroll
       for (int p = 0; p < a; ++p) v -= Lf[a * (a + 1) / 2 + p] * y[p];
       y[a] = v * inv[a];
@@ -256,83 +330,85 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     for (int q = 0; q < NTRI; ++q) Lm[q] = Lf[q];
 #pragma unroll
     for (int q = 0; q < LD; ++q) {
-      Lm[NTRI + q] = inv[q];
-      Lm[NTRI + LD + q] = y[q];
+      Lm[OFF_INV + q] = inv[q];
+      Lm[OFF_Y + q] = y[q];
     }
   }
   if (fail) atomicOr(&s.prep_fail, 1);
   __syncthreads();
 
-  // ---- phase 1b: Z blocks, one thread per edge
+  // ---- phase 1b: Z blocks, one thread per edge; the next record is in flight while this one is processed
   for (int j = tid; j < ne; j += TILE_THREADS) {
-    const int e = ea + j;
-    const int info = k.info[e];
-    const int p = info & 0xffff;
-    const int li = l0 + k.lm[e] - la; // tile-local landmark
+    Rec nxt;
+    if (j + TILE_THREADS < ne) load_rec(j + TILE_THREADS, nxt);
+    const int p = cur.info & 0xffff;
+    const int li = l0 + cur.lm - la; // tile-local landmark
     elm[j] = (unsigned short)li;
     double2* Zj = reinterpret_cast<double2*>(Zs + (size_t)j * ZN);
-    const int fi = b.free_idx[p0 + p];
-    if (fi < 0 || b.sys_idx[f0 + fi] < 0 || k.lvl[e]) { // fixed pose / excluded edge (level 1): no contribution
+    const double* Pp = Ps + (size_t)p * 13;
+    if (Pp[12] == 0.0 || cur.lvl) { // fixed pose / pose outside the system / excluded edge (level 1): no contribution
 #pragma unroll
       for (int q = 0; q < ZN / 2; ++q) Zj[q] = make_double2(0.0, 0.0);
-      continue;
-    }
-    const bool stereo = (info >> 30) & 1;
-    Cam cam;
-    load_cam(d.cameras, (info >> 16) & 0xff, cam);
-    double X[T::SD], m[T::MD], r[4], Jp[24], Jl[16];
-    load_lm<KIND>(k, la + li, X);
-    load_edge<KIND>(k, e, m);
-    eval_edge<KIND, true>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, m, r, Jp, Jl);
-    double wgt = 1.0;
-    if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
-    const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
-    const double* Lm = Ls + (size_t)li * LN;
-    double Lf[NTRI], inv[LD];
+    } else {
+      const bool stereo = (cur.info >> 30) & 1;
+      Cam cam;
+      load_cam(Cs, (cur.info >> 16) & 0xff, cam);
+      const double* Lm = Ls + (size_t)li * LN;
+      double X[SD], R[9], tt[3], r[4], Jp[24], Jl[16];
 #pragma unroll
-    for (int q = 0; q < NTRI; ++q) Lf[q] = Lm[q];
+      for (int q = 0; q < SD; ++q) X[q] = Lm[OFF_X + q];
 #pragma unroll
-    for (int q = 0; q < LD; ++q) inv[q] = Lm[NTRI + q];
-    double z[6][LD];
+      for (int q = 0; q < 9; ++q) R[q] = Pp[q];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
+      for (int q = 0; q < 3; ++q) tt[q] = Pp[9 + q];
+      eval_edge<KIND, true>(cam, o.bf_float, stereo, R, tt, X, cur.m, r, Jp, Jl);
+      double wgt = 1.0;
+      if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
+      const double wo = (KIND == 0 ? 1.0 : 0.1) * wgt;
+      double Lf[NTRI], inv[LD];
+#pragma unroll
+      for (int q = 0; q < NTRI; ++q) Lf[q] = Lm[q];
+#pragma unroll
+      for (int q = 0; q < LD; ++q) inv[q] = Lm[OFF_INV + q];
+      double z[6][LD];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = 0; c < LD; ++c) {
+          double h = 0;
+#pragma unroll
+          for (int rr = 0; rr < T::ROWS; ++rr) h += Jp[rr * 6 + a] * Jl[rr * LD + c];
+          double v = wo * h;
+#pragma unroll
+          for (int pp = 0; pp < c; ++pp) v -= Lf[c * (c + 1) / 2 + pp] * z[a][pp];
+          z[a][c] = v * inv[c];
+        }
+      }
 #pragma unroll
       for (int c = 0; c < LD; ++c) {
-        double h = 0;
-#pragma unroll
-        for (int rr = 0; rr < T::ROWS; ++rr) h += Jp[rr * 6 + a] * Jl[rr * LD + c];
-        double v = wo * h;
-#pragma unroll
-        for (int pp = 0; pp < c; ++pp) v -= Lf[c * (c + 1) / 2 + pp] * z[a][pp];
-        z[a][c] = v * inv[c];
+        Zj[c * 3 + 0] = make_double2(z[0][c], z[1][c]);
+        Zj[c * 3 + 1] = make_double2(z[2][c], z[3][c]);
+        Zj[c * 3 + 2] = make_double2(z[4][c], z[5][c]);
       }
     }
-#pragma unroll
-    for (int c = 0; c < LD; ++c) {
-      Zj[c * 3 + 0] = make_double2(z[0][c], z[1][c]);
-      Zj[c * 3 + 1] = make_double2(z[2][c], z[3][c]);
-      Zj[c * 3 + 2] = make_double2(z[4][c], z[5][c]);
-    }
+    cur = nxt;
   }
   __syncthreads();
 
   // ---- phase 2: pair products over the tile's entries, 8 lanes per pose pair
   const int lane8 = tid & 7, warp = tid >> 5, g4 = (tid >> 3) & 3;
   const int nquads = (n_ne + 3) >> 2;
-  const int* ord = td.order + (size_t)w * b.Pmax;
-  const int tt = KIND ? td.Tp + t : t;
-  double* out_base = td.hs_tile + ((size_t)w * (td.Tp + td.Tl) + tt) * b.Pmax * 42;
+  const int tt2 = KIND ? td.Tp + t : t;
+  double* out_base = td.hs_tile + ((size_t)w * (td.Tp + td.Tl) + tt2) * b.Pmax * 42;
   for (int quad = warp; quad < nquads; quad += TILE_THREADS / 32) {
     const int oi = quad * 4 + g4;
     const bool have = oi < n_ne;
     int li = 0, beg = 0, ncol = 0;
     bool diag = false;
     if (have) {
-      li = ord[oi];
-      const int p = b.ne_list[(size_t)w * b.Pmax + li];
-      int fi, fj;
-      pair_decode(p, s.nf, fi, fj);
-      diag = fi == fj;
+      const int ov = ords[oi];
+      li = ov & 0x3fffffff;
+      diag = (ov >> 30) & 1;
       beg = tso[li];
       ncol = (tso[li + 1] - beg) * LD;
     }
@@ -340,9 +416,9 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
 #pragma unroll
     for (int q = 0; q < 48; ++q) acc[q] = 0.0;
     for (int c = lane8; c < ncol; c += 8) {
-      const ushort2 cur = ent[beg + c / LD];
+      const ushort2 cur2 = ent[beg + c / LD];
       const int q = c % LD;
-      const int ji = cur.x;
+      const int ji = cur2.x;
       const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)ji * ZN + q * ZCOL);
       double za[6];
 #pragma unroll
@@ -352,7 +428,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
         za[2 * u + 1] = v.y;
       }
       if (diag) {
-        const double yq = Ls[(size_t)elm[ji] * LN + NTRI + LD + q];
+        const double yq = Ls[(size_t)elm[ji] * LN + OFF_Y + q];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
 #pragma unroll
@@ -360,7 +436,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
           acc[36 + r] += za[r] * yq;
         }
       } else {
-        const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)cur.y * ZN + q * ZCOL);
+        const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)cur2.y * ZN + q * ZCOL);
         double zb[6];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
@@ -382,6 +458,23 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
       out[1] = make_double2(acc[2], acc[3]);
       out[2] = make_double2(acc[4], acc[5]);
     }
+  }
+}
+
+// Loop condition of the whole-schedule CUDA graph (conditional WHILE node): non-zero while any window is still
+// iterating. `count` = 1 inside the loop body: one more super-step done (read back at download for the statistics).
+__global__ void __launch_bounds__(256) kt_cond(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                               cudaGraphConditionalHandle h, int count) {
+  __shared__ int s_any;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  int any = 0;
+  for (int w = threadIdx.x; w < d.n_windows; w += 256) any |= b.ws[w].stage != STAGE_DONE ? 1 : 0;
+  if (any) s_any = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cudaGraphSetConditional(h, s_any ? 1u : 0u);
+    if (count) ++*b.n_active;
   }
 }
 
