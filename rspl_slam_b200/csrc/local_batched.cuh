@@ -685,38 +685,51 @@ __global__ void __launch_bounds__(BT, 4) kb_pose_blocks(const __grid_constant__ 
   }
 }
 
-// one thread per window: chi0, lambda init (computeLambdaInit), stage NEED_LIN -> NEED_TRIAL
+// one WARP per window: chi0, lambda init (computeLambdaInit), stage NEED_LIN -> NEED_TRIAL. Lanes stride the chunk
+// partials / the free poses and a fixed butterfly adds them (deterministic); grid ceil(W / 4), 128 threads
 __global__ void __launch_bounds__(128) kb_begin_trial(const __grid_constant__ LocalDev d,
                                                       const __grid_constant__ BatchDev b) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= d.n_windows) return;
   WinState& s = b.ws[w];
-  s.restore = 0;
-  s.prep_fail = 0;
-  if (s.stage != STAGE_NEED_LIN) return;
+  const int stage = s.stage, it = s.it, nf = s.nf;
+  __syncwarp();
+  if (lane == 0) {
+    s.restore = 0;
+    s.prep_fail = 0;
+  }
+  if (stage != STAGE_NEED_LIN) return;
   double chi = 0, nact = 0, mx = 0;
   if (b.global) { // sums over every rank's landmarks (kb_global_sums + all-reduce)
     chi = b.gs[0];
     nact = b.gs[1];
     mx = b.gs[2];
   } else {
-    for (int c = 0; c < b.C; ++c) {
+    for (int c = lane; c < b.C; c += 32) {
       const double* pp = b.part + ((size_t)w * b.C + c) * 4;
       chi += pp[0];
       nact += pp[1];
       mx = fmax(mx, pp[2]);
     }
+    chi = warp_allreduce(chi);
+    nact = warp_allreduce(nact);
   }
+  if (it == 0) {
+    const int f0 = b.nf_begin[w];
+    for (int idx = lane; idx < nf * 6; idx += 32) {
+      const int fi = idx / 6, i = idx - 6 * fi;
+      if (b.sys_idx[f0 + fi] < 0) continue;
+      mx = fmax(mx, fabs(b.Hpp[(size_t)(f0 + fi) * 21 + up6(i, i)]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane != 0) return;
   if (nact == 0.0) { // no active edge: optimize() returns without iterating
     s.stage = STAGE_DONE;
     return;
   }
-  if (s.it == 0) {
-    const int f0 = b.nf_begin[w];
-    for (int fi = 0; fi < s.nf; ++fi) {
-      if (b.sys_idx[f0 + fi] < 0) continue;
-      for (int i = 0; i < 6; ++i) mx = fmax(mx, fabs(b.Hpp[(size_t)(f0 + fi) * 21 + up6(i, i)]));
-    }
+  if (it == 0) {
     s.lambda = 1e-5 * mx;
     s.ni = 2;
   }
@@ -1049,18 +1062,8 @@ struct TileDev {
   double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)
 };
 
-// sum of the per-tile partial reduced systems of a window (tile order: points then lines => deterministic)
-BA_DEV double tile_sum(const BatchDev& b, const TileDev& td, int w, int li, int el) {
-  double v = 0.0;
-  const int ntp = td.ntile[w * 2], ntl = td.ntile[w * 2 + 1];
-  const double* base = td.hs_tile + (size_t)w * (td.Tp + td.Tl) * b.Pmax * 42 + (size_t)li * 42 + el;
-  const size_t stride = (size_t)b.Pmax * 42;
-  for (int t = 0; t < ntp; ++t) v += base[t * stride];
-  for (int t = 0; t < ntl; ++t) v += base[(td.Tp + t) * stride];
-  return v;
-}
-
-// K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory
+// K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory.
+// TILED: the tiled Schur path (hs_part summed from the tiles by kt_tile_sum) also keeps the rotation of the pose backup.
 template <bool TILED>
 __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
                                                 const __grid_constant__ TileDev td) {
@@ -1088,7 +1091,7 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     pair_decode(p, nf, fi, fj);
     const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
     if (si < 0 || sj < 0) continue;
-    double v = TILED ? -tile_sum(b, td, w, li, rc) : -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
+    double v = -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
     if (fi == fj) {
       const int rr = r < c ? r : c, cc = r < c ? c : r;
       v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? lambda : 0.0);
@@ -1100,8 +1103,7 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
     const int si = b.sys_idx[f0 + fi];
     if (si < 0) continue;
     const int li = b.diag_pos[f0 + fi];
-    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] -
-                     (TILED ? tile_sum(b, td, w, li, 36 + r) : b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r]);
+    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r];
   }
   __syncthreads();
   __shared__ int s_chol;
@@ -1378,48 +1380,54 @@ __global__ void __launch_bounds__(256) kb_global_sums(const __grid_constant__ Ba
   }
 }
 
-// one thread per window: the Levenberg accept / reject logic (§9.9) and the window's next stage
+// one WARP per window: the Levenberg accept / reject logic (§9.9) and the window's next stage (every lane takes
+// the same decision from the same warp-reduced sums; lane 0 writes the state, the lanes share the pose restore);
+// grid ceil(W / 4), 128 threads
 __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= d.n_windows) return;
   WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const bool ok = s.solve_ok;
-  double chi1 = 0, scale = s.scale_pose;
+  double chi1 = 0, scale = 0;
   if (ok && b.global) {
     chi1 = b.gs[4];
-    scale += b.gs[5];
+    scale = b.gs[5];
   } else if (ok) {
-    for (int c = 0; c < b.C; ++c) {
+    for (int c = lane; c < b.C; c += 32) {
       const double* pp = b.part + ((size_t)w * b.C + c) * 4;
       chi1 += pp[0];
       scale += pp[1];
     }
+    chi1 = warp_allreduce(chi1);
+    scale = warp_allreduce(scale);
   }
+  scale += s.scale_pose;
   const double tempChi = ok ? chi1 : DBL_MAX; // a failed factorisation is a rejected step
   double rho = s.chi_cur - tempChi;
   rho /= (ok ? scale : 0.0) + 1e-3;
+  double lambda = s.lambda, ni = s.ni, chi_cur = s.chi_cur;
   bool stop_lambda = false, accepted = false;
   if (rho > 0 && isfinite(tempChi)) {
     const double c = 2 * rho - 1;
     double alpha = 1. - c * c * c;
     alpha = fmin(alpha, 2. / 3.);
-    s.lambda *= fmax(1. / 3., alpha);
-    s.ni = 2;
-    s.chi_cur = tempChi;
+    lambda *= fmax(1. / 3., alpha);
+    ni = 2;
+    chi_cur = tempChi;
     accepted = true;
   } else {
-    s.lambda *= s.ni;
-    s.ni *= 2;
-    if (!isfinite(s.lambda)) stop_lambda = true;
+    lambda *= ni;
+    ni *= 2;
+    if (!isfinite(lambda)) stop_lambda = true;
   }
   const int q1 = stop_lambda ? s.qmax : s.qmax + 1;
-  s.qmax = q1;
-  s.st.trials[s.pass]++;
-  if (ok) s.st.edges_evaluated += (long long)s.nact;
+  const int nf = s.nf, pass = s.pass, it = s.it, iters = s.iters;
+  const double nact = s.nact;
+  __syncwarp(); // every lane has read the state before lane 0 rewrites it
   if (!accepted && ok) { // pop(): poses here, landmarks in kb_restore
     const int p0 = d.pose_begin[w], f0 = b.nf_begin[w];
-    for (int fi = 0; fi < s.nf; ++fi) {
+    for (int fi = lane; fi < nf; fi += 32) {
       if (b.sys_idx[f0 + fi] < 0) continue;
       const size_t gp = (size_t)(p0 + b.pose_of[f0 + fi]);
       double q[4], R[9];
@@ -1428,16 +1436,23 @@ __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDe
       quat_to_R(q, R);
       for (int i = 0; i < 9; ++i) b.P_R[9 * gp + i] = R[i];
     }
-    s.restore = 1;
   }
+  if (lane != 0) return;
+  s.lambda = lambda;
+  s.ni = ni;
+  s.chi_cur = chi_cur;
+  s.qmax = q1;
+  s.st.trials[pass]++;
+  if (ok) s.st.edges_evaluated += (long long)nact;
+  if (!accepted && ok) s.restore = 1;
   if (!stop_lambda && rho < 0 && q1 < 10) {
     s.stage = STAGE_NEED_TRIAL; // retry with the larger lambda
     return;
   }
-  s.st.iters[s.pass]++;
-  s.it++;
-  const bool terminate = (q1 == 10 || rho == 0 || !isfinite(s.lambda));
-  s.stage = (terminate || s.it >= s.iters) ? STAGE_DONE : STAGE_NEED_LIN;
+  s.st.iters[pass]++;
+  s.it = it + 1;
+  const bool terminate = (q1 == 10 || rho == 0 || !isfinite(lambda));
+  s.stage = (terminate || it + 1 >= iters) ? STAGE_DONE : STAGE_NEED_LIN;
 }
 
 // grid (Cp + Cl, windows): chunk < Cp restores points, else lines

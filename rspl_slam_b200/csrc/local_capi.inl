@@ -516,7 +516,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     for (int i = 0; i < 6; ++i) CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
   }
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
-      g_win((W + 127) / 128), g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
+      g_win((W + 127) / 128), g_winw((W + 3) / 4), g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
   const bool fork_lines = b.Cp && b.Cl;
   int n_launch = 0;
@@ -544,17 +544,18 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     if (b.Cl) GK(sline, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
     GK(sm, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
     join(0);
-    GK(sm, ba::kb_begin_trial, g_win, 128, 0, d, b);
+    GK(sm, ba::kb_begin_trial, g_winw, 128, 0, d, b);
     fork(1);
     if (b.Cp && td.Tp) GK(sm, ba::kt_schur_tile<0>, g_tp, ba::TILE_THREADS, smem_tile[0], d, b, lo, td);
     if (b.Cl && td.Tl) GK(sline, ba::kt_schur_tile<1>, g_tl, ba::TILE_THREADS, smem_tile[1], d, b, lo, td);
     join(1);
+    GK(sm, ba::kt_tile_sum, dim3((b.Pmax * 42 + 255) / 256, W), 256, 0, d, b, td);
     GK(sm, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
     fork(2);
     if (b.Cp) GK(sm, ba::kt_backsub_rc<0>, g_pt, ba::BT, 0, d, b, lo, td);
     if (b.Cl) GK(sline, ba::kt_backsub_rc<1>, g_ln, ba::BT, 0, d, b, lo, td);
     join(2);
-    GK(sm, ba::kb_decide, g_win, 128, 0, d, b);
+    GK(sm, ba::kb_decide, g_winw, 128, 0, d, b);
     if (b.C) GK(sm, ba::kb_restore, g_lm, ba::BT, 0, d, b);
   };
   cudaGraph_t graph = nullptr;
@@ -734,7 +735,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   // (chunk | pose | pair) index fastest, window on grid.y: the CTAs of one window run together
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
-      g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128);
+      g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128), g_winw((W + 3) / 4);
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
   // reduced systems beyond shared memory: dense matrices in HBM + cuSOLVER Cholesky (dense_solver.inl)
@@ -873,7 +874,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w, b.gs, 2, kNcclFloat64, kNcclSum);
       if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 2, b.gs + 2, 1, kNcclFloat64, kNcclMax);
     }
-    LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_win, 128, 0, d, b);
+    LAUNCH(PC_CONTROL, ba::kb_begin_trial, g_winw, 128, 0, d, b);
     fork(1);
     if (tiled) {
       if (b.Cp && td.Tp) LAUNCH(PC_SCHUR_TILE, ba::kt_schur_tile<0>, g_tp, ba::TILE_THREADS, smem_tile[0], d, b, lo, td);
@@ -885,6 +886,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     join(1);
     if (!tiled) LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
     if (tiled) {
+      LAUNCH(PC_SOLVE, ba::kt_tile_sum, dim3((b.Pmax * 42 + 255) / 256, W), 256, 0, d, b, td);
       LAUNCH(PC_SOLVE, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
     } else if (!dense) {
       LAUNCH(PC_SOLVE, ba::kb_solve<false>, W, 256, smem_solve, d, b, td);
@@ -919,7 +921,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       ProfScope ps_(c, PC_COLLECTIVE);
       if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 4, b.gs + 4, 2, kNcclFloat64, kNcclSum);
     }
-    LAUNCH(PC_CONTROL, ba::kb_decide, g_win, 128, 0, d, b);
+    LAUNCH(PC_CONTROL, ba::kb_decide, g_winw, 128, 0, d, b);
     if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
   };
   // ... captured once into a CUDA graph and replayed (launch-bound for small batches: a C1 window

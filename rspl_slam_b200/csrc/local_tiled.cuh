@@ -393,14 +393,19 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     }
     cur = nxt;
   }
+  __shared__ int s_next_quad;
+  if (tid == 0) s_next_quad = TILE_THREADS / 32;
   __syncthreads();
 
-  // ---- phase 2: pair products over the tile's entries, 8 lanes per pose pair
-  const int lane8 = tid & 7, warp = tid >> 5, g4 = (tid >> 3) & 3;
+  // ---- phase 2: pair products over the tile's entries, 8 lanes per pose pair, four pairs ("quad") per warp at a
+  // time. The pairs are ordered by list length (kt_order), so the four lists of a quad have similar lengths; warps
+  // take the next quad from a shared counter, which evens out the long (diagonal) and short lists. Which warp
+  // computes a pair does not change its value.
+  const int lane = tid & 31, lane8 = tid & 7, g4 = (tid >> 3) & 3;
   const int nquads = (n_ne + 3) >> 2;
   const int tt2 = KIND ? td.Tp + t : t;
   double* out_base = td.hs_tile + ((size_t)w * (td.Tp + td.Tl) + tt2) * b.Pmax * 42;
-  for (int quad = warp; quad < nquads; quad += TILE_THREADS / 32) {
+  for (int quad = tid >> 5; quad < nquads;) {
     const int oi = quad * 4 + g4;
     const bool have = oi < n_ne;
     int li = 0, beg = 0, ncol = 0;
@@ -415,34 +420,43 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     double acc[48];
 #pragma unroll
     for (int q = 0; q < 48; ++q) acc[q] = 0.0;
-    for (int c = lane8; c < ncol; c += 8) {
-      const ushort2 cur2 = ent[beg + c / LD];
-      const int q = c % LD;
-      const int ji = cur2.x;
-      const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)ji * ZN + q * ZCOL);
-      double za[6];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const double2 v = a2[u];
-        za[2 * u] = v.x;
-        za[2 * u + 1] = v.y;
-      }
-      if (diag) {
+    if (diag) {
+      // Z_i Z_i^T is symmetric: only the upper triangle is accumulated (the reduced-system Cholesky reads nothing else)
+      for (int c = lane8; c < ncol; c += 8) {
+        const ushort2 cur2 = ent[beg + c / LD];
+        const int q = c % LD;
+        const int ji = cur2.x;
+        const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)ji * ZN + q * ZCOL);
         const double yq = Ls[(size_t)elm[ji] * LN + OFF_Y + q];
+        double za[6];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const double2 v = a2[u];
+          za[2 * u] = v.x;
+          za[2 * u + 1] = v.y;
+        }
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) acc[r * 6 + cc] += za[r] * za[cc];
+          for (int cc = r; cc < 6; ++cc) acc[r * 6 + cc] += za[r] * za[cc];
           acc[36 + r] += za[r] * yq;
         }
-      } else {
+      }
+    } else {
+      for (int c = lane8; c < ncol; c += 8) {
+        const ushort2 cur2 = ent[beg + c / LD];
+        const int q = c % LD;
+        const double2* a2 = reinterpret_cast<const double2*>(Zs + (size_t)cur2.x * ZN + q * ZCOL);
         const double2* b2 = reinterpret_cast<const double2*>(Zs + (size_t)cur2.y * ZN + q * ZCOL);
-        double zb[6];
+        double za[6], zb[6];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const double2 v = b2[u];
-          zb[2 * u] = v.x;
-          zb[2 * u + 1] = v.y;
+          const double2 v = a2[u];
+          za[2 * u] = v.x;
+          za[2 * u + 1] = v.y;
+          const double2 v2 = b2[u];
+          zb[2 * u] = v2.x;
+          zb[2 * u + 1] = v2.y;
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r)
@@ -458,7 +472,32 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
       out[1] = make_double2(acc[2], acc[3]);
       out[2] = make_double2(acc[4], acc[5]);
     }
+    int nq = 0;
+    if (lane == 0) nq = atomicAdd(&s_next_quad, 1);
+    quad = __shfl_sync(0xffffffffu, nq, 0);
   }
+}
+
+// Sum of the per-tile partial reduced systems of every window in tile order (points, then lines) -> hs_part, the
+// array kb_solve assembles from; one thread per (pair, element); grid (ceil(Pmax * 42 / 256), W)
+__global__ void __launch_bounds__(256) kt_tile_sum(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                   const __grid_constant__ TileDev td) {
+  const int w = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (b.ws[w].stage != STAGE_NEED_TRIAL || idx >= b.n_ne[w] * 42) return;
+  const int ntp = td.ntile[w * 2], ntl = td.ntile[w * 2 + 1];
+  const size_t stride = (size_t)b.Pmax * 42;
+  const double* base = td.hs_tile + (size_t)w * (td.Tp + td.Tl) * stride + idx;
+  double v = 0.0;
+  int t = 0;
+  for (; t + 4 <= ntp; t += 4) { // (four independent loads in flight; the additions stay in tile order)
+    const double a0 = base[(size_t)t * stride], a1 = base[(size_t)(t + 1) * stride], a2 = base[(size_t)(t + 2) * stride],
+                 a3 = base[(size_t)(t + 3) * stride];
+    v = (((v + a0) + a1) + a2) + a3;
+  }
+  for (; t < ntp; ++t) v += base[(size_t)t * stride];
+  for (t = 0; t < ntl; ++t) v += base[(size_t)(td.Tp + t) * stride];
+  b.hs_part[(size_t)w * stride + idx] = v;
 }
 
 // Loop condition of the whole-schedule CUDA graph (conditional WHILE node): non-zero while any window is still
