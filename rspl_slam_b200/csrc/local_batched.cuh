@@ -705,14 +705,23 @@ __global__ void __launch_bounds__(128) kb_begin_trial(const __grid_constant__ Lo
     nact = b.gs[1];
     mx = b.gs[2];
   } else {
-    for (int c = lane; c < b.C; c += 32) {
+    // (point and line chunks are summed separately: the slot of the first line chunk, Cp, depends on the largest
+    // window of the batch, and the result of a window must not)
+    double chi_l = 0, nact_l = 0;
+    for (int c = lane; c < b.Cp; c += 32) {
       const double* pp = b.part + ((size_t)w * b.C + c) * 4;
       chi += pp[0];
       nact += pp[1];
       mx = fmax(mx, pp[2]);
     }
-    chi = warp_allreduce(chi);
-    nact = warp_allreduce(nact);
+    for (int c = b.Cp + lane; c < b.C; c += 32) {
+      const double* pp = b.part + ((size_t)w * b.C + c) * 4;
+      chi_l += pp[0];
+      nact_l += pp[1];
+      mx = fmax(mx, pp[2]);
+    }
+    chi = warp_allreduce(chi) + warp_allreduce(chi_l);
+    nact = warp_allreduce(nact) + warp_allreduce(nact_l);
   }
   if (it == 0) {
     const int f0 = b.nf_begin[w];
@@ -1000,13 +1009,15 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   }
 }
 
-// Right-looking upper Cholesky of the reduced system by the WHOLE CTA (warp per trailing row, lanes
-// over its columns; two barriers per pivot), then the two triangular sweeps by warp 0. The
-// per-element update order is p = 0, 1, ... like the sequential algorithm. ~6 us for n = 54 and
-// ~15 us for n = 114 instead of 60 / 180 us with a single warp. Fails iff a pivot <= 0 (§9.11).
-BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, int n, int* s_flag) {
+// Right-looking upper Cholesky of the reduced system by the WHOLE CTA (warp per trailing row, lanes over its
+// columns; three barriers per pivot). The right-hand side rides along as one more column, so U^T y = bs is solved
+// by the same sweep; the back substitution U x = y is left to warp 0 (column-oriented, reciprocal diagonal kept
+// from the factorisation). The per-element update order is p = 0, 1, ... like the sequential algorithm.
+// Fails iff a pivot <= 0 (§9.11). `x` doubles as y; `dinv` [n] scratch.
+BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, double* dinv, int n, int* s_flag) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   if (tid == 0) *s_flag = 1;
+  for (int i = tid; i < n; i += blockDim.x) x[i] = bs[i];
   __syncthreads();
   for (int k = 0; k < n; ++k) {
     const double dk = A[(size_t)k * n + k];
@@ -1014,53 +1025,32 @@ BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, int n, in
       if (tid == 0) *s_flag = 0;
       break;
     }
-    const double ukk = sqrt(dk), inv = 1.0 / ukk;
-    __syncthreads(); // everyone has read the pivot before it is overwritten
-    for (int j = k + tid; j < n; j += blockDim.x) A[(size_t)k * n + j] = (j == k) ? ukk : A[(size_t)k * n + j] * inv;
+    const double inv = rsqrt(dk);
+    const double yk = x[k] * inv;
+    __syncthreads(); // everyone has read the pivot and x[k] before they are overwritten
+    for (int j = k + tid; j < n; j += blockDim.x) A[(size_t)k * n + j] = (j == k) ? dk * inv : A[(size_t)k * n + j] * inv;
+    if (tid == 0) {
+      x[k] = yk;
+      dinv[k] = inv;
+    }
     __syncthreads();
     for (int i = k + 1 + warp; i < n; i += nwarps) {
       const double uki = A[(size_t)k * n + i];
       for (int j = i + lane; j < n; j += 32) A[(size_t)i * n + j] -= uki * A[(size_t)k * n + j];
+      if (lane == 0) x[i] -= uki * yk;
     }
     __syncthreads();
   }
   __syncthreads();
   if (!*s_flag || tid >= 32) return;
-  for (int i = lane; i < n; i += 32) x[i] = bs[i];
-  __syncwarp();
-  for (int i = 0; i < n; ++i) { // U^T y = bs
-    const double yi = x[i] / A[(size_t)i * n + i];
-    __syncwarp();
-    if (lane == 0) x[i] = yi;
-    for (int j = i + 1 + lane; j < n; j += 32) x[j] -= A[(size_t)i * n + j] * yi;
-    __syncwarp();
-  }
   for (int i = n - 1; i >= 0; --i) { // U x = y
-    const double xi = x[i] / A[(size_t)i * n + i];
+    const double xi = x[i] * dinv[i];
     __syncwarp();
     if (lane == 0) x[i] = xi;
     for (int j = lane; j < i; j += 32) x[j] -= A[(size_t)j * n + i] * xi;
     __syncwarp();
   }
 }
-
-// Tables of the tiled Schur path (local_tiled.cuh): landmark tiles sized by shared memory, their slices of the
-// pair lists, the per-tile partial reduced systems.
-struct TileDev {
-  int Q;           // tile quantile in bytes of shared memory
-  int Tcap;        // tiles per (window, kind) <= Tcap
-  int Tp, Tl;      // grid widths: max tiles of points / lines over the windows
-  int* tile_lm;    // [(w*2+kind)*(Tcap+1) + t] first landmark (batch-global index) of tile t; entry ntile = end
-  int* ntile;      // [w*2+kind]
-  int cost_b[2];   // shared-memory bytes per edge (Z block, landmark index, its share of the staged pair entries)
-  int* tpb;        // [((w*2+kind)*(Tcap+1) + t)*Pmax + li] first entry of tile t in the kind-list of compact pair li
-  int* tso;        // [((w*2+kind)*Tcap + t)*(Pmax+1) + li] offset of pair li inside the tile's entry block; [n_ne] = total
-  int* tent_base;  // [(w*2+kind)*Tcap + t] position of the tile's entry block in tent
-  ushort2* tent;   // tile-major copy of the pair entries, edge indices relative to the tile's first edge
-  int* order;      // [w*Pmax + o] compact pair position, longest list first
-  double* hs_tile; // [((w*(Tp+Tl) + tt)*Pmax + li)*42], tt = t (points) or Tp + t (lines)
-  double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)
-};
 
 // K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory.
 // TILED: the tiled Schur path (hs_part summed from the tiles by kt_tile_sum) also keeps the rotation of the pose backup.
@@ -1076,7 +1066,8 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   double* Hs = reinterpret_cast<double*>(smem_raw);
   double* bs = Hs + (size_t)n * n;
   double* xs = bs + n;
-  double* sc_part = xs + n; // [nf] pose part of the LM scale
+  double* dinv = xs + n;     // [n] reciprocal diagonal of the factor
+  double* sc_part = dinv + n; // [nf] pose part of the LM scale
   __shared__ int s_ok;
   const double lambda = s.lambda;
   // assemble upper blocks: zero background, then the pairs of the compact list
@@ -1108,7 +1099,7 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   __syncthreads();
   __shared__ int s_chol;
   if (n > 0) {
-    cholesky_solve_cta(Hs, bs, xs, n, &s_chol);
+    cholesky_solve_cta(Hs, bs, xs, dinv, n, &s_chol);
     __syncthreads();
     if (tid == 0) s_ok = s_chol && !s.prep_fail;
   } else if (tid == 0) {
@@ -1394,13 +1385,19 @@ __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDe
     chi1 = b.gs[4];
     scale = b.gs[5];
   } else if (ok) {
-    for (int c = lane; c < b.C; c += 32) {
+    double chi_l = 0, scale_l = 0; // (points and lines separately, see kb_begin_trial)
+    for (int c = lane; c < b.Cp; c += 32) {
       const double* pp = b.part + ((size_t)w * b.C + c) * 4;
       chi1 += pp[0];
       scale += pp[1];
     }
-    chi1 = warp_allreduce(chi1);
-    scale = warp_allreduce(scale);
+    for (int c = b.Cp + lane; c < b.C; c += 32) {
+      const double* pp = b.part + ((size_t)w * b.C + c) * 4;
+      chi_l += pp[0];
+      scale_l += pp[1];
+    }
+    chi1 = warp_allreduce(chi1) + warp_allreduce(chi_l);
+    scale = warp_allreduce(scale) + warp_allreduce(scale_l);
   }
   scale += s.scale_pose;
   const double tempChi = ok ? chi1 : DBL_MAX; // a failed factorisation is a rejected step

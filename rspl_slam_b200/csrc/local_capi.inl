@@ -411,11 +411,11 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   long long total = 0;
   for (int k = 0; k < 2; ++k)
     for (int w = 0; w < W; ++w) total += cost(k, w);
-  // default: two CTAs per SM; small batches (single windows) get smaller tiles so that they spread over the SMs
+  // Two CTAs per SM. The tile size is the same for every batch: the tiles of a window (and with them the order of
+  // its sums) must not depend on what else is in the batch.
   long long Q = 100 << 10;
   if (const char* e = getenv("RSPL_BA_TILE_Q")) Q = atoll(e) > 4096 ? atoll(e) : Q;
-  else
-    while (Q > (12 << 10) && total / Q < 2LL * c->num_sms) Q >>= 1;
+  (void)total;
   for (int k = 0; k < 2; ++k) {
     const long long room = (long long)c->smem_optin - cost_a[k] - (long long)cost_b[k] * maxdeg[k] - fixed;
     if (room < 4096) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: landmark degree %d too large for the tiled Schur path", maxdeg[k]);
@@ -549,7 +549,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     if (b.Cp && td.Tp) GK(sm, ba::kt_schur_tile<0>, g_tp, ba::TILE_THREADS, smem_tile[0], d, b, lo, td);
     if (b.Cl && td.Tl) GK(sline, ba::kt_schur_tile<1>, g_tl, ba::TILE_THREADS, smem_tile[1], d, b, lo, td);
     join(1);
-    GK(sm, ba::kt_tile_sum, dim3((b.Pmax * 42 + 255) / 256, W), 256, 0, d, b, td);
+    GK(sm, ba::kt_tile_sum, dim3((b.Pmax * 42 * ba::TILE_SUM_LANES + 255) / 256, W), 256, 0, d, b, td);
     GK(sm, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
     fork(2);
     if (b.Cp) GK(sm, ba::kt_backsub_rc<0>, g_pt, ba::BT, 0, d, b, lo, td);
@@ -667,7 +667,7 @@ int local_solve_graph(RsplBaContext* c, const ba::LocalOpt& lo) {
   const int W = c->l_n_windows;
   if (W > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   const int n_max = 6 * b.NFmax;
-  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
+  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 3 * n_max + b.NFmax + 8);
   if (smem_solve > c->smem_optin || b.pairs_tmp) return RSPL_BA_ERR_STATE; // dense reduced system: host-driven path
   // one constraint per (pose, landmark) pair => a landmark's degree is bounded by the poses of its window
   const int deg_bound = c->l_max_poses < 254 ? c->l_max_poses : 254;
@@ -737,7 +737,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
       g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128), g_winw((W + 3) / 4);
   const int n_max = 6 * b.NFmax;
-  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 2 * n_max + b.NFmax + 8);
+  const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 3 * n_max + b.NFmax + 8);
   // reduced systems beyond shared memory: dense matrices in HBM + cuSOLVER Cholesky (dense_solver.inl)
   // (global BA always takes this route: its collectives sit between the kernels of a super-step)
   const bool global = c->global_mode;
@@ -886,7 +886,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     join(1);
     if (!tiled) LAUNCH(PC_SCHUR_REDUCE, ba::kb_schur_reduce, g_ne, 32, 0, d, b);
     if (tiled) {
-      LAUNCH(PC_SOLVE, ba::kt_tile_sum, dim3((b.Pmax * 42 + 255) / 256, W), 256, 0, d, b, td);
+      LAUNCH(PC_SOLVE, ba::kt_tile_sum, dim3((b.Pmax * 42 * ba::TILE_SUM_LANES + 255) / 256, W), 256, 0, d, b, td);
       LAUNCH(PC_SOLVE, ba::kb_solve<true>, W, 256, smem_solve, d, b, td);
     } else if (!dense) {
       LAUNCH(PC_SOLVE, ba::kb_solve<false>, W, 256, smem_solve, d, b, td);
