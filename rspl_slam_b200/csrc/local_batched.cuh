@@ -1052,6 +1052,24 @@ BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, double* d
   }
 }
 
+// Tables of the tiled Schur path (local_tiled.cuh): landmark tiles sized by shared memory, their slices of the
+// pair lists, the per-tile partial reduced systems.
+struct TileDev {
+  int Q;           // tile quantile in bytes of shared memory
+  int Tcap;        // tiles per (window, kind) <= Tcap
+  int Tp, Tl;      // grid widths: max tiles of points / lines over the windows
+  int* tile_lm;    // [(w*2+kind)*(Tcap+1) + t] first landmark (batch-global index) of tile t; entry ntile = end
+  int* ntile;      // [w*2+kind]
+  int cost_b[2];   // shared-memory bytes per edge (Z block, landmark index, its share of the staged pair entries)
+  int* tpb;        // [((w*2+kind)*(Tcap+1) + t)*Pmax + li] first entry of tile t in the kind-list of compact pair li
+  int* tso;        // [((w*2+kind)*Tcap + t)*(Pmax+1) + li] offset of pair li inside the tile's entry block; [n_ne] = total
+  int* tent_base;  // [(w*2+kind)*Tcap + t] position of the tile's entry block in tent
+  ushort2* tent;   // tile-major copy of the pair entries, edge indices relative to the tile's first edge
+  int* order;      // [w*Pmax + o] compact pair position, longest list first, | 1 << 30 for a diagonal pair
+  double* hs_tile; // [((w*(Tp+Tl) + tt)*Pmax + li)*42], tt = t (points) or Tp + t (lines)
+  double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)
+};
+
 // K4 + pose update: one CTA per window; reduced system assembled and factorised in shared memory.
 // TILED: the tiled Schur path (hs_part summed from the tiles by kt_tile_sum) also keeps the rotation of the pose backup.
 template <bool TILED>

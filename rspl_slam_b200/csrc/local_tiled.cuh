@@ -478,31 +478,31 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   }
 }
 
-// Sum of the per-tile partial reduced systems of every window -> hs_part, the array kb_solve assembles from.
-// TILE_SUM_LANES consecutive lanes share one (pair, element): lane j adds the tiles j, j + LANES, ... in order (point
-// tiles, then line tiles), a fixed butterfly adds the lanes. grid (ceil(Pmax * 42 * LANES / 256), W)
-constexpr int TILE_SUM_LANES = 4;
+// Sum of the per-tile partial reduced systems of every window in tile order (points, then lines) -> hs_part, the
+// array kb_solve assembles from; one thread per (pair, element), eight independent loads in flight, the additions
+// stay in tile order; grid (ceil(Pmax * 42 / 256), W)
+constexpr int TILE_SUM_LANES = 1;
 __global__ void __launch_bounds__(256) kt_tile_sum(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
                                                    const __grid_constant__ TileDev td) {
   const int w = blockIdx.y;
-  const int gid = blockIdx.x * 256 + threadIdx.x;
-  const int idx = gid / TILE_SUM_LANES, j = gid % TILE_SUM_LANES;
-  if (b.ws[w].stage != STAGE_NEED_TRIAL) return; // (uniform over the CTA)
-  const bool live = idx < b.n_ne[w] * 42;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (b.ws[w].stage != STAGE_NEED_TRIAL || idx >= b.n_ne[w] * 42) return;
   const int ntp = td.ntile[w * 2], ntl = td.ntile[w * 2 + 1];
   const size_t stride = (size_t)b.Pmax * 42;
-  const double* base = td.hs_tile + (size_t)w * (td.Tp + td.Tl) * stride + (live ? idx : 0);
-  double v = 0.0, vl = 0.0;
-  if (live) {
-    for (int t = j; t < ntp; t += TILE_SUM_LANES) v += base[(size_t)t * stride];
-    for (int t = j; t < ntl; t += TILE_SUM_LANES) vl += base[(size_t)(td.Tp + t) * stride];
-  }
+  const double* base = td.hs_tile + (size_t)w * (td.Tp + td.Tl) * stride + idx;
+  double v = 0.0;
+  int t = 0;
+  for (; t + 8 <= ntp; t += 8) {
+    double a[8];
 #pragma unroll
-  for (int o = TILE_SUM_LANES / 2; o > 0; o >>= 1) {
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-    vl += __shfl_xor_sync(0xffffffffu, vl, o);
+    for (int u = 0; u < 8; ++u) a[u] = base[(size_t)(t + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v += a[u];
   }
-  if (live && j == 0) b.hs_part[(size_t)w * stride + idx] = v + vl;
+  for (; t < ntp; ++t) v += base[(size_t)t * stride];
+  double vl = 0.0;
+  for (t = 0; t < ntl; ++t) vl += base[(size_t)(td.Tp + t) * stride];
+  b.hs_part[(size_t)w * stride + idx] = v + vl;
 }
 
 // Loop condition of the whole-schedule CUDA graph (conditional WHILE node): non-zero while any window is still
