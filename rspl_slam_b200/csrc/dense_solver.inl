@@ -94,6 +94,10 @@ struct DenseLayout {
   // the tiles: O(n t^2) instead of O(n^3) with library calls on t x t tiles. tile_poses[w] = 0: full dense.
   std::vector<int> tile_poses;
   std::vector<int> fused_t; // > 0: tile size (unknowns) of the one-launch banded solver (band_solver.cuh)
+  // Hand-written cyclic-reduction solver (bcr_solver.cuh): one window whose reduced system is banded within
+  // bcr_bsp <= 24 poses and at least 4 super-blocks long. 0: not used.
+  int bcr_bsp = 0;
+  ba::BcrDev bcr{};
   int* tile_info = nullptr; // [max tiles]
   int max_tiles = 0;
   std::vector<long long> off; // [W] offset of each window's matrix (doubles)
@@ -129,11 +133,24 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     L.total += (n * n + 31) & ~31LL;
     if (n > n_max) n_max = (int)n;
   }
+  // banded single window (global BA, long chains): the hand-written cyclic-reduction solver replaces the library
+  // calls and needs no dense n x n matrix
+  int bcr_bsp = 0;
+  if (W == 1 && !getenv("RSPL_BA_DENSE_FULL") && !getenv("RSPL_BA_DENSE_LIB")) {
+    const int nf = c->l_nf_begin[1] - c->l_nf_begin[0];
+    int bsp = band[0] > 6 ? band[0] : 6;
+    if (const char* e = getenv("RSPL_BA_BCR_POSES")) bsp = atoi(e) > bsp ? atoi(e) : bsp;
+    if (6 * bsp <= ba::BCR_BS_MAX && nf >= 4 * bsp) bcr_bsp = bsp;
+  }
+  if (bcr_bsp) {
+    L.total = 32;
+    n_max = 0;
+  }
   if ((size_t)L.total * sizeof(double) > ((size_t)64 << 30))
     return fail(c, RSPL_BA_ERR_UNSUPPORTED, "dense reduced systems of this batch need more than 64 GB");
   Arena a;
   const size_t o_H = a.take(sizeof(double) * (size_t)(L.total + 1));
-  const size_t o_b = a.take(sizeof(double) * (size_t)(6 * c->l_nf_begin[W] + 1));
+  const size_t o_b = a.take(sizeof(double) * (size_t)(6 * c->l_nf_begin[W] + ba::BCR_BS_MAX + 8)); // (+ padding of the last super-block)
   const size_t o_info = a.take(sizeof(int) * 2 * W); // [W] potrf info, [W] potrs info (parameter errors only)
   const size_t o_off = a.take(sizeof(long long) * W);
   // block-tridiagonal decision per window
@@ -163,6 +180,22 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
       if (tiles > L.max_tiles) L.max_tiles = tiles;
     }
   }
+  L.bcr_bsp = bcr_bsp;
+  size_t o_bD = 0, o_bE = 0, o_bGL = 0, o_bGR = 0, o_bg = 0;
+  int bcr_M = 0;
+  if (bcr_bsp) {
+    const int nf = c->l_nf_begin[1] - c->l_nf_begin[0];
+    bcr_M = (nf + bcr_bsp - 1) / bcr_bsp;
+    const size_t bb = (size_t)36 * bcr_bsp * bcr_bsp;
+    o_bD = a.take(sizeof(double) * bb * bcr_M);
+    o_bE = a.take(sizeof(double) * bb * (2 * (size_t)bcr_M + ba::BCR_MAX_LEVELS));
+    o_bGL = a.take(sizeof(double) * bb * bcr_M);
+    o_bGR = a.take(sizeof(double) * bb * bcr_M);
+    o_bg = a.take(sizeof(double) * 6 * bcr_bsp * bcr_M);
+    L.tile_poses[0] = 0;
+    L.fused_t[0] = 0;
+    L.max_tiles = 0;
+  }
   const size_t o_tinfo = a.take(sizeof(int) * (L.max_tiles + 1));
   CU_TRY(c, c->dense_buf.reserve(a.off));
   char* base = c->dense_buf.as<char>();
@@ -188,6 +221,26 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     L.tile_info = (int*)(base + o_tinfo);
   }
   L.work = (double*)(base + o_work);
+  if (L.bcr_bsp) {
+    ba::BcrDev& s = L.bcr;
+    s.bs = 6 * L.bcr_bsp;
+    s.M = bcr_M;
+    s.n = 0;
+    s.levels = 0;
+    s.D = (double*)(base + o_bD);
+    s.E = (double*)(base + o_bE);
+    s.GL = (double*)(base + o_bGL);
+    s.GR = (double*)(base + o_bGR);
+    s.g = (double*)(base + o_bg);
+    s.x = L.b;
+    s.info = L.info;
+    const size_t ld = s.bs + 1;
+    const size_t lbytes = sizeof(double) * s.bs * ld;
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 1024)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * s.bs + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 3 * s.bs + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * ba::BCR_KC * s.bs + 64)));
+  }
   CU_TRY(c, cudaFuncSetAttribute(ba::k_band_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::BAND_SMEM));
   if (L.max_tiles > 0) {
     CublasApi& bl = cublas_api();
@@ -202,6 +255,64 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
   CU_TRY(c, cudaMemcpyAsync(L.d_off, L.off.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(L.info, 0, sizeof(int) * 2 * W, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return RSPL_BA_OK;
+}
+
+// Assembly + factorisation + solve of the banded single window with the cyclic-reduction kernels (bcr_solver.cuh);
+// n_sys = pose blocks of the reduced system in the current pass. Enqueues ~3 log2(M) launches, no host sync.
+int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
+  ba::BcrDev& s = L.bcr;
+  cudaStream_t st = c->stream;
+  const int bsp = L.bcr_bsp;
+  s.n = 6 * n_sys;
+  s.M = (n_sys + bsp - 1) / bsp;
+  if (s.M < 1) s.M = 1;
+  const size_t bb = (size_t)s.bs * s.bs;
+  int Ml = s.M, levels = 0;
+  long long off = 0;
+  while (true) { // active blocks per level: M, ceil(M / 2), ...
+    s.eoff[levels] = off;
+    off += (long long)Ml * (long long)bb;
+    if (Ml <= 1) break;
+    Ml = (Ml + 1) / 2;
+    ++levels;
+    if (levels >= ba::BCR_MAX_LEVELS - 1) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "reduced system too long for the cyclic-reduction solver");
+  }
+  s.levels = levels;
+  {
+    ProfScope ps(c, PC_ASSEMBLE);
+    CU_TRY(c, cudaMemsetAsync(s.D, 0, sizeof(double) * bb * s.M, st));
+    CU_TRY(c, cudaMemsetAsync(s.E, 0, sizeof(double) * bb * s.M, st)); // level 0 (the higher levels are written in full)
+    CU_TRY(c, cudaMemsetAsync(s.info, 0, sizeof(int), st));
+    ba::bcr_pad<<<1, 64, 0, st>>>(s);
+    ba::kb_assemble_bcr<<<n_ne > 0 ? n_ne : 1, 64, 0, st>>>(c->ld, c->bd, s, bsp);
+    c->launches += 2;
+  }
+  ProfScope ps(c, PC_SOLVE);
+  const size_t ld = s.bs + 1;
+  const size_t lbytes = sizeof(double) * s.bs * ld;
+  int pch = (int)(((long long)c->smem_optin - 2048 - (long long)lbytes) / (long long)(sizeof(double) * s.bs));
+  if (pch > 2 * s.bs + 1) pch = 2 * s.bs + 1;
+  if (pch < 1) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "cyclic-reduction solver: super-block does not fit shared memory");
+  const size_t smem_el = lbytes + sizeof(double) * s.bs * pch + 64;
+  const size_t smem_up = sizeof(double) * 2 * ba::BCR_KC * s.bs + 64;
+  Ml = s.M;
+  for (int l = 0; l < levels; ++l) {
+    const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
+    if (n_odd > 0) ba::bcr_eliminate<<<n_odd, ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
+    ba::bcr_update<<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
+    c->launches += 2;
+    Ml = n_even;
+  }
+  ba::bcr_root<<<1, ba::BCR_THREADS, lbytes + sizeof(double) * s.bs + 64, st>>>(s);
+  c->launches += 1;
+  for (int l = levels - 1; l >= 0; --l) {
+    const int Mlev = (s.M + (1 << l) - 1) >> l; // active blocks at level l
+    const int n_odd = Mlev / 2;
+    if (n_odd > 0) ba::bcr_backsub<<<n_odd, ba::BCR_THREADS, lbytes + sizeof(double) * 3 * s.bs + 64, st>>>(s, l);
+    c->launches += 1;
+  }
+  CU_TRY(c, cudaGetLastError());
   return RSPL_BA_OK;
 }
 

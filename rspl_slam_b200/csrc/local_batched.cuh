@@ -18,6 +18,7 @@
 #pragma once
 
 #include "local_kernel.cuh"
+#include "bcr_solver.cuh"
 
 namespace ba {
 
@@ -1198,6 +1199,47 @@ __global__ void __launch_bounds__(64) kb_assemble_dense(const __grid_constant__ 
   } else if (tid < 42 && fi == fj) {
     const int r = tid - 36;
     b.dense_b[(size_t)6 * f0 + 6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - part[36 + r];
+  }
+}
+
+// Block-tridiagonal assembly for the cyclic-reduction solver (bcr_solver.cuh): pose pair (si, sj) of window 0 goes
+// to the diagonal super-block D[si / bsp] (both triangles) or to the level-0 coupling E[si / bsp]; D and E are
+// zeroed by the host before this launch. grid (longest compact pair list), 64 threads
+__global__ void __launch_bounds__(64) kb_assemble_bcr(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                      const __grid_constant__ BcrDev s, int bsp) {
+  const int w = 0, li = blockIdx.x, tid = threadIdx.x;
+  const WinState& st = b.ws[w];
+  if (st.stage != STAGE_NEED_TRIAL || li >= b.n_ne[w]) return;
+  const int nf = st.nf;
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
+  int fi, fj;
+  pair_decode(p, nf, fi, fj);
+  const int f0 = b.nf_begin[w];
+  const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
+  if (si < 0 || sj < 0) return;
+  const int bs = s.bs;
+  const size_t bb = (size_t)bs * bs;
+  const int I = si / bsp, J = sj / bsp;
+  const int r0 = 6 * (si - I * bsp), c0 = 6 * (sj - J * bsp);
+  const double* part = b.hs_part + ((size_t)w * b.Pmax + li) * 42;
+  if (tid < 36) {
+    const int r = tid / 6, c = tid % 6;
+    double v = -part[tid];
+    if (fi == fj) { // symmetric diagonal block from its upper triangle
+      const int rr = r < c ? r : c, cc = r < c ? c : r;
+      v = -part[rr * 6 + cc] + b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? st.lambda : 0.0);
+    }
+    if (I == J) {
+      s.D[(size_t)I * bb + (size_t)(r0 + r) * bs + c0 + c] = v;
+      if (si != sj) s.D[(size_t)I * bb + (size_t)(c0 + c) * bs + r0 + r] = v;
+    } else if (J == I + 1) {
+      s.E[s.eoff[0] + (size_t)I * bb + (size_t)(r0 + r) * bs + c0 + c] = v;
+    } else {
+      atomicOr(s.info, 2); // outside the band the solver was set up for (cannot happen: checked at setup)
+    }
+  } else if (tid < 42 && fi == fj) {
+    const int r = tid - 36;
+    s.x[(size_t)6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - part[36 + r];
   }
 }
 

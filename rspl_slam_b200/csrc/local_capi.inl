@@ -896,14 +896,18 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
         if (coll_rc == RSPL_BA_OK)
           coll_rc = comm_all_reduce(c, b.hs_part_w, b.hs_part, (size_t)42 * n_ne_host[0] + 1, kNcclFloat64, kNcclSum);
       }
-      {
-        ProfScope ps_(c, PC_ASSEMBLE);
-        if (cudaMemsetAsync(dl.H, 0, sizeof(double) * (size_t)dl.total, s) != cudaSuccess) dense_rc = RSPL_BA_ERR_CUDA;
-      }
-      LAUNCH(PC_ASSEMBLE, ba::kb_assemble_dense, g_ne, 64, 0, d, b);
-      {
-        ProfScope ps_(c, PC_SOLVE);
-        dense_rc = dense_factor_solve(c, dl, n_sys_host);
+      if (dl.bcr_bsp) { // banded single window: hand-written cyclic reduction (bcr_solver.cuh)
+        if (dense_rc == RSPL_BA_OK) dense_rc = bcr_assemble_solve(c, dl, n_sys_host[0], n_ne_host[0]);
+      } else {
+        {
+          ProfScope ps_(c, PC_ASSEMBLE);
+          if (cudaMemsetAsync(dl.H, 0, sizeof(double) * (size_t)dl.total, s) != cudaSuccess) dense_rc = RSPL_BA_ERR_CUDA;
+        }
+        LAUNCH(PC_ASSEMBLE, ba::kb_assemble_dense, g_ne, 64, 0, d, b);
+        {
+          ProfScope ps_(c, PC_SOLVE);
+          dense_rc = dense_factor_solve(c, dl, n_sys_host);
+        }
       }
       LAUNCH(PC_ASSEMBLE, ba::kb_post_solve, W, 256, 0, d, b);
     }
