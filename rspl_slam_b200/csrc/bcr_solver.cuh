@@ -74,9 +74,10 @@ __device__ __forceinline__ bool bcr_chol6(const double* Ls, int ld, int k0, doub
 }
 
 // In-place lower Cholesky of the n x n matrix in shared memory (n a multiple of 6), whole CTA, three barriers per
-// 6-column panel. The strictly upper part is not touched. *s_fail is set on a pivot <= 0.
-__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, int* s_fail) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+// 6-column panel. The strictly upper part is not touched; dinv [n] receives the reciprocal diagonal of the factor.
+// *s_fail is set on a pivot <= 0.
+__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s_fail) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   for (int k0 = 0; k0 < n; k0 += 6) {
     double Lk[6][6], inv[6];
     if (!bcr_chol6(Ls, ld, k0, Lk, inv)) *s_fail = 1; // (benign race: every thread writes the same value)
@@ -84,6 +85,7 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, int* s_fail) {
     if (tid < 36) {
       const int r = tid / 6, c = tid % 6;
       if (c <= r) Ls[(k0 + r) * ld + k0 + c] = Lk[r][c];
+      if (c == r) dinv[k0 + r] = inv[r];
     }
     for (int i = k0 + 6 + tid; i < n; i += nt) { // panel: X Lkk^T = A, one thread per row
       double xr[6];
@@ -98,24 +100,27 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, int* s_fail) {
       for (int c = 0; c < 6; ++c) Ls[i * ld + k0 + c] = xr[c];
     }
     __syncthreads();
-    const int m = n - k0 - 6; // trailing update of the lower triangle
-    for (int idx = tid; idx < m * m; idx += nt) {
-      const int i = idx / m, j = idx - i * m;
-      if (j > i) continue;
-      const double* pi = Ls + (k0 + 6 + i) * ld + k0;
-      const double* pj = Ls + (k0 + 6 + j) * ld + k0;
-      double v = Ls[(k0 + 6 + i) * ld + k0 + 6 + j];
+    // trailing update of the lower triangle: a warp per row i, lanes over the columns j <= i
+    for (int i = k0 + 6 + warp; i < n; i += nw) {
+      double pi[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) v -= pi[q] * pj[q];
-      Ls[(k0 + 6 + i) * ld + k0 + 6 + j] = v;
+      for (int q = 0; q < 6; ++q) pi[q] = Ls[i * ld + k0 + q];
+      for (int j = k0 + 6 + lane; j <= i; j += 32) {
+        const double* pj = Ls + j * ld + k0;
+        double v = Ls[i * ld + j];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v -= pi[q] * pj[q];
+        Ls[i * ld + j] = v;
+      }
     }
     __syncthreads();
   }
 }
 
-// Y = L^-1 X for the nc columns of the panel P [n][pld] in shared memory (right-looking, 6 rows at a time)
-__device__ void bcr_cta_forward(const double* Ls, int ld, int n, double* P, int pld, int nc) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+// Y = L^-1 X for the nc columns of the panel P [n][pld] in shared memory (right-looking, 6 rows at a time);
+// dinv = reciprocal diagonal of L
+__device__ void bcr_cta_forward(const double* Ls, int ld, const double* dinv, int n, double* P, int pld, int nc) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   for (int k0 = 0; k0 < n; k0 += 6) {
     for (int c = tid; c < nc; c += nt) { // Y_k = Lkk^-1 X_k, one thread per column
       double y[6];
@@ -124,20 +129,33 @@ __device__ void bcr_cta_forward(const double* Ls, int ld, int n, double* P, int 
         double v = P[(k0 + r) * pld + c];
 #pragma unroll
         for (int q = 0; q < r; ++q) v -= Ls[(k0 + r) * ld + k0 + q] * y[q];
-        y[r] = v / Ls[(k0 + r) * ld + k0 + r];
+        y[r] = v * dinv[k0 + r];
       }
 #pragma unroll
       for (int r = 0; r < 6; ++r) P[(k0 + r) * pld + c] = y[r];
     }
     __syncthreads();
-    const int m = n - k0 - 6;
-    for (int idx = tid; idx < m * nc; idx += nt) { // X_i -= L_ik Y_k
-      const int i = idx / nc, c = idx - i * nc;
-      const double* li = Ls + (k0 + 6 + i) * ld + k0;
-      double v = P[(k0 + 6 + i) * pld + c];
+    // X_i -= L_ik Y_k: a warp per row i, lanes over the columns (the six Y rows of a column stay in registers
+    // across two rows)
+    for (int i = k0 + 6 + 2 * warp; i < n; i += 2 * nw) {
+      const bool two = i + 1 < n;
+      double l0[6], l1[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) v -= li[q] * P[(k0 + q) * pld + c];
-      P[(k0 + 6 + i) * pld + c] = v;
+      for (int q = 0; q < 6; ++q) {
+        l0[q] = Ls[i * ld + k0 + q];
+        l1[q] = two ? Ls[(i + 1) * ld + k0 + q] : 0.0;
+      }
+      for (int c = lane; c < nc; c += 32) {
+        double v0 = P[i * pld + c], v1 = two ? P[(i + 1) * pld + c] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double yq = P[(k0 + q) * pld + c];
+          v0 -= l0[q] * yq;
+          v1 -= l1[q] * yq;
+        }
+        P[i * pld + c] = v0;
+        if (two) P[(i + 1) * pld + c] = v1;
+      }
     }
     __syncthreads();
   }
@@ -147,7 +165,7 @@ __device__ void bcr_cta_forward(const double* Ls, int ld, int n, double* P, int 
 __device__ void bcr_warp_backward(const double* Ls, int ld, int n, double* y) {
   const int lane = threadIdx.x & 31;
   for (int i = n - 1; i >= 0; --i) {
-    const double xi = y[i] / Ls[i * ld + i];
+    const double xi = y[i] / Ls[i * ld + i]; // (one division per unknown: the chain is n steps of shared-memory latency anyway)
     __syncwarp();
     if (lane == 0) y[i] = xi;
     for (int j = lane; j < i; j += 32) y[j] -= Ls[i * ld + j] * xi;
@@ -156,12 +174,13 @@ __device__ void bcr_warp_backward(const double* Ls, int ld, int n, double* y) {
 }
 
 // ---- level l, odd blocks: factorise and form GL, GR, g. grid = number of odd active blocks; dynamic smem =
-// (bs * ld + bs * pch) doubles + 16 bytes, pch = columns of one panel chunk (>= 1)
+// (bs * ld + bs + bs * pch) doubles + 16 bytes, pch = columns of one panel chunk (>= 1, odd)
 __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_constant__ BcrDev s, int level, int pch) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, ld = bcr_ld(bs), tid = threadIdx.x, nt = blockDim.x;
   double* Ls = reinterpret_cast<double*>(bcr_smem);
-  double* P = Ls + (size_t)bs * ld;
+  double* dinv = Ls + (size_t)bs * ld;
+  double* P = dinv + bs;
   int* s_fail = reinterpret_cast<int*>(P + (size_t)bs * pch);
   const int h = 1 << level;
   const int p = 2 * blockIdx.x + 1;
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
   if (tid == 0) *s_fail = 0;
   for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = Dg[idx];
   __syncthreads();
-  bcr_cta_cholesky(Ls, ld, bs, s_fail);
+  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail);
   if (*s_fail) {
     if (tid == 0) atomicOr(s.info, 1);
     return; // (uniform) the solve is rejected as a whole
@@ -188,16 +207,19 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
   const int ncol = 2 * bs + 1; // [ E(Il,I)^T | E(I,Ir) | b_I ]
   for (int c0 = 0; c0 < ncol; c0 += pch) {
     const int nc = ncol - c0 < pch ? ncol - c0 : pch;
+    // (columns of E(Il,I)^T are rows of E(Il,I): r fastest keeps those global reads coalesced; pch is odd, so the
+    // transposing shared-memory writes are conflict-free)
     for (int idx = tid; idx < bs * nc; idx += nt) {
-      const int r = idx / nc, c = c0 + idx % nc;
-      double v;
-      if (c < bs) v = El[(size_t)c * bs + r];
-      else if (c < 2 * bs) v = has_r ? Er[(size_t)r * bs + c - bs] : 0.0;
-      else v = s.x[(size_t)I * bs + r];
-      P[r * pch + idx % nc] = v;
+      const int cl = idx / bs, r = idx - cl * bs, c = c0 + cl;
+      if (c < bs) P[r * pch + cl] = El[(size_t)c * bs + r];
+    }
+    for (int idx = tid; idx < bs * nc; idx += nt) {
+      const int r = idx / nc, cl = idx - r * nc, c = c0 + cl;
+      if (c >= 2 * bs) P[r * pch + cl] = s.x[(size_t)I * bs + r];
+      else if (c >= bs) P[r * pch + cl] = has_r ? Er[(size_t)r * bs + c - bs] : 0.0;
     }
     __syncthreads();
-    bcr_cta_forward(Ls, ld, bs, P, pch, nc);
+    bcr_cta_forward(Ls, ld, dinv, bs, P, pch, nc);
     for (int idx = tid; idx < bs * nc; idx += nt) {
       const int r = idx / nc, c = c0 + idx % nc;
       const double v = P[r * pch + idx % nc];
@@ -215,7 +237,9 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
 constexpr int BCR_TILES_PER_THREAD = ((BCR_BS_MAX / 3) * (BCR_BS_MAX / 6) + BCR_THREADS - 1) / BCR_THREADS; // 3
 
 __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, int bs, double* As, double* Bs,
-                                              double (&acc)[BCR_TILES_PER_THREAD][18]) {
+                                              double (&acc)[BCR_TILES_PER_THREAD][18], const double* gvec, double* gs,
+                                              double& vacc) {
+  // gvec != null: thread r < bs also accumulates (A^T gvec)[r] from the staged slabs
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tc = bs / 6; // tiles per row of tiles
   for (int k0 = 0; k0 < bs; k0 += BCR_KC) {
@@ -225,7 +249,11 @@ __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, 
       As[idx] = A[(size_t)k0 * bs + idx];
       Bs[idx] = B[(size_t)k0 * bs + idx];
     }
+    if (gvec && tid < kc) gs[tid] = gvec[k0 + tid];
     __syncthreads();
+    if (gvec && tid < bs) {
+      for (int k = 0; k < kc; ++k) vacc += As[k * bs + tid] * gs[k];
+    }
 #pragma unroll
     for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
       const int tix = tid + u * nt;
@@ -248,12 +276,13 @@ __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, 
 }
 
 // ---- level l, even blocks: Schur updates from the two eliminated neighbours and the next level's coupling.
-// grid = number of even active blocks; dynamic smem = 2 * BCR_KC * bs doubles
+// grid = number of even active blocks; dynamic smem = (2 * BCR_KC * bs + BCR_KC) doubles
 __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant__ BcrDev s, int level) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, tid = threadIdx.x, nt = blockDim.x;
   double* As = reinterpret_cast<double*>(bcr_smem);
   double* Bs = As + (size_t)BCR_KC * bs;
+  double* gs = Bs + (size_t)BCR_KC * bs; // [BCR_KC]
   if (*s.info) return;
   const int h = 1 << level;
   const int p = 2 * blockIdx.x;
@@ -267,8 +296,10 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   for (int u = 0; u < BCR_TILES_PER_THREAD; ++u)
 #pragma unroll
     for (int q = 0; q < 18; ++q) acc[u][q] = 0.0;
-  if (has_l) bcr_ata_tiles(s.GR + (size_t)Il * bb, s.GR + (size_t)Il * bb, bs, As, Bs, acc);
-  if (has_r) bcr_ata_tiles(s.GL + (size_t)Ir * bb, s.GL + (size_t)Ir * bb, bs, As, Bs, acc);
+  double vl = 0.0, vr = 0.0, vdummy = 0.0; // b_J -= GR(Il)^T g(Il) + GL(Ir)^T g(Ir), thread r < bs
+  if (has_l) bcr_ata_tiles(s.GR + (size_t)Il * bb, s.GR + (size_t)Il * bb, bs, As, Bs, acc, s.g + (size_t)Il * bs, gs, vl);
+  if (has_r) bcr_ata_tiles(s.GL + (size_t)Ir * bb, s.GL + (size_t)Ir * bb, bs, As, Bs, acc, s.g + (size_t)Ir * bs, gs, vr);
+  if (tid < bs) s.x[(size_t)J * bs + tid] -= vl + vr;
   double* Dg = s.D + (size_t)J * bb;
 #pragma unroll
   for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
@@ -287,7 +318,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
     for (int u = 0; u < BCR_TILES_PER_THREAD; ++u)
 #pragma unroll
       for (int q = 0; q < 18; ++q) acc[u][q] = 0.0;
-    bcr_ata_tiles(s.GL + (size_t)Ir * bb, s.GR + (size_t)Ir * bb, bs, As, Bs, acc);
+    bcr_ata_tiles(s.GL + (size_t)Ir * bb, s.GR + (size_t)Ir * bb, bs, As, Bs, acc, nullptr, gs, vdummy);
     double* En = s.E + s.eoff[level + 1] + (size_t)(p / 2) * bb;
 #pragma unroll
     for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
@@ -301,42 +332,27 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
       }
     }
   }
-  // b_J -= GR(Il)^T g(Il) + GL(Ir)^T g(Ir)   (one thread per unknown, coalesced over the columns)
-  for (int r = tid; r < bs; r += nt) {
-    double v = 0.0;
-    if (has_l) {
-      const double* A = s.GR + (size_t)Il * bb;
-      const double* gv = s.g + (size_t)Il * bs;
-      for (int k = 0; k < bs; ++k) v += A[(size_t)k * bs + r] * gv[k];
-    }
-    double v2 = 0.0;
-    if (has_r) {
-      const double* A = s.GL + (size_t)Ir * bb;
-      const double* gv = s.g + (size_t)Ir * bs;
-      for (int k = 0; k < bs; ++k) v2 += A[(size_t)k * bs + r] * gv[k];
-    }
-    s.x[(size_t)J * bs + r] -= v + v2;
-  }
 }
 
-// ---- root: the last active block (block 0). One CTA; dynamic smem = (bs * ld + bs) doubles + 16 bytes
+// ---- root: the last active block (block 0). One CTA; dynamic smem = (bs * ld + 2 * bs) doubles + 16 bytes
 __global__ void __launch_bounds__(BCR_THREADS) bcr_root(const __grid_constant__ BcrDev s) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, ld = bcr_ld(bs), tid = threadIdx.x, nt = blockDim.x;
   double* Ls = reinterpret_cast<double*>(bcr_smem);
   double* y = Ls + (size_t)bs * ld;
-  int* s_fail = reinterpret_cast<int*>(y + bs);
+  double* dinv = y + bs;
+  int* s_fail = reinterpret_cast<int*>(dinv + bs);
   if (*s.info) return;
   if (tid == 0) *s_fail = 0;
   for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = s.D[idx];
   for (int r = tid; r < bs; r += nt) y[r] = s.x[r];
   __syncthreads();
-  bcr_cta_cholesky(Ls, ld, bs, s_fail);
+  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail);
   if (*s_fail) {
     if (tid == 0) atomicOr(s.info, 1);
     return;
   }
-  bcr_cta_forward(Ls, ld, bs, y, 1, 1);
+  bcr_cta_forward(Ls, ld, dinv, bs, y, 1, 1);
   if (tid < 32) bcr_warp_backward(Ls, ld, bs, y);
   __syncthreads();
   for (int r = tid; r < bs; r += nt) s.x[r] = y[r];

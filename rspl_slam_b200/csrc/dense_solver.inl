@@ -237,9 +237,9 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     const size_t ld = s.bs + 1;
     const size_t lbytes = sizeof(double) * s.bs * ld;
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 1024)));
-    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * s.bs + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 2 * s.bs + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 3 * s.bs + 64)));
-    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * ba::BCR_KC * s.bs + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
   }
   CU_TRY(c, cudaFuncSetAttribute(ba::k_band_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::BAND_SMEM));
   if (L.max_tiles > 0) {
@@ -291,11 +291,12 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   ProfScope ps(c, PC_SOLVE);
   const size_t ld = s.bs + 1;
   const size_t lbytes = sizeof(double) * s.bs * ld;
-  int pch = (int)(((long long)c->smem_optin - 2048 - (long long)lbytes) / (long long)(sizeof(double) * s.bs));
+  int pch = (int)(((long long)c->smem_optin - 2048 - (long long)lbytes - (long long)sizeof(double) * s.bs) / (long long)(sizeof(double) * s.bs));
   if (pch > 2 * s.bs + 1) pch = 2 * s.bs + 1;
+  if (!(pch & 1)) --pch; // odd: conflict-free transposed staging
   if (pch < 1) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "cyclic-reduction solver: super-block does not fit shared memory");
-  const size_t smem_el = lbytes + sizeof(double) * s.bs * pch + 64;
-  const size_t smem_up = sizeof(double) * 2 * ba::BCR_KC * s.bs + 64;
+  const size_t smem_el = lbytes + sizeof(double) * s.bs * (pch + 1) + 64;
+  const size_t smem_up = sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64;
   Ml = s.M;
   for (int l = 0; l < levels; ++l) {
     const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
@@ -304,7 +305,7 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
     c->launches += 2;
     Ml = n_even;
   }
-  ba::bcr_root<<<1, ba::BCR_THREADS, lbytes + sizeof(double) * s.bs + 64, st>>>(s);
+  ba::bcr_root<<<1, ba::BCR_THREADS, lbytes + sizeof(double) * 2 * s.bs + 64, st>>>(s);
   c->launches += 1;
   for (int l = levels - 1; l >= 0; --l) {
     const int Mlev = (s.M + (1 << l) - 1) >> l; // active blocks at level l
