@@ -162,10 +162,10 @@ __device__ void bcr_cta_forward(const double* Ls, int ld, const double* dinv, in
 }
 
 // x = L^-T y in place (one warp, column-oriented); y in shared memory
-__device__ void bcr_warp_backward(const double* Ls, int ld, int n, double* y) {
+__device__ void bcr_warp_backward(const double* Ls, int ld, const double* dinv, int n, double* y) {
   const int lane = threadIdx.x & 31;
   for (int i = n - 1; i >= 0; --i) {
-    const double xi = y[i] / Ls[i * ld + i]; // (one division per unknown: the chain is n steps of shared-memory latency anyway)
+    const double xi = y[i] * dinv[i];
     __syncwarp();
     if (lane == 0) y[i] = xi;
     for (int j = lane; j < i; j += 32) y[j] -= Ls[i * ld + j] * xi;
@@ -258,12 +258,13 @@ __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, 
     for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
       const int tix = tid + u * nt;
       if (tix >= (bs / 3) * tc) continue;
-      const int r0 = 3 * (tix / tc), cc0 = 6 * (tix % tc);
+      // (the six columns of a tile are cl, cl + tc, ..., so the lanes of a warp read consecutive shared-memory words)
+      const int r0 = 3 * (tix / tc), cl = tix % tc;
       for (int k = 0; k < kc; ++k) {
         const double a0 = As[k * bs + r0], a1 = As[k * bs + r0 + 1], a2 = As[k * bs + r0 + 2];
         double bv[6];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) bv[q] = Bs[k * bs + cc0 + q];
+        for (int q = 0; q < 6; ++q) bv[q] = Bs[k * bs + cl + q * tc];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           acc[u][q] += a0 * bv[q];
@@ -305,11 +306,11 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
     const int tix = tid + u * nt;
     if (tix < ntiles) {
-      const int r0 = 3 * (tix / tc), c0 = 6 * (tix % tc);
+      const int r0 = 3 * (tix / tc), cl = tix % tc;
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Dg[(size_t)(r0 + a) * bs + c0 + q] -= acc[u][a * 6 + q];
+        for (int q = 0; q < 6; ++q) Dg[(size_t)(r0 + a) * bs + cl + q * tc] -= acc[u][a * 6 + q];
     }
   }
   // E'(J, J + 2h) = -GL(Ir)^T GR(Ir)
@@ -324,11 +325,11 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
     for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
       const int tix = tid + u * nt;
       if (tix < ntiles) {
-        const int r0 = 3 * (tix / tc), c0 = 6 * (tix % tc);
+        const int r0 = 3 * (tix / tc), cl = tix % tc;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int q = 0; q < 6; ++q) En[(size_t)(r0 + a) * bs + c0 + q] = -acc[u][a * 6 + q];
+          for (int q = 0; q < 6; ++q) En[(size_t)(r0 + a) * bs + cl + q * tc] = -acc[u][a * 6 + q];
       }
     }
   }
@@ -353,13 +354,13 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_root(const __grid_constant__ 
     return;
   }
   bcr_cta_forward(Ls, ld, dinv, bs, y, 1, 1);
-  if (tid < 32) bcr_warp_backward(Ls, ld, bs, y);
+  if (tid < 32) bcr_warp_backward(Ls, ld, dinv, bs, y);
   __syncthreads();
   for (int r = tid; r < bs; r += nt) s.x[r] = y[r];
 }
 
 // ---- level l, odd blocks, after the coarser levels: x_I = L^-T (g - GL x_Il - GR x_Ir).
-// grid = number of odd active blocks; dynamic smem = (bs * ld + 3 * bs) doubles
+// grid = number of odd active blocks; dynamic smem = (bs * ld + 4 * bs) doubles
 __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant__ BcrDev s, int level) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, ld = bcr_ld(bs), tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant
   double* y = Ls + (size_t)bs * ld;
   double* xl = y + bs;
   double* xr = xl + bs;
+  double* dinv = xr + bs;
   if (*s.info) return;
   const int h = 1 << level;
   const int I = (2 * blockIdx.x + 1) * h, Il = I - h, Ir = I + h;
@@ -375,6 +377,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant
   const double* Dg = s.D + (size_t)I * bb;
   for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = Dg[idx];
   for (int r = tid; r < bs; r += nt) {
+    dinv[r] = 1.0 / Dg[(size_t)r * bs + r];
     xl[r] = s.x[(size_t)Il * bs + r];
     xr[r] = has_r ? s.x[(size_t)Ir * bs + r] : 0.0;
   }
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant
     if (lane == 0) y[r] = s.g[(size_t)I * bs + r] - v;
   }
   __syncthreads();
-  if (tid < 32) bcr_warp_backward(Ls, ld, bs, y);
+  if (tid < 32) bcr_warp_backward(Ls, ld, dinv, bs, y);
   __syncthreads();
   for (int r = tid; r < bs; r += nt) s.x[(size_t)I * bs + r] = y[r];
 }

@@ -238,7 +238,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     const size_t lbytes = sizeof(double) * s.bs * ld;
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 1024)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 2 * s.bs + 64)));
-    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 3 * s.bs + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 4 * s.bs + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
   }
   CU_TRY(c, cudaFuncSetAttribute(ba::k_band_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::BAND_SMEM));
@@ -310,7 +310,7 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   for (int l = levels - 1; l >= 0; --l) {
     const int Mlev = (s.M + (1 << l) - 1) >> l; // active blocks at level l
     const int n_odd = Mlev / 2;
-    if (n_odd > 0) ba::bcr_backsub<<<n_odd, ba::BCR_THREADS, lbytes + sizeof(double) * 3 * s.bs + 64, st>>>(s, l);
+    if (n_odd > 0) ba::bcr_backsub<<<n_odd, ba::BCR_THREADS, lbytes + sizeof(double) * 4 * s.bs + 64, st>>>(s, l);
     c->launches += 1;
   }
   CU_TRY(c, cudaGetLastError());
