@@ -42,7 +42,12 @@ typedef enum RsplBaStatus {
   RSPL_BA_OK = 0,
   RSPL_BA_ERR_INVALID = -1,     /* malformed input (null pointer, index out of range, bad offsets) */
   RSPL_BA_ERR_CUDA = -2,        /* CUDA runtime error / no device */
-  RSPL_BA_ERR_UNSUPPORTED = -3, /* problem exceeds a documented limit of this path */
+  RSPL_BA_ERR_UNSUPPORTED = -3, /* problem exceeds a documented limit of this path (g2o itself accepts these inputs):
+                                 *   - two constraints joining the same (pose, landmark) pair;
+                                 *   - a landmark with more than 254 observations in a window of <= 64 free poses
+                                 *     (larger windows: no limit);
+                                 *   - more than 255 cameras, 65535 poses in one window, 65535 windows in one call.
+                                 * Reported by the solve (host-driven paths) or by the download (graph path). */
   RSPL_BA_ERR_STATE = -4        /* staged call out of order (solve before upload, ...) */
 } RsplBaStatus;
 
@@ -249,7 +254,7 @@ int rspl_ba_local_phase_cycles(RsplBaContext* ctx, double* out8);
 
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
- * line, 3 stereo line. pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]
+ * line, 3 stereo line, 4 / 5 mono / stereo pose-only point edge (lm = the fixed world point Xw, Jl = 0). pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]
  * (3 used for points); meas [n][8]; cam5 [5]. Outputs (host): err [n][4], Jl [n][16], Jp [n][24]
  * (row-major dim x ld / dim x 6), chi2 [n]. */
 int rspl_ba_eval_edges(RsplBaContext* ctx, int edge_type, int32_t n, const double* pose7,

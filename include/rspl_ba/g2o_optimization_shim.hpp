@@ -37,6 +37,8 @@
 #define RSPL_BA_G2O_OPTIMIZATION_SHIM_HPP_
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <vector>
@@ -57,6 +59,25 @@ struct ThreadContext {
   ThreadContext(const ThreadContext&) = delete;
   ThreadContext& operator=(const ThreadContext&) = delete;
 };
+// What happens when the library refuses or fails a call. The reference has no error channel (void / int returns,
+// asserts), and g2o accepts inputs this library does not (limits below), so a failure must not pass silently as
+// "nothing optimised" / "0 inliers": the default handler prints rspl_ba_last_error and aborts, like the reference's
+// own assert(poses.size() == 1) (g2o_optimization.cc:259). Install another handler to log and carry on instead.
+//   Limits (RSPL_BA_ERR_UNSUPPORTED): at most one constraint per (pose, landmark) pair; at most 254 observations of
+//   a landmark in windows of up to 64 free poses; at most 255 cameras, 65535 poses per window, 65535 windows per call.
+//   RSPL_BA_ERR_CUDA: no CUDA device / driver error (there is no CPU fallback). RSPL_BA_ERR_INVALID: an id that is
+//   not in the containers (the reference would dereference a null vertex, g2o_optimization.cc:83).
+using FailureHandler = void (*)(const char* entry_point, int code, const char* message);
+inline void default_failure_handler(const char* entry_point, int code, const char* message) {
+  std::fprintf(stderr, "rspl_ba: %s failed with status %d: %s\n", entry_point, code, message ? message : "");
+  std::abort();
+}
+inline FailureHandler& failure_handler() {
+  static FailureHandler h = default_failure_handler;
+  return h;
+}
+inline void set_failure_handler(FailureHandler h) { failure_handler() = h ? h : default_failure_handler; }
+
 inline RsplBaContext* thread_context() {
   static thread_local ThreadContext tc;
   return tc.ctx;
@@ -415,17 +436,20 @@ inline void LocalmapOptimization(MapOfPoses& poses, MapOfPoints3d& points, MapOf
                                  VectorOfStereoPointConstraints& stereo_point_constraints,
                                  VectorOfMonoLineConstraints& mono_line_constraints,
                                  VectorOfStereoLineConstraints& stereo_line_constraints, const OptimizationConfig& cfg) {
-  (void)rspl_ba::LocalmapOptimizationImpl(rspl_ba::thread_context(), poses, points, lines, camera_list,
-                                          mono_point_constraints, stereo_point_constraints, mono_line_constraints,
-                                          stereo_line_constraints, cfg);
+  RsplBaContext* ctx = rspl_ba::thread_context();
+  const int rc = rspl_ba::LocalmapOptimizationImpl(ctx, poses, points, lines, camera_list, mono_point_constraints,
+                                                   stereo_point_constraints, mono_line_constraints, stereo_line_constraints, cfg);
+  if (rc != RSPL_BA_OK) rspl_ba::failure_handler()("LocalmapOptimization", rc, ctx ? rspl_ba_last_error(ctx) : "no CUDA context");
 }
 
 inline int FrameOptimization(MapOfPoses& poses, MapOfPoints3d& points, std::vector<CameraPtr>& camera_list,
                              VectorOfMonoPointConstraints& mono_point_constraints,
                              VectorOfStereoPointConstraints& stereo_point_constraints, const OptimizationConfig& cfg) {
   int n = 0;
-  (void)rspl_ba::FrameOptimizationImpl(rspl_ba::thread_context(), poses, points, camera_list, mono_point_constraints,
-                                       stereo_point_constraints, cfg, &n);
+  RsplBaContext* ctx = rspl_ba::thread_context();
+  const int rc = rspl_ba::FrameOptimizationImpl(ctx, poses, points, camera_list, mono_point_constraints, stereo_point_constraints,
+                                                cfg, &n);
+  if (rc != RSPL_BA_OK) rspl_ba::failure_handler()("FrameOptimization", rc, ctx ? rspl_ba_last_error(ctx) : "no CUDA context");
   return n;
 }
 #endif // RSPL_BA_DEFINE_REFERENCE_ENTRY_POINTS

@@ -766,23 +766,26 @@ __global__ void eval_edges_kernel(int type, int n, const double* pose7, const do
   for (int k = 0; k < 24; ++k) jp[k] = 0;
   double info = 1.0;
   int dim = 0;
-  if (type == 0 || type == 1) {
+  if (type == 0 || type == 1 || type == 4 || type == 5) {
+    // types 4 / 5: g2o::EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose (g2o_optimization.cc:288-333):
+    // the same residual and pose Jacobian with the world point held in the edge (Xw), no landmark Jacobian
+    const bool only_pose = type >= 4;
     double Xc[3];
     transform_point(R, t, X, Xc);
-    if (type == 1) {
+    if (type == 1 || type == 5) {
       const double bf_res = bf_float ? (double)(float)cam.bf : cam.bf;
       point_residual<true>(cam, bf_res, Xc, m, r);
       point_jac_pose<true>(cam, Xc, jp);
       double j9[9];
       point_jac_point<true>(cam, R, Xc, j9);
-      for (int k = 0; k < 9; ++k) jl[k] = j9[k];
+      for (int k = 0; k < 9; ++k) jl[k] = only_pose ? 0.0 : j9[k];
       dim = 3;
     } else {
       point_residual<false>(cam, cam.bf, Xc, m, r);
       point_jac_pose<false>(cam, Xc, jp);
       double j6[9];
       point_jac_point<false>(cam, R, Xc, j6);
-      for (int k = 0; k < 6; ++k) jl[k] = j6[k];
+      for (int k = 0; k < 6; ++k) jl[k] = only_pose ? 0.0 : j6[k];
       dim = 2;
     }
   } else if (type == 2) {
@@ -828,7 +831,7 @@ __global__ void oplus_kernel(int kind, int n, const double* state, const double*
 extern "C" int rspl_ba_eval_edges(RsplBaContext* c, int edge_type, int32_t n, const double* pose7, const double* lm,
                                   const double* meas, const double* cam5, int32_t stereo_bf_float, double* err,
                                   double* Jl, double* Jp, double* chi2) {
-  if (!c || n < 0 || edge_type < 0 || edge_type > 3 || !pose7 || !lm || !meas || !cam5 || !err || !Jl || !Jp || !chi2)
+  if (!c || n < 0 || edge_type < 0 || edge_type > 5 || !pose7 || !lm || !meas || !cam5 || !err || !Jl || !Jp || !chi2)
     return RSPL_BA_ERR_INVALID;
   if (n == 0) return RSPL_BA_OK;
   SetDevice guard(c->device);

@@ -240,6 +240,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.pose_tcw = (double*)(base + o_tcw);
   d.pose_out = (double*)(base + o_pout);
   d.slot_stride = slot_stride;
+  d.use_slots = max_free <= ba::PAIRS_LM_MIN_NF ? 1 : 0;
   d.stats = (void*)(base + o_stats);
   d.err = (int*)(base + o_err);
   d.maxdeg = d.err + 1;

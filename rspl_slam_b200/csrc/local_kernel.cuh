@@ -96,6 +96,7 @@ struct LocalDev {
   double* pose_tcw; // [7][n_poses] optimiser poses built by the setup kernel
   double* pose_out; // [7][n_poses]
   int slot_stride;  // >= max free poses per window
+  int use_slots;    // the landmark x free-pose slot table is in use (windows of <= 64 free poses): degrees <= 254
   int* setup_free_idx; // [n_poses] window-local free index or -1 (scratch of the setup kernel)
   KindDev k[2];
   void* stats;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(1024) setup_scan(const __grid_constant__ Local
     if (i < nl) {
       k.ebeg[l0 + i] = run + (warp ? s_warp[warp - 1] : 0) + x - v;
       k.cursor[l0 + i] = 0;
-      if (v > 254) atomicOr(d.err, LOCAL_ERR_DEGREE);
+      if (v > 254 && d.use_slots) atomicOr(d.err, LOCAL_ERR_DEGREE);
     }
     {
       const int mv = __reduce_max_sync(0xffffffffu, v);
@@ -272,14 +273,25 @@ BA_DEV void setup_landmark(const LocalDev& d, const KindDev& k, int w, int l) {
     }
     k.src[a + v + 1] = key;
   }
-  uint8_t* sl = k.slot + (size_t)l * d.slot_stride;
-  for (int u = 0; u < n; ++u) {
-    const int key = k.src[a + u];
-    const int c = key >> 30, idx = key & 0x3fffffff;
-    const int fi = free_idx[k.cls_pose[c][idx]];
-    if (fi >= 0) {
-      if (sl[fi] != SLOT_NONE) atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
-      sl[fi] = (uint8_t)u;
+  if (d.use_slots) {
+    uint8_t* sl = k.slot + (size_t)l * d.slot_stride;
+    for (int u = 0; u < n && u < 255; ++u) {
+      const int key = k.src[a + u];
+      const int c = key >> 30, idx = key & 0x3fffffff;
+      const int fi = free_idx[k.cls_pose[c][idx]];
+      if (fi >= 0) {
+        if (sl[fi] != SLOT_NONE) atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
+        sl[fi] = (uint8_t)u;
+      }
+    }
+  } else { // large windows build their pair lists from the landmarks (no slot table): look for a repeated pose directly
+    for (int u = 1; u < n; ++u) {
+      const int key = k.src[a + u];
+      const int pu = k.cls_pose[key >> 30][key & 0x3fffffff];
+      for (int v = 0; v < u; ++v) {
+        const int kv = k.src[a + v];
+        if (k.cls_pose[kv >> 30][kv & 0x3fffffff] == pu) atomicOr(d.err, LOCAL_ERR_DUP_EDGE);
+      }
     }
   }
   const int lo = k.lm_begin[w] + k.orig[l]; // the caller's landmark

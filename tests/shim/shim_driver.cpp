@@ -5,13 +5,20 @@
 // single-call latency through the reference signatures) and prints {"median_us", "min_us"} to stdout.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
 
+#ifdef RSPL_REFERENCE_BUILD
+// oracle/g2o_validation: the SAME driver compiled against the reference's own headers and linked with the unmodified
+// g2o_optimization.cc + edge sources and a real g2o (fixtures that pin the oracle against the reference itself)
+#include "g2o_optimization/g2o_optimization.h"
+#else
 #include "mock_types.h"
 #define RSPL_BA_DEFINE_REFERENCE_ENTRY_POINTS
 #include "rspl_ba/g2o_optimization_shim.hpp"
+#endif
 
 static std::vector<double> read_all(const char* path) {
   FILE* f = fopen(path, "rb");
@@ -34,7 +41,21 @@ int main(int argc, char** argv) {
   const int np = (int)next(), npt = (int)next(), nln = (int)next();
   const int nmp = (int)next(), nsp = (int)next(), nml = (int)next(), nsl = (int)next();
   OptimizationConfig cfg{next(), next(), next(), next(), 0.5};
+#ifdef RSPL_REFERENCE_BUILD
+  // the reference's Camera reads its intrinsics from a calibration file: RSPL_REF_CAMERA_YAML = <reference>/configs/euroc.yaml,
+  // whose LEFT.P / bf are the EuRoC values the synthetic generator uses (the five numbers in the dump are checked against it)
+  const double cam5[5] = {next(), next(), next(), next(), next()};
+  const char* cam_yaml = getenv("RSPL_REF_CAMERA_YAML");
+  if (!cam_yaml) { fprintf(stderr, "set RSPL_REF_CAMERA_YAML\n"); return 2; }
+  std::vector<CameraPtr> cams{std::make_shared<Camera>(std::string(cam_yaml))};
+  if (std::abs(cams[0]->Fx() - cam5[0]) > 1e-9 || std::abs(cams[0]->Fy() - cam5[1]) > 1e-9 || std::abs(cams[0]->Cx() - cam5[2]) > 1e-9 ||
+      std::abs(cams[0]->Cy() - cam5[3]) > 1e-9 || std::abs(cams[0]->BF() - cam5[4]) > 1e-9) {
+    fprintf(stderr, "camera file does not match the dumped intrinsics\n");
+    return 2;
+  }
+#else
   std::vector<CameraPtr> cams{std::make_shared<Camera>(Camera{next(), next(), next(), next(), next()})};
+#endif
   MapOfPoses poses;
   MapOfPoints3d points;
   MapOfLine3d lines;
@@ -97,9 +118,14 @@ int main(int argc, char** argv) {
     } else if (kind == 1) {
       r = FrameOptimization(P, X, cams, a, b, cfg);
     } else { // kind 2: pose-only with constraints on fixed lines (the extension; no reference signature)
+#ifndef RSPL_REFERENCE_BUILD
       int n = 0;
       (void)rspl_ba::FrameOptimizationWithLinesImpl(rspl_ba::thread_context(), P, X, L, cams, a, b, c, e, cfg, &n);
       r = n;
+#else
+      fprintf(stderr, "kind 2 (line extension) has no counterpart in the reference\n");
+      exit(2);
+#endif
     }
     return r;
   };

@@ -85,6 +85,32 @@ def test_edge_residual_and_jacobian_match_oracle(gpu_ctx, orc, edge_type):
                 assert np.abs((ep - em) / (2 * h) - g_jl[:, d]).max() <= 1e-7 * scale
 
 
+@pytest.mark.parametrize("edge_type", [4, 5])
+def test_pose_only_edges_match_oracle(gpu_ctx, orc, edge_type):
+    """g2o::EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose (the edges of FrameOptimization,
+    g2o_optimization.cc:288-333): residual and 2x6 / 3x6 pose Jacobian with the world point held in the edge."""
+    rng = np.random.default_rng(200 + edge_type)
+    n = 64
+    poses, pts, _, mpt, _ = _random_edges(orc, rng, n)
+    meas = mpt[:, :2] if edge_type == 4 else mpt
+    err, Jl, Jp, chi2 = gpu_ctx.eval_edges(edge_type, poses, pts, meas, EUROC_CAMERA)
+    dim = 2 if edge_type == 4 else 3
+    assert not Jl.any()
+    for i in range(n):
+        e, _, jp = orc.edge_eval(edge_type, poses[i], pts[i], meas[i], EUROC_CAMERA)
+        np.testing.assert_allclose(err[i, :dim], e, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(Jp[i, :dim * 6].reshape(dim, 6), jp, rtol=1e-9, atol=1e-9)
+        assert abs(chi2[i] - float(e @ e)) <= 1e-9 * max(1.0, chi2[i])
+        # and against a central difference of the oracle's residual through exp(u) * T
+        h = 1e-6
+        for d in range(6):
+            u = np.zeros(6)
+            u[d] = h
+            ep = orc.edge_eval(edge_type, orc.pose_oplus(poses[i], u), pts[i], meas[i], EUROC_CAMERA)[0]
+            em = orc.edge_eval(edge_type, orc.pose_oplus(poses[i], -u), pts[i], meas[i], EUROC_CAMERA)[0]
+            assert np.abs((ep - em) / (2 * h) - Jp[i, :dim * 6].reshape(dim, 6)[:, d]).max() <= 1e-6 * max(np.abs(jp).max(), 1.0)
+
+
 def test_stereo_bf_float_switch(gpu_ctx, orc):
     rng = np.random.default_rng(7)
     poses, pts, _, mpt, _ = _random_edges(orc, rng, 8)

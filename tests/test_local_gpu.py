@@ -198,6 +198,26 @@ def test_local_large_window_dense_reduced_solve(gpu_ctx, orc, local_path):
     assert np.array_equal(solo.sp_inlier, res.sp_inlier[batch.stereo_pt_begin[1]:])
 
 
+def test_local_c4_full_size_strided_parity(gpu_ctx, orc, local_path):
+    """BASELINE configs[3] at its full size: 1024 C1-shaped windows in ONE batch; every 64th window is checked against
+    the oracle (the whole batch would keep the CPU busy for minutes), and the statistics of all windows must be sane."""
+    if local_path == "persistent":
+        pytest.skip("full-size batch: default path only")
+    n, stride = 1024, 64
+    batch, probs = synth.make_local_batch(4, n)
+    res = gpu_ctx.local_batch(batch)
+    assert (res.stats["iters"][:, 0] > 0).all() and np.isfinite(res.stats["final_chi2"]).all()
+    sample = list(range(0, n, stride))
+    sub = LocalBatch.from_problems([probs[i] for i in sample])
+    # the sampled windows solved alone give bit-identical poses (batch composition does not matter) ...
+    solo = gpu_ctx.local_batch(sub)
+    for k, i in enumerate(sample):
+        a, b = batch.pose_begin[i], batch.pose_begin[i + 1]
+        assert np.array_equal(solo.pose_twc[:, sub.pose_begin[k]:sub.pose_begin[k + 1]], res.pose_twc[:, a:b])
+    # ... and match the oracle at the parity bar
+    _check(orc, [probs[i] for i in sample], sub, solo)
+
+
 def test_local_degenerate_windows(gpu_ctx, orc, local_path):
     """All poses fixed (nothing in the reduced system: only the landmarks move), a single free pose, and a
     window whose only constraints are lines -- each beside a normal window in the same batch."""
