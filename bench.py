@@ -650,8 +650,15 @@ def sub_steps(key, args):
     return args.steps, args.warmup
 
 
+def _log(msg):
+    if os.environ.get("RSPL_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', 0)} t={time.perf_counter():.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    _log("start")
     env = Env(args)
+    _log("env ready")
     multi = env.world > 1
     keys = (ALL_MULTI if multi else ALL_N1) if args.workload == "all" else [args.workload]
     if multi:
@@ -661,7 +668,9 @@ def run_ours(args):
         steps, warmup = (args.steps, args.warmup) if i == 0 else sub_steps(key, args)
         with_cpu = not multi  # the CPU baseline is reported on rank 0 at N = 1 only
         t0 = time.perf_counter()
+        _log(f"workload {key}: steps={steps} warmup={warmup}")
         results[key] = bench_global(env, steps, warmup, with_cpu) if key == "c5" else bench_units(env, key, steps, warmup, with_cpu)
+        _log(f"workload {key} done")
         if env.rank == 0 and results[key] is not None:
             results[key]["bench_wall_s"] = time.perf_counter() - t0
     if env.rank == 0:
