@@ -215,7 +215,7 @@ int64_t rspl_ba_launch_count(const RsplBaContext* ctx);
 int rspl_ba_sync(RsplBaContext* ctx);
 
 /* Per-kernel-class timing with CUDA events on the context stream (what bench.py's roofline uses).
- * Classes: 0 frame_opt, 1 local_setup, 2 local_solve (persistent), 3 init + pair lists, 4 linearize,
+ * Classes: 0 frame_opt, 1 local_setup, 2 (unused), 3 init + pair lists, 4 linearize,
  * 5 pose blocks, 6 Schur prep, 7 Schur reduce, 8 reduced solve, 9 back-substitution / update /
  * evaluation, 10 LM control kernels, 11 flagging + write-back, 12 collectives of the global-BA path,
  * 13 assembly of the dense reduced system + pose update (14-15 reserved, zero). get_profile synchronises the stream, returns milliseconds and launch counts
@@ -246,11 +246,6 @@ int64_t rspl_ba_collective_count(const RsplBaContext* ctx);
 int rspl_ba_global_upload(RsplBaContext* ctx, const RsplLocalBatch* shard);
 int rspl_ba_global_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
 int rspl_ba_global_download(RsplBaContext* ctx, RsplLocalBatchResult* out);
-
-/* Diagnostics: SM cycles per phase of the last local solve summed over windows. out8: 0 linearise,
- * 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky, 5 update/back-substitution/evaluation,
- * 6 LM decision/restore, 7 other. */
-int rspl_ba_local_phase_cycles(RsplBaContext* ctx, double* out8);
 
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono

@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_local_phase_cycles",
+    "rspl_ba_eval_edges", "rspl_ba_oplus",
     "rspl_ba_set_profiling", "rspl_ba_get_profile",
     "rspl_ba_comm_unique_id", "rspl_ba_comm_init", "rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank",
     "rspl_ba_collective_count", "rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download")
@@ -163,8 +163,6 @@ def load_library() -> C.CDLL:
     L.rspl_ba_eval_edges.restype = C.c_int
     L.rspl_ba_oplus.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p, c_f64p]
     L.rspl_ba_oplus.restype = C.c_int
-    L.rspl_ba_local_phase_cycles.argtypes = [ctx, c_f64p]
-    L.rspl_ba_local_phase_cycles.restype = C.c_int
     L.rspl_ba_set_profiling.argtypes = [ctx, C.c_int]
     L.rspl_ba_set_profiling.restype = C.c_int
     L.rspl_ba_get_profile.argtypes = [ctx, c_f64p, C.POINTER(C.c_int64)]
@@ -402,7 +400,7 @@ class Context:
         self.global_solve(opt)
         return self.global_download(self.alloc_local_result(shard))
 
-    PROFILE_CLASSES = ("frame_opt", "local_setup", "local_solve_persistent", "init_pairs", "linearize", "pose_blocks",
+    PROFILE_CLASSES = ("frame_opt", "local_setup", "unused", "init_pairs", "linearize", "pose_blocks",
                        "schur_prep", "schur_reduce", "reduced_solve", "backsub_update_eval", "lm_control", "flag_writeback",
                        "collectives", "dense_assemble", "schur_tile")
 
@@ -415,11 +413,6 @@ class Context:
         n = np.zeros(16, dtype=np.int64)
         self._check(self._L.rspl_ba_get_profile(self._ctx, _p(ms, c_f64p), n.ctypes.data_as(C.POINTER(C.c_int64))))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
-
-    def local_phase_cycles(self) -> np.ndarray:
-        out = np.zeros(8)
-        self._check(self._L.rspl_ba_local_phase_cycles(self._ctx, _p(out, c_f64p)))
-        return out
 
     # ---------------- unit-level ----------------
     def eval_edges(self, edge_type: int, pose7: np.ndarray, lm: np.ndarray, meas: np.ndarray, cam5: np.ndarray,

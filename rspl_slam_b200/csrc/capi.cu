@@ -120,7 +120,7 @@ struct RsplBaContext {
   uint64_t graph_stamp = 0;
   cudaStream_t s_body = nullptr;          // origin stream of the loop-body capture
   int l_graph_launches_step = 0;          // kernels per super-step of the last graph launch (0: not a graph launch)
-  int l_last_path = 0;                  // 1 persistent, 2 batched, 3 batched + dense reduced solve, 4 batched + tiled Schur (diagnostics)
+  int l_last_path = 0;                  // 2 host-driven + legacy Schur kernels, 3 host-driven + dense reduced solve, 4 tiled Schur (diagnostics)
   int l_super_steps = 0;
   // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
   DevBuf dense_buf;

@@ -10,7 +10,6 @@
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
-#include "band_solver.cuh"
 #include <dlfcn.h>
 
 namespace {
@@ -93,7 +92,6 @@ struct DenseLayout {
   // cut into tiles of >= band poses it is block-tridiagonal and its Cholesky factor has no fill outside
   // the tiles: O(n t^2) instead of O(n^3) with library calls on t x t tiles. tile_poses[w] = 0: full dense.
   std::vector<int> tile_poses;
-  std::vector<int> fused_t; // > 0: tile size (unknowns) of the one-launch banded solver (band_solver.cuh)
   // Hand-written cyclic-reduction solver (bcr_solver.cuh): one window whose reduced system is banded within
   // bcr_bsp <= 24 poses and at least 4 super-blocks long. 0: not used.
   int bcr_bsp = 0;
@@ -155,21 +153,9 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
   const size_t o_off = a.take(sizeof(long long) * W);
   // block-tridiagonal decision per window
   L.tile_poses.assign(W, 0);
-  L.fused_t.assign(W, 0);
   L.max_tiles = 0;
-  if (!getenv("RSPL_BA_DENSE_FULL") && getenv("RSPL_BA_BAND_FUSED")) {
-    // narrow band (<= 16 poses): the whole chain of tiles in one launch (band_solver.cuh). Opt-in: measured
-    // on the C5 system (n = 11 994, band 15) it takes 16.8 ms per factorisation + solve against 14.2 ms for
-    // the library-call chain below -- one CTA is latency-bound at ~126 us per tile.
-    for (int w = 0; w < W; ++w) {
-      const int nf = c->l_nf_begin[w + 1] - c->l_nf_begin[w];
-      const int tp = band[w] > 6 ? band[w] : 6;
-      if (6 * tp <= ba::BAND_T_MAX && nf >= 3 * tp) L.fused_t[w] = 6 * tp;
-    }
-  }
   const bool allow_tri = !getenv("RSPL_BA_DENSE_FULL") && cublas_api().ok;
   for (int w = 0; w < W && allow_tri; ++w) {
-    if (L.fused_t[w]) continue;
     const int nf = c->l_nf_begin[w + 1] - c->l_nf_begin[w];
     int min_tp = 64; // tiles of at least 384 unknowns: fewer, larger library calls (the chain of tiles is sequential)
     if (const char* e = getenv("RSPL_BA_TILE_POSES")) min_tp = atoi(e) > 0 ? atoi(e) : min_tp;
@@ -193,7 +179,6 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     o_bGR = a.take(sizeof(double) * bb * bcr_M);
     o_bg = a.take(sizeof(double) * 6 * bcr_bsp * bcr_M);
     L.tile_poses[0] = 0;
-    L.fused_t[0] = 0;
     L.max_tiles = 0;
   }
   const size_t o_tinfo = a.take(sizeof(int) * (L.max_tiles + 1));
@@ -241,7 +226,6 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 4 * s.bs + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
   }
-  CU_TRY(c, cudaFuncSetAttribute(ba::k_band_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::BAND_SMEM));
   if (L.max_tiles > 0) {
     CublasApi& bl = cublas_api();
     if (!c->cublas) {
@@ -326,11 +310,6 @@ int dense_factor_solve(RsplBaContext* c, const DenseLayout& L, const std::vector
     if (n == 0) continue;
     double* A = L.H + L.off[w];
     double* rhs = L.b + (size_t)6 * c->l_nf_begin[w];
-    if (L.fused_t[w] > 0) {
-      ba::k_band_chol_solve<<<1, ba::BAND_THREADS, ba::BAND_SMEM, c->stream>>>(A, rhs, n, L.fused_t[w], L.info + w);
-      c->launches += 1;
-      continue;
-    }
     if (L.tile_poses[w] > 0) {
       // block-tridiagonal Cholesky; column-major lower view M(i, j) = A[j * n + i], i >= j
       CublasApi& bl = cublas_api();

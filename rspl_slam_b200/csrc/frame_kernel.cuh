@@ -193,40 +193,6 @@ BA_DEV void accumulate_pose_dense(const double* J, const double* r, double wo, d
 }
 
 // line edges of a frame (extension): information 0.1 I (g2o_optimization.cc:133,154), line vertex fixed
-template <bool LINEARIZE, bool SINGLE_CAM, bool STEREO>
-BA_DEV void line_pass(const FrameDev& d, const FrameOpt& o, int e0, int e1, const double* R, const double* t, bool robust,
-                      int lane, double* acc) {
-  constexpr int ROWS = STEREO ? 4 : 2, MD = STEREO ? 8 : 4;
-  const int n = STEREO ? d.n_sline : d.n_mline;
-  const double* lw = STEREO ? d.sline_lw : d.mline_lw;
-  const double* ms = STEREO ? d.sline_meas : d.mline_meas;
-  const uint8_t* lvl = STEREO ? d.sline_lvl : d.mline_lvl;
-  const int* cams = STEREO ? d.sline_cam : d.mline_cam;
-  const double delta = STEREO ? o.delta_sline : o.delta_mline;
-  for (int e = e0 + lane; e < e1; e += 32) {
-    if (lvl[e]) continue;
-    Cam camv;
-    if (!SINGLE_CAM) load_cam(d.cameras, cams[e], camv);
-    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
-    double L[6], m[MD], r[4];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) L[q] = lw[(size_t)q * n + e];
-#pragma unroll
-    for (int q = 0; q < MD; ++q) m[q] = ms[(size_t)q * n + e];
-    double Jp[24], Jl[16];
-    if (LINEARIZE) line_linearize<STEREO>(cam, R, t, L, m, r, Jp, Jl);
-    else line_residual<STEREO>(cam, R, t, L, m, r);
-    double chi2 = 0;
-#pragma unroll
-    for (int q = 0; q < ROWS; ++q) chi2 += r[q] * r[q];
-    chi2 *= 0.1;
-    double w = 1.0;
-    const double rho0 = robust ? huber(chi2, delta, w) : chi2;
-    acc[NACC - 1] += rho0;
-    if (LINEARIZE) accumulate_pose_dense<ROWS>(Jp, r, 0.1 * w, acc);
-  }
-}
-
 // Line edges, one lane per residual ROW: a frame has few line edges (60 in config C2) of very different cost (2 or 4
 // rows), so a lane per edge leaves most of the warp idle (one pass over 20 mono + two over 40 stereo edges). Here
 // the item space is 4 rows x (mono + stereo edges) -- rows 2, 3 of a mono edge are empty -- so 32 lanes take 8 whole
@@ -492,12 +458,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
           edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
           if (HAS_LINES) {
-#ifdef RSPL_BA_LINE_PER_EDGE
-            line_pass<true, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, acc);
-            line_pass<true, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, acc);
-#else
             line_pass_rows<true, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, acc);
-#endif
           }
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
@@ -558,12 +519,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
             a2[NACC - 1] = 0;
             edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
             if (HAS_LINES) {
-#ifdef RSPL_BA_LINE_PER_EDGE
-              line_pass<false, SINGLE_CAM, false>(d, o, ml0, ml1, T.R, T.t, robust, lane, a2);
-              line_pass<false, SINGLE_CAM, true>(d, o, sl0, sl1, T.R, T.t, robust, lane, a2);
-#else
               line_pass_rows<false, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, a2);
-#endif
             }
             tempChi = warp_allreduce(a2[NACC - 1]);
           }

@@ -146,12 +146,11 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const size_t o_pout = a.take(sizeof(double) * 7 * NP);
   const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
   const size_t o_err = a.take(sizeof(int) * 4); // error flag, max degree of points / lines
-  const size_t o_phase = a.take(sizeof(long long) * 8 * W);
   const size_t o_sfi = a.take(sizeof(int) * NP);
   const int slot_stride = (max_free + 3) & ~3;
   struct KOff {
     size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
-    size_t meas, info, lm, src, chi2, lvl, Wb, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
+    size_t meas, info, lm, src, chi2, lvl, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
   } ko[2];
   for (int k = 0; k < 2; ++k) {
     const int LD = k ? 4 : 3, SD = k ? 6 : 3, MD = k ? 8 : 3, HD = k ? 10 : 6, WD = 6 * LD;
@@ -173,7 +172,6 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     o.src = a.take(sizeof(int) * ne);
     o.chi2 = a.take(sizeof(double) * ne);
     o.lvl = a.take(ne);
-    o.Wb = a.take(sizeof(double) * WD * ne);
     o.Zb = a.take(sizeof(double) * WD * ne);
     o.ebeg = a.take(sizeof(int) * (nl + 1));
     o.cursor = a.take(sizeof(int) * nl);
@@ -244,7 +242,6 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.stats = (void*)(base + o_stats);
   d.err = (int*)(base + o_err);
   d.maxdeg = d.err + 1;
-  d.phase = (long long*)(base + o_phase);
   d.setup_free_idx = (int*)(base + o_sfi);
   for (int k = 0; k < 2; ++k) {
     ba::KindDev& kd = d.k[k];
@@ -268,7 +265,6 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     kd.src = (int*)(base + o.src);
     kd.chi2 = (double*)(base + o.chi2);
     kd.lvl = (uint8_t*)(base + o.lvl);
-    kd.W = (double*)(base + o.Wb);
     kd.Z = (double*)(base + o.Zb);
     kd.ebeg = (int*)(base + o.ebeg);
     kd.cursor = (int*)(base + o.cursor);
@@ -1030,7 +1026,6 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
   lo.bf_float = opt->stereo_bf_float;
   lo.max_poses = c->l_max_poses;
   lo.max_free = c->l_max_free_poses;
-  const size_t smem = ba::local_smem_bytes(lo.max_poses, lo.max_free);
   if (c->l_n_windows > 65535) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: more than 65535 windows in one call");
   c->l_graph_launches_step = 0;
   {
@@ -1042,26 +1037,8 @@ extern "C" int rspl_ba_local_batch_solve(RsplBaContext* c, const RsplBaOptions* 
     enqueue_local_setup(c, c->stream);
   }
   CU_TRY(c, cudaGetLastError());
-  // Path: one kernel per LM phase over all windows (local_batched.cuh) is the default for every batch
-  // size: measured on B200 it is 5x (C1) to 9x (C3) faster than the one-CTA-per-window persistent
-  // kernel even for a single window (5.8 ms vs 30 ms), because a lone CTA of 256 threads cannot hide
-  // the latency of its dependent loads. The persistent kernel (whole LM loop in one launch, zero host
-  // involvement) stays selectable with RSPL_BA_LOCAL_PATH=persistent; the tests run both.
-  bool batched = true;
-  if (const char* env = getenv("RSPL_BA_LOCAL_PATH")) {
-    if (!strcmp(env, "persistent")) batched = false;
-    else if (!strcmp(env, "batched")) batched = true;
-  }
-  if (batched || c->global_mode || smem > c->smem_optin || lo.max_poses > 255) return local_solve_batched(c, lo);
-  c->l_last_path = 1;
-  CU_TRY(c, cudaFuncSetAttribute(ba::local_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope ps(c, PC_LOCAL_PERSISTENT);
-    ba::local_solve_kernel<<<c->l_n_windows, ba::LOCAL_THREADS, smem, c->stream>>>(c->ld, lo);
-  }
-  c->launches++;
-  CU_TRY(c, cudaGetLastError());
-  return RSPL_BA_OK;
+  // host-driven path: profiling, dense reduced systems (large windows, global BA)
+  return local_solve_batched(c, lo);
 }
 
 extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResult* out) {
@@ -1129,21 +1106,4 @@ extern "C" int rspl_ba_global_solve(RsplBaContext* c, const RsplBaOptions* opt) 
 }
 extern "C" int rspl_ba_global_download(RsplBaContext* c, RsplLocalBatchResult* out) {
   return rspl_ba_local_batch_download(c, out);
-}
-
-// Diagnostics: cycles per phase of the last local solve, summed over windows (thread-0 clock64
-// deltas): 0 linearise (landmark-major), 1 pose blocks, 2 Schur prep, 3 Schur reduce, 4 Cholesky,
-// 5 update + back-substitution + evaluation, 6 LM decision / restore, 7 everything else.
-extern "C" int rspl_ba_local_phase_cycles(RsplBaContext* c, double* out8) {
-  if (!c || !out8) return RSPL_BA_ERR_INVALID;
-  if (!c->local_solved) return fail(c, RSPL_BA_ERR_STATE, "local_phase_cycles before solve");
-  for (int i = 0; i < 8; ++i) out8[i] = 0;
-  if (c->l_n_windows == 0) return RSPL_BA_OK;
-  SetDevice guard(c->device);
-  std::vector<long long> h((size_t)8 * c->l_n_windows);
-  CU_TRY(c, cudaMemcpyAsync(h.data(), c->ld.phase, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  for (int w = 0; w < c->l_n_windows; ++w)
-    for (int i = 0; i < 8; ++i) out8[i] += (double)h[(size_t)w * 8 + i];
-  return RSPL_BA_OK;
 }

@@ -160,9 +160,9 @@ def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
     assert np.abs(res.pose_twc[:3].T - ref.pose_p).max() < 1e-9
     assert list(res.stats["iters"][0][:2]) == st["iters"][:2] and list(res.stats["trials"][0][:2]) == st["trials"][:2]
     assert abs(res.stats["final_chi2"][0] - st["final_chi2"]) <= 1e-9 * st["final_chi2"]
-    # the same system through the one-launch banded solver (band_solver.cuh, opt-in) and through the full dense
-    # factorisation
-    for var in ("RSPL_BA_BAND_FUSED", "RSPL_BA_DENSE_FULL"):
+    # (the default above is the hand-written cyclic-reduction solver, bcr_solver.cuh) the same system through the
+    # library tile chain (cuSOLVER / cuBLAS on block-tridiagonal tiles) and through the full dense factorisation
+    for var in ("RSPL_BA_DENSE_LIB", "RSPL_BA_DENSE_FULL"):
         monkeypatch.setenv(var, "1")
         other = gpu_ctx.local_batch(batch)
         monkeypatch.delenv(var)

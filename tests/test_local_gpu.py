@@ -13,11 +13,13 @@ from rspl_slam_b200.problem import LocalBatch, OptimizationConfig
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["persistent", "batched"])
+@pytest.fixture(autouse=True, params=["graph", "host"])
 def local_path(request, monkeypatch):
-    """Every test runs through both device paths: the one-CTA-per-window persistent kernel and
-    the batched one-kernel-per-phase path (selected by batch size in production)."""
-    monkeypatch.setenv("RSPL_BA_LOCAL_PATH", request.param)
+    """Every test runs through both drivers of the same kernels: the cached whole-schedule CUDA graph with device-side
+    loop conditions (default) and the host-driven super-step loop (profiling / dense path). The results are bitwise
+    identical; windows whose reduced system does not fit shared memory take the host-driven dense path either way."""
+    if request.param == "host":
+        monkeypatch.setenv("RSPL_BA_GRAPH", "off")
     return request.param
 
 
@@ -181,8 +183,6 @@ def test_local_large_window_dense_reduced_solve(gpu_ctx, orc, local_path):
     """Windows whose reduced camera system (6 x free poses) exceeds shared memory keep it in HBM and
     factorise it with the dense path (dense_solver.inl) -- the single-GPU end of SURVEY 8(e) C5.
     40 and 48 keyframes: n = 234 / 282 (shared memory holds n <= ~160)."""
-    if local_path == "persistent":
-        pytest.skip("the persistent kernel is limited to reduced systems that fit shared memory")
     probs = [synth.make_local_problem(synth.config_seed(5, 1), n_kf=40, n_points=5000, n_lines=500, loops=1),
              synth.make_local_problem(synth.config_seed(5, 2), n_kf=48, n_points=4000, n_lines=300)]
     batch = LocalBatch.from_problems(probs)
@@ -201,8 +201,8 @@ def test_local_large_window_dense_reduced_solve(gpu_ctx, orc, local_path):
 def test_local_c4_full_size_strided_parity(gpu_ctx, orc, local_path):
     """BASELINE configs[3] at its full size: 1024 C1-shaped windows in ONE batch; every 64th window is checked against
     the oracle (the whole batch would keep the CPU busy for minutes), and the statistics of all windows must be sane."""
-    if local_path == "persistent":
-        pytest.skip("full-size batch: default path only")
+    if local_path == "host":
+        pytest.skip("full-size batch: default driver only")
     n, stride = 1024, 64
     batch, probs = synth.make_local_batch(4, n)
     res = gpu_ctx.local_batch(batch)
