@@ -58,7 +58,7 @@ __device__ __forceinline__ bool bcr_chol6(const double* Ls, int ld, int k0, doub
     double dsum = Lk[j][j];
 #pragma unroll
     for (int p = 0; p < j; ++p) dsum -= Lk[j][p] * Lk[j][p];
-    if (!(dsum > 0.0)) ok = false;
+    if (dsum <= 0.0) ok = false; // (NaN falls through, like Eigen's LLT test)
     const double rs = rsqrt(dsum);
     inv[j] = rs;
     Lk[j][j] = dsum * rs;

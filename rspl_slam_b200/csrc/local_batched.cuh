@@ -79,6 +79,8 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   int* n_ne;       // [W]
   int* ne_flag;    // [W][Pmax] scratch: 1 = keep
   int* diag_pos;   // [NF] list position of the diagonal pair of a free pose
+  int2* blk;       // [W][Pmax] per compact pair and pass: x = si | sj << 16 (block coordinates in the reduced system) or -1,
+                   //           y = free-pose offset f0 + fi for a diagonal pair, else -1 (kb_pair_blocks)
   int2* pairs_tmp; // scratch of the same size (landmark-driven builder of large windows), may be null
   int* pair_cursor; // [W][2*Pmax] scratch of that builder
   const long long* pair_base; // [W+1] region of each window inside `pairs`
@@ -520,6 +522,17 @@ __global__ void __launch_bounds__(128) kb_begin_pass(const __grid_constant__ Loc
   s.stage = s.iters > 0 ? STAGE_NEED_LIN : STAGE_DONE;
 }
 
+// block coordinates of the compact pairs in this pass's reduced system; grid (ceil(Pmax / 256), windows)
+__global__ void __launch_bounds__(256) kb_pair_blocks(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
+  const int w = blockIdx.y, li = blockIdx.x * 256 + threadIdx.x;
+  if (li >= b.n_ne[w]) return;
+  const int f0 = b.nf_begin[w];
+  int fi, fj;
+  pair_decode(b.ne_list[(size_t)w * b.Pmax + li], b.ws[w].nf, fi, fj);
+  const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
+  b.blk[(size_t)w * b.Pmax + li] = make_int2((si < 0 || sj < 0) ? -1 : (si | (sj << 16)), fi == fj ? f0 + fi : -1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1: linearise, one thread per landmark (edges of a landmark in g2o order)
 // ------------------------------------------------------------------------------------------------
@@ -538,15 +551,33 @@ BA_DEV void linearize_one(const LocalDev& d, const BatchDev& b, const LocalOpt& 
 #pragma unroll
   for (int q = 0; q < T::LD; ++q) bb[q] = 0;
   const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  // the record of the next edge is requested before this one is evaluated (the landmarks of a warp have the same
+  // degree, so the loop is latency- rather than divergence-bound)
+  int info_n = 0;
+  unsigned char lvl_n = 1;
+  double m_n[T::MD];
+  if (ea < eb) {
+    lvl_n = k.lvl[ea];
+    info_n = k.info[ea];
+    load_edge<KIND>(k, ea, m_n);
+  }
   for (int e = ea; e < eb; ++e) {
-    if (k.lvl[e]) continue;
-    const int info = k.info[e];
+    const int info = info_n;
+    const bool skip = lvl_n != 0;
+    double m[T::MD];
+#pragma unroll
+    for (int q = 0; q < T::MD; ++q) m[q] = m_n[q];
+    if (e + 1 < eb) {
+      lvl_n = k.lvl[e + 1];
+      info_n = k.info[e + 1];
+      load_edge<KIND>(k, e + 1, m_n);
+    }
+    if (skip) continue;
     const int p = info & 0xffff;
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
-    double m[T::MD], r[4], Jp[24], Jl[16];
-    load_edge<KIND>(k, e, m);
+    double r[4], Jp[24], Jl[16];
     eval_edge<KIND, true>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, m, r,
                           Jp, Jl);
     const double c2 = edge_chi2<KIND>(r);
@@ -1010,49 +1041,6 @@ __global__ void __launch_bounds__(32) kb_schur_reduce(const __grid_constant__ Lo
   }
 }
 
-// Right-looking upper Cholesky of the reduced system by the WHOLE CTA (warp per trailing row, lanes over its
-// columns; three barriers per pivot). The right-hand side rides along as one more column, so U^T y = bs is solved
-// by the same sweep; the back substitution U x = y is left to warp 0 (column-oriented, reciprocal diagonal kept
-// from the factorisation). The per-element update order is p = 0, 1, ... like the sequential algorithm.
-// Fails iff a pivot <= 0 (§9.11). `x` doubles as y; `dinv` [n] scratch.
-BA_DEV void cholesky_solve_cta(double* A, const double* bs, double* x, double* dinv, int n, int* s_flag) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  if (tid == 0) *s_flag = 1;
-  for (int i = tid; i < n; i += blockDim.x) x[i] = bs[i];
-  __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    const double dk = A[(size_t)k * n + k];
-    if (dk <= 0.0) { // uniform: every thread reads the same pivot
-      if (tid == 0) *s_flag = 0;
-      break;
-    }
-    const double inv = rsqrt(dk);
-    const double yk = x[k] * inv;
-    __syncthreads(); // everyone has read the pivot and x[k] before they are overwritten
-    for (int j = k + tid; j < n; j += blockDim.x) A[(size_t)k * n + j] = (j == k) ? dk * inv : A[(size_t)k * n + j] * inv;
-    if (tid == 0) {
-      x[k] = yk;
-      dinv[k] = inv;
-    }
-    __syncthreads();
-    for (int i = k + 1 + warp; i < n; i += nwarps) {
-      const double uki = A[(size_t)k * n + i];
-      for (int j = i + lane; j < n; j += 32) A[(size_t)i * n + j] -= uki * A[(size_t)k * n + j];
-      if (lane == 0) x[i] -= uki * yk;
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (!*s_flag || tid >= 32) return;
-  for (int i = n - 1; i >= 0; --i) { // U x = y
-    const double xi = x[i] * dinv[i];
-    __syncwarp();
-    if (lane == 0) x[i] = xi;
-    for (int j = lane; j < i; j += 32) x[j] -= A[(size_t)j * n + i] * xi;
-    __syncwarp();
-  }
-}
-
 // Tables of the tiled Schur path (local_tiled.cuh): landmark tiles sized by shared memory, their slices of the
 // pair lists, the per-tile partial reduced systems.
 struct TileDev {
@@ -1082,45 +1070,51 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   if (s.stage != STAGE_NEED_TRIAL) return;
   const int nf = s.nf, f0 = b.nf_begin[w], p0 = d.pose_begin[w];
   const int n = 6 * s.n_sys;
+  // lower triangle, row-major with an odd leading dimension (conflict-free rows and columns); the 6 x 6-blocked
+  // factorisation and the two sweeps are bcr_solver.cuh's shared-memory routines
+  const int ld = n + 1;
   double* Hs = reinterpret_cast<double*>(smem_raw);
-  double* bs = Hs + (size_t)n * n;
-  double* xs = bs + n;
-  double* dinv = xs + n;     // [n] reciprocal diagonal of the factor
+  double* xs = Hs + (size_t)n * ld;
+  double* dinv = xs + n;      // [n] reciprocal diagonal of the factor
   double* sc_part = dinv + n; // [nf] pose part of the LM scale
   __shared__ int s_ok;
+  __shared__ int s_fail;
   const double lambda = s.lambda;
-  // assemble upper blocks: zero background, then the pairs of the compact list
-  for (int idx = tid; idx < n * n; idx += blockDim.x) Hs[idx] = 0.0;
+  // assemble: zero background, then the pairs of the compact list (block (si, sj), si <= sj, goes to the lower
+  // triangle as its transpose)
+  for (int idx = tid; idx < n * ld; idx += blockDim.x) Hs[idx] = 0.0;
+  if (tid == 0) s_fail = 0;
   __syncthreads();
   const int n_ne = b.n_ne[w];
-  const int* list = b.ne_list + (size_t)w * b.Pmax;
+  const int2* blk = b.blk + (size_t)w * b.Pmax;
   for (int idx = tid; idx < n_ne * 36; idx += blockDim.x) {
-    const int li = idx / 36, rc = idx % 36, r = rc / 6, c = rc % 6;
-    const int p = list[li];
-    int fi, fj;
-    pair_decode(p, nf, fi, fj);
-    const int si = b.sys_idx[f0 + fi], sj = b.sys_idx[f0 + fj];
-    if (si < 0 || sj < 0) continue;
+    const int li = idx / 36, rc = idx - 36 * li, r = rc / 6, c = rc - 6 * r;
+    const int2 bk = blk[li];
+    if (bk.x < 0) continue;
+    const int si = bk.x & 0xffff, sj = bk.x >> 16;
     double v = -b.hs_part[((size_t)w * b.Pmax + li) * 42 + rc];
-    if (fi == fj) {
-      const int rr = r < c ? r : c, cc = r < c ? c : r;
-      v += b.Hpp[(size_t)(f0 + fi) * 21 + up6(rr, cc)] + (r == c ? lambda : 0.0);
+    if (bk.y >= 0) { // diagonal pair: only r <= c is meaningful (and only the lower triangle of Hs is read)
+      if (r > c) continue;
+      v += b.Hpp[(size_t)bk.y * 21 + up6(r, c)] + (r == c ? lambda : 0.0);
     }
-    Hs[(size_t)(6 * si + r) * n + 6 * sj + c] = v;
+    Hs[(size_t)(6 * sj + c) * ld + 6 * si + r] = v;
   }
   for (int idx = tid; idx < nf * 6; idx += blockDim.x) {
-    const int fi = idx / 6, r = idx % 6;
+    const int fi = idx / 6, r = idx - 6 * fi;
     const int si = b.sys_idx[f0 + fi];
     if (si < 0) continue;
     const int li = b.diag_pos[f0 + fi];
-    bs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r];
+    xs[6 * si + r] = b.bp[(size_t)(f0 + fi) * 6 + r] - b.hs_part[((size_t)w * b.Pmax + li) * 42 + 36 + r];
   }
   __syncthreads();
-  __shared__ int s_chol;
   if (n > 0) {
-    cholesky_solve_cta(Hs, bs, xs, dinv, n, &s_chol);
+    bcr_cta_cholesky(Hs, ld, n, dinv, &s_fail); // fails iff a pivot <= 0, like LinearSolverEigen (§9.11)
+    if (!s_fail) {
+      bcr_cta_forward(Hs, ld, dinv, n, xs, 1, 1);
+      if (tid < 32) bcr_warp_backward(Hs, ld, dinv, n, xs);
+    }
     __syncthreads();
-    if (tid == 0) s_ok = s_chol && !s.prep_fail;
+    if (tid == 0) s_ok = !s_fail && !s.prep_fail;
   } else if (tid == 0) {
     s_ok = !s.prep_fail;
   }

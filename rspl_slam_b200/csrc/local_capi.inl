@@ -339,6 +339,7 @@ int batched_prepare(RsplBaContext* c) {
   const size_t o_ne_flag = a.take(sizeof(int) * (size_t)W * (Pmax > 0 ? Pmax : 1));
   const size_t o_n_ne = a.take(sizeof(int) * W);
   const size_t o_diag_pos = a.take(sizeof(int) * (NF + 1));
+  const size_t o_blk = a.take(sizeof(int2) * (size_t)W * (Pmax > 0 ? Pmax : 1));
   const size_t o_pairs_tmp = big_pairs ? a.take(sizeof(int2) * (size_t)(n_pairs + 1)) : 0;
   const size_t o_cursor = big_pairs ? a.take(sizeof(int) * (size_t)W * 2 * (Pmax > 0 ? Pmax : 1)) : 0;
   const size_t o_pbase = a.take(sizeof(long long) * (W + 1));
@@ -381,6 +382,7 @@ int batched_prepare(RsplBaContext* c) {
   b.ne_flag = (int*)(base + o_ne_flag);
   b.n_ne = (int*)(base + o_n_ne);
   b.diag_pos = (int*)(base + o_diag_pos);
+  b.blk = (int2*)(base + o_blk);
   b.pairs_tmp = big_pairs ? (int2*)(base + o_pairs_tmp) : nullptr;
   b.pair_cursor = big_pairs ? (int*)(base + o_cursor) : nullptr;
   b.pair_base = (const long long*)(base + o_pbase);
@@ -580,6 +582,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
       cudaMemsetAsync(b.pact_w, 0, sizeof(int) * (size_t)c->l_np, s);
       if (b.C) GK(s, ba::kb_mark_active, g_lm, ba::BT, 0, d, b);
       GK(s, ba::kb_begin_pass, g_win, 128, 0, d, b, lo, pass);
+      GK(s, ba::kb_pair_blocks, dim3((b.Pmax + 255) / 256, W), 256, 0, d, b);
       // WHILE node: created by hand behind the nodes captured so far, its body captured from s_body
       cudaStreamCaptureStatus st;
       cudaGraph_t g = nullptr;
@@ -962,6 +965,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       if (coll_rc != RSPL_BA_OK) return coll_rc;
     }
     LAUNCH(PC_CONTROL, ba::kb_begin_pass, g_win, 128, 0, d, b, lo, pass);
+    LAUNCH(PC_CONTROL, ba::kb_pair_blocks, dim3((b.Pmax + 255) / 256, W), 256, 0, d, b);
     if (dense) { // the host needs the system sizes of this pass for the library calls
       std::vector<ba::WinState> ws(W);
       CU_TRY(c, cudaMemcpyAsync(ws.data(), b.ws, sizeof(ba::WinState) * W, cudaMemcpyDeviceToHost, s));
