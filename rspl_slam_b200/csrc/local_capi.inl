@@ -148,6 +148,16 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   const size_t o_err = a.take(sizeof(int) * 4); // error flag, max degree of points / lines
   const size_t o_sfi = a.take(sizeof(int) * NP);
   const int slot_stride = (max_free + 3) & ~3;
+  // large-window setup variants (local_kernel.cuh): multi-CTA landmark ordering, pose lists by scatter + sort
+  const int max_lm_w = c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns;
+  const bool big_order = max_lm_w > 16384, big_pose = max_poses > 64;
+  const int order_chunks = big_order ? (max_lm_w + ba::ORDER_CHUNK - 1) / ba::ORDER_CHUNK : 0;
+  const size_t o_ohist = big_order ? a.take(sizeof(int) * (size_t)W * 2 * order_chunks * 256) : 0;
+  size_t o_pcur[2] = {0, 0}, o_ptmp[2] = {0, 0};
+  for (int k = 0; k < 2 && big_pose; ++k) {
+    o_pcur[k] = a.take(sizeof(int) * (size_t)NP);
+    o_ptmp[k] = a.take(sizeof(int) * ((size_t)n_cls[k][0] + n_cls[k][1] + 1));
+  }
   struct KOff {
     size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
     size_t meas, info, lm, src, chi2, lvl, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
@@ -243,6 +253,12 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   d.err = (int*)(base + o_err);
   d.maxdeg = d.err + 1;
   d.setup_free_idx = (int*)(base + o_sfi);
+  d.order_hist = big_order ? (int*)(base + o_ohist) : nullptr;
+  d.order_chunks = order_chunks;
+  for (int k = 0; k < 2; ++k) {
+    d.pose_cursor[k] = big_pose ? (int*)(base + o_pcur[k]) : nullptr;
+    d.plist_tmp[k] = big_pose ? (int*)(base + o_ptmp[k]) : nullptr;
+  }
   for (int k = 0; k < 2; ++k) {
     ba::KindDev& kd = d.k[k];
     const KOff& o = ko[k];
@@ -474,15 +490,35 @@ void enqueue_local_setup(RsplBaContext* c, cudaStream_t s) {
   const dim3 g_l((max_lm + T - 1) / T > 0 ? (max_lm + T - 1) / T : 1, W, 2);
   ba::setup_poses<<<W, T, 0, s>>>(c->ld);
   ba::setup_edges<0><<<g_e, T, 0, s>>>(c->ld);
-  ba::setup_order<<<dim3(W, 2), T, 0, s>>>(c->ld);
+  if (c->ld.order_hist) { // large windows: the counting sort spread over 1024-landmark chunks (same result)
+    const dim3 g_c(c->ld.order_chunks, W, 2);
+    ba::setup_order_hist<<<g_c, T, 0, s>>>(c->ld);
+    ba::setup_order_offsets<<<dim3(W, 2), 256, 0, s>>>(c->ld);
+    ba::setup_order_place<<<g_c, T, 0, s>>>(c->ld);
+    c->launches += 2;
+  } else {
+    ba::setup_order<<<dim3(W, 2), T, 0, s>>>(c->ld);
+  }
   ba::setup_scan<<<dim3(W, 2), 1024, 0, s>>>(c->ld);
   ba::setup_edges<1><<<g_e, T, 0, s>>>(c->ld);
   ba::setup_landmarks<<<g_l, T, 0, s>>>(c->ld);
   ba::setup_gather<<<g_e, T, 0, s>>>(c->ld);
   const dim3 g_pl(c->l_max_poses, W, 2);
-  ba::setup_pose_lists<0><<<g_pl, T, 0, s>>>(c->ld);
-  ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, s>>>(c->ld);
-  ba::setup_pose_lists<1><<<g_pl, T, 0, s>>>(c->ld);
+  if (c->ld.pose_cursor[0]) { // large windows: count / scatter per pose with integer atomics, then sort every list (same result)
+    for (int k = 0; k < 2; ++k) {
+      cudaMemsetAsync(c->ld.k[k].pbeg, 0, sizeof(int) * ((size_t)c->l_np + 1), s);
+      cudaMemsetAsync(c->ld.pose_cursor[k], 0, sizeof(int) * (size_t)c->l_np, s);
+    }
+    ba::setup_pose_scatter<0><<<g_e, T, 0, s>>>(c->ld);
+    ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, s>>>(c->ld);
+    ba::setup_pose_scatter<1><<<g_e, T, 0, s>>>(c->ld);
+    ba::setup_pose_sort<<<g_pl, T, 0, s>>>(c->ld);
+    c->launches += 1;
+  } else {
+    ba::setup_pose_lists<0><<<g_pl, T, 0, s>>>(c->ld);
+    ba::setup_pose_scan<<<(2 * W + 127) / 128, 128, 0, s>>>(c->ld);
+    ba::setup_pose_lists<1><<<g_pl, T, 0, s>>>(c->ld);
+  }
   c->launches += 10;
 }
 

@@ -87,6 +87,11 @@ struct LocalDev {
   int slot_stride;  // >= max free poses per window
   int use_slots;    // the landmark x free-pose slot table is in use (windows of <= 64 free poses): degrees <= 254
   int* setup_free_idx; // [n_poses] window-local free index or -1 (scratch of the setup kernel)
+  // scratch of the large-window setup variants (null when the batch has no large window)
+  int* order_hist;     // [(w*2+kind)][order_chunks][256] degree histograms per 1024-landmark chunk -> bucket offsets
+  int order_chunks;
+  int* pose_cursor[2]; // [n_poses] per kind: fill cursors of the pose-major lists
+  int* plist_tmp[2];   // [n_edge] per kind: scratch of the list sort
   KindDev k[2];
   void* stats;
   int* err; // device error flag
@@ -195,6 +200,88 @@ __global__ void __launch_bounds__(LOCAL_THREADS) setup_order(const __grid_consta
     }
     __syncthreads();
     if (dg >= 0 && rank == total - 1) s_start[bk] += total; // the last landmark of the bucket in this chunk advances it
+    __syncthreads();
+  }
+}
+
+// ---- the same stable counting sort for LARGE windows (global BA: 10^6 landmarks in one window), spread over
+// 1024-landmark chunks: histogram per chunk -> per-bucket offsets of every chunk -> placement per chunk. The result is
+// identical to setup_order's.
+constexpr int ORDER_CHUNK = 1024;
+// grid (chunks, windows, kinds), 256 threads
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_order_hist(const __grid_constant__ LocalDev d) {
+  __shared__ int s_h[256];
+  const int c = blockIdx.x, w = blockIdx.y, kind = blockIdx.z, tid = threadIdx.x;
+  const KindDev& k = d.k[kind];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  s_h[tid] = 0;
+  __syncthreads();
+  for (int i = c * ORDER_CHUNK + tid; i < nl && i < (c + 1) * ORDER_CHUNK; i += LOCAL_THREADS) {
+    const int dg = k.cursor[l0 + i];
+    atomicAdd(&s_h[dg < 255 ? dg : 255], 1);
+  }
+  __syncthreads();
+  d.order_hist[((size_t)(w * 2 + kind) * d.order_chunks + c) * 256 + tid] = s_h[tid];
+}
+// histograms -> first internal index of every (chunk, bucket), largest degree first; grid (windows, kinds), 256 threads
+__global__ void __launch_bounds__(256) setup_order_offsets(const __grid_constant__ LocalDev d) {
+  __shared__ int s_start[256];
+  const int w = blockIdx.x, kind = blockIdx.y, b = threadIdx.x;
+  const KindDev& k = d.k[kind];
+  const int nl = k.lm_begin[w + 1] - k.lm_begin[w];
+  const int nc = (nl + ORDER_CHUNK - 1) / ORDER_CHUNK;
+  int* h = d.order_hist + (size_t)(w * 2 + kind) * d.order_chunks * 256;
+  int tot = 0;
+  for (int c = 0; c < nc; ++c) tot += h[(size_t)c * 256 + b];
+  s_start[b] = tot;
+  __syncthreads();
+  if (b == 0) {
+    int run = 0;
+    for (int q = 255; q >= 0; --q) {
+      const int cnt = s_start[q];
+      s_start[q] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+  int run = s_start[b];
+  for (int c = 0; c < nc; ++c) {
+    const int cnt = h[(size_t)c * 256 + b];
+    h[(size_t)c * 256 + b] = run;
+    run += cnt;
+  }
+}
+// placement of one chunk (four rounds of 256 landmarks, stable inside the chunk); grid (chunks, windows, kinds)
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_order_place(const __grid_constant__ LocalDev d) {
+  __shared__ int s_start[256];
+  __shared__ int s_deg[LOCAL_THREADS];
+  const int c = blockIdx.x, w = blockIdx.y, kind = blockIdx.z, tid = threadIdx.x;
+  const KindDev& k = d.k[kind];
+  const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
+  if (c * ORDER_CHUNK >= nl) return;
+  s_start[tid] = d.order_hist[((size_t)(w * 2 + kind) * d.order_chunks + c) * 256 + tid];
+  __syncthreads();
+  const int end = nl < (c + 1) * ORDER_CHUNK ? nl : (c + 1) * ORDER_CHUNK;
+  for (int base = c * ORDER_CHUNK; base < end; base += LOCAL_THREADS) {
+    const int i = base + tid;
+    const int dg = i < end ? k.cursor[l0 + i] : -1;
+    const int bk = dg < 255 ? dg : 255;
+    s_deg[tid] = dg < 0 ? -1 : bk;
+    __syncthreads();
+    int rank = 0, total = 0;
+    if (dg >= 0) {
+      for (int t2 = 0; t2 < LOCAL_THREADS; ++t2) {
+        const int same = s_deg[t2] == bk ? 1 : 0;
+        total += same;
+        rank += t2 < tid ? same : 0;
+      }
+      const int pos = s_start[bk] + rank;
+      k.newidx[l0 + i] = pos;
+      k.orig[l0 + pos] = i;
+      k.ebeg[l0 + pos] = dg;
+    }
+    __syncthreads();
+    if (dg >= 0 && rank == total - 1) s_start[bk] += total;
     __syncthreads();
   }
 }
@@ -382,6 +469,71 @@ __global__ void __launch_bounds__(128) setup_pose_scan(const __grid_constant__ L
     run += cnt;
   }
   if (w == d.n_windows - 1) k.pbeg[d.n_poses] = k.n_edge;
+}
+
+// ---- pose-major lists of LARGE windows (hundreds of poses): setup_pose_lists costs O(poses x edges); here the edges
+// are counted and scattered per pose with integer atomics (arbitrary order) and every list is then sorted ascending,
+// which makes the result identical to setup_pose_lists' and deterministic.
+// MODE 0 counts into pbeg (zeroed by the host), MODE 1 scatters behind pose_cursor (zeroed by the host);
+// grid (edge chunks, windows, kinds)
+template <int MODE>
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_pose_scatter(const __grid_constant__ LocalDev d) {
+  const int w = blockIdx.y, kind = blockIdx.z;
+  const KindDev& k = d.k[kind];
+  const int e0 = edge_base(k, w), ne = edge_base(k, w + 1) - e0;
+  const int i = blockIdx.x * LOCAL_THREADS + threadIdx.x;
+  if (i >= ne) return;
+  const int p = d.pose_begin[w] + (k.info[e0 + i] & 0xffff);
+  if (MODE == 0) {
+    atomicAdd(&k.pbeg[p], 1);
+  } else {
+    const int pos = atomicAdd(&d.pose_cursor[kind][p], 1);
+    k.plist[k.pbeg[p] + pos] = e0 + i;
+  }
+}
+// ascending sort of one pose's list: bitonic in shared memory up to POSE_SORT_CAP entries, rank sort through
+// plist_tmp beyond; grid (poses, windows, kinds), 256 threads
+constexpr int POSE_SORT_CAP = 8192;
+__global__ void __launch_bounds__(LOCAL_THREADS) setup_pose_sort(const __grid_constant__ LocalDev d) {
+  __shared__ int s_v[POSE_SORT_CAP];
+  const int p = blockIdx.x, w = blockIdx.y, kind = blockIdx.z, tid = threadIdx.x;
+  const KindDev& k = d.k[kind];
+  const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
+  if (p >= np) return;
+  const int a = k.pbeg[p0 + p], n = k.pbeg[p0 + p + 1] - a;
+  if (n < 2) return;
+  int* seg = k.plist + a;
+  if (n <= POSE_SORT_CAP) {
+    int N = 1;
+    while (N < n) N <<= 1;
+    for (int i = tid; i < N; i += LOCAL_THREADS) s_v[i] = i < n ? seg[i] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= N; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < N / 2; i += LOCAL_THREADS) {
+          const int lo = 2 * i - (i & (stride - 1)); // index with bit `stride` cleared
+          const int hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const int x = s_v[lo], y = s_v[hi];
+          if ((x > y) == up) {
+            s_v[lo] = y;
+            s_v[hi] = x;
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < n; i += LOCAL_THREADS) seg[i] = s_v[i];
+  } else {
+    int* tmp = d.plist_tmp[kind] + a;
+    for (int i = tid; i < n; i += LOCAL_THREADS) {
+      const int v = seg[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += seg[j] < v ? 1 : 0;
+      tmp[rank] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += LOCAL_THREADS) seg[i] = tmp[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
