@@ -773,7 +773,8 @@ __global__ void eval_edges_kernel(int type, int n, const double* pose7, const do
     double Xc[3];
     transform_point(R, t, X, Xc);
     if (type == 1 || type == 5) {
-      const double bf_res = bf_float ? (double)(float)cam.bf : cam.bf;
+      // (the `const float& bf` of EdgeStereoSE3ProjectXYZ::cam_project; the pose-only edge keeps bf a double)
+      const double bf_res = (bf_float && !only_pose) ? (double)(float)cam.bf : cam.bf;
       point_residual<true>(cam, bf_res, Xc, m, r);
       point_jac_pose<true>(cam, Xc, jp);
       double j9[9];

@@ -536,34 +536,17 @@ BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& 
 #pragma unroll
   for (int a = 0; a < LD; ++a) u[a] = 0.0;
   const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
-  // (the record of the next edge is requested before this one is evaluated; the records are kept for the second loop)
-  int info_n = 0;
-  unsigned char lvl_n = 1;
-  double m_n[T::MD];
-  if (ea < eb) {
-    lvl_n = k.lvl[ea];
-    info_n = k.info[ea];
-    load_edge<KIND>(k, ea, m_n);
-  }
   for (int e = ea; e < eb; ++e) {
-    const int info = info_n;
-    const bool skip = lvl_n != 0;
-    double m[T::MD];
-#pragma unroll
-    for (int q = 0; q < T::MD; ++q) m[q] = m_n[q];
-    if (e + 1 < eb) {
-      lvl_n = k.lvl[e + 1];
-      info_n = k.info[e + 1];
-      load_edge<KIND>(k, e + 1, m_n);
-    }
-    if (skip) continue;
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
     const int p = info & 0xffff;
     const int fi = b.free_idx[p0 + p];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
-    double r[4], Jp[24], Jl[16];
+    double m[T::MD], r[4], Jp[24], Jl[16];
+    load_edge<KIND>(k, e, m);
     eval_edge<KIND, true>(cam, o.bf_float, stereo, td.P_bR + 9 * (size_t)(p0 + p), b.P_bt + 3 * (size_t)(p0 + p), X, m, r, Jp, Jl);
     double wgt = 1.0;
     if (robust) huber(edge_chi2<KIND>(r), o.delta[2 * KIND + (stereo ? 1 : 0)], wgt);
@@ -618,28 +601,15 @@ BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& 
   }
 #pragma unroll
   for (int q = 0; q < T::SD; ++q) k.x[(size_t)q * k.n_lm + l] = Xn[q];
-  if (ea < eb) {
-    lvl_n = k.lvl[ea];
-    info_n = k.info[ea];
-    load_edge<KIND>(k, ea, m_n);
-  }
   for (int e = ea; e < eb; ++e) {
-    const int info = info_n;
-    const bool skip = lvl_n != 0;
-    double m[T::MD];
-#pragma unroll
-    for (int q = 0; q < T::MD; ++q) m[q] = m_n[q];
-    if (e + 1 < eb) {
-      lvl_n = k.lvl[e + 1];
-      info_n = k.info[e + 1];
-      load_edge<KIND>(k, e + 1, m_n);
-    }
-    if (skip) continue;
+    if (k.lvl[e]) continue;
+    const int info = k.info[e];
     const int p = info & 0xffff;
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
-    double r[4];
+    double m[T::MD], r[4];
+    load_edge<KIND>(k, e, m);
     eval_edge<KIND, false>(cam, o.bf_float, stereo, b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), Xn, m, r,
                            nullptr, nullptr);
     const double c2 = edge_chi2<KIND>(r);
