@@ -1055,6 +1055,8 @@ struct TileDev {
   int* tent_base;  // [(w*2+kind)*Tcap + t] position of the tile's entry block in tent
   ushort2* tent;   // tile-major copy of the pair entries, edge indices relative to the tile's first edge
   int* order;      // [w*Pmax + o] compact pair position, longest list first, | 1 << 30 for a diagonal pair
+  int4* desc;      // [((w*2+kind)*Tcap + t)*2]: {la, lb, ea, eb}, {n_ent, tent_base, n_ne, valid}: everything a tile CTA
+                   // needs to find its data, in one 32-byte read (kt_tiles_desc)
   double* hs_tile; // [((w*(Tp+Tl) + tt)*Pmax + li)*42], tt = t (points) or Tp + t (lines)
   double* P_bR;    // [NP][9] rotation of the pose backup (pre-update state of the current trial)
 };

@@ -447,6 +447,7 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   const size_t o_tlm = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1));
   const size_t o_tso = a.take(sizeof(int) * (size_t)W * 2 * Tcap * (Pmax + 1));
   const size_t o_tb = a.take(sizeof(int) * (size_t)W * 2 * Tcap);
+  const size_t o_desc = a.take(sizeof(int4) * (size_t)W * 2 * Tcap * 2);
   const size_t o_tent = a.take(sizeof(ushort2) * (size_t)(c->l_pair_base[W] + 8LL * Tcap * W + 8));
   const size_t o_nt = a.take(sizeof(int) * (size_t)W * 2);
   const size_t o_tpb = a.take(sizeof(int) * (size_t)W * 2 * (Tcap + 1) * Pmax);
@@ -465,6 +466,7 @@ int tiles_prepare(RsplBaContext* c, const int maxdeg[2], size_t smem_tile[2]) {
   td.tpb = (int*)(base + o_tpb);
   td.tso = (int*)(base + o_tso);
   td.tent_base = (int*)(base + o_tb);
+  td.desc = (int4*)(base + o_desc);
   td.tent = (ushort2*)(base + o_tent);
   td.cost_b[0] = cost_b[0];
   td.cost_b[1] = cost_b[1];
@@ -613,6 +615,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     GK(s, ba::kt_tiles_scan, dim3(td.Tcap, W, 2), 32, 0, d, b, td);
     GK(s, ba::kt_tiles_base, (W + 127) / 128, 128, 0, d, b, td);
     GK(s, ba::kt_tiles_fill, dim3(((size_t)b.Pmax * td.Tcap + 255) / 256, W, 2), 256, 0, d, b, td);
+    GK(s, ba::kt_tiles_desc, dim3((td.Tcap + 127) / 128, W, 2), 128, 0, d, b, td);
     GK(s, ba::kt_order, (W + 3) / 4, 128, 0, d, b, td);
     for (int pass = 0; pass < 2 && ok; ++pass) {
       cudaMemsetAsync(b.pact_w, 0, sizeof(int) * (size_t)c->l_np, s);
@@ -863,6 +866,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     LAUNCH(PC_PAIRS, ba::kt_tiles_scan, dim3(td.Tcap, W, 2), 32, 0, d, b, td);
     LAUNCH(PC_PAIRS, ba::kt_tiles_base, (W + 127) / 128, 128, 0, d, b, td);
     LAUNCH(PC_PAIRS, ba::kt_tiles_fill, dim3(((size_t)b.Pmax * td.Tcap + 255) / 256, W, 2), 256, 0, d, b, td);
+    LAUNCH(PC_PAIRS, ba::kt_tiles_desc, dim3((td.Tcap + 127) / 128, W, 2), 128, 0, d, b, td);
     LAUNCH(PC_PAIRS, ba::kt_order, (W + 3) / 4, 128, 0, d, b, td);
     CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[0]));
     CU_TRY(c, cudaFuncSetAttribute(ba::kt_schur_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile[1]));

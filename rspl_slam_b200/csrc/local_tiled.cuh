@@ -159,6 +159,25 @@ __global__ void __launch_bounds__(256) kt_tiles_fill(const __grid_constant__ Loc
   }
 }
 
+// one descriptor per (tile, window, kind); grid (ceil(Tcap / 128), W, 2)
+__global__ void __launch_bounds__(128) kt_tiles_desc(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                     const __grid_constant__ TileDev td) {
+  const int w = blockIdx.y, kind = blockIdx.z, t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= td.Tcap) return;
+  const size_t wk = (size_t)(w * 2 + kind);
+  const size_t tile_id = wk * td.Tcap + t;
+  int4 a = make_int4(0, 0, 0, 0), c = make_int4(0, 0, 0, 0);
+  if (t < td.ntile[wk]) {
+    const KindDev& k = d.k[kind];
+    const int* tl = td.tile_lm + wk * (td.Tcap + 1) + t;
+    const int n_ne = b.n_ne[w];
+    a = make_int4(tl[0], tl[1], k.ebeg[tl[0]], k.ebeg[tl[1]]);
+    c = make_int4(td.tso[tile_id * (b.Pmax + 1) + n_ne], td.tent_base[tile_id], n_ne, 1);
+  }
+  td.desc[2 * tile_id] = a;
+  td.desc[2 * tile_id + 1] = c;
+}
+
 // processing order of the compact pairs of a window: longest list first (stable rank sort), so that the four
 // 8-lane groups of a warp work on lists of similar length; one warp per window, grid ceil(W / 4), 128 threads
 __global__ void __launch_bounds__(128) kt_order(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
@@ -222,17 +241,16 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   extern __shared__ __align__(16) unsigned char tile_smem[];
   const int w = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
   WinState& s = b.ws[w];
-  if (s.stage != STAGE_NEED_TRIAL) return;
-  if (t >= td.ntile[w * 2 + KIND]) return;
-  const KindDev& k = d.k[KIND];
   const size_t tile_id = (size_t)(w * 2 + KIND) * td.Tcap + t;
-  const int* tl = td.tile_lm + (size_t)(w * 2 + KIND) * (td.Tcap + 1) + t;
-  const int la = tl[0], lb = tl[1];
-  const int n_ne = b.n_ne[w];
+  // (the window state and the tile descriptor are independent reads: one memory latency, not a chain of five)
+  const int4 d0 = td.desc[2 * tile_id], d1 = td.desc[2 * tile_id + 1];
+  if (s.stage != STAGE_NEED_TRIAL) return;
+  if (!d1.w) return;
+  const KindDev& k = d.k[KIND];
+  const int la = d0.x, lb = d0.y, ea = d0.z, eb = d0.w;
+  const int n_ent = d1.x, n_ne = d1.z;
   const int* tso_g = td.tso + tile_id * (b.Pmax + 1);
   const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0, f0 = b.nf_begin[w], l0 = k.lm_begin[w];
-  const int ea = k.ebeg[la], eb = k.ebeg[lb];
-  const int n_ent = tso_g[n_ne];
   const int nl = lb - la, ne = eb - ea;
   const int n_ent4 = (n_ent + 3) >> 2;
   // ---- shared-memory layout
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
 
   // ---- stage the window tables and the tile's pair entries
   {
-    const uint4* src = reinterpret_cast<const uint4*>(td.tent + td.tent_base[tile_id]);
+    const uint4* src = reinterpret_cast<const uint4*>(td.tent + d1.y);
     uint4 v[3];
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
