@@ -364,6 +364,8 @@ def bench_units(env, key, steps, warmup, with_cpu):
         n_units = 1 if key == "frame1" else args.frames
         nl = args.frame_lines if key == "c2" else 0
         batch = synth.make_frame_batch(2, n_units, first_instance=rank * n_units, n_points=C2_POINTS, n_lines=nl)
+        if key == "frame1":  # a single call, as the reference makes them: one CTA per frame
+            opt = capi.make_options(frame_latency_mode=1)
         upload, solve = ctx.frame_batch_upload, ctx.frame_batch_solve
         out = ctx.alloc_frame_result(batch, pinned=True)
         download = lambda: ctx.frame_batch_download(out)

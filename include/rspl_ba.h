@@ -65,7 +65,9 @@ typedef struct RsplBaOptions {
   int32_t frame_rounds;      /*  4, g2o_optimization.cc:339 */
   int32_t frame_iters;       /* 10, g2o_optimization.cc:336 */
   int32_t stereo_bf_float;   /* 1: g2o's EdgeStereoSE3ProjectXYZ::cam_project(xyz, const float& bf) */
-  int32_t reserved;
+  int32_t frame_latency_mode; /* FrameOptimization batches: 0 = one warp per frame (throughput, default); 1 = one CTA
+                               * per frame (latency: single calls, what the reference makes). Both are deterministic;
+                               * they agree to rounding, not bitwise (different summation trees). */
 } RsplBaOptions;
 
 /* Per-problem statistics (optional outputs). */

@@ -410,7 +410,8 @@ int FrameOptimizationWithLinesImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOf
   out.mono_line_inlier = o_ml.data();
   out.stereo_line_inlier = o_sl.data();
   out.num_inliers = &n_inl;
-  const RsplBaOptions opt = detail::make_options(cfg);
+  RsplBaOptions opt = detail::make_options(cfg);
+  opt.frame_latency_mode = 1; // one frame per call (map_builder.cc:583-584): the whole CTA works on it
   const int rc = rspl_ba_frame_batch(ctx, &in, &opt, &out);
   if (rc != RSPL_BA_OK) return rc;
   for (size_t i = 0; i < nm; ++i) mono_point_constraints[i]->inlier = o_m[i] != 0;

@@ -33,7 +33,7 @@ class RsplBaOptions(C.Structure):
     _fields_ = [("thr_mono_point", C.c_double), ("thr_stereo_point", C.c_double), ("thr_mono_line", C.c_double),
                 ("thr_stereo_line", C.c_double), ("local_iters_pass1", C.c_int32), ("local_iters_pass2", C.c_int32),
                 ("frame_rounds", C.c_int32), ("frame_iters", C.c_int32), ("stereo_bf_float", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("frame_latency_mode", C.c_int32)]
 
 
 class RsplBaStats(C.Structure):
@@ -193,7 +193,7 @@ def _p(a: Optional[np.ndarray], ct):
 
 
 def make_options(cfg: Optional[OptimizationConfig] = None, local_iters=(10, 5), frame_rounds: int = 4,
-                 frame_iters: int = 10, stereo_bf_float: int = 1) -> RsplBaOptions:
+                 frame_iters: int = 10, stereo_bf_float: int = 1, frame_latency_mode: int = 0) -> RsplBaOptions:
     o = RsplBaOptions()
     load_library().rspl_ba_default_options(C.byref(o))
     if cfg is not None:
@@ -201,6 +201,7 @@ def make_options(cfg: Optional[OptimizationConfig] = None, local_iters=(10, 5), 
         o.thr_mono_line, o.thr_stereo_line = cfg.mono_line, cfg.stereo_line
     o.local_iters_pass1, o.local_iters_pass2 = local_iters
     o.frame_rounds, o.frame_iters, o.stereo_bf_float = frame_rounds, frame_iters, stereo_bf_float
+    o.frame_latency_mode = frame_latency_mode
     return o
 
 

@@ -235,7 +235,7 @@ extern "C" void rspl_ba_default_options(RsplBaOptions* o) {
   o->frame_rounds = 4;
   o->frame_iters = 10;
   o->stereo_bf_float = 1;
-  o->reserved = 0;
+  o->frame_latency_mode = 0;
 }
 
 extern "C" int rspl_ba_create(int device, void* stream, RsplBaContext** out) {
@@ -582,16 +582,25 @@ int frame_launch(RsplBaContext* c, const RsplBaOptions* opt, int f0, int f1, cud
   fo.cam0 = c->f_cam0;
   fo.frame0 = f0;
   fo.frame1 = f1;
-  const int grid = (f1 - f0 + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
   const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr &&
                                                    c->fd.mline_cam == nullptr && c->fd.sline_cam == nullptr);
   {
     ProfScope ps(c, PC_FRAME);
     const bool lines = c->f_n_mline + c->f_n_sline > 0;
-    if (single_cam && !lines) ba::frame_opt_kernel<true, false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-    else if (!lines) ba::frame_opt_kernel<false, false><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-    else if (single_cam) ba::frame_opt_kernel<true, true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-    else ba::frame_opt_kernel<false, true><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    if (opt->frame_latency_mode) { // one CTA per frame (single calls of the reference's FrameOptimization)
+      constexpr int W8 = ba::FRAME_CTA_WARPS;
+      const int grid = f1 - f0, threads = 32 * W8;
+      if (single_cam && !lines) ba::frame_opt_kernel<true, false, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
+      else if (!lines) ba::frame_opt_kernel<false, false, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
+      else if (single_cam) ba::frame_opt_kernel<true, true, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
+      else ba::frame_opt_kernel<false, true, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
+    } else {
+      const int grid = (f1 - f0 + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
+      if (single_cam && !lines) ba::frame_opt_kernel<true, false, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+      else if (!lines) ba::frame_opt_kernel<false, false, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+      else if (single_cam) ba::frame_opt_kernel<true, true, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+      else ba::frame_opt_kernel<false, true, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+    }
   }
   c->launches++;
   CU_TRY(c, cudaGetLastError());

@@ -87,6 +87,7 @@ struct DevStats { // layout == RsplBaStats
 constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
 constexpr int FRAME_WARPS = FRAME_THREADS / 32;
 constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
+constexpr int FRAME_CTA_WARPS = 8;  // latency variant: one CTA of 8 warps per frame
 
 // per-warp (= per-frame) state that is touched once per trial: kept in shared memory so the
 // edge loops keep their registers
@@ -198,11 +199,11 @@ BA_DEV void accumulate_pose_dense(const double* J, const double* r, double wo, d
 // the item space is 4 rows x (mono + stereo edges) -- rows 2, 3 of a mono edge are empty -- so 32 lanes take 8 whole
 // edges per step; the chi2 of an edge (needed by its Huber weight) is a 2-step shuffle sum over its 4 lanes. The
 // camera-frame line is recomputed by each of the 4 lanes (27 FMAs) instead of shared.
-template <bool LINEARIZE, bool SINGLE_CAM>
+template <bool LINEARIZE, bool SINGLE_CAM, int STRIDE>
 BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml1, int sl0, int sl1, const double* R,
                            const double* t, bool robust, int lane, double* acc) {
   const int nm = ml1 - ml0, n_items = 4 * (nm + (sl1 - sl0));
-  for (int base = 0; base < n_items; base += 32) { // uniform trip count: the shuffles below need the whole warp
+  for (int base = 0; base < n_items; base += STRIDE) { // uniform trip count: the shuffles below need the whole warp
     const int item = base + lane;
     const bool valid = item < n_items;
     const int ei = valid ? item >> 2 : 0, row = item & 3;
@@ -330,10 +331,10 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
 // One pass of a warp over its frame's active edges at the pose (R,t).
 //  LINEARIZE: accumulate H, b and the robust chi2 (= computeActiveErrors + activeRobustChi2 + buildSystem)
 //  else      : robust chi2 only (= computeActiveErrors + activeRobustChi2)
-template <bool LINEARIZE, bool SINGLE_CAM>
+template <bool LINEARIZE, bool SINGLE_CAM, int STRIDE>
 BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int s0, int s1, const double* R,
                       const double* t, bool robust, int lane, double* acc) {
-  for (int e = m0 + lane; e < m1; e += 32) {
+  for (int e = m0 + lane; e < m1; e += STRIDE) {
     if (d.mono_lvl[e]) continue;
     Cam camv;
     if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
@@ -353,7 +354,7 @@ BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int 
       accumulate_pose_only<2>(J, r, w, acc);
     }
   }
-  for (int e = s0 + lane; e < s1; e += 32) {
+  for (int e = s0 + lane; e < s1; e += STRIDE) {
     if (d.stereo_lvl[e]) continue;
     Cam camv;
     if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
@@ -386,14 +387,50 @@ BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
 // broadcast and no block barrier is ever needed); lanes stride over the frame's edges.
 // HAS_LINES: the batch carries the line extension (the point-only instantiation is the reference's path and
 // keeps its register budget).
-template <bool SINGLE_CAM, bool HAS_LINES>
-__global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLOCKS : FRAME_MIN_BLOCKS)
+// WPF = warps per frame. 1 (default, throughput): four frames per CTA, one warp each, no block barrier. FRAME_CTA_WARPS
+// (latency: the reference calls FrameOptimization with ONE frame, map_builder.cc:583-584): the whole CTA works on one
+// frame, its threads stride the edges, and the sums go through a fixed-order cross-warp reduction in shared memory
+// (deterministic, but a different association than the one-warp variant: the two modes agree to rounding, not bitwise).
+template <int WPF>
+BA_DEV void frame_sync() {
+  if (WPF == 1) __syncwarp();
+  else __syncthreads();
+}
+// every thread of the frame ends with the same totals; red: [WPF][N] shared scratch
+template <int WPF, int N>
+BA_DEV void frame_allreduce(double* v, double* red) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_allreduce(v[k]);
+  if (WPF > 1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) red[warp * N + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double sum = red[k];
+#pragma unroll
+      for (int w2 = 1; w2 < WPF; ++w2) sum += red[w2 * N + k];
+      v[k] = sum;
+    }
+  }
+}
+
+template <bool SINGLE_CAM, bool HAS_LINES, int WPF>
+__global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 ? (HAS_LINES ? FRAME_LINES_MIN_BLOCKS : FRAME_MIN_BLOCKS) : 2)
     frame_opt_kernel(const __grid_constant__ FrameDev d, const __grid_constant__ FrameOpt o) {
-  __shared__ WarpState wstate[FRAME_WARPS];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int f = o.frame0 + blockIdx.x * FRAME_WARPS + warp;
+  constexpr int STRIDE = 32 * WPF;
+  __shared__ WarpState wstate[WPF == 1 ? FRAME_WARPS : 1];
+  __shared__ double red[WPF == 1 ? 1 : WPF * NACC];
+  __shared__ int red_i[WPF == 1 ? 1 : WPF];
+  const int warp = threadIdx.x >> 5;
+  const int lane = WPF == 1 ? (threadIdx.x & 31) : threadIdx.x; // index of this thread within its frame
+  const int f = WPF == 1 ? o.frame0 + blockIdx.x * FRAME_WARPS + warp : o.frame0 + blockIdx.x;
   if (f >= o.frame1) return;
-  WarpState& ws = wstate[warp];
+  WarpState& ws = wstate[WPF == 1 ? warp : 0];
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];
   const int ml0 = HAS_LINES ? d.mline_begin[f] : 0, ml1 = HAS_LINES ? d.mline_begin[f + 1] : 0;
@@ -421,25 +458,25 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
     for (int i = 0; i < 4; ++i) ws.st.iters[i] = ws.st.trials[i] = 0;
     ws.st.edges_linearized = ws.st.edges_evaluated = 0;
   }
-  for (int e = m0 + lane; e < m1; e += 32) {
+  for (int e = m0 + lane; e < m1; e += STRIDE) {
     d.mono_lvl[e] = 0;
     d.mono_inl[e] = d.mono_inl_in ? d.mono_inl_in[e] : 1;
   }
-  for (int e = s0 + lane; e < s1; e += 32) {
+  for (int e = s0 + lane; e < s1; e += STRIDE) {
     d.stereo_lvl[e] = 0;
     d.stereo_inl[e] = d.stereo_inl_in ? d.stereo_inl_in[e] : 1;
   }
   if (HAS_LINES) {
-    for (int e = ml0 + lane; e < ml1; e += 32) {
+    for (int e = ml0 + lane; e < ml1; e += STRIDE) {
       d.mline_lvl[e] = 0;
       d.mline_inl[e] = d.mline_inl_in ? d.mline_inl_in[e] : 1;
     }
-    for (int e = sl0 + lane; e < sl1; e += 32) {
+    for (int e = sl0 + lane; e < sl1; e += STRIDE) {
       d.sline_lvl[e] = 0;
       d.sline_inl[e] = d.sline_inl_in ? d.sline_inl_in[e] : 1;
     }
   }
-  __syncwarp();
+  frame_sync<WPF>();
 
   bool robust = true;
   int n_active = n_edges; // every edge starts at level 0
@@ -456,12 +493,11 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
           double acc[NACC];
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
-          edge_pass<true, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
+          edge_pass<true, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
           if (HAS_LINES) {
-            line_pass_rows<true, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, acc);
+            line_pass_rows<true, SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, acc);
           }
-#pragma unroll
-          for (int k = 0; k < NACC; ++k) acc[k] = warp_allreduce(acc[k]);
+          frame_allreduce<WPF, NACC>(acc, red);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
             double mx = 0;
 #pragma unroll
@@ -470,7 +506,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
             ni = 2;
           }
           chi_cur = acc[NACC - 1];
-          __syncwarp();
+          frame_sync<WPF>();
           if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 21; ++k) ws.H[k] = acc[k];
@@ -478,7 +514,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
             for (int k = 0; k < 6; ++k) ws.b[k] = acc[21 + k];
             ws.Te = T;
           }
-          __syncwarp();
+          frame_sync<WPF>();
         }
         if (lane == 0) {
           ws.st.edges_linearized += n_active;
@@ -504,24 +540,25 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
           }
           PoseRt Tn;
           poseRt_oplus(T, x, Tn);
-          __syncwarp();
+          frame_sync<WPF>();
           if (lane == 0) {
             ws.Tbackup = T;
             ws.Te = Tn;
 #pragma unroll
             for (int k = 0; k < 6; ++k) ws.x[k] = x[k];
           }
-          __syncwarp();
+          frame_sync<WPF>();
           T = Tn;
           double tempChi;
           {
             double a2[NACC];
             a2[NACC - 1] = 0;
-            edge_pass<false, SINGLE_CAM>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
+            edge_pass<false, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
             if (HAS_LINES) {
-              line_pass_rows<false, SINGLE_CAM>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, a2);
+              line_pass_rows<false, SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, a2);
             }
-            tempChi = warp_allreduce(a2[NACC - 1]);
+            frame_allreduce<WPF, 1>(a2 + NACC - 1, red);
+            tempChi = a2[NACC - 1];
           }
           if (lane == 0) {
             ws.st.edges_evaluated += n_active;
@@ -561,7 +598,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
     const double* Re = Tev.R;
     const double* te = Tev.t;
     int my_out = 0;
-    for (int e = m0 + lane; e < m1; e += 32) {
+    for (int e = m0 + lane; e < m1; e += STRIDE) {
       Cam camv;
       if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
       const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
@@ -581,7 +618,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
       d.mono_lvl[e] = out ? 1 : 0;
       my_out += out;
     }
-    for (int e = s0 + lane; e < s1; e += 32) {
+    for (int e = s0 + lane; e < s1; e += STRIDE) {
       Cam camv;
       if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
       const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
@@ -600,7 +637,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
       my_out += out;
     }
     if (HAS_LINES) { // same classification for the line edges (extension)
-      for (int e = ml0 + lane; e < ml1; e += 32) {
+      for (int e = ml0 + lane; e < ml1; e += STRIDE) {
         Cam camv;
         if (!SINGLE_CAM) load_cam(d.cameras, d.mline_cam[e], camv);
         const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
@@ -619,7 +656,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
         d.mline_lvl[e] = out ? 1 : 0;
         my_out += out;
       }
-      for (int e = sl0 + lane; e < sl1; e += 32) {
+      for (int e = sl0 + lane; e < sl1; e += STRIDE) {
         Cam camv;
         if (!SINGLE_CAM) load_cam(d.cameras, d.sline_cam[e], camv);
         const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
@@ -640,9 +677,17 @@ __global__ void __launch_bounds__(FRAME_THREADS, HAS_LINES ? FRAME_LINES_MIN_BLO
       }
     }
     num_outlier = __reduce_add_sync(0xffffffffu, my_out);
+    if (WPF > 1) {
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red_i[warp] = num_outlier;
+      __syncthreads();
+      num_outlier = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < (WPF > 1 ? WPF : 1); ++w2) num_outlier += red_i[w2];
+    }
     n_active = n_edges - num_outlier;
     if (round == 2) robust = false; // e->setRobustKernel(0) (:364,:384)
-    __syncwarp(); // level / inlier flags written above are read by other lanes' next passes? no: each lane
+    frame_sync<WPF>(); // level / inlier flags written above are read by other lanes' next passes? no: each lane
                   // re-reads only the edges it wrote (same stride), the barrier just orders the round
     if (n_edges < 10) break; // optimizer.edges().size() < 10 (:387)
   }

@@ -43,6 +43,26 @@ def test_frame_batch_matches_oracle_c2_shape(gpu_ctx, orc):
     assert (res.stats["edges_linearized"] > 0).all()
 
 
+def test_frame_latency_mode_matches_oracle(gpu_ctx, orc):
+    """frame_latency_mode = 1 (one CTA per frame, what the shim's single-frame FrameOptimization uses): same parity
+    bar, with and without the line extension, ragged / tiny frames included; agrees with the one-warp-per-frame
+    mode to rounding."""
+    opt = capi.make_options(frame_latency_mode=1)
+    probs = [synth.make_frame_problem(synth.config_seed(2, 300 + i), n_points=n, stereo_frac=0.7)
+             for i, n in enumerate([400, 37, 9, 3, 600, 250])]
+    batch = FrameBatch.from_problems(probs)
+    res = gpu_ctx.frame_batch(batch, opt)
+    _check_against_oracle(orc, probs, batch, res)
+    thr = gpu_ctx.frame_batch(batch)
+    assert np.array_equal(thr.stereo_inlier, res.stereo_inlier) and np.abs(thr.pose_twc - res.pose_twc).max() < 1e-9
+    lprobs = [synth.make_frame_problem(synth.config_seed(2, 320 + i), n_points=200, n_lines=40) for i in range(4)]
+    lbatch = FrameBatch.from_problems(lprobs)
+    _check_against_oracle(orc, lprobs, lbatch, gpu_ctx.frame_batch(lbatch, opt))
+    # bitwise reproducible within the mode
+    again = gpu_ctx.frame_batch(batch, opt)
+    assert np.array_equal(again.pose_twc.view(np.uint64), res.pose_twc.view(np.uint64))
+
+
 def test_frame_batch_mixed_mono_stereo_and_ragged(gpu_ctx, orc):
     """Ragged edge counts, mono+stereo mixes, tiny frames (<10 edges -> single round, :387), an
     empty frame, and caller-provided ->inlier = false flags."""

@@ -71,7 +71,8 @@ def test_shim_frame_equals_direct_cabi(driver, gpu_ctx, tmp_path):
     subprocess.run([driver, fin, fout], check=True)
     out = np.fromfile(fout, dtype=np.float64)
     batch = FrameBatch.from_problems([p])
-    res = gpu_ctx.frame_batch(batch)
+    from rspl_slam_b200 import capi
+    res = gpu_ctx.frame_batch(batch, capi.make_options(frame_latency_mode=1))  # (the shim's single-frame calls use it)
     assert int(out[0]) == int(res.num_inliers[0])
     assert np.array_equal(out[1:8].view(np.uint64), np.ascontiguousarray(res.pose_twc[:, 0]).view(np.uint64))
     k = 8 + 3 * len(p.point_id)
@@ -91,7 +92,8 @@ def test_shim_frame_with_lines_equals_direct_cabi(driver, gpu_ctx, tmp_path):
     subprocess.run([driver, fin, fout], check=True)
     out = np.fromfile(fout, dtype=np.float64)
     batch = FrameBatch.from_problems([p])
-    res = gpu_ctx.frame_batch(batch)
+    from rspl_slam_b200 import capi
+    res = gpu_ctx.frame_batch(batch, capi.make_options(frame_latency_mode=1))  # (the shim's single-frame calls use it)
     assert int(out[0]) == int(res.num_inliers[0])
     assert np.array_equal(out[1:8].view(np.uint64), np.ascontiguousarray(res.pose_twc[:, 0]).view(np.uint64))
     k = 8 + 3 * len(p.point_id) + 6 * len(p.line_id)
