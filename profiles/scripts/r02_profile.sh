@@ -1,0 +1,18 @@
+#!/bin/bash
+# Round-2 profiling pass on the GPU box (run through gpurun): launch lists and `--set full` captures of the dominant
+# kernels. Local-BA kernels are captured with RSPL_BA_GRAPH=off: ncu cannot profile kernel nodes of a graph that holds
+# conditional nodes (the default whole-schedule graph), the host-driven driver launches the same kernels one by one.
+set -x
+cd "$(dirname "$0")/../.."
+O=gpurun_out
+NCU="ncu --clock-control none"
+# launch lists (cold-cache, serialised: the SHARE per kernel is what counts)
+RSPL_BA_GRAPH=off $NCU --metrics gpu__time_duration.sum -c 3000 --csv --log-file $O/r02_launches_c2.csv python bench.py --workload c2 --steps 2 --warmup 1 > $O/r02_ncu_c2.log 2>&1
+RSPL_BA_GRAPH=off $NCU --metrics gpu__time_duration.sum -c 6000 --csv --log-file $O/r02_launches_c4.csv python profiles/scripts/r02_ncu_target.py local 1024 > $O/r02_ncu_c4.log 2>&1
+# full captures
+$NCU --set full --import-source on -k regex:frame_opt_kernel -s 1 -c 1 -o $O/r02_frame_c2 python profiles/scripts/r02_ncu_target.py frame 4096 60 > $O/r02_ncu_f1.log 2>&1
+$NCU --set full --import-source on -k regex:frame_opt_kernel -s 1 -c 1 -o $O/r02_frame_c2p python profiles/scripts/r02_ncu_target.py frame 4096 0 > $O/r02_ncu_f2.log 2>&1
+RSPL_BA_GRAPH=off $NCU --set full --import-source on -k regex:"kt_schur_tile" -s 20 -c 2 -o $O/r02_tile_final python profiles/scripts/r02_ncu_target.py local 1024 > $O/r02_ncu_t.log 2>&1
+RSPL_BA_GRAPH=off $NCU --set full --import-source on -k regex:"kt_backsub_rc|kb_pose_blocks|kb_linearize|kb_solve|kt_tile_sum" -s 12 -c 7 -o $O/r02_local_others python profiles/scripts/r02_ncu_target.py local 1024 > $O/r02_ncu_o.log 2>&1
+$NCU --set full --import-source on -k regex:"bcr_eliminate|bcr_update" -s 4 -c 4 -o $O/r02_bcr python profiles/scripts/r02_c5_target.py 600 > $O/r02_ncu_b.log 2>&1
+ls -la $O/*.ncu-rep
