@@ -235,10 +235,13 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
 // C[r][c] += sum_k A[k][r] B[k][c] over the bs rows of the global blocks A, B (both [bs][bs] row-major), for the
 // 3 x 6 register tiles of this thread; slabs of BCR_KC rows are staged in shared memory
 constexpr int BCR_TILES_PER_THREAD = ((BCR_BS_MAX / 3) * (BCR_BS_MAX / 6) + BCR_THREADS - 1) / BCR_THREADS; // 3
+// (super-blocks of <= 96 unknowns have at most 512 tiles: one per thread, which leaves the registers to unroll the
+// k loop and keep several shared-memory loads in flight)
+__host__ __device__ constexpr int bcr_tiles_per_thread(int bs) { return ((bs / 3) * (bs / 6) + BCR_THREADS - 1) / BCR_THREADS; }
 
+template <int TPT>
 __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, int bs, double* As, double* Bs,
-                                              double (&acc)[BCR_TILES_PER_THREAD][18], const double* gvec, double* gs,
-                                              double& vacc) {
+                                              double (&acc)[TPT][18], const double* gvec, double* gs, double& vacc) {
   // gvec != null: thread r < bs also accumulates (A^T gvec)[r] from the staged slabs
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tc = bs / 6; // tiles per row of tiles
@@ -255,11 +258,12 @@ __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, 
       for (int k = 0; k < kc; ++k) vacc += As[k * bs + tid] * gs[k];
     }
 #pragma unroll
-    for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
+    for (int u = 0; u < TPT; ++u) {
       const int tix = tid + u * nt;
       if (tix >= (bs / 3) * tc) continue;
       // (the six columns of a tile are cl, cl + tc, ..., so the lanes of a warp read consecutive shared-memory words)
       const int r0 = 3 * (tix / tc), cl = tix % tc;
+#pragma unroll(TPT == 1 ? 5 : 1)
       for (int k = 0; k < kc; ++k) {
         const double a0 = As[k * bs + r0], a1 = As[k * bs + r0 + 1], a2 = As[k * bs + r0 + 2];
         double bv[6];
@@ -278,6 +282,7 @@ __device__ __forceinline__ void bcr_ata_tiles(const double* A, const double* B, 
 
 // ---- level l, even blocks: Schur updates from the two eliminated neighbours and the next level's coupling.
 // grid = number of even active blocks; dynamic smem = (2 * BCR_KC * bs + BCR_KC) doubles
+template <int TPT>
 __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant__ BcrDev s, int level) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, tid = threadIdx.x, nt = blockDim.x;
@@ -291,10 +296,10 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   const bool has_l = p > 0, has_r = Ir < s.M;
   const size_t bb = (size_t)bs * bs;
   const int tc = bs / 6, ntiles = (bs / 3) * tc;
-  double acc[BCR_TILES_PER_THREAD][18];
+  double acc[TPT][18];
   // D_J -= GR(Il)^T GR(Il) + GL(Ir)^T GL(Ir)
 #pragma unroll
-  for (int u = 0; u < BCR_TILES_PER_THREAD; ++u)
+  for (int u = 0; u < TPT; ++u)
 #pragma unroll
     for (int q = 0; q < 18; ++q) acc[u][q] = 0.0;
   double vl = 0.0, vr = 0.0, vdummy = 0.0; // b_J -= GR(Il)^T g(Il) + GL(Ir)^T g(Ir), thread r < bs
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   if (tid < bs) s.x[(size_t)J * bs + tid] -= vl + vr;
   double* Dg = s.D + (size_t)J * bb;
 #pragma unroll
-  for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
+  for (int u = 0; u < TPT; ++u) {
     const int tix = tid + u * nt;
     if (tix < ntiles) {
       const int r0 = 3 * (tix / tc), cl = tix % tc;
@@ -316,13 +321,13 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   // E'(J, J + 2h) = -GL(Ir)^T GR(Ir)
   if (has_r && J + 2 * h < s.M) {
 #pragma unroll
-    for (int u = 0; u < BCR_TILES_PER_THREAD; ++u)
+    for (int u = 0; u < TPT; ++u)
 #pragma unroll
       for (int q = 0; q < 18; ++q) acc[u][q] = 0.0;
     bcr_ata_tiles(s.GL + (size_t)Ir * bb, s.GR + (size_t)Ir * bb, bs, As, Bs, acc, nullptr, gs, vdummy);
     double* En = s.E + s.eoff[level + 1] + (size_t)(p / 2) * bb;
 #pragma unroll
-    for (int u = 0; u < BCR_TILES_PER_THREAD; ++u) {
+    for (int u = 0; u < TPT; ++u) {
       const int tix = tid + u * nt;
       if (tix < ntiles) {
         const int r0 = 3 * (tix / tc), cl = tix % tc;

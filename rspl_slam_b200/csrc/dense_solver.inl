@@ -224,7 +224,8 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_eliminate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 1024)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 2 * s.bs + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 4 * s.bs + 64)));
-    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update<ba::BCR_TILES_PER_THREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
   }
   if (L.max_tiles > 0) {
     CublasApi& bl = cublas_api();
@@ -285,7 +286,8 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   for (int l = 0; l < levels; ++l) {
     const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
     if (n_odd > 0) ba::bcr_eliminate<<<n_odd, ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
-    ba::bcr_update<<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
+    if (ba::bcr_tiles_per_thread(s.bs) == 1) ba::bcr_update<1><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
+    else ba::bcr_update<ba::BCR_TILES_PER_THREAD><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
     c->launches += 2;
     Ml = n_even;
   }

@@ -577,9 +577,11 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     };
     cudaStream_t sline = fork_lines ? sl : sm;
     fork(0);
+    // (the pose blocks follow the short line kernel on the second stream: they are independent of the point
+    // linearisation, and both are latency-bound at ~25 % resident warps, so they overlap well)
     if (b.Cp) GK(sm, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) GK(sline, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
-    GK(sm, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    GK(sline, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
     join(0);
     GK(sm, ba::kb_begin_trial, g_winw, 128, 0, d, b);
     fork(1);
