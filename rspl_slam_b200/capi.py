@@ -118,11 +118,12 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("RSPL_BA_LIB", LIB_PATH)  # A/B builds of the same library (profiles/scripts)
+    if not os.path.exists(path):
         raise FileNotFoundError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     ctx = C.c_void_p
     L.rspl_ba_version.restype = C.c_int
     L.rspl_ba_default_options.argtypes = [C.POINTER(RsplBaOptions)]

@@ -229,6 +229,61 @@ BA_DEV void poseRt_oplus(const PoseRt& T, const double* u, PoseRt& out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// cp.async (global -> shared memory without staging registers); groups are per thread
+// ------------------------------------------------------------------------------------------------
+BA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BA_DEV void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+BA_DEV void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+BA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+BA_DEV void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Branch-free reciprocal / reciprocal square root (K7 hot loops). The CUDA library versions test the exponent range
+// and call an out-of-line slow path; that conditional call ends the basic block, so the compiler cannot interleave
+// the evaluation of several edges. These are the same MUFU seed + FMA refinement without the range test: results
+// within 1 ulp of the IEEE quotient for normal arguments (|x| in ~[1e-290, 1e290]); 0, denormals and infinities
+// give NaN instead of +-inf / 0 (a depth of exactly 0 or a chi2 of 0 under the square root never reach them:
+// see the callers).
+// ------------------------------------------------------------------------------------------------
+BA_DEV double rcp_nr(double z) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z)); // MUFU.RCP64H: ~20 bits
+  double e = fma(-z, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y); // y (1 + e + e^2): ~60 bits
+  e = fma(-z, y, 1.0);
+  return fma(y, e, y); // final correction
+}
+BA_DEV double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // MUFU.RSQ64H: ~20 bits
+  double e = fma(-x, y * y, 1.0);
+  double p = fma(e, 0.375, 0.5);
+  y = fma(p, e * y, y); // y (1 + e/2 + 3 e^2/8): ~60 bits
+  e = fma(-x, y * y, 1.0);
+  return fma(0.5 * e, y, y); // final correction
+}
+
+// Huber with the range-test-free rsqrt (outliers only)
+BA_DEV double huber_nr(double e, double delta, double& w) {
+  const double dsqr = delta * delta;
+  if (e <= dsqr) {
+    w = 1.0;
+    return e;
+  }
+  const double rs = rsqrt_nr(e);
+  w = delta * rs;
+  return 2 * (e * rs) * delta - dsqr;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Huber (RobustKernelHuber::robustify); returns rho0, writes the weight rho1
 // ------------------------------------------------------------------------------------------------
 BA_DEV double huber(double e, double delta, double& w) {
@@ -270,11 +325,27 @@ BA_DEV void point_residual(const Cam& cam, double bf_res, const double* Xc, cons
   }
 }
 
+// the same with 1 / z given (K7: rcp_nr); the mono rows use x * (1/z) instead of x / z (rounding only)
+template <bool STEREO>
+BA_DEV void point_residual_iz(const Cam& cam, double bf_res, const double* Xc, double invz, const double* m, double* r) {
+  const double u = Xc[0] * invz * cam.fx + cam.cx;
+  const double v = Xc[1] * invz * cam.fy + cam.cy;
+  r[0] = m[0] - u;
+  r[1] = m[1] - v;
+  if (STEREO) r[2] = m[2] - (u - bf_res * invz);
+}
+
 // d r / d xi (rows x 6, omega first), row-major Jp[row*6+col]
 template <bool STEREO>
+BA_DEV void point_jac_pose_iz(const Cam& cam, const double* Xc, double invz, double* Jp);
+template <bool STEREO>
 BA_DEV void point_jac_pose(const Cam& cam, const double* Xc, double* Jp) {
+  point_jac_pose_iz<STEREO>(cam, Xc, 1.0 / Xc[2], Jp);
+}
+template <bool STEREO>
+BA_DEV void point_jac_pose_iz(const Cam& cam, const double* Xc, double invz, double* Jp) {
   const double x = Xc[0], y = Xc[1];
-  const double invz = 1.0 / Xc[2], invz2 = invz * invz;
+  const double invz2 = invz * invz;
   Jp[0] = x * y * invz2 * cam.fx;
   Jp[1] = -(1 + x * x * invz2) * cam.fx;
   Jp[2] = y * invz * cam.fx;

@@ -576,34 +576,45 @@ int frame_copy_in(RsplBaContext* c, const RsplFrameBatch* in, const FrameOffsets
   return RSPL_BA_OK;
 }
 
+// one instantiation of K7
+template <bool SINGLE_CAM, bool HAS_LINES, int WPF>
+cudaError_t frame_kernel_launch(int n_frames, cudaStream_t stream, const ba::FrameDev& fd, const ba::FrameOpt& fo) {
+  constexpr int warps = WPF == 1 ? ba::FRAME_WARPS : WPF;
+  constexpr int frames_per_cta = WPF == 1 ? ba::FRAME_WARPS : 1;
+  const int grid = (n_frames + frames_per_cta - 1) / frames_per_cta;
+  ba::frame_opt_kernel<SINGLE_CAM, HAS_LINES, WPF><<<grid, 32 * warps, 0, stream>>>(fd, fo);
+  return cudaGetLastError();
+}
+
 int frame_launch(RsplBaContext* c, const RsplBaOptions* opt, int f0, int f1, cudaStream_t stream = nullptr) {
   if (!stream) stream = c->stream;
   ba::FrameOpt fo = make_frame_opt(*opt);
   fo.cam0 = c->f_cam0;
+  fo.b0 = fo.cam0.bf / fo.cam0.fx;
   fo.frame0 = f0;
   fo.frame1 = f1;
   const bool single_cam = c->fd.n_cameras == 1 || (c->fd.mono_cam == nullptr && c->fd.stereo_cam == nullptr &&
                                                    c->fd.mline_cam == nullptr && c->fd.sline_cam == nullptr);
+  cudaError_t e;
   {
     ProfScope ps(c, PC_FRAME);
     const bool lines = c->f_n_mline + c->f_n_sline > 0;
+    const int n = f1 - f0;
     if (opt->frame_latency_mode) { // one CTA per frame (single calls of the reference's FrameOptimization)
       constexpr int W8 = ba::FRAME_CTA_WARPS;
-      const int grid = f1 - f0, threads = 32 * W8;
-      if (single_cam && !lines) ba::frame_opt_kernel<true, false, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
-      else if (!lines) ba::frame_opt_kernel<false, false, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
-      else if (single_cam) ba::frame_opt_kernel<true, true, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
-      else ba::frame_opt_kernel<false, true, W8><<<grid, threads, 0, stream>>>(c->fd, fo);
+      if (single_cam && !lines) e = frame_kernel_launch<true, false, W8>(n, stream, c->fd, fo);
+      else if (!lines) e = frame_kernel_launch<false, false, W8>(n, stream, c->fd, fo);
+      else if (single_cam) e = frame_kernel_launch<true, true, W8>(n, stream, c->fd, fo);
+      else e = frame_kernel_launch<false, true, W8>(n, stream, c->fd, fo);
     } else {
-      const int grid = (f1 - f0 + ba::FRAME_WARPS - 1) / ba::FRAME_WARPS;
-      if (single_cam && !lines) ba::frame_opt_kernel<true, false, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-      else if (!lines) ba::frame_opt_kernel<false, false, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-      else if (single_cam) ba::frame_opt_kernel<true, true, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
-      else ba::frame_opt_kernel<false, true, 1><<<grid, ba::FRAME_THREADS, 0, stream>>>(c->fd, fo);
+      if (single_cam && !lines) e = frame_kernel_launch<true, false, 1>(n, stream, c->fd, fo);
+      else if (!lines) e = frame_kernel_launch<false, false, 1>(n, stream, c->fd, fo);
+      else if (single_cam) e = frame_kernel_launch<true, true, 1>(n, stream, c->fd, fo);
+      else e = frame_kernel_launch<false, true, 1>(n, stream, c->fd, fo);
     }
   }
   c->launches++;
-  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, e);
   return RSPL_BA_OK;
 }
 

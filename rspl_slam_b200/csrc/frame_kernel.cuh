@@ -66,6 +66,7 @@ struct FrameOpt {
   double thr_mline, thr_sline, delta_mline, delta_sline; // line extension
   int rounds, iters;
   Cam cam0;                        // camera 0, read straight from the constant bank when SINGLE_CAM
+  double b0;                       // cam0.bf / cam0.fx (stereo line edges), divided once on the host
   int frame0, frame1;              // frame range of this launch (chunks of a pipelined batch)
 };
 
@@ -79,15 +80,27 @@ struct DevStats { // layout == RsplBaStats
 };
 
 #ifndef FRAME_MIN_BLOCKS
-#define FRAME_MIN_BLOCKS 4 // 128 registers: best of {3, 4, 5} measured on B200 (profiles/README.md)
+#define FRAME_MIN_BLOCKS 4 // x 4 warps per SM = 128 registers: best of {3, 4, 5} measured on B200 (profiles/README.md)
 #endif
 #ifndef FRAME_LINES_MIN_BLOCKS
 #define FRAME_LINES_MIN_BLOCKS 4 // instantiation with the line extension: 3 / 4 / 5 CTAs per SM measured 4.03 / 3.60 / 5.34 ms (C2 with 60 lines)
 #endif
-constexpr int FRAME_THREADS = 128;           // 4 warps = 4 frames per CTA
-constexpr int FRAME_WARPS = FRAME_THREADS / 32;
+#ifndef FRAME_WARPS_PER_CTA
+#define FRAME_WARPS_PER_CTA 1 // frames per CTA in throughput mode (one warp each); 1 / 2 / 4: c2p 1.76 / 1.81 / 1.80 ms (finer tail)
+#endif
+constexpr int FRAME_WARPS = FRAME_WARPS_PER_CTA;
+constexpr int FRAME_THREADS = 32 * FRAME_WARPS;
 constexpr int NACC = 28; // 21 (H upper) + 6 (b) + 1 (robust chi2)
 constexpr int FRAME_CTA_WARPS = 8;  // latency variant: one CTA of 8 warps per frame
+
+// Measured and dropped in round 2 (gpurun_out logs summarised in profiles/README.md): software prefetch of the next
+// record into registers (no gain); a cp.async ring through shared memory (c2p 1.92 -> 2.36 ms: the 8-byte LDGSTS and
+// their address arithmetic cost more issue slots than the hidden latency was worth); evaluating 2 / 4 / 8 edges of a
+// lane side by side in one branch-free block (slower by 2 - 40 %: in throughput mode the kernel is bound by issue slots
+// and the FP64 pipe together with latency, and every variant that adds instructions loses). What helped: levels in a
+// register bit mask, one warp per CTA (finer tail), reciprocal / rsqrt without the library's range test and
+// out-of-line slow path (halves the single-frame latency: the serial 6x6 solve is a chain of six rsqrt).
+constexpr int LINE_LVL_CAP = 256;     // line levels of a frame kept in shared memory (beyond: global)
 
 // per-warp (= per-frame) state that is touched once per trial: kept in shared memory so the
 // edge loops keep their registers
@@ -194,45 +207,86 @@ BA_DEV void accumulate_pose_dense(const double* J, const double* r, double wo, d
 }
 
 // line edges of a frame (extension): information 0.1 I (g2o_optimization.cc:133,154), line vertex fixed
-// Line edges, one lane per residual ROW: a frame has few line edges (60 in config C2) of very different cost (2 or 4
+// Image-line quantities of one camera from the camera-frame moment (w0, w1, w2), with explicit fma so that the row
+// mapping (linearising pass) and the edge mapping (residual-only pass) produce the same bits: the Levenberg loop
+// compares their chi2 sums (rho == 0 terminates).
+BA_DEV void line_to_camera_fma(const double* R, const double* t, const double* L, LineCam& lc) {
+  double Rw[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Rw[i] = fma(R[3 * i + 2], L[2], fma(R[3 * i + 1], L[1], R[3 * i] * L[0]));
+    lc.dc[i] = fma(R[3 * i + 2], L[5], fma(R[3 * i + 1], L[4], R[3 * i] * L[3]));
+  }
+  lc.wc[0] = Rw[0] + fma(t[1], lc.dc[2], -(t[2] * lc.dc[1]));
+  lc.wc[1] = Rw[1] + fma(t[2], lc.dc[0], -(t[0] * lc.dc[2]));
+  lc.wc[2] = Rw[2] + fma(t[0], lc.dc[1], -(t[1] * lc.dc[0]));
+}
+struct LineImg {
+  double l0, l1, l2, inv;
+};
+BA_DEV LineImg line_image(const Cam& cam, double w0, double w1, double w2) {
+  const double kv0 = -cam.fy * cam.cx, kv1 = -cam.fx * cam.cy, kv2 = cam.fx * cam.fy;
+  LineImg im;
+  im.l0 = cam.fy * w0;
+  im.l1 = cam.fx * w1;
+  im.l2 = fma(kv2, w2, fma(kv1, w1, kv0 * w0));
+  im.inv = rsqrt_nr(fma(im.l1, im.l1, im.l0 * im.l0));
+  return im;
+}
+BA_DEV double line_row(const LineImg& im, double mx, double my) { return fma(mx, im.l0, fma(my, im.l1, im.l2)) * im.inv; }
+// right camera: T with t.x -= b (edge_project_stereo_line.cc:34-35)
+BA_DEV void line_right(const LineCam& lc, double b, double& w1, double& w2) {
+  w1 = fma(b, lc.dc[2], lc.wc[1]);
+  w2 = fma(-b, lc.dc[1], lc.wc[2]);
+}
+
+// The levels of the first LINE_LVL_CAP line edges of the frame (mono first, then stereo) live in shared memory (llvl).
+BA_DEV bool line_excluded(const FrameDev& d, const uint8_t* llvl, int ei, bool st, int e) {
+  return ei < LINE_LVL_CAP ? llvl[ei] != 0 : (st ? d.sline_lvl[e] : d.mline_lvl[e]) != 0;
+}
+
+// Linearising pass over the line edges, one lane per residual ROW: a frame has few line edges (60 in config C2) of very different cost (2 or 4
 // rows), so a lane per edge leaves most of the warp idle (one pass over 20 mono + two over 40 stereo edges). Here
 // the item space is 4 rows x (mono + stereo edges) -- rows 2, 3 of a mono edge are empty -- so 32 lanes take 8 whole
 // edges per step; the chi2 of an edge (needed by its Huber weight) is a 2-step shuffle sum over its 4 lanes. The
 // camera-frame line is recomputed by each of the 4 lanes (27 FMAs) instead of shared.
-template <bool LINEARIZE, bool SINGLE_CAM, int STRIDE>
-BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml1, int sl0, int sl1, const double* R,
-                           const double* t, bool robust, int lane, double* acc) {
+template <bool SINGLE_CAM, int STRIDE>
+BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml1, int sl0, int sl1, const uint8_t* llvl,
+                           const double* R, const double* t, bool robust, int lane, double* acc) {
   const int nm = ml1 - ml0, n_items = 4 * (nm + (sl1 - sl0));
   for (int base = 0; base < n_items; base += STRIDE) { // uniform trip count: the shuffles below need the whole warp
     const int item = base + lane;
-    const bool valid = item < n_items;
-    const int ei = valid ? item >> 2 : 0, row = item & 3;
+    const int ei = item >> 2, row = item & 3;
     const bool st = ei >= nm;
     const int e = st ? sl0 + (ei - nm) : ml0 + ei;
-    const bool act = valid && (st || row < 2) && !(st ? d.sline_lvl[e] : d.mline_lvl[e]);
+    const bool act = item < n_items && (st || row < 2) && !line_excluded(d, llvl, ei, st, e);
+    double L[6] = {0, 0, 0, 0, 0, 0}, mx = 0, my = 0;
+    if (act) {
+      const size_t stride = st ? d.n_sline : d.n_mline;
+      const double* lw = (st ? d.sline_lw : d.mline_lw) + e;
+      const int mq = 4 * (row >> 1) + 2 * (row & 1); // endpoint (x, y) of this row: left 1, left 2, right 1, right 2
+      const double* ms = (st ? d.sline_meas : d.mline_meas) + mq * stride + e;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) L[q] = lw[q * stride];
+      mx = ms[0];
+      my = ms[stride];
+    }
     double r = 0.0, J[6] = {0, 0, 0, 0, 0, 0};
     if (act) {
       Cam camv;
       if (!SINGLE_CAM) load_cam(d.cameras, st ? d.sline_cam[e] : d.mline_cam[e], camv);
       const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
-      const int stride = st ? d.n_sline : d.n_mline;
-      const double* lw = st ? d.sline_lw : d.mline_lw;
-      const double* ms = st ? d.sline_meas : d.mline_meas;
-      double L[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) L[q] = lw[(size_t)q * stride + e];
-      const int mq = 4 * (row >> 1) + 2 * (row & 1); // endpoint (x, y) of this row: left 1, left 2, right 1, right 2
-      const double mx = ms[(size_t)mq * stride + e], my = ms[(size_t)(mq + 1) * stride + e];
       LineCam lc;
-      line_to_camera(R, t, L, lc);
-      const double b = cam.bf / cam.fx;
+      line_to_camera_fma(R, t, L, lc);
+      const double b = SINGLE_CAM ? o.b0 : cam.bf / cam.fx;
       const bool right = row >= 2;
-      const double wv[3] = {lc.wc[0], right ? lc.wc[1] + b * lc.dc[2] : lc.wc[1], right ? lc.wc[2] - b * lc.dc[1] : lc.wc[2]};
+      double w1 = lc.wc[1], w2 = lc.wc[2];
+      if (right) line_right(lc, b, w1, w2);
+      const LineImg im = line_image(cam, lc.wc[0], w1, w2);
       const double kv0 = -cam.fy * cam.cx, kv1 = -cam.fx * cam.cy, kv2 = cam.fx * cam.fy;
-      const double l0 = cam.fy * wv[0], l1 = cam.fx * wv[1], l2 = kv0 * wv[0] + kv1 * wv[1] + kv2 * wv[2];
-      const double inv = rsqrt(l0 * l0 + l1 * l1);
-      r = (mx * l0 + my * l1 + l2) * inv;
-      if (LINEARIZE) {
+      const double l0 = im.l0, l1 = im.l1, inv = im.inv;
+      r = line_row(im, mx, my);
+      {
         const double n0 = l0 * inv, n1 = l1 * inv;
         const double a0 = (mx - r * n0) * inv, a1 = (my - r * n1) * inv, a2 = inv;
         const double g[3] = {a0 * cam.fy + a2 * kv0, a1 * cam.fx + a2 * kv1, a2 * kv2};
@@ -255,15 +309,15 @@ BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml
         J[5] = c[2];
       }
     }
-    double c2 = r * r;
-    c2 += __shfl_xor_sync(0xffffffffu, c2, 1);
-    c2 += __shfl_xor_sync(0xffffffffu, c2, 2);
+    double c2 = __dmul_rn(r, r);
+    c2 = __dadd_rn(c2, __shfl_xor_sync(0xffffffffu, c2, 1));
+    c2 = __dadd_rn(c2, __shfl_xor_sync(0xffffffffu, c2, 2));
     c2 *= 0.1;
     double w = 1.0;
-    const double rho0 = robust ? huber(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
+    const double rho0 = robust ? huber_nr(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
     if (act) {
       if (row == 0) acc[NACC - 1] += rho0;
-      if (LINEARIZE) {
+      {
         const double wo = 0.1 * w;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -273,6 +327,48 @@ BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml
         }
       }
     }
+  }
+}
+
+// Residual-only pass over the line edges, one lane per EDGE: the camera-frame line and the two normalisations are
+// computed once per edge instead of once per row (the row mapping above pays them four times, which only the
+// linearising pass amortises over its 27 accumulations per row). Mono edges first, then stereo.
+template <bool SINGLE_CAM, int STRIDE>
+BA_DEV void line_pass_edges(const FrameDev& d, const FrameOpt& o, int ml0, int ml1, int sl0, int sl1, const uint8_t* llvl,
+                            const double* R, const double* t, bool robust, int lane, double* acc) {
+  const int nm = ml1 - ml0, ne = nm + (sl1 - sl0);
+  for (int ei = lane; ei < ne; ei += STRIDE) {
+    const bool st = ei >= nm;
+    const int e = st ? sl0 + (ei - nm) : ml0 + ei;
+    if (line_excluded(d, llvl, ei, st, e)) continue;
+    Cam camv;
+    if (!SINGLE_CAM) load_cam(d.cameras, st ? d.sline_cam[e] : d.mline_cam[e], camv);
+    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
+    const size_t stride = st ? d.n_sline : d.n_mline;
+    const double* lw = (st ? d.sline_lw : d.mline_lw) + e;
+    const double* ms = (st ? d.sline_meas : d.mline_meas) + e;
+    double L[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) L[q] = lw[q * stride];
+    LineCam lc;
+    line_to_camera_fma(R, t, L, lc);
+    double c2;
+    {
+      const LineImg im = line_image(cam, lc.wc[0], lc.wc[1], lc.wc[2]);
+      const double r0 = line_row(im, ms[0], ms[stride]), r1 = line_row(im, ms[2 * stride], ms[3 * stride]);
+      c2 = __dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1));
+    }
+    if (st) {
+      double w1, w2;
+      line_right(lc, SINGLE_CAM ? o.b0 : cam.bf / cam.fx, w1, w2);
+      const LineImg im = line_image(cam, lc.wc[0], w1, w2);
+      const double r2 = line_row(im, ms[4 * stride], ms[5 * stride]), r3 = line_row(im, ms[6 * stride], ms[7 * stride]);
+      // same association as the row mapping: (r0^2 + r1^2) + (r2^2 + r3^2)
+      c2 = __dadd_rn(c2, __dadd_rn(__dmul_rn(r2, r2), __dmul_rn(r3, r3)));
+    }
+    c2 *= 0.1;
+    double w = 1.0;
+    acc[NACC - 1] += robust ? huber_nr(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
   }
 }
 
@@ -298,7 +394,7 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
 #pragma unroll
     for (int p = 0; p < k; ++p) d -= U[p][k] * U[p][k];
     if (d <= 0.0) ok = false; // NaN falls through like Eigen's test
-    const double r = rsqrt(d);
+    const double r = rsqrt_nr(d);
     inv[k] = r;
     U[k][k] = d * r;
 #pragma unroll
@@ -328,52 +424,51 @@ BA_DEV bool solve6(const double* Hp, const double* b, double lambda, double* x) 
   return true;
 }
 
-// One pass of a warp over its frame's active edges at the pose (R,t).
+// level of the k-th edge of this thread in a class: the first 32 live in a register bit mask, the rest in HBM
+BA_DEV bool edge_excluded(uint32_t mask, const uint8_t* lvl, int k, int e) {
+  return k < 32 ? ((mask >> k) & 1u) != 0 : lvl[e] != 0;
+}
+
+// One pass of a warp over the active point edges of one class (mono | stereo) of its frame at the pose (R,t).
 //  LINEARIZE: accumulate H, b and the robust chi2 (= computeActiveErrors + activeRobustChi2 + buildSystem)
 //  else      : robust chi2 only (= computeActiveErrors + activeRobustChi2)
-template <bool LINEARIZE, bool SINGLE_CAM, int STRIDE>
-BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int s0, int s1, const double* R,
-                      const double* t, bool robust, int lane, double* acc) {
-  for (int e = m0 + lane; e < m1; e += STRIDE) {
-    if (d.mono_lvl[e]) continue;
+// The thread's k-th edge is e0 + lane + k * STRIDE.
+template <bool LINEARIZE, bool STEREO, bool SINGLE_CAM, int STRIDE>
+BA_DEV void point_pass(const FrameDev& d, const FrameOpt& o, int e0, int e1, uint32_t lvlmask, const double* R,
+                       const double* t, bool robust, int lane, double* acc) {
+  const double* xw = STEREO ? d.stereo_xw : d.mono_xw;
+  const double* ms = STEREO ? d.stereo_meas : d.mono_meas;
+  const uint8_t* lvl = STEREO ? d.stereo_lvl : d.mono_lvl;
+  const size_t n = STEREO ? d.n_stereo : d.n_mono;
+  const double delta = STEREO ? o.delta_stereo : o.delta_mono;
+  for (int e = e0 + lane, k = 0; e < e1; e += STRIDE, ++k) {
+    if (edge_excluded(lvlmask, lvl, k, e)) continue;
     Cam camv;
-    if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
+    if (!SINGLE_CAM) load_cam(d.cameras, (STEREO ? d.stereo_cam : d.mono_cam)[e], camv);
     const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
-    const double X[3] = {d.mono_xw[e], d.mono_xw[d.n_mono + e], d.mono_xw[2 * d.n_mono + e]};
-    const double m[2] = {d.mono_meas[e], d.mono_meas[d.n_mono + e]};
-    double Xc[3], r[2];
-    transform_point(R, t, X, Xc);
-    point_residual<false>(cam, cam.bf, Xc, m, r);
-    const double chi2 = r[0] * r[0] + r[1] * r[1];
-    double w = 1.0;
-    const double rho0 = robust ? huber(chi2, o.delta_mono, w) : chi2;
-    acc[NACC - 1] += rho0;
-    if (LINEARIZE) {
-      double J[12];
-      point_jac_pose<false>(cam, Xc, J);
-      accumulate_pose_only<2>(J, r, w, acc);
-    }
-  }
-  for (int e = s0 + lane; e < s1; e += STRIDE) {
-    if (d.stereo_lvl[e]) continue;
-    Cam camv;
-    if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
-    const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
-    const double X[3] = {d.stereo_xw[e], d.stereo_xw[d.n_stereo + e], d.stereo_xw[2 * d.n_stereo + e]};
-    const double m[3] = {d.stereo_meas[e], d.stereo_meas[d.n_stereo + e], d.stereo_meas[2 * d.n_stereo + e]};
+    const double X[3] = {xw[e], xw[n + e], xw[2 * n + e]};
+    const double m[3] = {ms[e], ms[n + e], STEREO ? ms[2 * n + e] : 0.0};
     double Xc[3], r[3];
     transform_point(R, t, X, Xc);
-    point_residual<true>(cam, cam.bf, Xc, m, r);
-    const double chi2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double invz = rcp_nr(Xc[2]);
+    point_residual_iz<STEREO>(cam, cam.bf, Xc, invz, m, r);
+    const double chi2 = STEREO ? r[0] * r[0] + r[1] * r[1] + r[2] * r[2] : r[0] * r[0] + r[1] * r[1];
     double w = 1.0;
-    const double rho0 = robust ? huber(chi2, o.delta_stereo, w) : chi2;
+    const double rho0 = robust ? huber_nr(chi2, delta, w) : chi2;
     acc[NACC - 1] += rho0;
     if (LINEARIZE) {
-      double J[18];
-      point_jac_pose<true>(cam, Xc, J);
-      accumulate_pose_only<3>(J, r, w, acc);
+      double J[STEREO ? 18 : 12];
+      point_jac_pose_iz<STEREO>(cam, Xc, invz, J);
+      accumulate_pose_only<STEREO ? 3 : 2>(J, r, w, acc);
     }
   }
+}
+
+template <bool LINEARIZE, bool SINGLE_CAM, int STRIDE>
+BA_DEV void edge_pass(const FrameDev& d, const FrameOpt& o, int m0, int m1, int s0, int s1, uint32_t mlvl, uint32_t slvl,
+                      const double* R, const double* t, bool robust, int lane, double* acc) {
+  point_pass<LINEARIZE, false, SINGLE_CAM, STRIDE>(d, o, m0, m1, mlvl, R, t, robust, lane, acc);
+  point_pass<LINEARIZE, true, SINGLE_CAM, STRIDE>(d, o, s0, s1, slvl, R, t, robust, lane, acc);
 }
 
 BA_DEV void pose_to_Rt(const Pose& T, double* R, double* t) {
@@ -420,9 +515,11 @@ BA_DEV void frame_allreduce(double* v, double* red) {
 }
 
 template <bool SINGLE_CAM, bool HAS_LINES, int WPF>
-__global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 ? (HAS_LINES ? FRAME_LINES_MIN_BLOCKS : FRAME_MIN_BLOCKS) : 2)
+__global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF),
+                                  WPF == 1 ? (HAS_LINES ? FRAME_LINES_MIN_BLOCKS : FRAME_MIN_BLOCKS) * 4 / FRAME_WARPS : 2)
     frame_opt_kernel(const __grid_constant__ FrameDev d, const __grid_constant__ FrameOpt o) {
   constexpr int STRIDE = 32 * WPF;
+  __shared__ uint8_t line_lvl[HAS_LINES ? (WPF == 1 ? FRAME_WARPS : 1) * LINE_LVL_CAP : 1];
   __shared__ WarpState wstate[WPF == 1 ? FRAME_WARPS : 1];
   __shared__ double red[WPF == 1 ? 1 : WPF * NACC];
   __shared__ int red_i[WPF == 1 ? 1 : WPF];
@@ -431,6 +528,8 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
   const int f = WPF == 1 ? o.frame0 + blockIdx.x * FRAME_WARPS + warp : o.frame0 + blockIdx.x;
   if (f >= o.frame1) return;
   WarpState& ws = wstate[WPF == 1 ? warp : 0];
+  uint8_t* llvl = line_lvl + (HAS_LINES && WPF == 1 ? warp : 0) * LINE_LVL_CAP;
+  uint32_t mlvl = 0, slvl = 0; // levels of this thread's first 32 mono / stereo edges (bit k: edge begin + lane + k * STRIDE)
   const int m0 = d.mono_begin[f], m1 = d.mono_begin[f + 1];
   const int s0 = d.stereo_begin[f], s1 = d.stereo_begin[f + 1];
   const int ml0 = HAS_LINES ? d.mline_begin[f] : 0, ml1 = HAS_LINES ? d.mline_begin[f + 1] : 0;
@@ -475,6 +574,7 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
       d.sline_lvl[e] = 0;
       d.sline_inl[e] = d.sline_inl_in ? d.sline_inl_in[e] : 1;
     }
+    for (int i = lane; i < LINE_LVL_CAP; i += STRIDE) llvl[i] = 0;
   }
   frame_sync<WPF>();
 
@@ -493,9 +593,9 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
           double acc[NACC];
 #pragma unroll
           for (int k = 0; k < NACC; ++k) acc[k] = 0;
-          edge_pass<true, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, acc);
+          edge_pass<true, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, mlvl, slvl, T.R, T.t, robust, lane, acc);
           if (HAS_LINES) {
-            line_pass_rows<true, SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, acc);
+            line_pass_rows<SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, llvl, T.R, T.t, robust, lane, acc);
           }
           frame_allreduce<WPF, NACC>(acc, red);
           if (it == 0) { // computeLambdaInit: tau * max diag, ni = 2
@@ -553,9 +653,9 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
           {
             double a2[NACC];
             a2[NACC - 1] = 0;
-            edge_pass<false, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, T.R, T.t, robust, lane, a2);
+            edge_pass<false, SINGLE_CAM, STRIDE>(d, o, m0, m1, s0, s1, mlvl, slvl, T.R, T.t, robust, lane, a2);
             if (HAS_LINES) {
-              line_pass_rows<false, SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, T.R, T.t, robust, lane, a2);
+              line_pass_edges<SINGLE_CAM, STRIDE>(d, o, ml0, ml1, sl0, sl1, llvl, T.R, T.t, robust, lane, a2);
             }
             frame_allreduce<WPF, 1>(a2 + NACC - 1, red);
             tempChi = a2[NACC - 1];
@@ -598,7 +698,7 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
     const double* Re = Tev.R;
     const double* te = Tev.t;
     int my_out = 0;
-    for (int e = m0 + lane; e < m1; e += STRIDE) {
+    for (int e = m0 + lane, k = 0; e < m1; e += STRIDE, ++k) {
       Cam camv;
       if (!SINGLE_CAM) load_cam(d.cameras, d.mono_cam[e], camv);
       const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
@@ -607,7 +707,7 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
       // active edges keep the error of their last evaluation; the reference recomputes only
       // edges whose ->inlier is false (:347-349), at the current estimate
       const bool recompute = !d.mono_inl[e];
-      const bool was_active = !d.mono_lvl[e] && n_active > 0;
+      const bool was_active = !edge_excluded(mlvl, d.mono_lvl, k, e) && n_active > 0;
       double Xc[3], r[2];
       if (recompute || !was_active) transform_point(T.R, T.t, X, Xc);
       else transform_point(Re, te, X, Xc);
@@ -615,17 +715,18 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1]);
       const bool out = (double)chi2 > o.thr_mono;
       d.mono_inl[e] = out ? 0 : 1;
-      d.mono_lvl[e] = out ? 1 : 0;
+      if (k < 32) mlvl = (mlvl & ~(1u << k)) | ((uint32_t)out << k);
+      else d.mono_lvl[e] = out ? 1 : 0;
       my_out += out;
     }
-    for (int e = s0 + lane; e < s1; e += STRIDE) {
+    for (int e = s0 + lane, k = 0; e < s1; e += STRIDE, ++k) {
       Cam camv;
       if (!SINGLE_CAM) load_cam(d.cameras, d.stereo_cam[e], camv);
       const Cam& cam = SINGLE_CAM ? o.cam0 : camv;
       const double X[3] = {d.stereo_xw[e], d.stereo_xw[d.n_stereo + e], d.stereo_xw[2 * d.n_stereo + e]};
       const double m[3] = {d.stereo_meas[e], d.stereo_meas[d.n_stereo + e], d.stereo_meas[2 * d.n_stereo + e]};
       const bool recompute = !d.stereo_inl[e];
-      const bool was_active = !d.stereo_lvl[e] && n_active > 0;
+      const bool was_active = !edge_excluded(slvl, d.stereo_lvl, k, e) && n_active > 0;
       double Xc[3], r[3];
       if (recompute || !was_active) transform_point(T.R, T.t, X, Xc);
       else transform_point(Re, te, X, Xc);
@@ -633,7 +734,8 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
       const float chi2 = (float)(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
       const bool out = (double)chi2 > o.thr_stereo;
       d.stereo_inl[e] = out ? 0 : 1;
-      d.stereo_lvl[e] = out ? 1 : 0;
+      if (k < 32) slvl = (slvl & ~(1u << k)) | ((uint32_t)out << k);
+      else d.stereo_lvl[e] = out ? 1 : 0;
       my_out += out;
     }
     if (HAS_LINES) { // same classification for the line edges (extension)
@@ -647,13 +749,15 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
 #pragma unroll
         for (int q = 0; q < 4; ++q) m[q] = d.mline_meas[(size_t)q * d.n_mline + e];
         const bool recompute = !d.mline_inl[e];
-        const bool was_active = !d.mline_lvl[e] && n_active > 0;
+        const int ei = e - ml0;
+        const bool was_active = !line_excluded(d, llvl, ei, false, e) && n_active > 0;
         if (recompute || !was_active) line_residual<false>(cam, T.R, T.t, L, m, r);
         else line_residual<false>(cam, Re, te, L, m, r);
         const float chi2 = (float)(0.1 * (r[0] * r[0] + r[1] * r[1]));
         const bool out = (double)chi2 > o.thr_mline;
         d.mline_inl[e] = out ? 0 : 1;
-        d.mline_lvl[e] = out ? 1 : 0;
+        if (ei < LINE_LVL_CAP) llvl[ei] = out ? 1 : 0;
+        else d.mline_lvl[e] = out ? 1 : 0;
         my_out += out;
       }
       for (int e = sl0 + lane; e < sl1; e += STRIDE) {
@@ -666,13 +770,15 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
 #pragma unroll
         for (int q = 0; q < 8; ++q) m[q] = d.sline_meas[(size_t)q * d.n_sline + e];
         const bool recompute = !d.sline_inl[e];
-        const bool was_active = !d.sline_lvl[e] && n_active > 0;
+        const int ei = (ml1 - ml0) + (e - sl0);
+        const bool was_active = !line_excluded(d, llvl, ei, true, e) && n_active > 0;
         if (recompute || !was_active) line_residual<true>(cam, T.R, T.t, L, m, r);
         else line_residual<true>(cam, Re, te, L, m, r);
         const float chi2 = (float)(0.1 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]));
         const bool out = (double)chi2 > o.thr_sline;
         d.sline_inl[e] = out ? 0 : 1;
-        d.sline_lvl[e] = out ? 1 : 0;
+        if (ei < LINE_LVL_CAP) llvl[ei] = out ? 1 : 0;
+        else d.sline_lvl[e] = out ? 1 : 0;
         my_out += out;
       }
     }
@@ -687,8 +793,7 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF), WPF == 1 
     }
     n_active = n_edges - num_outlier;
     if (round == 2) robust = false; // e->setRobustKernel(0) (:364,:384)
-    frame_sync<WPF>(); // level / inlier flags written above are read by other lanes' next passes? no: each lane
-                  // re-reads only the edges it wrote (same stride), the barrier just orders the round
+    frame_sync<WPF>(); // the line levels in shared memory are read by other lanes (row mapping of line_pass_rows)
     if (n_edges < 10) break; // optimizer.edges().size() < 10 (:387)
   }
 

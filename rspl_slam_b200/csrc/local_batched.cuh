@@ -892,20 +892,6 @@ __global__ void __launch_bounds__(BT) kb_schur_prep(const __grid_constant__ Loca
 constexpr int RED_STAGES = RED_STAGES_N;
 constexpr int RED_RING = RED_STAGES * 6 * 32; // double2 per warp: [stage][piece][lane], conflict-free both ways
 
-BA_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-BA_DEV void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-BA_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-BA_DEV void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-BA_DEV void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
 template <int KIND>
 BA_DEV void schur_pair_entries(const KindDev& k, int w, const int2* ent, int n, bool diag, int lane, double* acc,
                                double2* ring) {
