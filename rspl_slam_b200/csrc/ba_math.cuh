@@ -35,6 +35,38 @@ BA_DEV void cross3(const double* a, const double* b, double* o) {
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Reciprocal / reciprocal square root / square root without the library's range test (all hot loops). The CUDA library versions test the exponent range
+// and call an out-of-line slow path; that conditional call ends the basic block, so the compiler cannot interleave
+// the evaluation of several edges. These are the same MUFU seed + FMA refinement without the range test: results
+// within 1 ulp of the IEEE quotient for normal arguments (|x| in ~[1e-290, 1e290]); 0, denormals and infinities
+// give NaN instead of +-inf / 0 (a depth of exactly 0 or a chi2 of 0 under the square root never reach them:
+// see the callers).
+// ------------------------------------------------------------------------------------------------
+BA_DEV double rcp_nr(double z) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z)); // MUFU.RCP64H: ~20 bits
+  double e = fma(-z, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y); // y (1 + e + e^2): ~60 bits
+  e = fma(-z, y, 1.0);
+  return fma(y, e, y); // final correction
+}
+BA_DEV double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // MUFU.RSQ64H: ~20 bits
+  double e = fma(-x, y * y, 1.0);
+  double p = fma(e, 0.375, 0.5);
+  y = fma(p, e * y, y); // y (1 + e/2 + 3 e^2/8): ~60 bits
+  e = fma(-x, y * y, 1.0);
+  return fma(0.5 * e, y, y); // final correction
+}
+BA_DEV double sqrt_nr(double x) { // x * rsqrt(x), exact at 0
+  const double r = x * rsqrt_nr(x);
+  return x == 0.0 ? 0.0 : r;
+}
+
+
 BA_DEV void quat_to_R(const double* q, double* R) {
   const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
   const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
@@ -245,45 +277,6 @@ BA_DEV void cp_async_wait() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Branch-free reciprocal / reciprocal square root (K7 hot loops). The CUDA library versions test the exponent range
-// and call an out-of-line slow path; that conditional call ends the basic block, so the compiler cannot interleave
-// the evaluation of several edges. These are the same MUFU seed + FMA refinement without the range test: results
-// within 1 ulp of the IEEE quotient for normal arguments (|x| in ~[1e-290, 1e290]); 0, denormals and infinities
-// give NaN instead of +-inf / 0 (a depth of exactly 0 or a chi2 of 0 under the square root never reach them:
-// see the callers).
-// ------------------------------------------------------------------------------------------------
-BA_DEV double rcp_nr(double z) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z)); // MUFU.RCP64H: ~20 bits
-  double e = fma(-z, y, 1.0);
-  e = fma(e, e, e);
-  y = fma(y, e, y); // y (1 + e + e^2): ~60 bits
-  e = fma(-z, y, 1.0);
-  return fma(y, e, y); // final correction
-}
-BA_DEV double rsqrt_nr(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); // MUFU.RSQ64H: ~20 bits
-  double e = fma(-x, y * y, 1.0);
-  double p = fma(e, 0.375, 0.5);
-  y = fma(p, e * y, y); // y (1 + e/2 + 3 e^2/8): ~60 bits
-  e = fma(-x, y * y, 1.0);
-  return fma(0.5 * e, y, y); // final correction
-}
-
-// Huber with the range-test-free rsqrt (outliers only)
-BA_DEV double huber_nr(double e, double delta, double& w) {
-  const double dsqr = delta * delta;
-  if (e <= dsqr) {
-    w = 1.0;
-    return e;
-  }
-  const double rs = rsqrt_nr(e);
-  w = delta * rs;
-  return 2 * (e * rs) * delta - dsqr;
-}
-
-// ------------------------------------------------------------------------------------------------
 // Huber (RobustKernelHuber::robustify); returns rho0, writes the weight rho1
 // ------------------------------------------------------------------------------------------------
 BA_DEV double huber(double e, double delta, double& w) {
@@ -292,9 +285,9 @@ BA_DEV double huber(double e, double delta, double& w) {
     w = 1.0;
     return e;
   }
-  // one rsqrt instead of sqrt + divide (the pair costs ~50 fp64 instructions on the device):
+  // one rsqrt (without range test) instead of sqrt + divide (the pair costs ~50 fp64 instructions on the device):
   // rho1 = delta / sqrt(e), rho0 = 2 delta sqrt(e) - delta^2 with sqrt(e) = e * rsqrt(e)
-  const double rs = rsqrt(e);
+  const double rs = rsqrt_nr(e);
   w = delta * rs;
   return 2 * (e * rs) * delta - dsqr;
 }
@@ -310,22 +303,7 @@ BA_DEV void transform_point(const double* R, const double* t, const double* X, d
   Xc[2] = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
 }
 
-template <bool STEREO>
-BA_DEV void point_residual(const Cam& cam, double bf_res, const double* Xc, const double* m, double* r) {
-  const double invz = 1.0 / Xc[2];
-  if (STEREO) {
-    const double u = Xc[0] * invz * cam.fx + cam.cx;
-    const double v = Xc[1] * invz * cam.fy + cam.cy;
-    r[0] = m[0] - u;
-    r[1] = m[1] - v;
-    r[2] = m[2] - (u - bf_res * invz);
-  } else {
-    r[0] = m[0] - (Xc[0] / Xc[2] * cam.fx + cam.cx);
-    r[1] = m[1] - (Xc[1] / Xc[2] * cam.fy + cam.cy);
-  }
-}
-
-// the same with 1 / z given (K7: rcp_nr); the mono rows use x * (1/z) instead of x / z (rounding only)
+// 1 / z given (rcp_nr: within an ulp of the reference's division; its mono edge divides x / z, here x * (1 / z))
 template <bool STEREO>
 BA_DEV void point_residual_iz(const Cam& cam, double bf_res, const double* Xc, double invz, const double* m, double* r) {
   const double u = Xc[0] * invz * cam.fx + cam.cx;
@@ -335,12 +313,17 @@ BA_DEV void point_residual_iz(const Cam& cam, double bf_res, const double* Xc, d
   if (STEREO) r[2] = m[2] - (u - bf_res * invz);
 }
 
+template <bool STEREO>
+BA_DEV void point_residual(const Cam& cam, double bf_res, const double* Xc, const double* m, double* r) {
+  point_residual_iz<STEREO>(cam, bf_res, Xc, rcp_nr(Xc[2]), m, r);
+}
+
 // d r / d xi (rows x 6, omega first), row-major Jp[row*6+col]
 template <bool STEREO>
 BA_DEV void point_jac_pose_iz(const Cam& cam, const double* Xc, double invz, double* Jp);
 template <bool STEREO>
 BA_DEV void point_jac_pose(const Cam& cam, const double* Xc, double* Jp) {
-  point_jac_pose_iz<STEREO>(cam, Xc, 1.0 / Xc[2], Jp);
+  point_jac_pose_iz<STEREO>(cam, Xc, rcp_nr(Xc[2]), Jp);
 }
 template <bool STEREO>
 BA_DEV void point_jac_pose_iz(const Cam& cam, const double* Xc, double invz, double* Jp) {
@@ -372,7 +355,7 @@ BA_DEV void point_jac_pose_iz(const Cam& cam, const double* Xc, double invz, dou
 template <bool STEREO>
 BA_DEV void point_jac_point(const Cam& cam, const double* R, const double* Xc, double* Jl) {
   const double x = Xc[0], y = Xc[1];
-  const double invz = 1.0 / Xc[2], invz2 = invz * invz;
+  const double invz = rcp_nr(Xc[2]), invz2 = invz * invz;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     Jl[k] = -cam.fx * R[k] * invz + cam.fx * x * R[6 + k] * invz2;
@@ -412,7 +395,7 @@ BA_DEV void line_image_residual(const Cam& cam, const double* wv, const double* 
   const double l2 = kv0 * wv[0] + kv1 * wv[1] + kv2 * wv[2];
   // 1 / |l_xy| with one rsqrt instead of a square root and three divisions (differs from the divisions of
   // edge_project_line.cc:32-33 by rounding only)
-  const double inv = rsqrt(l0 * l0 + l1 * l1);
+  const double inv = rsqrt_nr(l0 * l0 + l1 * l1);
   e[0] = (m[0] * l0 + m[1] * l1 + l2) * inv;
   e[1] = (m[2] * l0 + m[3] * l1 + l2) * inv;
   if (WITH_G) {
@@ -445,7 +428,7 @@ BA_DEV void line_residual(const Cam& cam, const double* R, const double* t, cons
   line_image_residual<false>(cam, lc.wc, m, r, nullptr);
   if (STEREO) {
     double wr[3];
-    line_right_moment(lc, cam.bf / cam.fx, wr);
+    line_right_moment(lc, cam.bf * rcp_nr(cam.fx), wr);
     line_image_residual<false>(cam, wr, m + 4, r + 2, nullptr);
   }
 }
@@ -458,7 +441,7 @@ BA_DEV void line_linearize(const Cam& cam, const double* R, const double* t, con
   line_to_camera(R, t, L, lc);
   double g[12]; // up to 4 rows x 3: d e / d (camera-frame moment of that image)
   line_image_residual<true>(cam, lc.wc, m, r, g);
-  const double b = cam.bf / cam.fx;
+  const double b = cam.bf * rcp_nr(cam.fx);
   if (STEREO) {
     double wr[3];
     line_right_moment(lc, b, wr);
@@ -490,21 +473,21 @@ BA_DEV void line_linearize(const Cam& cam, const double* R, const double* t, con
     Jp[6 * k + 5] = c[2];
   }
   // ---- line: orthonormal representation U = [w/|w|, d/|d|, (w x d)/|w x d|], c = |w|/|d|
-  const double nd = sqrt(L[3] * L[3] + L[4] * L[4] + L[5] * L[5]);
-  const double nw = sqrt(L[0] * L[0] + L[1] * L[1] + L[2] * L[2]);
-  const double cw = nw / nd;
+  const double dd = L[3] * L[3] + L[4] * L[4] + L[5] * L[5], ww = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
+  const double ind = rsqrt_nr(dd), inw = rsqrt_nr(ww);
+  const double nd = dd * ind, cw = (ww * inw) * ind;
   double u0[3], u1[3], u2[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    u0[i] = L[i] / nw;
-    u1[i] = L[3 + i] / nd;
+    u0[i] = L[i] * inw;
+    u1[i] = L[3 + i] * ind;
   }
   cross3(u0, u1, u2);
   {
-    const double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
-    u2[0] /= n2;
-    u2[1] /= n2;
-    u2[2] /= n2;
+    const double in2 = rsqrt_nr(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    u2[0] *= in2;
+    u2[1] *= in2;
+    u2[2] *= in2;
   }
   // world-frame tangent directions of the normalised line (w~, d~):
   //  a0: dw = 0,            dd =  2 u2
@@ -549,14 +532,14 @@ BA_DEV void line_linearize(const Cam& cam, const double* R, const double* t, con
 // Line3D::oplus (vertex_line3d.h:26-29): orthonormal representation update + normalisation
 BA_DEV void line_oplus(const double* L, const double* v, double* o) {
   const double w[3] = {L[0], L[1], L[2]}, d[3] = {L[3], L[4], L[5]};
-  const double mx = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  const double my = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-  const double wn = 1.0 / sqrt(mx * mx + my * my);
+  const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], ww = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double dn = rsqrt_nr(dd), mn = rsqrt_nr(ww); // 1 / |d|, 1 / |w|
+  const double mx = dd * dn, my = ww * mn;
+  const double wn = rsqrt_nr(mx * mx + my * my);
   const double W00 = my * wn, W01 = -mx * wn, W10 = mx * wn, W11 = my * wn;
-  const double mn = 1.0 / my, dn = 1.0 / mx;
   double mdc[3];
   cross3(w, d, mdc);
-  const double mdcn = 1.0 / sqrt(mdc[0] * mdc[0] + mdc[1] * mdc[1] + mdc[2] * mdc[2]);
+  const double mdcn = rsqrt_nr(mdc[0] * mdc[0] + mdc[1] * mdc[1] + mdc[2] * mdc[2]);
   double U[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -566,12 +549,12 @@ BA_DEV void line_oplus(const double* L, const double* v, double* o) {
   }
   double s, c;
   sincos(v[3], &s, &c);
-  double q[4] = {v[0], v[1], v[2], sqrt(1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))};
-  const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  q[0] /= qn;
-  q[1] /= qn;
-  q[2] /= qn;
-  q[3] /= qn;
+  double q[4] = {v[0], v[1], v[2], sqrt_nr(1 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))};
+  const double qn = rsqrt_nr(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= qn;
+  q[1] *= qn;
+  q[2] *= qn;
+  q[3] *= qn;
   double Ru[9];
   quat_to_R(q, Ru);
   // Un = U * Ru (only columns 0 and 1 are used); Wn = W * Rot2(v3) (only column 0 is used)
@@ -586,7 +569,7 @@ BA_DEV void line_oplus(const double* L, const double* v, double* o) {
   }
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) { // fromOrthonormal normalises, oplus normalises again
-    const double n = 1.0 / sqrt(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
+    const double n = rsqrt_nr(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
 #pragma unroll
     for (int i = 0; i < 6; ++i) o[i] *= n;
   }

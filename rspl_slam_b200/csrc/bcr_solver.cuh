@@ -59,7 +59,7 @@ __device__ __forceinline__ bool bcr_chol6(const double* Ls, int ld, int k0, doub
 #pragma unroll
     for (int p = 0; p < j; ++p) dsum -= Lk[j][p] * Lk[j][p];
     if (dsum <= 0.0) ok = false; // (NaN falls through, like Eigen's LLT test)
-    const double rs = rsqrt(dsum);
+    const double rs = ba::rsqrt_nr(dsum);
     inv[j] = rs;
     Lk[j][j] = dsum * rs;
 #pragma unroll

@@ -314,7 +314,7 @@ BA_DEV void line_pass_rows(const FrameDev& d, const FrameOpt& o, int ml0, int ml
     c2 = __dadd_rn(c2, __shfl_xor_sync(0xffffffffu, c2, 2));
     c2 *= 0.1;
     double w = 1.0;
-    const double rho0 = robust ? huber_nr(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
+    const double rho0 = robust ? huber(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
     if (act) {
       if (row == 0) acc[NACC - 1] += rho0;
       {
@@ -368,7 +368,7 @@ BA_DEV void line_pass_edges(const FrameDev& d, const FrameOpt& o, int ml0, int m
     }
     c2 *= 0.1;
     double w = 1.0;
-    acc[NACC - 1] += robust ? huber_nr(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
+    acc[NACC - 1] += robust ? huber(c2, st ? o.delta_sline : o.delta_mline, w) : c2;
   }
 }
 
@@ -454,7 +454,7 @@ BA_DEV void point_pass(const FrameDev& d, const FrameOpt& o, int e0, int e1, uin
     point_residual_iz<STEREO>(cam, cam.bf, Xc, invz, m, r);
     const double chi2 = STEREO ? r[0] * r[0] + r[1] * r[1] + r[2] * r[2] : r[0] * r[0] + r[1] * r[1];
     double w = 1.0;
-    const double rho0 = robust ? huber_nr(chi2, delta, w) : chi2;
+    const double rho0 = robust ? huber(chi2, delta, w) : chi2;
     acc[NACC - 1] += rho0;
     if (LINEARIZE) {
       double J[STEREO ? 18 : 12];

@@ -623,9 +623,9 @@ BA_DEV bool small_chol(const double* Hup, double lambda, double* Lf, double* inv
 #pragma unroll
     for (int p = 0; p < j; ++p) dsum -= Lf[j * (j + 1) / 2 + p] * Lf[j * (j + 1) / 2 + p];
     if (!(dsum > 0.0)) ok = false;
-    const double ljj = sqrt(dsum);
-    Lf[j * (j + 1) / 2 + j] = ljj;
-    inv[j] = 1.0 / ljj;
+    const double rs = rsqrt_nr(dsum); // 1 / l_jj without sqrt + divide (and their range tests)
+    Lf[j * (j + 1) / 2 + j] = dsum * rs;
+    inv[j] = rs;
 #pragma unroll
     for (int i = j + 1; i < N; ++i) {
       double s = A[i][j];
