@@ -36,6 +36,7 @@
 #ifndef RSPL_BA_G2O_OPTIMIZATION_SHIM_HPP_
 #define RSPL_BA_G2O_OPTIMIZATION_SHIM_HPP_
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -85,13 +86,38 @@ inline RsplBaContext* thread_context() {
 
 namespace detail {
 
-template <class Map>
-std::map<int, int> index_of_ids(const Map& m) {
-  std::map<int, int> idx;
-  int i = 0;
-  for (const auto& kv : m) idx[kv.first] = i++;
-  return idx;
-}
+// id -> position in the ordered container (the compact index the C-ABI takes). The ids of a window are nearly
+// contiguous (frame / mappoint / mapline counters), so a dense table answers in one load; sparse id sets fall back to a
+// binary search over the sorted keys. (A std::map lookup per constraint was 1 ms of a 13 k-constraint window.)
+class IdIndex {
+ public:
+  template <class Map>
+  explicit IdIndex(const Map& m) {
+    keys_.reserve(m.size());
+    for (const auto& kv : m) keys_.push_back(kv.first); // ascending: std::map order
+    if (keys_.empty()) return;
+    lo_ = keys_.front();
+    const long long span = (long long)keys_.back() - lo_ + 1;
+    if (span <= 8LL * (long long)keys_.size() + 4096) {
+      dense_.assign((size_t)span, -1);
+      for (size_t i = 0; i < keys_.size(); ++i) dense_[(size_t)((long long)keys_[i] - lo_)] = (int32_t)i;
+    }
+  }
+  // position of id, or -1
+  int32_t find(int id) const {
+    if (!dense_.empty()) {
+      const long long k = (long long)id - lo_;
+      return k < 0 || k >= (long long)dense_.size() ? -1 : dense_[(size_t)k];
+    }
+    const auto it = std::lower_bound(keys_.begin(), keys_.end(), id);
+    return it == keys_.end() || *it != id ? -1 : (int32_t)(it - keys_.begin());
+  }
+
+ private:
+  std::vector<int> keys_;
+  std::vector<int32_t> dense_;
+  long long lo_ = 0;
+};
 
 template <class CameraList>
 std::vector<double> flatten_cameras(const CameraList& cams) {
@@ -120,7 +146,7 @@ RsplBaOptions make_options(const Cfg& cfg) {
 
 // one constraint class -> pose / landmark index arrays + measurement planes
 template <class Vec, class GetLm, class GetMeas>
-int flatten_edges(const Vec& cons, int dim, const std::map<int, int>& pose_idx, const std::map<int, int>& lm_idx,
+int flatten_edges(const Vec& cons, int dim, const IdIndex& pose_idx, const IdIndex& lm_idx,
                   GetLm get_lm, GetMeas get_meas, std::vector<int32_t>& pose, std::vector<int32_t>& lm,
                   std::vector<int32_t>& cam, std::vector<double>& meas) {
   const size_t n = cons.size();
@@ -130,11 +156,10 @@ int flatten_edges(const Vec& cons, int dim, const std::map<int, int>& pose_idx, 
   meas.assign(n * dim, 0.0);
   for (size_t i = 0; i < n; ++i) {
     const auto& c = cons[i];
-    auto pi = pose_idx.find(c->id_pose);
-    auto li = lm_idx.find(get_lm(*c));
-    if (pi == pose_idx.end() || li == lm_idx.end()) return RSPL_BA_ERR_INVALID; // the reference would null-deref here
-    pose[i] = pi->second;
-    lm[i] = li->second;
+    const int32_t pi = pose_idx.find(c->id_pose), li = lm_idx.find(get_lm(*c));
+    if (pi < 0 || li < 0) return RSPL_BA_ERR_INVALID; // the reference would null-deref here
+    pose[i] = pi;
+    lm[i] = li;
     cam[i] = c->id_camera;
     for (int k = 0; k < dim; ++k) meas[(size_t)k * n + i] = get_meas(*c, k);
   }
@@ -154,8 +179,7 @@ int LocalmapOptimizationImpl(RsplBaContext* ctx, MapOfPosesT& poses, MapOfPoints
                              StereoLnT& stereo_line_constraints, const CfgT& cfg) {
   if (!ctx) return RSPL_BA_ERR_CUDA;
   const int np = (int)poses.size(), npt = (int)points.size(), nln = (int)lines.size();
-  const std::map<int, int> pose_idx = detail::index_of_ids(poses), point_idx = detail::index_of_ids(points),
-                           line_idx = detail::index_of_ids(lines);
+  const detail::IdIndex pose_idx(poses), point_idx(points), line_idx(lines);
   std::vector<double> pose_twc((size_t)7 * np), point_xyz((size_t)3 * npt), line_wd((size_t)6 * nln);
   std::vector<uint8_t> pose_fixed(np);
   {

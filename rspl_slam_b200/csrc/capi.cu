@@ -85,6 +85,9 @@ struct RsplBaContext {
   cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined one-shot call
   cudaStream_t s_cmp[4] = {nullptr, nullptr, nullptr, nullptr}; // chunk kernels may overlap each other
   std::vector<cudaEvent_t> pipe_ev;
+  size_t f_arena_bytes = 0;                 // size of the frame arena of the current batch
+  void* f_stage = nullptr;                  // pinned mirror of the arena for small batches (one H2D, one D2H per call)
+  size_t f_stage_cap = 0;
 
   // ---- local batch state
   DevBuf local_buf;
@@ -287,6 +290,7 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   SetDevice guard(c->device);
   cudaStreamSynchronize(c->stream);
   c->frame_buf.release();
+  if (c->f_stage) cudaFreeHost(c->f_stage);
   c->local_buf.release();
   c->batch_buf.release();
   c->tile_buf.release();
@@ -472,6 +476,7 @@ int frame_prepare(RsplBaContext* c, const RsplFrameBatch* in, FrameOffsets& o) {
     o.lslv = a.take(nsl);
   }
   CU_TRY(c, c->frame_buf.reserve(a.off));
+  c->f_arena_bytes = a.off;
   char* base = c->frame_buf.as<char>();
   ba::FrameDev& d = c->fd;
   d.n_frames = F;
@@ -714,6 +719,75 @@ extern "C" int rspl_ba_frame_batch_download(RsplBaContext* c, RsplFrameBatchResu
   return RSPL_BA_OK;
 }
 
+// Small batches (the reference's call pattern: ONE frame, map_builder.cc:583-584): the ~30 per-plane copies of the
+// general path cost more than the kernel (each cudaMemcpyAsync is 3-5 us of host time plus a DMA round trip). Here the
+// inputs are gathered into a pinned mirror of the device arena on the host, the arena goes up in ONE copy, and the
+// outputs (contiguous in the arena) come back in one copy per group and are scattered to the caller's arrays.
+static constexpr size_t FRAME_STAGE_MAX = 256 << 10;
+
+static int frame_batch_staged(RsplBaContext* c, const RsplFrameBatch* in, const RsplBaOptions* opt, RsplFrameBatchResult* out,
+                       const FrameOffsets& o) {
+  const int F = c->f_n_frames, nm = c->f_n_mono, ns = c->f_n_stereo, nml = c->f_n_mline, nsl = c->f_n_sline;
+  const bool lines = nml + nsl > 0;
+  if (c->f_stage_cap < c->f_arena_bytes) {
+    if (c->f_stage) cudaFreeHost(c->f_stage);
+    c->f_stage = nullptr;
+    c->f_stage_cap = 0;
+    CU_TRY(c, cudaHostAlloc(&c->f_stage, FRAME_STAGE_MAX, cudaHostAllocDefault));
+    c->f_stage_cap = FRAME_STAGE_MAX;
+  }
+  char* h = (char*)c->f_stage;
+  char* base = c->frame_buf.as<char>();
+#define PUT(off, src, bytes)                          \
+  do {                                                \
+    if ((src) && (bytes) > 0) memcpy(h + (off), (src), (bytes)); \
+  } while (0)
+  PUT(o.cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
+  PUT(o.pose, in->pose_twc, sizeof(double) * 7 * F);
+  PUT(o.mb, in->mono_begin, sizeof(int) * (F + 1));
+  PUT(o.sb, in->stereo_begin, sizeof(int) * (F + 1));
+  PUT(o.mm, in->mono_meas, sizeof(double) * 2 * nm);
+  PUT(o.mx, in->mono_xw, sizeof(double) * 3 * nm);
+  PUT(o.mc, in->mono_cam, sizeof(int) * nm);
+  PUT(o.mi, in->mono_inlier, (size_t)nm);
+  PUT(o.sm, in->stereo_meas, sizeof(double) * 3 * ns);
+  PUT(o.sx, in->stereo_xw, sizeof(double) * 3 * ns);
+  PUT(o.sc, in->stereo_cam, sizeof(int) * ns);
+  PUT(o.si, in->stereo_inlier, (size_t)ns);
+  size_t in_end = o.si + ns; // inputs of the point part end here; the outputs follow
+  if (lines) {
+    PUT(o.lmb, in->mono_line_begin, sizeof(int) * (F + 1));
+    PUT(o.lsb, in->stereo_line_begin, sizeof(int) * (F + 1));
+    PUT(o.lml, in->mono_line_lw, sizeof(double) * 6 * nml);
+    PUT(o.lmm, in->mono_line_meas, sizeof(double) * 4 * nml);
+    PUT(o.lmc, in->mono_line_cam, sizeof(int) * nml);
+    PUT(o.lmi, in->mono_line_inlier, (size_t)nml);
+    PUT(o.lsl, in->stereo_line_lw, sizeof(double) * 6 * nsl);
+    PUT(o.lsm, in->stereo_line_meas, sizeof(double) * 8 * nsl);
+    PUT(o.lsc, in->stereo_line_cam, sizeof(int) * nsl);
+    PUT(o.lsi, in->stereo_line_inlier, (size_t)nsl);
+    in_end = o.lsi + nsl; // one copy over the outputs of the point part in between (their content is don't-care)
+  }
+#undef PUT
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base, h, in_end, cudaMemcpyHostToDevice, s));
+  int rc = frame_launch(c, opt, 0, F, s);
+  if (rc != RSPL_BA_OK) return rc;
+  // outputs of the point part: [o.op, o.st + stats) is one contiguous range of the arena
+  const size_t out0 = o.op, out1 = o.st + sizeof(ba::DevStats) * F;
+  CU_TRY(c, cudaMemcpyAsync(h + out0, base + out0, out1 - out0, cudaMemcpyDeviceToHost, s));
+  if (lines) CU_TRY(c, cudaMemcpyAsync(h + o.olmi, base + o.olmi, (o.olsi + nsl) - o.olmi, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  memcpy(out->pose_twc, h + o.op, sizeof(double) * 7 * F);
+  if (nm) memcpy(out->mono_inlier, h + o.omi, nm);
+  if (ns) memcpy(out->stereo_inlier, h + o.osi, ns);
+  if (nml) memcpy(out->mono_line_inlier, h + o.olmi, nml);
+  if (nsl) memcpy(out->stereo_line_inlier, h + o.olsi, nsl);
+  if (out->num_inliers) memcpy(out->num_inliers, h + o.ni, sizeof(int) * F);
+  if (out->stats) memcpy(out->stats, h + o.st, sizeof(RsplBaStats) * F);
+  return RSPL_BA_OK;
+}
+
 // One call with host buffers. Frames are independent, so the batch is cut into chunks and the
 // three stages run as a pipeline on three streams: H2D of chunk k+1 and D2H of chunk k-1 overlap
 // the kernel of chunk k (B200 has separate copy engines per direction). Returns when every result
@@ -737,6 +811,7 @@ extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, c
   c->f_mb.assign(in->mono_begin, in->mono_begin + F + 1);
   c->f_sb.assign(in->stereo_begin, in->stereo_begin + F + 1);
   frame_keep_line_offsets(c, in);
+  if (c->f_arena_bytes <= FRAME_STAGE_MAX) return frame_batch_staged(c, in, opt, out, o);
   int n_chunks = F / 512;
   int max_chunks = 4;
   if (const char* e = getenv("RSPL_BA_FRAME_CHUNKS")) max_chunks = atoi(e) > 0 ? atoi(e) : max_chunks;
