@@ -1564,9 +1564,11 @@ __global__ void __launch_bounds__(256) kb_flag(const __grid_constant__ LocalDev 
 
 __global__ void __launch_bounds__(256) kb_writeback(const __grid_constant__ LocalDev d,
                                                     const __grid_constant__ BatchDev b) {
+  // grid (windows, chunks): the chunks share a window's landmarks (one huge window is as parallel as many small ones)
   const int w = blockIdx.x, tid = threadIdx.x;
-  write_landmarks<0>(d.k[0], w);
-  write_landmarks<1>(d.k[1], w);
+  write_landmarks<0>(d.k[0], w, blockIdx.y, gridDim.y);
+  write_landmarks<1>(d.k[1], w, blockIdx.y, gridDim.y);
+  if (blockIdx.y) return;
   const int p0 = d.pose_begin[w], np = d.pose_begin[w + 1] - p0;
   for (int p = tid; p < np; p += blockDim.x) {
     Pose T;

@@ -555,6 +555,8 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
       g_win((W + 127) / 128), g_winw((W + 3) / 4), g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
+  const int lm_chunks = ((c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns) + 256 * 8 - 1) / (256 * 8) > 0
+                            ? ((c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns) + 256 * 8 - 1) / (256 * 8) : 1;
   const bool fork_lines = b.Cp && b.Cl;
   int n_launch = 0;
 #define GK(stream, kern, grid, block, shm, ...)      \
@@ -659,7 +661,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     }
     if (ok) {
       GK(s, ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
-      GK(s, ba::kb_writeback, W, 256, 0, d, b);
+      GK(s, ba::kb_writeback, dim3(W, lm_chunks), 256, 0, d, b);
     }
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     ok = ok && e == cudaSuccess && graph;
@@ -875,6 +877,8 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
   }
   const dim3 g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
+  const int lm_chunks = ((c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns) + 256 * 8 - 1) / (256 * 8) > 0
+                            ? ((c->l_max_pts > c->l_max_lns ? c->l_max_pts : c->l_max_lns) + 256 * 8 - 1) / (256 * 8) : 1;
   // one super-step = a fixed sequence of launches with constant arguments
   int dense_rc = RSPL_BA_OK, coll_rc = RSPL_BA_OK;
   const int NF_all = c->l_nf_begin[W];
@@ -1043,7 +1047,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     if (pass == 0) LAUNCH(PC_FLAG_WRITEBACK, ba::kb_flag<false>, dim3(W, edge_chunks), 256, 0, d, b, lo);
   }
   LAUNCH(PC_FLAG_WRITEBACK, ba::kb_flag<true>, dim3(W, edge_chunks), 256, 0, d, b, lo);
-  LAUNCH(PC_FLAG_WRITEBACK, ba::kb_writeback, W, 256, 0, d, b);
+  LAUNCH(PC_FLAG_WRITEBACK, ba::kb_writeback, dim3(W, lm_chunks), 256, 0, d, b);
 #undef LAUNCH
 #undef LAUNCH_LN
   CU_TRY(c, cudaGetLastError());

@@ -638,10 +638,10 @@ BA_DEV bool small_chol(const double* Hup, double lambda, double* Lf, double* inv
 }
 
 template <int KIND>
-BA_DEV void write_landmarks(const KindDev& k, int w) {
+BA_DEV void write_landmarks(const KindDev& k, int w, int chunk, int n_chunks) {
   using T = KT<KIND>;
   const int l0 = k.lm_begin[w], nl = k.lm_begin[w + 1] - l0;
-  for (int i = threadIdx.x; i < nl; i += LOCAL_THREADS)
+  for (int i = chunk * blockDim.x + threadIdx.x; i < nl; i += n_chunks * blockDim.x)
 #pragma unroll
     for (int q = 0; q < T::SD; ++q) k.lm_out[(size_t)q * k.n_lm + l0 + k.orig[l0 + i]] = k.x[(size_t)q * k.n_lm + l0 + i];
 }
