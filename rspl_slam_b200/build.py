@@ -13,6 +13,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+CHECKED_LIB_PATH = os.path.join(_HERE, "..", "build", "checked", "librspl_ba_checked.so")
+
+
 def _nvcc() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -40,3 +43,20 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(r.stderr)
     return LIB_PATH
+
+
+def build_checked(force: bool = False) -> str:
+    """The same library with -DRSPL_BA_CHECKED (bounds / invariant asserts in the kernels, ba_math.cuh: BA_CHECK) into
+    build/checked/ (git-ignored, travels to the GPU box); loaded through RSPL_BA_LIB by tests/test_checked_build.py."""
+    out = os.path.abspath(CHECKED_LIB_PATH)
+    if not force and os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in sources()):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DRSPL_BA_CHECKED", "-o", out, os.path.join(CSRC, "capi.cu")]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc (checked build) failed:\n" + r.stdout + r.stderr)
+    return out

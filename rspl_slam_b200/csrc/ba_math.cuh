@@ -29,6 +29,23 @@ struct Pose {
   double t[3];
 };
 
+// Checked build (-DRSPL_BA_CHECKED, tests/test_checked_build.py): bounds / invariant asserts in the kernels. The pool's
+// compute-sanitizer is closed, so this is the substitute for memcheck: a violated assert prints its location and traps
+// (the launch then fails with an error the tests see). Compiled out of the shipped library.
+#ifdef RSPL_BA_CHECKED
+#include <stdio.h>
+#define BA_CHECK(cond)                                                                                      \
+  do {                                                                                                      \
+    if (!(cond)) {                                                                                          \
+      printf("BA_CHECK failed: %s (%s:%d) block (%d,%d,%d) thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);                                           \
+      __trap();                                                                                             \
+    }                                                                                                       \
+  } while (0)
+#else
+#define BA_CHECK(cond) ((void)0)
+#endif
+
 BA_DEV void cross3(const double* a, const double* b, double* o) {
   o[0] = a[1] * b[2] - a[2] * b[1];
   o[1] = a[2] * b[0] - a[0] * b[2];

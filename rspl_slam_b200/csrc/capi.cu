@@ -335,10 +335,11 @@ enum ProfClass {
   PC_SCHUR_REDUCE, PC_SOLVE, PC_BACKSUB, PC_CONTROL, PC_FLAG_WRITEBACK, PC_COLLECTIVE, PC_ASSEMBLE, PC_SCHUR_TILE, PC_COUNT
 };
 // records an event pair around one launch when profiling is on
-struct ProfScope {
+struct ProfScope { // event pair around launches on `stream` (default: the context stream)
   RsplBaContext* c;
   int idx = -1;
-  ProfScope(RsplBaContext* ctx, int cls) : c(ctx) {
+  cudaStream_t st;
+  ProfScope(RsplBaContext* ctx, int cls, cudaStream_t stream = nullptr) : c(ctx), st(stream ? stream : ctx->stream) {
     if (!c->prof) return;
     if (c->prof_used == c->prof_pool.size()) {
       RsplBaContext::ProfEv e;
@@ -347,10 +348,10 @@ struct ProfScope {
     }
     idx = (int)c->prof_used++;
     c->prof_pool[idx].cls = cls;
-    cudaEventRecord(c->prof_pool[idx].a, c->stream);
+    cudaEventRecord(c->prof_pool[idx].a, st);
   }
   ~ProfScope() {
-    if (idx >= 0) cudaEventRecord(c->prof_pool[idx].b, c->stream);
+    if (idx >= 0) cudaEventRecord(c->prof_pool[idx].b, st);
   }
 };
 } // namespace
@@ -602,7 +603,7 @@ int frame_launch(RsplBaContext* c, const RsplBaOptions* opt, int f0, int f1, cud
                                                    c->fd.mline_cam == nullptr && c->fd.sline_cam == nullptr);
   cudaError_t e;
   {
-    ProfScope ps(c, PC_FRAME);
+    ProfScope ps(c, PC_FRAME, stream);
     const bool lines = c->f_n_mline + c->f_n_sline > 0;
     const int n = f1 - f0;
     if (opt->frame_latency_mode) { // one CTA per frame (single calls of the reference's FrameOptimization)
@@ -822,20 +823,37 @@ extern "C" int rspl_ba_frame_batch(RsplBaContext* c, const RsplFrameBatch* in, c
   // everything queued earlier on the context stream completes first
   CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * n_chunks], c->stream));
   CU_TRY(c, cudaStreamWaitEvent(c->s_in, c->pipe_ev[2 * n_chunks], 0));
+  // on a failure in the middle of the pipeline every stream is drained before returning: copies into the caller's
+  // buffers may still be in flight, and the caller is free to release them once the call is back
+  auto drain = [&]() {
+    cudaStreamSynchronize(c->s_in);
+    for (int i = 0; i < 4; ++i) cudaStreamSynchronize(c->s_cmp[i]);
+    cudaStreamSynchronize(c->s_out);
+    cudaStreamSynchronize(c->stream);
+  };
+#define PIPE_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      drain();                                                                                \
+      return fail(c, RSPL_BA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));              \
+    }                                                                                         \
+  } while (0)
   for (int k = 0; k < n_chunks; ++k) {
     const int f0 = (int)((long long)F * k / n_chunks), f1 = (int)((long long)F * (k + 1) / n_chunks);
     cudaStream_t cs = n_chunks > 1 ? c->s_cmp[k & 3] : c->stream;
     rc = frame_copy_in(c, in, o, f0, f1, k == 0, c->s_in);
-    if (rc != RSPL_BA_OK) return rc;
-    CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * k], c->s_in));
-    CU_TRY(c, cudaStreamWaitEvent(cs, c->pipe_ev[2 * k], 0));
+    if (rc != RSPL_BA_OK) return drain(), rc;
+    PIPE_TRY(cudaEventRecord(c->pipe_ev[2 * k], c->s_in));
+    PIPE_TRY(cudaStreamWaitEvent(cs, c->pipe_ev[2 * k], 0));
     rc = frame_launch(c, opt, f0, f1, cs);
-    if (rc != RSPL_BA_OK) return rc;
-    CU_TRY(c, cudaEventRecord(c->pipe_ev[2 * k + 1], cs));
-    CU_TRY(c, cudaStreamWaitEvent(c->s_out, c->pipe_ev[2 * k + 1], 0));
+    if (rc != RSPL_BA_OK) return drain(), rc;
+    PIPE_TRY(cudaEventRecord(c->pipe_ev[2 * k + 1], cs));
+    PIPE_TRY(cudaStreamWaitEvent(c->s_out, c->pipe_ev[2 * k + 1], 0));
     rc = frame_copy_out(c, out, c->f_mb.data(), c->f_sb.data(), f0, f1, c->s_out);
-    if (rc != RSPL_BA_OK) return rc;
+    if (rc != RSPL_BA_OK) return drain(), rc;
   }
+#undef PIPE_TRY
   CU_TRY(c, cudaStreamSynchronize(c->s_out));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return RSPL_BA_OK;

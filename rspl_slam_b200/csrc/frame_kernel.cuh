@@ -535,6 +535,8 @@ __global__ void __launch_bounds__(32 * (WPF == 1 ? FRAME_WARPS : WPF),
   const int ml0 = HAS_LINES ? d.mline_begin[f] : 0, ml1 = HAS_LINES ? d.mline_begin[f + 1] : 0;
   const int sl0 = HAS_LINES ? d.sline_begin[f] : 0, sl1 = HAS_LINES ? d.sline_begin[f + 1] : 0;
   const int n_edges = (m1 - m0) + (s1 - s0) + (ml1 - ml0) + (sl1 - sl0);
+  BA_CHECK(0 <= m0 && m0 <= m1 && m1 <= d.n_mono && 0 <= s0 && s0 <= s1 && s1 <= d.n_stereo);
+  BA_CHECK(!HAS_LINES || (0 <= ml0 && ml0 <= ml1 && ml1 <= d.n_mline && 0 <= sl0 && sl0 <= sl1 && sl1 <= d.n_sline));
 
   // ---- setup: pose (g2o_optimization.cc:271), flags, levels
   PoseRt T; // optimiser pose Tcw as rotation matrix + translation (quaternion only at the boundary)

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(BT) kb_pairs(const __grid_constant__ LocalDev 
       pb[2 * p + 1] = n1;
     }
   } else {
+    BA_CHECK(pb[2 * p] >= b.pair_base[w] && pb[2 * p + 1] >= pb[2 * p] && pb[2 * p + 1] <= b.pair_base[w + 1]);
     pair_scan_kind<0, 1>(d, b, d.k[0], w, pose_i, fj, diag, lane, b.pairs + pb[2 * p]);
     pair_scan_kind<1, 1>(d, b, d.k[1], w, pose_i, fj, diag, lane, b.pairs + pb[2 * p + 1]);
   }
@@ -574,6 +575,7 @@ BA_DEV void linearize_one(const LocalDev& d, const BatchDev& b, const LocalOpt& 
     }
     if (skip) continue;
     const int p = info & 0xffff;
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
@@ -808,6 +810,7 @@ BA_DEV void schur_prep_one(const LocalDev& d, const BatchDev& b, const LocalOpt&
   for (int e = ea; e < eb; ++e) {
     const int info = k.info[e];
     const int p = info & 0xffff;
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
     const int fi = b.free_idx[p0 + p];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
     double* Ze = k.Z + (size_t)e * ZBlk<KIND>::N;
@@ -1337,6 +1340,7 @@ BA_DEV void backsub_one(const LocalDev& d, const BatchDev& b, const LocalOpt& o,
     if (k.lvl[e]) continue;
     const int info = k.info[e];
     const int p = info & 0xffff;
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
@@ -1540,6 +1544,8 @@ BA_DEV void flag_edges(const LocalDev& d, const BatchDev& b, const LocalOpt& o, 
     bool depth_ok = true;
     if (KIND == 0) {
       const int p = info & 0xffff;
+      BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
       double X[3], Xc[3];
       load_lm<0>(k, l0 + k.lm[e], X);
       transform_point(b.P_R + 9 * (size_t)(p0 + p), b.P_t + 3 * (size_t)(p0 + p), X, Xc);

@@ -394,6 +394,7 @@ BA_DEV void setup_gather_one(const KindDev& k, int l0, int e) {
   const int cam = k.cls_cam[c] ? k.cls_cam[c][idx] : 0;
   k.info[e] = k.cls_pose[c][idx] | (cam << 16) | (c << 30);
   k.lm[e] = k.newidx[l0 + k.cls_lm[c][idx]];
+  BA_CHECK(k.lm[e] >= 0 && l0 + k.lm[e] < k.n_lm);
   const int nm = c ? T::MD : (KIND == 0 ? 2 : 4); // mono: 2 of 3 (points), 4 of 8 (lines)
 #pragma unroll
   for (int q = 0; q < T::MD; ++q)

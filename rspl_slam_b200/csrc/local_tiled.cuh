@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) kt_tiles_fill(const __grid_constant__ Loc
   ushort2* dst = td.tent + td.tent_base[wk * td.Tcap + t] + td.tso[(wk * td.Tcap + t) * (b.Pmax + 1) + li];
   for (int i = beg; i < end; ++i) {
     const int2 e = b.pairs[i];
+    BA_CHECK(e.x >= ea && e.y >= ea && e.x - ea < 65536 && e.y - ea < 65536);
     dst[i - beg] = make_ushort2((unsigned short)(e.x - ea), (unsigned short)(e.y - ea));
   }
 }
@@ -263,6 +264,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   int* tso = reinterpret_cast<int*>(ent4 + n_ent4);                         // [n_ne + 1]
   int* ords = tso + n_ne + 1;                                               // [n_ne] processing order | diag << 30
   unsigned short* elm = reinterpret_cast<unsigned short*>(ords + n_ne);     // [ne] tile-local landmark of an edge
+#ifdef RSPL_BA_CHECKED
+  {
+    unsigned dyn_smem;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_smem));
+    BA_CHECK(reinterpret_cast<unsigned char*>(elm + ne) <= tile_smem + dyn_smem);
+    BA_CHECK(nl > 0 && ne >= 0 && la >= l0 && lb <= k.lm_begin[w + 1] && eb <= k.n_edge);
+  }
+#endif
   const double lambda = s.lambda;
   const bool robust = s.robust;
 
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     Rec nxt;
     if (j + TILE_THREADS < ne) load_rec(j + TILE_THREADS, nxt);
     const int p = cur.info & 0xffff;
+    BA_CHECK(p < np && cur.lm >= la - l0 && cur.lm < lb - l0);
     const int li = l0 + cur.lm - la; // tile-local landmark
     elm[j] = (unsigned short)li;
     double2* Zj = reinterpret_cast<double2*>(Zs + (size_t)j * ZN);
@@ -558,6 +568,7 @@ BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& 
     if (k.lvl[e]) continue;
     const int info = k.info[e];
     const int p = info & 0xffff;
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
     const int fi = b.free_idx[p0 + p];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
     const bool stereo = (info >> 30) & 1;
@@ -623,6 +634,7 @@ BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& 
     if (k.lvl[e]) continue;
     const int info = k.info[e];
     const int p = info & 0xffff;
+    BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);

@@ -1,0 +1,57 @@
+"""The library compiled with -DRSPL_BA_CHECKED (bounds / invariant asserts inside the kernels, `BA_CHECK` in
+ba_math.cuh) runs the frame, local, large-window and global paths on small problems without tripping an assert and
+with the same results as the shipped build. Substitute for compute-sanitizer memcheck, which is closed on the pool."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+from rspl_slam_b200 import capi, synth
+from rspl_slam_b200.problem import FrameBatch, LocalBatch
+ctx = capi.Context(device=0)
+out = {}
+fb = synth.make_frame_batch(2, 24, n_points=150, stereo_frac=0.8, n_lines=12)
+r = ctx.frame_batch(fb)
+out["frame_pose"] = r.pose_twc.tolist()
+out["frame_inl"] = int(r.stereo_inlier.sum()) + int(r.mono_inlier.sum())
+lat = capi.make_options(); lat.frame_latency_mode = 1
+r1 = ctx.frame_batch(FrameBatch.from_problems([synth.make_frame_problem(synth.config_seed(2, 5), n_points=200)]), lat)
+out["frame1_pose"] = r1.pose_twc.tolist()
+probs = [synth.make_local_problem(synth.config_seed(1, 300 + i), n_kf=4 + i, n_points=120 + 40 * i, n_lines=15 + 5 * i) for i in range(3)]
+lr = ctx.local_batch(LocalBatch.from_problems(probs))
+out["local_pose"] = lr.pose_twc.tolist()
+out["local_inl"] = int(lr.sp_inlier.sum()) + int(lr.mp_inlier.sum()) + int(lr.sl_inlier.sum()) + int(lr.ml_inlier.sum())
+big = synth.make_global_problem(synth.config_seed(5, 1), n_kf=40, n_points=3000, n_lines=300)
+gr = ctx.local_batch(LocalBatch.from_problems([big]))
+out["big_pose"] = gr.pose_twc.tolist()
+ctx.close()
+print("RESULT" + json.dumps(out))
+"""
+
+
+def _run(lib):
+    env = dict(os.environ)
+    if lib:
+        env["RSPL_BA_LIB"] = lib
+    r = subprocess.run([sys.executable, "-c", CHILD % ROOT], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, "child failed (a BA_CHECK assert traps the kernel):\n" + r.stdout[-3000:] + r.stderr[-3000:]
+    assert "BA_CHECK failed" not in r.stdout
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1]
+    return json.loads(line[len("RESULT"):])
+
+
+@pytest.mark.gpu
+def test_checked_build_runs_clean_and_matches_shipped_build():
+    from rspl_slam_b200 import build
+    lib = build.build_checked()
+    checked = _run(lib)
+    shipped = _run(None)
+    assert checked == shipped  # same kernels, same bits: the asserts only observe
