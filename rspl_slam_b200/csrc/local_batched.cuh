@@ -312,59 +312,78 @@ __global__ void __launch_bounds__(BT) kb_pairs_lm(const __grid_constant__ LocalD
   }
 }
 
-// exclusive scan of one window's 2P counts by a whole CTA (1024 threads, chunks with a running total);
-// grid = windows
+// Exclusive scan of a chunk of SCAN_ITEMS * 1024 values by a CTA of 1024 threads: thread t owns SCAN_ITEMS consecutive
+// values v[] (replaced by their exclusive prefixes within the chunk); returns the chunk total to every thread.
+// s_warp: 32 ints of shared memory. Two barriers per chunk.
+constexpr int SCAN_ITEMS = 8;
+BA_DEV int cta_scan_chunk(int (&v)[SCAN_ITEMS], int* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int sum = 0;
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u) {
+    const int x = v[u];
+    v[u] = sum;
+    sum += x;
+  }
+  int x = sum; // inclusive warp scan of the thread sums
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads(); // s_warp of the previous chunk has been read
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  int t = s_warp[lane]; // every warp scans the 32 warp totals itself (no third barrier)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, t, o);
+    if (lane >= o) t += y;
+  }
+  const int total = __shfl_sync(0xffffffffu, t, 31);
+  const int warp_before = __shfl_sync(0xffffffffu, t, warp > 0 ? warp - 1 : 0);
+  const int before = (warp ? warp_before : 0) + x - sum;
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u) v[u] += before;
+  return total;
+}
+
+// exclusive scan of one window's 2P counts by a whole CTA (1024 threads x 8 values per chunk, running total in a
+// register of every thread); grid = windows
 __global__ void __launch_bounds__(1024) kb_pairs_scan_cta(const __grid_constant__ LocalDev d,
                                                           const __grid_constant__ BatchDev b) {
   __shared__ int s_warp[32];
-  __shared__ long long s_run;
-  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = blockIdx.x, tid = threadIdx.x;
   const int nf = b.ws[w].nf;
   const int n = nf * (nf + 1); // 2 * pairs
   int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
-  if (tid == 0) s_run = b.pair_base[w];
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + tid;
-    const int v = i < n ? pb[i] : 0;
-    int x = v; // inclusive warp scan
+  long long run = b.pair_base[w];
+  for (int base = 0; base < n; base += 1024 * SCAN_ITEMS) {
+    const int i0 = base + tid * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int t = s_warp[lane];
+    for (int u = 0; u < SCAN_ITEMS; ++u) v[u] = i0 + u < n ? pb[i0 + u] : 0;
+    const int total = cta_scan_chunk(v, s_warp);
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
-      }
-      s_warp[lane] = t;
-    }
-    __syncthreads();
-    const long long run = s_run;
-    const int before = (warp ? s_warp[warp - 1] : 0) + x - v;
-    if (i < n) pb[i] = (int)(run + before);
-    __syncthreads();
-    if (tid == 0) s_run = run + s_warp[31];
-    __syncthreads();
+    for (int u = 0; u < SCAN_ITEMS; ++u)
+      if (i0 + u < n) pb[i0 + u] = (int)(run + v[u]);
+    run += total;
   }
   if (tid == 0) {
-    pb[n] = (int)s_run;
-    if (s_run > b.pair_base[w + 1]) atomicOr(d.err, LOCAL_ERR_DUP_EDGE); // capacity: only with duplicate edges
+    pb[n] = (int)run;
+    if (run > b.pair_base[w + 1]) atomicOr(d.err, LOCAL_ERR_DUP_EDGE); // capacity: only with duplicate edges
   }
 }
 
 // one warp per (window, pair): order the pair's point and line lists by their first edge (rank sort
 // through pairs_tmp: the keys of a list are distinct)
+// grid (ceil(max compact pairs / BW), windows): only the pairs of the compact list are visited (3 % of the 2 M pairs
+// of a 2000-keyframe chain)
 __global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
   const int w = blockIdx.y, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * BW + (threadIdx.x >> 5);
-  const int nf = b.ws[w].nf;
-  if (p >= nf * (nf + 1) / 2 || (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  const int li = blockIdx.x * BW + (threadIdx.x >> 5);
+  if (li >= b.n_ne[w] || (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
   const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
   for (int kind = 0; kind < 2; ++kind) {
     const int beg = pb[kind], n = pb[kind + 1] - beg;
@@ -398,52 +417,34 @@ __global__ void __launch_bounds__(256) kb_pairs_flag(const __grid_constant__ Loc
   b.ne_flag[(size_t)w * b.Pmax + p] = keep;
 }
 
-// flags -> ascending compact list (CTA scan in chunks of 1024 with a running total); grid = windows
+// flags -> ascending compact list (CTA scan, 1024 threads x 8 flags per chunk); grid = windows
 __global__ void __launch_bounds__(1024) kb_pairs_compact(const __grid_constant__ LocalDev d,
                                                          const __grid_constant__ BatchDev b) {
   __shared__ int s_warp[32];
-  __shared__ int s_run;
-  const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int w = blockIdx.x, tid = threadIdx.x;
   const int nf = b.ws[w].nf, f0 = b.nf_begin[w];
   const int n = nf * (nf + 1) / 2;
   const int* flag = b.ne_flag + (size_t)w * b.Pmax;
   int* list = b.ne_list + (size_t)w * b.Pmax;
-  if (tid == 0) s_run = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int p = base + tid;
-    const int v = p < n ? (flag[p] ? 1 : 0) : 0;
-    int x = v;
+  int run = 0;
+  for (int base = 0; base < n; base += 1024 * SCAN_ITEMS) {
+    const int p0 = base + tid * SCAN_ITEMS;
+    int v[SCAN_ITEMS], keep[SCAN_ITEMS];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= o) x += y;
-    }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      int t = s_warp[lane];
+    for (int u = 0; u < SCAN_ITEMS; ++u) keep[u] = v[u] = p0 + u < n ? (flag[p0 + u] ? 1 : 0) : 0;
+    const int total = cta_scan_chunk(v, s_warp);
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += y;
-      }
-      s_warp[lane] = t;
-    }
-    __syncthreads();
-    const int run = s_run;
-    if (v) {
-      const int pos = run + (warp ? s_warp[warp - 1] : 0) + x - 1;
+    for (int u = 0; u < SCAN_ITEMS; ++u) {
+      if (!keep[u]) continue;
+      const int p = p0 + u, pos = run + v[u];
       list[pos] = p;
       int fi, fj;
       pair_decode(p, nf, fi, fj);
       if (fi == fj) b.diag_pos[f0 + fi] = pos;
     }
-    __syncthreads();
-    if (tid == 0) s_run = run + s_warp[31];
-    __syncthreads();
+    run += total;
   }
-  if (tid == 0) b.n_ne[w] = s_run;
+  if (tid == 0) b.n_ne[w] = run;
 }
 
 // largest free-pose index distance of a pose pair that shares a landmark (dense path: is the reduced

@@ -807,8 +807,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     CU_TRY(c, cudaMemsetAsync(b.pair_cursor, 0, sizeof(int) * (size_t)W * 2 * b.Pmax, s));
     LAUNCH(PC_PAIRS, ba::kb_pairs_lm<0>, g_lm, ba::BT, 0, d, b);
     LAUNCH(PC_PAIRS, ba::kb_pairs_scan_cta, W, 1024, 0, d, b);
-    LAUNCH(PC_PAIRS, ba::kb_pairs_lm<1>, g_lm, ba::BT, 0, d, b);
-    LAUNCH(PC_PAIRS, ba::kb_pairs_sort, g_pair, ba::BT, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_lm<1>, g_lm, ba::BT, 0, d, b); // (lists in arbitrary order: sorted below, once the compact list exists)
   } else {
     LAUNCH(PC_PAIRS, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
     LAUNCH(PC_PAIRS, ba::kb_pairs_scan, g_win, 128, 0, d, b);
@@ -834,6 +833,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: a landmark has more than 254 observations");
   int n_ne_max = 1;
   for (int w = 0; w < W; ++w) n_ne_max = n_ne_host[w] > n_ne_max ? n_ne_host[w] : n_ne_max;
+  if (b.pairs_tmp) LAUNCH(PC_PAIRS, ba::kb_pairs_sort, dim3((n_ne_max + ba::BW - 1) / ba::BW, W), ba::BT, 0, d, b);
   const dim3 g_ne(n_ne_max, W);
   if (dense) {
     // which pose pairs share landmarks: a banded pattern allows the block-tridiagonal factorisation

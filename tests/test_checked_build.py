@@ -29,7 +29,7 @@ probs = [synth.make_local_problem(synth.config_seed(1, 300 + i), n_kf=4 + i, n_p
 lr = ctx.local_batch(LocalBatch.from_problems(probs))
 out["local_pose"] = lr.pose_twc.tolist()
 out["local_inl"] = int(lr.sp_inlier.sum()) + int(lr.mp_inlier.sum()) + int(lr.sl_inlier.sum()) + int(lr.ml_inlier.sum())
-big = synth.make_global_problem(synth.config_seed(5, 1), n_kf=40, n_points=3000, n_lines=300)
+big = synth.make_global_problem(synth.config_seed(5, 1), n_kf=80, n_points=6000, n_lines=600)
 gr = ctx.local_batch(LocalBatch.from_problems([big]))
 out["big_pose"] = gr.pose_twc.tolist()
 ctx.close()
