@@ -20,6 +20,7 @@
 #include "local_kernel.cuh"
 #include "local_batched.cuh"
 #include "local_tiled.cuh"
+#include "dense_chol.cuh"
 
 static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
 
@@ -125,10 +126,8 @@ struct RsplBaContext {
   int l_graph_launches_step = 0;          // kernels per super-step of the last graph launch (0: not a graph launch)
   int l_last_path = 0;                  // 2 host-driven + legacy Schur kernels, 3 host-driven + dense reduced solve, 4 tiled Schur (diagnostics)
   int l_super_steps = 0;
-  // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): cuSOLVER, loaded lazily
+  // dense reduced-system solve (windows whose 6*NF x 6*NF system exceeds shared memory): dense_chol.cuh / bcr_solver.cuh
   DevBuf dense_buf;
-  void* cusolver = nullptr; // cusolverDnHandle_t
-  void* cublas = nullptr;   // cublasHandle_t (block-tridiagonal variant)
   // global BA: NCCL communicator (comm.inl); the uploaded window is then one shard of the problem
   void* comm = nullptr; // ncclComm_t
   int comm_ranks = 1, comm_rank = 0;

@@ -86,7 +86,7 @@ struct BatchDev { // extra state of the batched path (all in HBM)
   const long long* pair_base; // [W+1] region of each window inside `pairs`
   int* n_active;  // device counter for the host poll
   // dense-solve path (reduced systems too large for shared memory): per window a row-major n x n
-  // matrix with the upper triangle filled (= column-major lower for cuSOLVER), rhs / solution, potrf info
+  // matrix with the upper triangle filled (= column-major lower for dense_chol.cuh), rhs / solution, factorisation info
   double* dense_H;
   const long long* dense_off; // [W] offset of the window's matrix in dense_H
   double* dense_b;            // [6 * NF] by free-pose offset
@@ -1157,7 +1157,7 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   }
 }
 
-// Dense-solve path, K4 split in three: assemble -> cuSOLVER potrf / potrs (host-enqueued) -> pose update.
+// Dense-solve path, K4 split in three: assemble -> dense Cholesky / cyclic reduction (host-enqueued) -> pose update.
 // grid (longest compact pair list, W), 64 threads: one CTA per pose pair block.
 __global__ void __launch_bounds__(64) kb_assemble_dense(const __grid_constant__ LocalDev d,
                                                         const __grid_constant__ BatchDev b) {

@@ -529,7 +529,7 @@ void enqueue_local_setup(RsplBaContext* c, cudaStream_t s) {
 // [pass 2: WHILE { super-step }] -> final flags -> write-back. The loop conditions are set on the device (kt_cond,
 // cudaGraphSetConditional), so the host neither polls nor synchronises; the instantiated graph is cached in the
 // context under the byte image of every kernel argument block, so a call with the same shapes and buffers is a
-// single cudaGraphLaunch. Used whenever the reduced systems fit shared memory (no cuSOLVER, no NCCL in the loop)
+// single cudaGraphLaunch. Used whenever the reduced systems fit shared memory (no HBM-resident solve, no NCCL in the loop)
 // and profiling is off.
 struct LocalGraphKey {
   ba::LocalDev d;
@@ -781,7 +781,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       g_pair1(b.Pmax > 0 ? b.Pmax : 1, W), g_win((W + 127) / 128), g_winw((W + 3) / 4);
   const int n_max = 6 * b.NFmax;
   const size_t smem_solve = sizeof(double) * ((size_t)n_max * n_max + 3 * n_max + b.NFmax + 8);
-  // reduced systems beyond shared memory: dense matrices in HBM + cuSOLVER Cholesky (dense_solver.inl)
+  // reduced systems beyond shared memory: cyclic reduction or dense Cholesky in HBM (dense_solver.inl)
   // (global BA always takes this route: its collectives sit between the kernels of a super-step)
   const bool global = c->global_mode;
   if (global && W != 1) return fail(c, RSPL_BA_ERR_INVALID, "global BA: upload exactly one window (this rank's shard)");

@@ -148,9 +148,9 @@ def test_global_ba_on_the_c5_generator(gpu_ctx, orc):
 
 def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
     """A 160-keyframe chain without loop closures: pose pairs share landmarks only within 15 keyframes, so
-    the reduced system (n = 954) is banded and is factorised tile by tile (dense_solver.inl). Points only:
+    the reduced system (n = 954) is banded and goes to the cyclic-reduction solver (bcr_solver.cuh). Points only:
     all Jacobians analytic on both sides, the result must agree with the oracle to rounding, and with the
-    full dense factorisation of the same system."""
+    hand-written dense Cholesky (dense_chol.cuh) of the same system."""
     full = synth.make_global_problem(synth.config_seed(5, 41), n_kf=160, n_points=16000, n_lines=0, loops=2)
     batch = LocalBatch.from_problems([full])
     res = gpu_ctx.local_batch(batch)
@@ -160,9 +160,8 @@ def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
     assert np.abs(res.pose_twc[:3].T - ref.pose_p).max() < 1e-9
     assert list(res.stats["iters"][0][:2]) == st["iters"][:2] and list(res.stats["trials"][0][:2]) == st["trials"][:2]
     assert abs(res.stats["final_chi2"][0] - st["final_chi2"]) <= 1e-9 * st["final_chi2"]
-    # (the default above is the hand-written cyclic-reduction solver, bcr_solver.cuh) the same system through the
-    # library tile chain (cuSOLVER / cuBLAS on block-tridiagonal tiles) and through the full dense factorisation
-    for var in ("RSPL_BA_DENSE_LIB", "RSPL_BA_DENSE_FULL"):
+    # the same system through the dense factorisation in HBM (what non-banded systems take)
+    for var in ("RSPL_BA_DENSE_FULL",):
         monkeypatch.setenv(var, "1")
         other = gpu_ctx.local_batch(batch)
         monkeypatch.delenv(var)
