@@ -82,10 +82,23 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s
     double Lk[6][6], inv[6];
     if (!bcr_chol6(Ls, ld, k0, Lk, inv)) *s_fail = 1; // (benign race: every thread writes the same value)
     __syncthreads();                                  // everyone has read the diagonal block
-    if (tid < 36) {
-      const int r = tid / 6, c = tid % 6;
-      if (c <= r) Ls[(k0 + r) * ld + k0 + c] = Lk[r][c];
-      if (c == r) dinv[k0 + r] = inv[r];
+    // (static indices, one writer: a thread-dependent index into Lk moves the whole block to local memory -- 336 bytes
+    // of stack traffic per thread and panel; it made kb_solve, bcr_eliminate and bcr_root 1.3 - 1.6 x slower)
+    {
+      // thread r * 6 + c publishes L[r][c]: the value is picked with a select chain over static indices, the store
+      // itself has a computed address
+      double v = 0.0, iv = 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) v = tid == r * 6 + c ? Lk[r][c] : v;
+        iv = tid == r * 7 ? inv[r] : iv;
+      }
+      const int r = tid / 6, c = tid - 6 * r;
+      if (tid < 36 && c <= r) {
+        Ls[(k0 + r) * ld + k0 + c] = v;
+        if (c == r) dinv[k0 + r] = iv;
+      }
     }
     for (int i = k0 + 6 + tid; i < n; i += nt) { // panel: X Lkk^T = A, one thread per row
       double xr[6];

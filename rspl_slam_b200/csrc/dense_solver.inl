@@ -23,6 +23,7 @@ struct DenseLayout {
   double* b = nullptr;
   double* Ld = nullptr;       // [n_max][DC_NB] panel diagonal factors (dense_chol.cuh)
   double* dinv = nullptr;     // [n_max]
+  double* ywork = nullptr;    // [n_max] L^-1 b
   int* info = nullptr;
   long long* d_off = nullptr;
 };
@@ -60,6 +61,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
   const size_t o_off = a.take(sizeof(long long) * W);
   const size_t o_Ld = a.take(sizeof(double) * ((size_t)n_max * ba::DC_NB + 8));
   const size_t o_dinv = a.take(sizeof(double) * ((size_t)n_max + 8));
+  const size_t o_yw = a.take(sizeof(double) * ((size_t)n_max + 8));
   L.bcr_bsp = bcr_bsp;
   size_t o_bD = 0, o_bE = 0, o_bGL = 0, o_bGR = 0, o_bg = 0;
   int bcr_M = 0;
@@ -81,6 +83,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
   L.d_off = (long long*)(base + o_off);
   L.Ld = (double*)(base + o_Ld);
   L.dinv = (double*)(base + o_dinv);
+  L.ywork = (double*)(base + o_yw);
   if (L.bcr_bsp) {
     ba::BcrDev& s = L.bcr;
     s.bs = 6 * L.bcr_bsp;
@@ -103,7 +106,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update<ba::BCR_TILES_PER_THREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
   } else {
     CU_TRY(c, cudaFuncSetAttribute(ba::dc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::DC_UPDATE_SMEM));
-    CU_TRY(c, cudaFuncSetAttribute(ba::dc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - 1024)));
+    CU_TRY(c, cudaFuncSetAttribute(ba::dc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - ba::DC_SOLVE_STATIC_SMEM)));
   }
   CU_TRY(c, cudaMemcpyAsync(L.d_off, L.off.data(), sizeof(long long) * W, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(L.info, 0, sizeof(int) * 2 * W, c->stream));
@@ -183,6 +186,7 @@ int dense_factor_solve(RsplBaContext* c, const DenseLayout& L, const std::vector
     s.A = L.H + L.off[w];
     s.Ld = L.Ld;
     s.dinv = L.dinv;
+    s.y = L.ywork;
     s.rhs = L.b + (size_t)6 * c->l_nf_begin[w];
     s.info = L.info + w; // a pivot <= 0 leaves info != 0; the substitutions then run on garbage, which kb_post_solve
                          // ignores (rejected step, like g2o's LinearSolverEigen returning false)
@@ -196,7 +200,7 @@ int dense_factor_solve(RsplBaContext* c, const DenseLayout& L, const std::vector
       c->launches += 2;
     }
     const size_t xbytes = sizeof(double) * (size_t)n + 64;
-    const bool in_smem = xbytes + 1024 <= c->smem_optin;
+    const bool in_smem = xbytes + ba::DC_SOLVE_STATIC_SMEM <= c->smem_optin;
     ba::dc_solve<<<1, ba::DC_SOLVE_THREADS, in_smem ? xbytes : 0, st>>>(s, in_smem ? 1 : 0);
     c->launches += 1;
   }
