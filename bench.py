@@ -50,7 +50,7 @@ BYTES_POSE_ONLY_MONO = 52
 BYTES_POSE_ONLY_STEREO_LINE = 124  # 64 meas + 48 world line + 4 flag + 8 chi2 (same accounting, line extension)
 BYTES_POSE_ONLY_MONO_LINE = 92
 C2_FRAMES, C2_POINTS, C2_LINES = 4096, 400, 60
-ALL_N1 = ["c2", "c2p", "c4", "c1", "c3", "frame1", "c5"]
+ALL_N1 = ["c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri"]
 ALL_MULTI = ["c2", "c2p", "c4", "c5"]
 
 
@@ -73,7 +73,82 @@ def workload_name(key, args):
     if key == "c5":
         return (f"C5 global BA: {args.kf} KF / {args.points} points / {args.lines} lines on a 3-loop trajectory, LM 10+5, "
                 "landmarks partitioned over the GPUs")
+    if key == "tri":
+        return (f"TRI batched Map::TriangulateMappoint (SURVEY 8f-4): {TRI_POINTS} new map points x 0-8 observations from "
+                f"{TRI_FRAMES} keyframes")
     raise ValueError(key)
+
+
+TRI_POINTS, TRI_FRAMES = 1_000_000, 16
+TRI_METRIC, TRI_UNIT = "map points triangulated/sec", "points/s"
+
+
+def _tri_batch(n_points):
+    """the generator is a python loop: a 20 k-point sample is tiled to the benchmark size (same content per tile)"""
+    from rspl_slam_b200 import synth
+    b = synth.make_triangulation_batch(20261018 + 6000, n_points=min(n_points, 20000), n_frames=TRI_FRAMES, max_obs=8)
+    reps = (n_points + len(b["obs_begin"]) - 2) // (len(b["obs_begin"]) - 1)
+    if reps > 1:
+        nobs = np.diff(b["obs_begin"])
+        nobs_t = np.tile(nobs, reps)[:n_points]
+        n_full = int(nobs_t.sum())
+        b = dict(b, obs_begin=np.concatenate([[0], np.cumsum(nobs_t)]).astype(np.int32),
+                 obs_frame=np.tile(b["obs_frame"], reps)[:n_full].copy(),
+                 obs_uv=np.ascontiguousarray(np.tile(b["obs_uv"], (1, reps))[:, :n_full]))
+    return b
+
+
+def bench_tri(env, steps, warmup, with_cpu):
+    """SURVEY 8(f) rank 4. value: points per second of the kernel alone (event pair around the launch, inputs
+    resident); e2e: the same through rspl_ba_triangulate_points with host arrays (copies inside)."""
+    from oracle import orc
+    ctx, args = env.ctx, env.args
+    b = _tri_batch(TRI_POINTS)
+    n, n_obs = len(b["obs_begin"]) - 1, int(b["obs_begin"][-1])
+    call = lambda: ctx.triangulate_points(b["obs_begin"], b["obs_frame"], b["obs_uv"], b["frame_twc"], b["cam5"])
+    for _ in range(warmup):
+        call()
+    ctx.set_profiling(True)
+    t0 = time.perf_counter()
+    with ClockSampler(env.local_rank) as clk:
+        for _ in range(steps):
+            env.flush.zero_()
+            env.torch.cuda.synchronize(env.dev)
+            xyz, ok, cnt = call()
+    wall = time.perf_counter() - t0
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    ms_kernel = prof["frame_opt"][0] / max(prof["frame_opt"][1], 1)
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    e2e_s = (time.perf_counter() - t1) / steps
+    alg_bytes = 20.0 * n_obs + 29.0 * n  # frame index + pixel (20 B) per observation; offsets + position + flag per point
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    res = {
+        "metric": TRI_METRIC, "value": n / (ms_kernel * 1e-3), "unit": TRI_UNIT, "n_gpus": env.world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_kernel, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name("tri", args), "l2": "flushed (256 MiB write) between timed steps",
+                   "timing": "CUDA event pair around the kernel (profiling class of the C-ABI call)"},
+        "points_ok": int(cnt), "observations": n_obs,
+        "e2e": {"value": n / e2e_s, "unit": TRI_UNIT, "h2d_bytes_per_step": int(20 * n_obs + 28 * n + 4 + 56 * TRI_FRAMES),
+                "d2h_bytes_per_step": int(25 * n), "ms_per_step": 1e3 * e2e_s,
+                "api": "rspl_ba_triangulate_points (pageable host arrays in, host arrays out)"},
+        "gpu_launches": int(prof["frame_opt"][1]),
+        "roofline": {"bound": "hbm", "kernel": "ba::triangulate_points_kernel", "achieved": achieved, "peak": env.peak,
+                     "unit": "GB/s", "frac": achieved / env.peak, "traffic": None, "peak_source": env.peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms_kernel},
+        "clocks": clk.summary(), "wall_s_timed_region": wall,
+    }
+    if with_cpu:
+        sample = _tri_batch(200_000)
+        t2 = time.perf_counter()
+        orc.triangulate_points(sample["obs_begin"], sample["obs_frame"], sample["obs_uv"], sample["frame_twc"], sample["cam5"])
+        dt = time.perf_counter() - t2
+        res["cpu_baseline"] = {"value": 200_000 / dt, "unit": TRI_UNIT, "cores": 1, "kind": "port",
+                               "sample": "200000 of 1000000 points, 1 thread", "seconds": dt}
+    return res
 
 
 def _peaks():
@@ -199,8 +274,29 @@ def cpu_baseline(key, args, budget=6.0):
             "lm_iters_per_sec": sum(sum(s["iters"]) for s in st) / dt}
 
 
+def reference_tri(args, steps, warmup):
+    from oracle import orc
+    sample = _tri_batch(200_000)
+    ts = []
+    for step in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.triangulate_points(sample["obs_begin"], sample["obs_frame"], sample["obs_uv"], sample["frame_twc"], sample["cam5"])
+        if step >= warmup:
+            ts.append(time.perf_counter() - t0)
+    value = 200_000 * len(ts) / float(sum(ts))
+    return {"impl": "reference", "metric": TRI_METRIC, "value": value, "unit": TRI_UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * float(sum(ts)) / len(ts), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name("tri", args),
+                       "reference_impl": "CPU oracle (restatement of map.cc:292-339 + Eigen's ColPivHouseholderQR)"},
+            "cpu_baseline": {"value": value, "unit": TRI_UNIT, "cores": 1, "kind": "port", "sample": "200000 of 1000000 points, 1 thread"},
+            "e2e": {"value": value, "unit": TRI_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def reference_one(key, args, steps, warmup, budget):
     from oracle import orc
+    if key == "tri":
+        return reference_tri(args, steps, warmup)
     threads = orc.max_threads()
     use = threads if key in ("c2", "c2p", "c4") else 1
     base, runner, desc = _oracle_sample(key, args, use, budget)
@@ -663,6 +759,8 @@ def sub_steps(key, args):
         return max(5, min(args.steps, 30)), 3
     if key == "c5":
         return max(1, min(args.steps, 3)), 1
+    if key == "tri":
+        return max(2, min(args.steps, 5)), 2
     return args.steps, args.warmup
 
 
@@ -685,7 +783,12 @@ def run_ours(args):
         with_cpu = not multi  # the CPU baseline is reported on rank 0 at N = 1 only
         t0 = time.perf_counter()
         _log(f"workload {key}: steps={steps} warmup={warmup}")
-        results[key] = bench_global(env, steps, warmup, with_cpu) if key == "c5" else bench_units(env, key, steps, warmup, with_cpu)
+        if key == "c5":
+            results[key] = bench_global(env, steps, warmup, with_cpu)
+        elif key == "tri":
+            results[key] = bench_tri(env, steps, warmup, with_cpu)
+        else:
+            results[key] = bench_units(env, key, steps, warmup, with_cpu)
         _log(f"workload {key} done")
         if env.rank == 0 and results[key] is not None:
             results[key]["bench_wall_s"] = time.perf_counter() - t0
@@ -704,7 +807,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "c2", "c2p", "c4", "c1", "c3", "frame1", "c5"],
+    ap.add_argument("--workload", default="all", choices=["all", "c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri"],
                     help="all: C2 headline + every other configuration as `workloads` sub-objects")
     ap.add_argument("--frame-lines", type=int, default=C2_LINES, help="lines per frame (c2)")
     ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")

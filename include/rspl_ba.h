@@ -249,6 +249,18 @@ int rspl_ba_global_upload(RsplBaContext* ctx, const RsplLocalBatch* shard);
 int rspl_ba_global_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
 int rspl_ba_global_download(RsplBaContext* ctx, RsplLocalBatchResult* out);
 
+/* --- triangulation of new map points -------------------------------------
+ * Replaces the per-point body of Map::TriangulateMappoint (/root/reference/src/map.cc:292-339) for a whole batch of
+ * points: point i has the observations obs_begin[i] .. obs_begin[i+1] - 1 (its observers with a valid keypoint,
+ * map.cc:299-314): keyframe index obs_frame[o] into frame_twc and left-image pixel (obs_uv[o], obs_uv[n_obs + o]).
+ * frame_twc [7][n_frames] = Frame::GetPose() as p, q (x, y, z, w); cam5 = fx, fy, cx, cy, bf. out_ok[i] is the
+ * reference's bool: 0 with fewer than two observations or when the 3 x 3 normal matrix has rank < 3 under
+ * ColPivHouseholderQR with threshold 1e-5; out_xyz [3][n_points] of such a point is left untouched (the reference
+ * does not call SetPosition then). *n_done (may be null): number of points triangulated. All pointers are host. */
+int rspl_ba_triangulate_points(RsplBaContext* ctx, int32_t n_points, const int32_t* obs_begin, const int32_t* obs_frame,
+                               const double* obs_uv, int32_t n_frames, const double* frame_twc, const double* cam5,
+                               double* out_xyz, uint8_t* out_ok, int32_t* n_done);
+
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
  * line, 3 stereo line, 4 / 5 mono / stereo pose-only point edge (lm = the fixed world point Xw, Jl = 0). pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]

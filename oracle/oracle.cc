@@ -24,6 +24,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <vector>
 
@@ -1569,4 +1570,137 @@ extern "C" int orc_edge_eval(int edge_type, const double* pose7, const double* l
 extern "C" void orc_huber(double chi2, double thr, double* rho3) {
   const float d = std::sqrt(thr);
   huber(chi2, (double)d, rho3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Triangulation of new map points: Map::TriangulateMappoint (src/map.cc:292-339). The least-squares
+// point closest to the observation rays: A = N I - sum b b^T / |b|^2, rhs = sum c - sum b (b . c) / |b|^2
+// (:320-326), solved with Eigen::ColPivHouseholderQR<Matrix3d> under setThreshold(1e-5) (:328-334).
+// Eigen is not vendored by the reference; the QR below restates its algorithm (Householder reflections with
+// column pivoting on the largest remaining column norm; rank = pivots with |R_ii| > threshold * max |R_jj|).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Qr3 {
+  double R[3][3]; // upper triangle after the reflections, Householder vectors below
+  double tau[3];
+  int perm[3];
+  int rank;
+};
+void qr3_colpiv(const double A[3][3], double threshold, Qr3& q) {
+  double M[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[i][j] = A[i][j];
+  for (int j = 0; j < 3; ++j) q.perm[j] = j;
+  double maxpivot = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    int best = k;
+    double best_n2 = -1.0;
+    for (int j = k; j < 3; ++j) {
+      double n2 = 0.0;
+      for (int i = k; i < 3; ++i) n2 += M[i][j] * M[i][j];
+      if (n2 > best_n2) {
+        best_n2 = n2;
+        best = j;
+      }
+    }
+    if (best != k) {
+      for (int i = 0; i < 3; ++i) std::swap(M[i][k], M[i][best]);
+      std::swap(q.perm[k], q.perm[best]);
+    }
+    // makeHouseholder on M[k..2][k]
+    double tail2 = 0.0;
+    for (int i = k + 1; i < 3; ++i) tail2 += M[i][k] * M[i][k];
+    const double c0 = M[k][k];
+    double beta, tau;
+    if (tail2 <= std::numeric_limits<double>::min()) {
+      tau = 0.0;
+      beta = c0;
+      for (int i = k + 1; i < 3; ++i) M[i][k] = 0.0;
+    } else {
+      beta = std::sqrt(c0 * c0 + tail2);
+      if (c0 >= 0.0) beta = -beta;
+      for (int i = k + 1; i < 3; ++i) M[i][k] /= (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    M[k][k] = beta;
+    q.tau[k] = tau;
+    if (std::fabs(beta) > maxpivot) maxpivot = std::fabs(beta);
+    // apply H = I - tau v v^T (v = [1, essential]) to the remaining columns
+    for (int j = k + 1; j < 3; ++j) {
+      double dot = M[k][j];
+      for (int i = k + 1; i < 3; ++i) dot += M[i][k] * M[i][j];
+      dot *= tau;
+      M[k][j] -= dot;
+      for (int i = k + 1; i < 3; ++i) M[i][j] -= dot * M[i][k];
+    }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) q.R[i][j] = M[i][j];
+  q.rank = 0;
+  for (int i = 0; i < 3; ++i)
+    if (std::fabs(M[i][i]) > threshold * maxpivot) ++q.rank;
+}
+void qr3_solve(const Qr3& q, const double b[3], double x[3]) {
+  double c[3] = {b[0], b[1], b[2]};
+  for (int k = 0; k < 3; ++k) { // c = Q^T b
+    double dot = c[k];
+    for (int i = k + 1; i < 3; ++i) dot += q.R[i][k] * c[i];
+    dot *= q.tau[k];
+    c[k] -= dot;
+    for (int i = k + 1; i < 3; ++i) c[i] -= dot * q.R[i][k];
+  }
+  double y[3];
+  for (int i = 2; i >= 0; --i) {
+    double v = c[i];
+    for (int j = i + 1; j < 3; ++j) v -= q.R[i][j] * y[j];
+    y[i] = v / q.R[i][i];
+  }
+  for (int j = 0; j < 3; ++j) x[q.perm[j]] = y[j];
+}
+} // namespace
+
+extern "C" int orc_triangulate_points(int32_t n_points, const int32_t* obs_begin, const int32_t* obs_frame, const double* obs_uv,
+                                      int32_t n_obs, const double* frame_twc, int32_t n_frames, const double* cam5,
+                                      double* out_xyz, uint8_t* out_ok) {
+  const double fx_inv = 1.0 / cam5[0], fy_inv = 1.0 / cam5[1], cx = cam5[2], cy = cam5[3];
+  int n_done = 0;
+  for (int i = 0; i < n_points; ++i) {
+    out_ok[i] = 0;
+    const int o0 = obs_begin[i], o1 = obs_begin[i + 1];
+    const int N = o1 - o0;
+    if (N < 2) continue; // :317
+    double BBt[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, csum[3] = {0, 0, 0}, bbc[3] = {0, 0, 0};
+    for (int o = o0; o < o1; ++o) {
+      const int f = obs_frame[o];
+      const M3 R3 = q_to_R(Quat{frame_twc[3 * n_frames + f], frame_twc[4 * n_frames + f], frame_twc[5 * n_frames + f],
+                                frame_twc[6 * n_frames + f]});
+      const double c[3] = {frame_twc[f], frame_twc[n_frames + f], frame_twc[2 * n_frames + f]};
+      const double bp[3] = {(obs_uv[o] - cx) * fx_inv, (obs_uv[n_obs + o] - cy) * fy_inv, 1.0};
+      double b[3];
+      for (int r = 0; r < 3; ++r) b[r] = R3.m[r][0] * bp[0] + R3.m[r][1] * bp[1] + R3.m[r][2] * bp[2];
+      const double inv_n2 = 1.0 / (b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+      const double bc = b[0] * c[0] + b[1] * c[1] + b[2] * c[2];
+      for (int r = 0; r < 3; ++r) {
+        for (int s2 = 0; s2 < 3; ++s2) BBt[r][s2] += b[r] * inv_n2 * b[s2];
+        csum[r] += c[r];
+        bbc[r] += b[r] * inv_n2 * bc;
+      }
+    }
+    double A[3][3], rhs[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int s2 = 0; s2 < 3; ++s2) A[r][s2] = (r == s2 ? (double)N : 0.0) - BBt[r][s2];
+      rhs[r] = csum[r] - bbc[r];
+    }
+    Qr3 qr;
+    qr3_colpiv(A, 1e-5, qr);
+    if (qr.rank < 3) continue; // :332
+    double x[3];
+    qr3_solve(qr, rhs, x);
+    out_xyz[i] = x[0];
+    out_xyz[n_points + i] = x[1];
+    out_xyz[2 * n_points + i] = x[2];
+    out_ok[i] = 1;
+    ++n_done;
+  }
+  return n_done;
 }

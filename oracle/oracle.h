@@ -163,6 +163,17 @@ int orc_edge_eval(int edge_type, const double* pose7, const double* lm, const do
 /* Huber (§9.5): delta = (float)sqrt(thr); out rho[3] */
 void orc_huber(double chi2, double thr, double* rho3);
 
+
+/* ---- triangulation of new map points (Map::TriangulateMappoint, src/map.cc:292-339) ----
+ * Point i has the observations obs_begin[i] .. obs_begin[i+1]: keyframe index obs_frame[o] and left-image pixel
+ * obs_uv[o], obs_uv[n_obs + o]. frame_twc [7][n_frames]: p (3), q (x, y, z, w) of Frame::GetPose(). cam5 = fx, fy, cx,
+ * cy, bf (bearing = R * ((u - cx) / fx, (v - cy) / fy, 1), camera.cc:150-155). out_ok[i] = the reference's bool
+ * (fewer than two observations or rank < 3 of the 3 x 3 normal matrix under Eigen's ColPivHouseholderQR with
+ * threshold 1e-5: false, out_xyz untouched). Returns the number of points triangulated. */
+int orc_triangulate_points(int32_t n_points, const int32_t* obs_begin, const int32_t* obs_frame, const double* obs_uv,
+                           int32_t n_obs, const double* frame_twc, int32_t n_frames, const double* cam5, double* out_xyz,
+                           uint8_t* out_ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,6 +282,26 @@ def edge_eval(edge_type: int, pose7, lm, meas, cam5, stereo_bf_float: int = 1):
     return err[:dim].copy(), Jl[:dim * ld].reshape(dim, ld).copy() if ld else np.zeros((dim, 0)), Jp[:dim * 6].reshape(dim, 6).copy()
 
 
+def triangulate_points(obs_begin, obs_frame, obs_uv, frame_twc, cam5, xyz_init=None):
+    """Map::TriangulateMappoint (map.cc:292-339) for a batch of points; same layout as rspl_ba_triangulate_points.
+    Returns (xyz [3][n], ok [n] uint8, number triangulated)."""
+    obs_begin = np.ascontiguousarray(obs_begin, dtype=np.int32)
+    obs_frame = np.ascontiguousarray(obs_frame, dtype=np.int32)
+    obs_uv = np.ascontiguousarray(obs_uv, dtype=np.float64)
+    frame_twc = np.ascontiguousarray(frame_twc, dtype=np.float64)
+    cam5 = np.ascontiguousarray(cam5, dtype=np.float64)
+    n = len(obs_begin) - 1
+    xyz = np.zeros((3, n)) if xyz_init is None else np.ascontiguousarray(xyz_init, dtype=np.float64).copy()
+    ok = np.zeros(n, dtype=np.uint8)
+    L = lib()
+    c_i32p, c_u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    L.orc_triangulate_points.argtypes = [C.c_int32, c_i32p, c_i32p, c_f64p, C.c_int32, c_f64p, C.c_int32, c_f64p, c_f64p, c_u8p]
+    L.orc_triangulate_points.restype = C.c_int
+    cnt = L.orc_triangulate_points(n, _p(obs_begin, c_i32p), _p(obs_frame, c_i32p), _p(obs_uv, c_f64p), obs_uv.shape[1],
+                                   _p(frame_twc, c_f64p), frame_twc.shape[1], _p(cam5, c_f64p), _p(xyz, c_f64p), _p(ok, c_u8p))
+    return xyz, ok, int(cnt)
+
+
 def huber(chi2: float, thr: float) -> np.ndarray:
     out = np.zeros(3)
     lib().orc_huber(chi2, thr, _p(out, c_f64p))

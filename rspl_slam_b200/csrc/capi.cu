@@ -21,6 +21,7 @@
 #include "local_batched.cuh"
 #include "local_tiled.cuh"
 #include "dense_chol.cuh"
+#include "triangulate.cuh"
 
 static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
 
@@ -993,6 +994,68 @@ extern "C" int rspl_ba_oplus(RsplBaContext* c, int kind, int32_t n, const double
   CU_TRY(c, cudaGetLastError());
   CU_TRY(c, cudaMemcpyAsync(out, base + o_o, sizeof(double) * 7 * n, cudaMemcpyDeviceToHost, s));
   CU_TRY(c, cudaStreamSynchronize(s));
+  return RSPL_BA_OK;
+}
+
+// Batched Map::TriangulateMappoint (triangulate.cuh). Host arrays in, host arrays out; out_xyz of a point that is not
+// triangulated is left untouched. *n_done (optional) receives the number of points triangulated.
+extern "C" int rspl_ba_triangulate_points(RsplBaContext* c, int32_t n_points, const int32_t* obs_begin,
+                                          const int32_t* obs_frame, const double* obs_uv, int32_t n_frames,
+                                          const double* frame_twc, const double* cam5, double* out_xyz, uint8_t* out_ok,
+                                          int32_t* n_done) {
+  if (!c || n_points < 0 || n_frames < 0 || !cam5) return RSPL_BA_ERR_INVALID;
+  if (n_done) *n_done = 0;
+  if (n_points == 0) return RSPL_BA_OK;
+  if (!offsets_ok(obs_begin, n_points) || !out_xyz || !out_ok) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: bad offsets or null outputs");
+  const int n_obs = obs_begin[n_points];
+  if (n_obs > 0 && (!obs_frame || !obs_uv || !frame_twc)) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: null observation arrays");
+  for (int o = 0; o < n_obs; ++o)
+    if (obs_frame[o] < 0 || obs_frame[o] >= n_frames) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: keyframe index out of range");
+  if (!(cam5[0] != 0.0) || !(cam5[1] != 0.0)) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: zero focal length");
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  Arena a;
+  const size_t o_beg = a.take(sizeof(int) * ((size_t)n_points + 1)), o_fr = a.take(sizeof(int) * (size_t)n_obs);
+  const size_t o_uv = a.take(sizeof(double) * 2 * (size_t)n_obs), o_tw = a.take(sizeof(double) * 7 * (size_t)n_frames);
+  const size_t o_xyz = a.take(sizeof(double) * 3 * (size_t)n_points), o_ok = a.take((size_t)n_points), o_cnt = a.take(sizeof(int));
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_beg, obs_begin, sizeof(int) * ((size_t)n_points + 1), cudaMemcpyHostToDevice, s));
+  if (n_obs > 0) {
+    CU_TRY(c, cudaMemcpyAsync(base + o_fr, obs_frame, sizeof(int) * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+    CU_TRY(c, cudaMemcpyAsync(base + o_uv, obs_uv, sizeof(double) * 2 * (size_t)n_obs, cudaMemcpyHostToDevice, s));
+  }
+  if (n_frames > 0) CU_TRY(c, cudaMemcpyAsync(base + o_tw, frame_twc, sizeof(double) * 7 * (size_t)n_frames, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemcpyAsync(base + o_xyz, out_xyz, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyHostToDevice, s)); // untouched where !ok
+  CU_TRY(c, cudaMemsetAsync(base + o_cnt, 0, sizeof(int), s));
+  ba::TriDev d;
+  d.n_points = n_points;
+  d.n_obs = n_obs;
+  d.n_frames = n_frames;
+  d.obs_begin = (const int*)(base + o_beg);
+  d.obs_frame = (const int*)(base + o_fr);
+  d.obs_uv = (const double*)(base + o_uv);
+  d.frame_twc = (const double*)(base + o_tw);
+  d.fx_inv = 1.0 / cam5[0]; // Camera::_fx_inv (camera.cc)
+  d.fy_inv = 1.0 / cam5[1];
+  d.cx = cam5[2];
+  d.cy = cam5[3];
+  d.out_xyz = (double*)(base + o_xyz);
+  d.out_ok = (uint8_t*)(base + o_ok);
+  d.n_done = (int*)(base + o_cnt);
+  {
+    ProfScope ps(c, PC_FRAME);
+    ba::triangulate_points_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(d);
+  }
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(out_xyz, base + o_xyz, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(out_ok, base + o_ok, (size_t)n_points, cudaMemcpyDeviceToHost, s));
+  int cnt = 0;
+  CU_TRY(c, cudaMemcpyAsync(&cnt, base + o_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  if (n_done) *n_done = cnt;
   return RSPL_BA_OK;
 }
 

@@ -443,3 +443,48 @@ def make_frame_batch(config: int, n_frames: int, first_instance: int = 0, n_poin
                 mline_inlier=np.ones(lmb[-1], dtype=U8),
                 sline_lw=c(lsl, 6), sline_meas=c(lsm, 8), sline_cam=np.zeros(lsb[-1], dtype=I32),
                 sline_inlier=np.ones(lsb[-1], dtype=U8)) if n_lines > 0 else {}))
+
+
+def make_triangulation_batch(seed: int, n_points: int = 4096, n_frames: int = 12, max_obs: int = 6, pixel_sigma: float = 1.0,
+                             degenerate_frac: float = 0.05):
+    """Inputs of the batched Map::TriangulateMappoint (SURVEY 8(f) rank 4): keyframes 0.25 m apart on a gently curving
+    path looking forward (8(d) trajectory), points at 1-10 m depth in front of them, each observed by 0..max_obs
+    keyframes with N(0, pixel_sigma) pixel noise. A fraction of the points is made rank-deficient on purpose (all
+    observations from one keyframe: parallel rays through one centre). Returns a dict of the C-ABI arrays + `truth`."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy, _ = EUROC_CAMERA
+    twc = np.zeros((7, n_frames))
+    Rs = []
+    yaw = 0.0
+    pos = np.zeros(3)
+    for f in range(n_frames):
+        yaw += np.deg2rad(rng.uniform(-5, 5))
+        Rwc = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
+        Rs.append(Rwc)
+        twc[:3, f] = pos
+        twc[3:, f] = R_to_quat(Rwc)
+        pos = pos + Rwc @ np.array([0.0, 0.0, 0.25])
+    truth = np.zeros((n_points, 3))
+    begin, frames, us, vs = [0], [], [], []
+    for i in range(n_points):
+        f0 = int(rng.integers(0, n_frames))
+        depth = rng.uniform(1.0, 10.0)
+        pc = np.array([rng.uniform(-0.6, 0.6) * depth, rng.uniform(-0.4, 0.4) * depth, depth])
+        X = Rs[f0] @ pc + twc[:3, f0]
+        truth[i] = X
+        n_obs = int(rng.integers(0, max_obs + 1))
+        if rng.random() < degenerate_frac:
+            cand = [f0] * max(n_obs, 2)  # every ray through the same centre and direction: rank 2
+        else:
+            cand = list(rng.permutation(n_frames)[:n_obs])
+        for f in cand:
+            xc = Rs[f].T @ (X - twc[:3, f])
+            if xc[2] < 0.2:
+                continue
+            frames.append(int(f))
+            us.append(fx * xc[0] / xc[2] + cx + rng.normal(0, pixel_sigma))
+            vs.append(fy * xc[1] / xc[2] + cy + rng.normal(0, pixel_sigma))
+        begin.append(len(frames))
+    return dict(obs_begin=np.asarray(begin, dtype=I32), obs_frame=np.asarray(frames, dtype=I32),
+                obs_uv=np.ascontiguousarray(np.stack([np.asarray(us, dtype=F64), np.asarray(vs, dtype=F64)])),
+                frame_twc=np.ascontiguousarray(twc), cam5=EUROC_CAMERA.copy(), truth=truth)
