@@ -348,6 +348,94 @@ BA_DEV int cta_scan_chunk(int (&v)[SCAN_ITEMS], int* s_warp) {
   return total;
 }
 
+// ---- device-wide versions of the two scans for LARGE windows (millions of pairs: the one-CTA loops below took
+// 2.7 + 0.9 ms on C5): chunk sums -> scan of the chunk sums -> rescan of every chunk with its offset. WHICH 0: the
+// 2P pair counts (pair_beg), 1: the keep flags (-> compact list). scratch: [W][n_chunks] ints. grid (chunks, windows).
+constexpr int SCAN_CHUNK = 1024 * SCAN_ITEMS;
+template <int WHICH>
+BA_DEV int big_scan_len(const BatchDev& b, int w) {
+  const int nf = b.ws[w].nf;
+  return WHICH == 0 ? nf * (nf + 1) : nf * (nf + 1) / 2;
+}
+template <int WHICH>
+BA_DEV int big_scan_value(const BatchDev& b, int w, int i) {
+  return WHICH == 0 ? b.pair_beg[(size_t)w * (2 * b.Pmax + 1) + i] : (b.ne_flag[(size_t)w * b.Pmax + i] ? 1 : 0);
+}
+template <int WHICH>
+__global__ void __launch_bounds__(1024) kb_big_scan_sums(const __grid_constant__ BatchDev b, int* scratch, int n_chunks) {
+  __shared__ int s_warp[32];
+  const int w = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = big_scan_len<WHICH>(b, w);
+  const int i0 = chunk * SCAN_CHUNK + tid * SCAN_ITEMS;
+  int sum = 0;
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u) sum += i0 + u < n ? big_scan_value<WHICH>(b, w, i0 + u) : 0;
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if (lane == 0) s_warp[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    const int t = __reduce_add_sync(0xffffffffu, s_warp[lane]);
+    if (lane == 0) scratch[(size_t)w * n_chunks + chunk] = t;
+  }
+}
+// grid = windows, 1024 threads: exclusive scan of the chunk sums in place (n_chunks <= SCAN_CHUNK), totals
+template <int WHICH>
+__global__ void __launch_bounds__(1024) kb_big_scan_offsets(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                            int* scratch, int n_chunks) {
+  __shared__ int s_warp[32];
+  const int w = blockIdx.x, tid = threadIdx.x;
+  int* part = scratch + (size_t)w * n_chunks;
+  const int i0 = tid * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u) v[u] = i0 + u < n_chunks ? part[i0 + u] : 0;
+  const int total = cta_scan_chunk(v, s_warp);
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u)
+    if (i0 + u < n_chunks) part[i0 + u] = v[u];
+  if (tid == 0) {
+    if (WHICH == 0) {
+      const long long run = b.pair_base[w] + total;
+      b.pair_beg[(size_t)w * (2 * b.Pmax + 1) + big_scan_len<0>(b, w)] = (int)run;
+      if (run > b.pair_base[w + 1]) atomicOr(d.err, LOCAL_ERR_DUP_EDGE); // capacity: only with duplicate edges
+    } else {
+      b.n_ne[w] = total;
+    }
+  }
+}
+template <int WHICH>
+__global__ void __launch_bounds__(1024) kb_big_scan_apply(const __grid_constant__ BatchDev b, const int* scratch, int n_chunks) {
+  __shared__ int s_warp[32];
+  const int w = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int n = big_scan_len<WHICH>(b, w);
+  if (chunk * SCAN_CHUNK >= n) return;
+  const int i0 = chunk * SCAN_CHUNK + tid * SCAN_ITEMS;
+  int v[SCAN_ITEMS], in[SCAN_ITEMS];
+#pragma unroll
+  for (int u = 0; u < SCAN_ITEMS; ++u) in[u] = v[u] = i0 + u < n ? big_scan_value<WHICH>(b, w, i0 + u) : 0;
+  cta_scan_chunk(v, s_warp);
+  const int off = scratch[(size_t)w * n_chunks + chunk];
+  if (WHICH == 0) {
+    int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1);
+    const long long base = b.pair_base[w] + off;
+#pragma unroll
+    for (int u = 0; u < SCAN_ITEMS; ++u)
+      if (i0 + u < n) pb[i0 + u] = (int)(base + v[u]);
+  } else {
+    const int nf = b.ws[w].nf, f0 = b.nf_begin[w];
+    int* list = b.ne_list + (size_t)w * b.Pmax;
+#pragma unroll
+    for (int u = 0; u < SCAN_ITEMS; ++u) {
+      if (!in[u]) continue;
+      const int p = i0 + u, pos = off + v[u];
+      list[pos] = p;
+      int fi, fj;
+      pair_decode(p, nf, fi, fj);
+      if (fi == fj) b.diag_pos[f0 + fi] = pos;
+    }
+  }
+}
+
 // exclusive scan of one window's 2P counts by a whole CTA (1024 threads x 8 values per chunk, running total in a
 // register of every thread); grid = windows
 __global__ void __launch_bounds__(1024) kb_pairs_scan_cta(const __grid_constant__ LocalDev d,
@@ -378,7 +466,11 @@ __global__ void __launch_bounds__(1024) kb_pairs_scan_cta(const __grid_constant_
 // one warp per (window, pair): order the pair's point and line lists by their first edge (rank sort
 // through pairs_tmp: the keys of a list are distinct)
 // grid (ceil(max compact pairs / BW), windows): only the pairs of the compact list are visited (3 % of the 2 M pairs
-// of a 2000-keyframe chain)
+// of a 2000-keyframe chain). Lists of up to PAIRS_SORT_SHORT entries: rank sort by one warp; longer ones (the diagonal
+// pair of a pose lists every edge of the pose: ~2000 entries on C5, where the quadratic rank sort cost 4.6 ms) are
+// left to kb_pairs_sort_long.
+constexpr int PAIRS_SORT_SHORT = 128;
+constexpr int PAIRS_SORT_CAP = 4096; // entries of the shared-memory bitonic sort (32 KB); beyond: CTA-wide rank sort
 __global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
   const int w = blockIdx.y, lane = threadIdx.x & 31;
   const int li = blockIdx.x * BW + (threadIdx.x >> 5);
@@ -387,7 +479,7 @@ __global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ Loca
   const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
   for (int kind = 0; kind < 2; ++kind) {
     const int beg = pb[kind], n = pb[kind + 1] - beg;
-    if (n < 2) continue;
+    if (n < 2 || n > PAIRS_SORT_SHORT) continue;
     int2* seg = b.pairs + beg;
     int2* tmp = b.pairs_tmp + beg;
     for (int i = lane; i < n; i += 32) {
@@ -399,6 +491,57 @@ __global__ void __launch_bounds__(BT) kb_pairs_sort(const __grid_constant__ Loca
     __syncwarp();
     for (int i = lane; i < n; i += 32) seg[i] = tmp[i];
     __syncwarp();
+  }
+}
+
+// one CTA per pair of the compact list: lists longer than PAIRS_SORT_SHORT by a bitonic sort in shared memory (keys
+// are distinct, so every sort gives the same order); grid (max compact pairs, windows), 256 threads
+__global__ void __launch_bounds__(256) kb_pairs_sort_long(const __grid_constant__ LocalDev d,
+                                                          const __grid_constant__ BatchDev b) {
+  __shared__ int2 buf[PAIRS_SORT_CAP];
+  const int w = blockIdx.y, li = blockIdx.x, tid = threadIdx.x;
+  if (li >= b.n_ne[w] || (*d.err & LOCAL_ERR_DUP_EDGE)) return;
+  const int p = b.ne_list[(size_t)w * b.Pmax + li];
+  const int* pb = b.pair_beg + (size_t)w * (2 * b.Pmax + 1) + 2 * p;
+  for (int kind = 0; kind < 2; ++kind) {
+    const int beg = pb[kind], n = pb[kind + 1] - beg;
+    if (n <= PAIRS_SORT_SHORT) continue; // (uniform over the CTA)
+    int2* seg = b.pairs + beg;
+    if (n > PAIRS_SORT_CAP) { // rank sort through pairs_tmp, whole CTA
+      int2* tmp = b.pairs_tmp + beg;
+      for (int i = tid; i < n; i += 256) {
+        const int2 v = seg[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += seg[j].x < v.x ? 1 : 0;
+        tmp[rank] = v;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += 256) seg[i] = tmp[i];
+      __syncthreads();
+      continue;
+    }
+    int m = 256;
+    while (m < n) m <<= 1;
+    for (int i = tid; i < m; i += 256) buf[i] = i < n ? seg[i] : make_int2(0x7fffffff, 0);
+    __syncthreads();
+    for (int k2 = 2; k2 <= m; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < m; i += 256) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const int2 a = buf[i], c = buf[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a.x > c.x) == up) {
+              buf[i] = c;
+              buf[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = tid; i < n; i += 256) seg[i] = buf[i];
+    __syncthreads();
   }
 }
 

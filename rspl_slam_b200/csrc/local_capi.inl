@@ -806,7 +806,18 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     CU_TRY(c, cudaMemsetAsync(b.pair_beg, 0, sizeof(int) * n_cnt, s));
     CU_TRY(c, cudaMemsetAsync(b.pair_cursor, 0, sizeof(int) * (size_t)W * 2 * b.Pmax, s));
     LAUNCH(PC_PAIRS, ba::kb_pairs_lm<0>, g_lm, ba::BT, 0, d, b);
-    LAUNCH(PC_PAIRS, ba::kb_pairs_scan_cta, W, 1024, 0, d, b);
+    {
+      // device-wide scan of the 2P counts (pairs_tmp is free until the sort: scratch for the chunk sums)
+      const int nch = (int)((2 * (long long)b.Pmax + ba::SCAN_CHUNK - 1) / ba::SCAN_CHUNK);
+      if (nch <= ba::SCAN_CHUNK && (size_t)W * nch * sizeof(int) <= sizeof(int2) * (size_t)(c->l_pair_base[W] + 1)) {
+        int* scratch = (int*)b.pairs_tmp;
+        LAUNCH(PC_PAIRS, ba::kb_big_scan_sums<0>, dim3(nch, W), 1024, 0, b, scratch, nch);
+        LAUNCH(PC_PAIRS, ba::kb_big_scan_offsets<0>, W, 1024, 0, d, b, scratch, nch);
+        LAUNCH(PC_PAIRS, ba::kb_big_scan_apply<0>, dim3(nch, W), 1024, 0, b, scratch, nch);
+      } else {
+        LAUNCH(PC_PAIRS, ba::kb_pairs_scan_cta, W, 1024, 0, d, b);
+      }
+    }
     LAUNCH(PC_PAIRS, ba::kb_pairs_lm<1>, g_lm, ba::BT, 0, d, b); // (lists in arbitrary order: sorted below, once the compact list exists)
   } else {
     LAUNCH(PC_PAIRS, ba::kb_pairs<0>, g_pair, ba::BT, 0, d, b);
@@ -820,7 +831,17 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     rc = comm_all_reduce(c, b.ne_flag, b.ne_flag, (size_t)b.Pmax, kNcclInt32, kNcclMax);
     if (rc != RSPL_BA_OK) return rc;
   }
-  LAUNCH(PC_PAIRS, ba::kb_pairs_compact, W, 1024, 0, d, b);
+  {
+    const int nch = (int)(((long long)b.Pmax + ba::SCAN_CHUNK - 1) / ba::SCAN_CHUNK);
+    if (b.pairs_tmp && nch <= ba::SCAN_CHUNK && (size_t)W * nch * sizeof(int) <= sizeof(int2) * (size_t)(c->l_pair_base[W] + 1)) {
+      int* scratch = (int*)b.pairs_tmp; // (free again: the sort below is the next user)
+      LAUNCH(PC_PAIRS, ba::kb_big_scan_sums<1>, dim3(nch, W), 1024, 0, b, scratch, nch);
+      LAUNCH(PC_PAIRS, ba::kb_big_scan_offsets<1>, W, 1024, 0, d, b, scratch, nch);
+      LAUNCH(PC_PAIRS, ba::kb_big_scan_apply<1>, dim3(nch, W), 1024, 0, b, scratch, nch);
+    } else {
+      LAUNCH(PC_PAIRS, ba::kb_pairs_compact, W, 1024, 0, d, b);
+    }
+  }
   std::vector<int> n_ne_host(W, 0);
   int setup_flags[4] = {0, 0, 0, 0}; // error flag, max degree of points / lines
   CU_TRY(c, cudaMemcpyAsync(n_ne_host.data(), b.n_ne, sizeof(int) * W, cudaMemcpyDeviceToHost, s));
@@ -833,7 +854,10 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
     return fail(c, RSPL_BA_ERR_UNSUPPORTED, "local batch: a landmark has more than 254 observations");
   int n_ne_max = 1;
   for (int w = 0; w < W; ++w) n_ne_max = n_ne_host[w] > n_ne_max ? n_ne_host[w] : n_ne_max;
-  if (b.pairs_tmp) LAUNCH(PC_PAIRS, ba::kb_pairs_sort, dim3((n_ne_max + ba::BW - 1) / ba::BW, W), ba::BT, 0, d, b);
+  if (b.pairs_tmp) {
+    LAUNCH(PC_PAIRS, ba::kb_pairs_sort, dim3((n_ne_max + ba::BW - 1) / ba::BW, W), ba::BT, 0, d, b);
+    LAUNCH(PC_PAIRS, ba::kb_pairs_sort_long, dim3(n_ne_max, W), 256, 0, d, b);
+  }
   const dim3 g_ne(n_ne_max, W);
   if (dense) {
     // which pose pairs share landmarks: a banded pattern allows the block-tridiagonal factorisation
