@@ -292,34 +292,36 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
   Rec cur;
   if (tid < ne) load_rec(tid, cur);
 
-  // ---- stage the window tables and the tile's pair entries
+  // ---- the first landmark of this thread (phase 1a), requested now as well
+  double Hup0[T::HD], bl0[LD], X0[SD];
+  bool act0 = false;
+  if (tid < nl) {
+    const int l = la + tid;
+    act0 = k.act[l];
+#pragma unroll
+    for (int q = 0; q < T::HD; ++q) Hup0[q] = k.H[(size_t)q * k.n_lm + l];
+#pragma unroll
+    for (int q = 0; q < LD; ++q) bl0[q] = k.b[(size_t)q * k.n_lm + l];
+#pragma unroll
+    for (int q = 0; q < SD; ++q) X0[q] = k.x[(size_t)q * k.n_lm + l];
+  }
+
+  // ---- stage the window tables and the tile's pair entries: cp.async, so that every copy is in flight at once and
+  // none holds registers (they are waited for at the barrier that ends phase 1a, which does not read them)
   {
     const uint4* src = reinterpret_cast<const uint4*>(td.tent + d1.y);
-    uint4 v[3];
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int i = tid + u * TILE_THREADS;
-      if (i < n_ent4) v[u] = src[i];
+    for (int i = tid; i < n_ent4; i += TILE_THREADS) cp_async16(ent4 + i, src + i);
+    for (int i = tid; i <= n_ne; i += TILE_THREADS) cp_async4(tso + i, tso_g + i);
+    for (int i = tid; i < n_ne; i += TILE_THREADS) cp_async4(ords + i, td.order + (size_t)w * b.Pmax + i);
+    for (int i = tid; i < np * 12; i += TILE_THREADS) {
+      const int p = i / 12, q = i - p * 12;
+      cp_async8(Ps + (size_t)p * 13 + q, q < 9 ? b.P_R + 9 * (size_t)(p0 + p) + q : b.P_t + 3 * (size_t)(p0 + p) + q - 9);
     }
-    for (int i = tid + 3 * TILE_THREADS; i < n_ent4; i += TILE_THREADS) ent4[i] = src[i];
-    for (int i = tid; i <= n_ne; i += TILE_THREADS) tso[i] = tso_g[i];
-    for (int i = tid; i < n_ne; i += TILE_THREADS) ords[i] = td.order[(size_t)w * b.Pmax + i];
-    for (int i = tid; i < np * 13; i += TILE_THREADS) {
-      const int p = i / 13, q = i - p * 13;
-      double v2;
-      if (q < 9) v2 = b.P_R[9 * (size_t)(p0 + p) + q];
-      else if (q < 12) v2 = b.P_t[3 * (size_t)(p0 + p) + q - 9];
-      else {
-        const int fi = b.free_idx[p0 + p];
-        v2 = (fi >= 0 && b.sys_idx[f0 + fi] >= 0) ? 1.0 : 0.0;
-      }
-      Ps[i] = v2;
-    }
-    for (int i = tid; i < d.n_cameras * 5; i += TILE_THREADS) Cs[i] = d.cameras[i];
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int i = tid + u * TILE_THREADS;
-      if (i < n_ent4) ent4[i] = v[u];
+    for (int i = tid; i < d.n_cameras * 5; i += TILE_THREADS) cp_async8(Cs + i, d.cameras + i);
+    cp_async_commit();
+    for (int p = tid; p < np; p += TILE_THREADS) {
+      const int fi = b.free_idx[p0 + p];
+      Ps[(size_t)p * 13 + 12] = (fi >= 0 && b.sys_idx[f0 + fi] >= 0) ? 1.0 : 0.0;
     }
   }
 
@@ -329,13 +331,24 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     const int l = la + i;
     double* Lm = Ls + (size_t)i * LN;
     double Hup[T::HD], bl[LD], X[SD];
-    const bool act = k.act[l];
+    bool act;
+    if (i == tid) { // requested in the prologue
+      act = act0;
 #pragma unroll
-    for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+      for (int q = 0; q < T::HD; ++q) Hup[q] = Hup0[q];
 #pragma unroll
-    for (int q = 0; q < LD; ++q) bl[q] = k.b[(size_t)q * k.n_lm + l];
+      for (int q = 0; q < LD; ++q) bl[q] = bl0[q];
 #pragma unroll
-    for (int q = 0; q < SD; ++q) X[q] = k.x[(size_t)q * k.n_lm + l];
+      for (int q = 0; q < SD; ++q) X[q] = X0[q];
+    } else {
+      act = k.act[l];
+#pragma unroll
+      for (int q = 0; q < T::HD; ++q) Hup[q] = k.H[(size_t)q * k.n_lm + l];
+#pragma unroll
+      for (int q = 0; q < LD; ++q) bl[q] = k.b[(size_t)q * k.n_lm + l];
+#pragma unroll
+      for (int q = 0; q < SD; ++q) X[q] = k.x[(size_t)q * k.n_lm + l];
+    }
 #pragma unroll
     for (int q = 0; q < SD; ++q) Lm[OFF_X + q] = X[q];
     if (!act) { // every edge of an inactive landmark is excluded (level 1): its Z blocks are zero
@@ -362,6 +375,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS)
     }
   }
   if (fail) atomicOr(&s.prep_fail, 1);
+  cp_async_wait<0>(); // the staged tables
   __syncthreads();
 
   // ---- phase 1b: Z blocks, one thread per edge; the next record is in flight while this one is processed
