@@ -217,7 +217,8 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
       H2D(ko[k].cls_begin[cl], kh[k].cls_begin[cl], sizeof(int) * (W + 1));
       H2D(ko[k].cls_pose[cl], kh[k].cls_pose[cl], sizeof(int) * n_cls[k][cl]);
       H2D(ko[k].cls_lm[cl], kh[k].cls_lm[cl], sizeof(int) * n_cls[k][cl]);
-      if (kh[k].cls_cam[cl]) H2D(ko[k].cls_cam[cl], kh[k].cls_cam[cl], sizeof(int) * n_cls[k][cl]);
+      // (one camera: the indices are validated on the host below and never read on the device, so they stay there)
+      if (kh[k].cls_cam[cl] && in->n_cameras > 1) H2D(ko[k].cls_cam[cl], kh[k].cls_cam[cl], sizeof(int) * n_cls[k][cl]);
       H2D(ko[k].cls_meas[cl], kh[k].cls_meas[cl], sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
     }
   }
@@ -269,7 +270,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
       kd.cls_begin[cl] = (const int*)(base + o.cls_begin[cl]);
       kd.cls_pose[cl] = (const int*)(base + o.cls_pose[cl]);
       kd.cls_lm[cl] = (const int*)(base + o.cls_lm[cl]);
-      kd.cls_cam[cl] = kh[k].cls_cam[cl] ? (const int*)(base + o.cls_cam[cl]) : nullptr;
+      kd.cls_cam[cl] = (kh[k].cls_cam[cl] && in->n_cameras > 1) ? (const int*)(base + o.cls_cam[cl]) : nullptr;
       kd.cls_meas[cl] = (const double*)(base + o.cls_meas[cl]);
       kd.cls_n[cl] = n_cls[k][cl];
       kd.out_inl[cl] = (uint8_t*)(base + o.out_inl[cl]);

@@ -323,10 +323,13 @@ class FrameBatch:
             sline_cam=_i(self.sline_cam[b0:b1]), sline_inlier=_u(self.sline_inlier[b0:b1]))
 
     def h2d_bytes(self) -> int:
+        """bytes the library copies to the device: every array except, with a single camera, the per-edge camera
+        indices (validated on the host, never read by the kernels)"""
+        single = len(self.cameras) == 1
         return sum(int(getattr(self, k).nbytes) for k in (
             "cameras", "pose_twc", "mono_begin", "stereo_begin", "mono_meas", "mono_xw", "mono_cam",
             "mono_inlier", "stereo_meas", "stereo_xw", "stereo_cam", "stereo_inlier") + self._LINE_FIELDS
-            if getattr(self, k) is not None)
+            if getattr(self, k) is not None and not (single and k.endswith("_cam")))
 
 
 @dataclass
@@ -445,7 +448,10 @@ class LocalBatch:
         return LocalBatch(**kw)
 
     def h2d_bytes(self) -> int:
-        return sum(int(v.nbytes) for v in self.__dict__.values() if isinstance(v, np.ndarray))
+        """bytes the library copies to the device (with a single camera the per-edge camera indices stay on the host)"""
+        single = len(self.cameras) == 1
+        return sum(int(v.nbytes) for k, v in self.__dict__.items()
+                   if isinstance(v, np.ndarray) and not (single and k.endswith("_cam")))
 
 
 @dataclass
