@@ -72,7 +72,7 @@ def workload_name(key, args):
         return f"one FrameOptimization call: 1 frame x {C2_POINTS} stereo points, Huber + 4 rounds x LM10 (latency)"
     if key == "c5":
         return (f"C5 global BA: {args.kf} KF / {args.points} points / {args.lines} lines on a 3-loop trajectory, LM 10+5, "
-                "landmarks partitioned over the GPUs")
+                "landmarks partitioned over the GPUs" + (f", loop closures every {args.closures} blocks" if getattr(args, "closures", 0) else ""))
     if key == "tri":
         return (f"TRI batched Map::TriangulateMappoint (SURVEY 8f-4): {TRI_POINTS} new map points x 0-8 observations from "
                 f"{TRI_FRAMES} keyframes")
@@ -671,7 +671,8 @@ def bench_global(env, steps, warmup, with_cpu):
     rank, world = env.rank, env.world
     _comm_init(env, ctx)
     parity = global_parity_check(env) if world > 1 else None
-    full = synth.make_global_problem(synth.config_seed(5, 0), n_kf=args.kf, n_points=args.points, n_lines=args.lines, loops=3)
+    full = synth.make_global_problem(synth.config_seed(5, 0), n_kf=args.kf, n_points=args.points, n_lines=args.lines, loops=3,
+                                     closure_every=args.closures)
     shard = shard_landmarks(full, rank, world)
     batch = LocalBatch.from_problems([shard.problem])
     pinned = _pin_batch(batch, capi)
@@ -813,6 +814,8 @@ def main():
     ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")
     ap.add_argument("--points", type=int, default=1_000_000, help="points of the global problem (c5)")
     ap.add_argument("--lines", type=int, default=100_000, help="lines of the global problem (c5)")
+    ap.add_argument("--closures", type=int, default=0,
+                    help="c5: every N-th keyframe block also shares landmarks with the next lap (loop closures; 0 = none)")
     ap.add_argument("--frames", type=int, default=C2_FRAMES, help="frames per GPU (c2)")
     ap.add_argument("--windows", type=int, default=1024, help="windows per GPU (c4)")
     args = ap.parse_args()

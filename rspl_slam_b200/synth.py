@@ -110,7 +110,7 @@ def make_local_problem(seed: int, n_kf: int = 10, n_points: int = 3000, n_lines:
                        first_kf_id: int = 0, stereo_point_frac: float = 0.85, stereo_line_frac: float = 0.70,
                        outlier_frac: float = 0.05, pixel_sigma: float = 1.0, loops: int = 0,
                        point_cap=(2, 6), line_cap=(2, 5), extra_fixed: bool = True,
-                       trajectory=None) -> LocalProblem:
+                       trajectory=None, kf_ids=None) -> LocalProblem:
     """One local-BA window (config C1 with the defaults; C3: n_kf=20, n_points=10000, n_lines=1000).
     ``trajectory`` = (Rwc, twc) places the window on a given path (used by make_global_problem)."""
     rng = np.random.default_rng(seed)
@@ -118,7 +118,8 @@ def make_local_problem(seed: int, n_kf: int = 10, n_points: int = 3000, n_lines:
     wh = EUROC_IMAGE_WH
     b = cam[4] / cam[0]
     Rwc, twc = trajectory if trajectory is not None else make_trajectory(rng, n_kf, loops=loops)
-    pose_id = np.arange(first_kf_id, first_kf_id + n_kf, dtype=I32)
+    pose_id = np.arange(first_kf_id, first_kf_id + n_kf, dtype=I32) if kf_ids is None else np.asarray(kf_ids, dtype=I32)
+    assert len(pose_id) == n_kf  # (kf_ids: explicit, ascending keyframe ids of a block that is not one run: loop closures)
     # fixed: KF 0 if in the window, else one extra fixed KF (map.cc:559,593) = the oldest one here
     pose_fixed = np.zeros(n_kf, dtype=U8)
     if first_kf_id == 0 or extra_fixed:
@@ -254,17 +255,24 @@ def make_local_problem(seed: int, n_kf: int = 10, n_points: int = 3000, n_lines:
 
 
 def make_global_problem(seed: int, n_kf: int = 2000, n_points: int = 1_000_000, n_lines: int = 100_000,
-                        loops: int = 3, block: int = 16) -> LocalProblem:
+                        loops: int = 3, block: int = 16, closure_every: int = 0) -> LocalProblem:
     """Config C5: ONE problem over a long multi-loop trajectory, keyframe 0 fixed. Built from
     overlapping blocks of ``block`` consecutive keyframes (stride block/2): the landmarks of a block are
     sampled in its frusta and observed by 2-6 (points) / 2-5 (lines) of its keyframes, exactly like a
     local window, so the cost is linear in the problem size; the overlap chains the blocks together.
-    Poses are perturbed once, globally (2 cm, 0.5 deg, §8d)."""
+    Poses are perturbed once, globally (2 cm, 0.5 deg, §8d).
+    ``closure_every`` = c > 0 adds LOOP CLOSURES: every c-th block gets a sibling block made of its first half and the
+    keyframes at the same place one lap later, whose landmarks are seen from both laps (cross-loop covisibility: the
+    reduced camera system is then no longer banded). 0 (the default and the C5 bench): none."""
     rng = np.random.default_rng(seed)
     Rwc, twc = make_trajectory(rng, n_kf, loops=loops)
     stride = max(block // 2, 1)
     starts = list(range(0, max(n_kf - stride, 1), stride))
-    nb = len(starts)
+    lap = n_kf // loops if loops > 0 else 0
+    half = max(block // 2, 2)
+    closures = [s0 for bi, s0 in enumerate(starts)
+                if closure_every > 0 and lap > block and bi % closure_every == 0 and s0 + lap + half <= n_kf]
+    nb = len(starts) + len(closures)
     parts = []
     for bi, s0 in enumerate(starts):
         e0 = min(s0 + block, n_kf)
@@ -272,6 +280,13 @@ def make_global_problem(seed: int, n_kf: int = 2000, n_points: int = 1_000_000, 
         nlb = n_lines // nb + (1 if bi < n_lines % nb else 0)
         parts.append(make_local_problem(seed + 7919 * (bi + 1), n_kf=e0 - s0, n_points=npb, n_lines=nlb, first_kf_id=s0,
                                         trajectory=(Rwc[s0:e0], twc[s0:e0])))
+    for ci, s0 in enumerate(closures):
+        bi = len(starts) + ci
+        ids = np.concatenate([np.arange(s0, s0 + half), np.arange(s0 + lap, s0 + lap + half)])
+        npb = n_points // nb + (1 if bi < n_points % nb else 0)
+        nlb = n_lines // nb + (1 if bi < n_lines % nb else 0)
+        parts.append(make_local_problem(seed + 7919 * (bi + 1), n_kf=len(ids), n_points=npb, n_lines=nlb, kf_ids=ids,
+                                        extra_fixed=False, trajectory=(Rwc[ids], twc[ids])))
     pt_space = max(int(p.point_id.max()) + 1 if len(p.point_id) else 1 for p in parts)
     ln_space = max(int(p.line_id.max()) + 1 if len(p.line_id) else 1 for p in parts)
     cat = lambda name: np.concatenate([getattr(p, name) for p in parts])

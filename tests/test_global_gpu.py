@@ -166,3 +166,23 @@ def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
         other = gpu_ctx.local_batch(batch)
         monkeypatch.delenv(var)
         assert np.array_equal(other.sp_inlier, res.sp_inlier) and np.abs(other.pose_twc - res.pose_twc).max() < 1e-9
+
+
+def test_loop_closures_take_the_dense_cholesky(gpu_ctx, orc):
+    """A three-lap trajectory whose laps SHARE landmarks (cross-loop covisibility, `closure_every`): the reduced camera
+    system (n = 570) is not banded within 24 poses, so it goes to the hand-written dense Cholesky in HBM
+    (dense_chol.cuh). Points only (all Jacobians analytic on both sides): agreement with the oracle to rounding."""
+    full = synth.make_global_problem(synth.config_seed(5, 77), n_kf=96, n_points=6000, n_lines=0, loops=3, closure_every=2)
+    obs = {}
+    for pid, kf in list(zip(full.sp_id_point, full.sp_id_pose)) + list(zip(full.mp_id_point, full.mp_id_pose)):
+        lo, hi = obs.get(pid, (kf, kf))
+        obs[pid] = (min(lo, kf), max(hi, kf))
+    assert max(hi - lo for lo, hi in obs.values()) > 24  # closures present: beyond the cyclic-reduction band
+    batch = LocalBatch.from_problems([full])
+    res = gpu_ctx.local_batch(batch)
+    ref = full.copy()
+    st = orc.local_ba(ref)
+    assert np.array_equal(res.sp_inlier, ref.sp_inlier) and np.array_equal(res.mp_inlier, ref.mp_inlier)
+    assert np.abs(res.pose_twc[:3].T - ref.pose_p).max() < 1e-9
+    assert list(res.stats["iters"][0][:2]) == st["iters"][:2] and list(res.stats["trials"][0][:2]) == st["trials"][:2]
+    assert abs(res.stats["final_chi2"][0] - st["final_chi2"]) <= 1e-9 * st["final_chi2"]
