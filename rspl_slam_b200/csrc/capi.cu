@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/rspl_ba.h"
@@ -92,6 +93,12 @@ struct RsplBaContext {
   size_t f_stage_cap = 0;
 
   // ---- local batch state
+  // plane strides of the caller's arrays when the uploaded batch is a window range of a larger one (the chunked
+  // one-shot call, local_capi.inl); 0 = the planes are contiguous (stride = count)
+  struct LocalStrides {
+    size_t pose = 0, lm[2] = {0, 0}, cls[2][2] = {{0, 0}, {0, 0}};
+  } l_stride;
+  std::vector<RsplBaContext*> kids; // child contexts of the chunked one-shot local call (own streams and workspaces)
   DevBuf local_buf;
   ba::LocalDev ld{};
   bool local_uploaded = false;
@@ -174,23 +181,48 @@ bool offsets_ok(const int32_t* b, int n) {
   return true;
 }
 
+// The O(edges) input checks run on a few host threads: at 13.6 M constraints (C4) one thread needs ~15 ms to read
+// the index arrays, longer than the 10 ms their upload takes on the link it is hidden behind.
+template <class F>
+bool parallel_all(long long n_items, long long min_per_thread, F&& ok_range) {
+  unsigned hw = std::thread::hardware_concurrency();
+  long long nt = hw ? (hw < 8 ? hw : 8) : 1;
+  if (n_items / (min_per_thread > 0 ? min_per_thread : 1) < nt) nt = n_items / (min_per_thread > 0 ? min_per_thread : 1);
+  if (nt <= 1) return ok_range(0, n_items);
+  std::vector<std::thread> th;
+  std::vector<char> ok((size_t)nt, 1);
+  for (long long t = 0; t < nt; ++t)
+    th.emplace_back([&, t]() { ok[(size_t)t] = ok_range(n_items * t / nt, n_items * (t + 1) / nt) ? 1 : 0; });
+  bool all = true;
+  for (long long t = 0; t < nt; ++t) {
+    th[(size_t)t].join();
+    all = all && ok[(size_t)t];
+  }
+  return all;
+}
+
 bool indices_ok(const int32_t* idx, const int32_t* ebeg, const int32_t* vbeg, int n_units) {
   // every edge of unit u references a vertex in [0, vbeg[u+1]-vbeg[u])
   // (branch-free inner loop so that the compiler vectorises it: this runs over every edge of a batch)
-  unsigned bad = 0;
-  for (int u = 0; u < n_units; ++u) {
-    const unsigned nv = (unsigned)(vbeg[u + 1] - vbeg[u]);
-    const int a = ebeg[u], b = ebeg[u + 1];
-    for (int e = a; e < b; ++e) bad |= (unsigned)((unsigned)idx[e] >= nv);
-  }
-  return bad == 0;
+  const long long n_edges = n_units > 0 ? (long long)ebeg[n_units] : 0;
+  return parallel_all(n_units, n_units > 0 ? (1LL << 18) * n_units / (n_edges > 0 ? n_edges : 1) + 1 : 1, [&](long long u0, long long u1) {
+    unsigned bad = 0;
+    for (long long u = u0; u < u1; ++u) {
+      const unsigned nv = (unsigned)(vbeg[u + 1] - vbeg[u]);
+      const int a = ebeg[u], b = ebeg[u + 1];
+      for (int e = a; e < b; ++e) bad |= (unsigned)((unsigned)idx[e] >= nv);
+    }
+    return bad == 0;
+  });
 }
 
 bool cams_ok(const int32_t* cam, int n, int n_cameras) {
   if (!cam) return true;
-  unsigned bad = 0;
-  for (int i = 0; i < n; ++i) bad |= (unsigned)((unsigned)cam[i] >= (unsigned)n_cameras);
-  return bad == 0;
+  return parallel_all(n, 1 << 18, [&](long long i0, long long i1) {
+    unsigned bad = 0;
+    for (long long i = i0; i < i1; ++i) bad |= (unsigned)((unsigned)cam[i] >= (unsigned)n_cameras);
+    return bad == 0;
+  });
 }
 
 struct SetDevice {
@@ -287,6 +319,8 @@ static void comm_release(RsplBaContext* c);  // comm.inl
 
 extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   if (!c) return;
+  for (RsplBaContext* k : c->kids) rspl_ba_destroy(k);
+  c->kids.clear();
   SetDevice guard(c->device);
   cudaStreamSynchronize(c->stream);
   c->frame_buf.release();

@@ -205,23 +205,33 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   do {                                                                                                    \
     if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s)); \
   } while (0)
+  // component planes [comps][n]: one copy when the caller's planes are contiguous, one per component when the batch is
+  // a window range of a larger one (stride = the plane length of the whole batch)
+#define H2D_PLANES(off, src, comps, n, stride)                                                                       \
+  do {                                                                                                               \
+    if ((stride) == 0 || (stride) == (size_t)(n)) H2D((off), (src), sizeof(double) * (size_t)(comps) * (size_t)(n));  \
+    else                                                                                                             \
+      for (int q_ = 0; q_ < (comps); ++q_)                                                                           \
+        H2D((off) + sizeof(double) * (size_t)q_ * (size_t)(n), (src) + (size_t)q_ * (stride), sizeof(double) * (size_t)(n)); \
+  } while (0)
   H2D(o_cam, in->cameras, sizeof(double) * 5 * in->n_cameras);
   H2D(o_pb, in->pose_begin, sizeof(int) * (W + 1));
-  H2D(o_ptw, in->pose_twc, sizeof(double) * 7 * NP);
+  H2D_PLANES(o_ptw, in->pose_twc, 7, NP, c->l_stride.pose);
   H2D(o_pfx, in->pose_fixed, (size_t)NP);
   for (int k = 0; k < 2; ++k) {
     const int SD = k ? 6 : 3;
     H2D(ko[k].lm_begin, kh[k].lm_begin, sizeof(int) * (W + 1));
-    H2D(ko[k].lm_in, kh[k].lm_in, sizeof(double) * SD * n_lm[k]);
+    H2D_PLANES(ko[k].lm_in, kh[k].lm_in, SD, n_lm[k], c->l_stride.lm[k]);
     for (int cl = 0; cl < 2; ++cl) {
       H2D(ko[k].cls_begin[cl], kh[k].cls_begin[cl], sizeof(int) * (W + 1));
       H2D(ko[k].cls_pose[cl], kh[k].cls_pose[cl], sizeof(int) * n_cls[k][cl]);
       H2D(ko[k].cls_lm[cl], kh[k].cls_lm[cl], sizeof(int) * n_cls[k][cl]);
       // (one camera: the indices are validated on the host below and never read on the device, so they stay there)
       if (kh[k].cls_cam[cl] && in->n_cameras > 1) H2D(ko[k].cls_cam[cl], kh[k].cls_cam[cl], sizeof(int) * n_cls[k][cl]);
-      H2D(ko[k].cls_meas[cl], kh[k].cls_meas[cl], sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
+      H2D_PLANES(ko[k].cls_meas[cl], kh[k].cls_meas[cl], kh[k].md[cl], n_cls[k][cl], c->l_stride.cls[k][cl]);
     }
   }
+#undef H2D_PLANES
 #undef H2D
   // index validation on the host while the DMA engine works (a rejected batch has been copied for nothing,
   // but is never solved: local_uploaded stays false)
@@ -1134,9 +1144,16 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
   } while (0)
   D2H(&err, d.err, sizeof(int));
   if (c->l_graph_launches_step) D2H(&steps, c->bd.n_active, sizeof(int));
-  D2H(out->pose_twc, d.pose_out, sizeof(double) * 7 * c->l_np);
-  D2H(out->point_xyz, d.k[0].lm_out, sizeof(double) * 3 * c->l_npt);
-  D2H(out->line_wd, d.k[1].lm_out, sizeof(double) * 6 * c->l_nln);
+#define D2H_PLANES(dst, src, comps, n, stride)                                                                       \
+  do {                                                                                                               \
+    if ((stride) == 0 || (stride) == (size_t)(n)) D2H((dst), (src), sizeof(double) * (size_t)(comps) * (size_t)(n));  \
+    else                                                                                                             \
+      for (int q_ = 0; q_ < (comps); ++q_) D2H((dst) + (size_t)q_ * (stride), (src) + (size_t)q_ * (size_t)(n), sizeof(double) * (size_t)(n)); \
+  } while (0)
+  D2H_PLANES(out->pose_twc, d.pose_out, 7, c->l_np, c->l_stride.pose);
+  D2H_PLANES(out->point_xyz, d.k[0].lm_out, 3, c->l_npt, c->l_stride.lm[0]);
+  D2H_PLANES(out->line_wd, d.k[1].lm_out, 6, c->l_nln, c->l_stride.lm[1]);
+#undef D2H_PLANES
   D2H(out->mp_inlier, d.k[0].out_inl[0], (size_t)c->l_n[0]);
   D2H(out->sp_inlier, d.k[0].out_inl[1], (size_t)c->l_n[1]);
   D2H(out->ml_inlier, d.k[1].out_inl[0], (size_t)c->l_n[2]);
@@ -1156,8 +1173,154 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
   return RSPL_BA_OK;
 }
 
+namespace {
+
+// Window range [w0, w1) of a batch as a batch of its own: rebased offset arrays, shifted array pointers; the component
+// planes keep the stride of the whole batch (RsplBaContext::l_stride tells upload / download).
+struct LocalChunk {
+  std::vector<int32_t> beg[7]; // pose, point, line, mono pt, stereo pt, mono ln, stereo ln
+  RsplLocalBatch in;
+  RsplLocalBatchResult out;
+  RsplBaContext::LocalStrides stride;
+};
+
+void make_local_chunk(const RsplLocalBatch* in, const RsplLocalBatchResult* out, int w0, int w1, LocalChunk& ch) {
+  const int W = in->n_windows, n = w1 - w0;
+  const int32_t* src[7] = {in->pose_begin, in->point_begin, in->line_begin, in->mono_pt_begin, in->stereo_pt_begin,
+                           in->mono_ln_begin, in->stereo_ln_begin};
+  size_t b0[7], tot[7];
+  for (int a = 0; a < 7; ++a) {
+    b0[a] = (size_t)src[a][w0];
+    tot[a] = (size_t)src[a][W];
+    ch.beg[a].resize(n + 1);
+    for (int w = 0; w <= n; ++w) ch.beg[a][w] = src[a][w0 + w] - src[a][w0];
+  }
+  ch.in = *in;
+  ch.in.n_windows = n;
+  ch.in.pose_begin = ch.beg[0].data();
+  ch.in.point_begin = ch.beg[1].data();
+  ch.in.line_begin = ch.beg[2].data();
+  ch.in.mono_pt_begin = ch.beg[3].data();
+  ch.in.stereo_pt_begin = ch.beg[4].data();
+  ch.in.mono_ln_begin = ch.beg[5].data();
+  ch.in.stereo_ln_begin = ch.beg[6].data();
+  auto sh = [](auto* p, size_t off) { return p ? p + off : p; };
+  ch.in.pose_twc = sh(in->pose_twc, b0[0]);
+  ch.in.pose_fixed = sh(in->pose_fixed, b0[0]);
+  ch.in.point_xyz = sh(in->point_xyz, b0[1]);
+  ch.in.line_wd = sh(in->line_wd, b0[2]);
+  ch.in.mp_pose = sh(in->mp_pose, b0[3]);
+  ch.in.mp_point = sh(in->mp_point, b0[3]);
+  ch.in.mp_cam = sh(in->mp_cam, b0[3]);
+  ch.in.mp_meas = sh(in->mp_meas, b0[3]);
+  ch.in.sp_pose = sh(in->sp_pose, b0[4]);
+  ch.in.sp_point = sh(in->sp_point, b0[4]);
+  ch.in.sp_cam = sh(in->sp_cam, b0[4]);
+  ch.in.sp_meas = sh(in->sp_meas, b0[4]);
+  ch.in.ml_pose = sh(in->ml_pose, b0[5]);
+  ch.in.ml_line = sh(in->ml_line, b0[5]);
+  ch.in.ml_cam = sh(in->ml_cam, b0[5]);
+  ch.in.ml_meas = sh(in->ml_meas, b0[5]);
+  ch.in.sl_pose = sh(in->sl_pose, b0[6]);
+  ch.in.sl_line = sh(in->sl_line, b0[6]);
+  ch.in.sl_cam = sh(in->sl_cam, b0[6]);
+  ch.in.sl_meas = sh(in->sl_meas, b0[6]);
+  ch.out = *out;
+  ch.out.pose_twc = sh(out->pose_twc, b0[0]);
+  ch.out.point_xyz = sh(out->point_xyz, b0[1]);
+  ch.out.line_wd = sh(out->line_wd, b0[2]);
+  ch.out.mp_inlier = sh(out->mp_inlier, b0[3]);
+  ch.out.sp_inlier = sh(out->sp_inlier, b0[4]);
+  ch.out.ml_inlier = sh(out->ml_inlier, b0[5]);
+  ch.out.sl_inlier = sh(out->sl_inlier, b0[6]);
+  ch.out.stats = sh(out->stats, (size_t)w0);
+  ch.stride.pose = tot[0];
+  ch.stride.lm[0] = tot[1];
+  ch.stride.lm[1] = tot[2];
+  ch.stride.cls[0][0] = tot[3];
+  ch.stride.cls[0][1] = tot[4];
+  ch.stride.cls[1][0] = tot[5];
+  ch.stride.cls[1][1] = tot[6];
+}
+
+// Large batches of independent windows: the windows are cut into chunks (balanced by constraint count) that go through
+// child contexts with their own streams and workspaces, so that the upload of chunk k + 1 overlaps the solve of chunk k
+// (the whole-schedule graph launch is asynchronous) and the download of chunk k the solve of chunk k + 1. Windows are
+// independent and every window's result is independent of the batch it is in, so the bits do not change.
+int local_batch_chunked(RsplBaContext* c, const RsplLocalBatch* in, const RsplBaOptions* opt, RsplLocalBatchResult* out,
+                        int n_chunks) {
+  const int W = in->n_windows;
+  while ((int)c->kids.size() < n_chunks) {
+    RsplBaContext* k = nullptr;
+    const int rc = rspl_ba_create(c->device, nullptr, &k);
+    if (rc != RSPL_BA_OK || !k) return fail(c, rc != RSPL_BA_OK ? rc : RSPL_BA_ERR_CUDA, "local batch: child context");
+    c->kids.push_back(k);
+  }
+  // boundaries by cumulative constraint count
+  std::vector<int> bounds(n_chunks + 1, W);
+  bounds[0] = 0;
+  {
+    auto edges_upto = [&](int w) {
+      return (long long)in->mono_pt_begin[w] + in->stereo_pt_begin[w] + in->mono_ln_begin[w] + in->stereo_ln_begin[w];
+    };
+    const long long total = edges_upto(W);
+    int w = 0;
+    for (int k = 1; k < n_chunks; ++k) {
+      while (w < W && edges_upto(w) * n_chunks < total * k) ++w;
+      bounds[k] = w;
+    }
+  }
+  std::vector<LocalChunk> chunks(n_chunks);
+  std::vector<int64_t> launches0(n_chunks);
+  int rc = RSPL_BA_OK, bad = -1, n_started = 0;
+  for (int k = 0; k < n_chunks && rc == RSPL_BA_OK; ++k) {
+    if (bounds[k + 1] <= bounds[k]) continue;
+    RsplBaContext* kc = c->kids[k];
+    launches0[k] = kc->launches;
+    make_local_chunk(in, out, bounds[k], bounds[k + 1], chunks[k]);
+    kc->l_stride = chunks[k].stride;
+    rc = rspl_ba_local_batch_upload(kc, &chunks[k].in);
+    if (rc == RSPL_BA_OK) rc = rspl_ba_local_batch_solve(kc, opt);
+    if (rc != RSPL_BA_OK) bad = k;
+    n_started = k + 1;
+  }
+  for (int k = 0; k < n_started; ++k) {
+    if (bounds[k + 1] <= bounds[k]) continue;
+    RsplBaContext* kc = c->kids[k];
+    if (rc == RSPL_BA_OK) {
+      rc = rspl_ba_local_batch_download(kc, &chunks[k].out);
+      if (rc != RSPL_BA_OK) bad = k;
+    } else {
+      cudaStreamSynchronize(kc->stream); // a failed call returns with nothing in flight
+    }
+    kc->l_stride = RsplBaContext::LocalStrides();
+    c->launches += kc->launches - launches0[k];
+  }
+  c->local_uploaded = c->local_solved = false; // nothing stays resident in this context after a chunked call
+  if (rc != RSPL_BA_OK) return fail(c, rc, "%s", bad >= 0 ? c->kids[bad]->err : "local batch: chunk failed");
+  return RSPL_BA_OK;
+}
+
+} // namespace
+
 extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch* in, const RsplBaOptions* opt,
                                    RsplLocalBatchResult* out) {
+  if (c && in && opt && out && in->n_windows >= 128 && !c->prof && !c->global_mode && c->comm_ranks == 1 &&
+      in->pose_begin && in->mono_pt_begin && in->stereo_pt_begin && in->mono_ln_begin && in->stereo_ln_begin &&
+      in->point_begin && in->line_begin) {
+    int n_chunks = 4;
+    if (const char* e = getenv("RSPL_BA_LOCAL_CHUNKS")) n_chunks = atoi(e) > 0 ? atoi(e) : n_chunks;
+    if (n_chunks > 16) n_chunks = 16;
+    const int W = in->n_windows;
+    // (the offset arrays are only trusted after this cheap check; everything else is validated per chunk)
+    const bool offs = offsets_ok(in->pose_begin, W) && offsets_ok(in->point_begin, W) && offsets_ok(in->line_begin, W) &&
+                      offsets_ok(in->mono_pt_begin, W) && offsets_ok(in->stereo_pt_begin, W) &&
+                      offsets_ok(in->mono_ln_begin, W) && offsets_ok(in->stereo_ln_begin, W);
+    const long long edges = offs ? (long long)in->mono_pt_begin[W] + in->stereo_pt_begin[W] + in->mono_ln_begin[W] + in->stereo_ln_begin[W] : 0;
+    long long min_mb = 64; // below that the upload is too short to be worth overlapping
+    if (const char* e = getenv("RSPL_BA_LOCAL_CHUNK_MIN_MB")) min_mb = atoll(e) >= 0 ? atoll(e) : min_mb;
+    if (offs && n_chunks > 1 && edges * 36 >= (min_mb << 20)) return local_batch_chunked(c, in, opt, out, n_chunks);
+  }
   int rc = rspl_ba_local_batch_upload(c, in);
   if (rc != RSPL_BA_OK) return rc;
   rc = rspl_ba_local_batch_solve(c, opt);

@@ -231,3 +231,22 @@ def test_local_degenerate_windows(gpu_ctx, orc, local_path):
     batch = LocalBatch.from_problems(probs)
     res = gpu_ctx.local_batch(batch)
     _check(orc, probs, batch, res)
+
+
+def test_chunked_one_shot_call_gives_the_same_bits(gpu_ctx, monkeypatch):
+    """Large batches go through rspl_ba_local_batch in window chunks on child contexts (upload of chunk k + 1 under the
+    solve of chunk k). Windows are independent and batch-invariant, so the results must be bit-identical to the
+    unchunked call; ragged chunk boundaries (3 chunks over 150 windows of different sizes) included."""
+    probs = [synth.make_local_problem(synth.config_seed(1, 700 + i), n_kf=3 + i % 4, n_points=40 + 7 * (i % 5), n_lines=4 + i % 3)
+             for i in range(150)]
+    batch = LocalBatch.from_problems(probs)
+    monkeypatch.setenv("RSPL_BA_LOCAL_CHUNKS", "1")
+    ref = gpu_ctx.local_batch(batch)
+    monkeypatch.setenv("RSPL_BA_LOCAL_CHUNKS", "3")
+    monkeypatch.setenv("RSPL_BA_LOCAL_CHUNK_MIN_MB", "0")
+    launches0 = gpu_ctx.launch_count
+    res = gpu_ctx.local_batch(batch)
+    assert gpu_ctx.launch_count > launches0  # the children's launches are accounted to the caller's context
+    for name in ("pose_twc", "point_xyz", "line_wd", "mp_inlier", "sp_inlier", "ml_inlier", "sl_inlier"):
+        assert np.array_equal(getattr(res, name), getattr(ref, name)), name
+    assert np.array_equal(res.stats["iters"], ref.stats["iters"]) and np.array_equal(res.stats["final_chi2"], ref.stats["final_chi2"])
