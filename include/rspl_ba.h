@@ -200,6 +200,9 @@ int rspl_ba_frame_batch_solve(RsplBaContext* ctx, const RsplBaOptions* opt);
 int rspl_ba_frame_batch_download(RsplBaContext* ctx, RsplFrameBatchResult* out);
 
 /* --- LocalmapOptimization ------------------------------------------------------------------- */
+/* One call = upload + solve + download. Large batches (>= 128 windows, >= 64 MB) are processed in window chunks on
+ * child contexts so that copies overlap the solves (same results); such a call leaves the batch of an earlier
+ * rspl_ba_local_batch_upload resident, a small one replaces it. */
 int rspl_ba_local_batch(RsplBaContext* ctx, const RsplLocalBatch* in, const RsplBaOptions* opt,
                         RsplLocalBatchResult* out);
 int rspl_ba_local_batch_upload(RsplBaContext* ctx, const RsplLocalBatch* in);

@@ -115,6 +115,8 @@ struct RsplBaContext {
   int l_max_pts = 0, l_max_lns = 0, l_max_edges = 0;
   cudaStream_t s_aux = nullptr;           // the line kernels of a super-step run beside the point kernels
   cudaEvent_t fork_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s_aux2 = nullptr;          // ... and the pose blocks beside both (graph path)
+  cudaEvent_t fork_ev2[2] = {nullptr, nullptr};
   // tiled Schur path (local_tiled.cuh)
   DevBuf tile_buf;
   ba::TileDev td{};
@@ -341,6 +343,9 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (c->s_body) cudaStreamDestroy(c->s_body);
   if (c->s_aux) cudaStreamDestroy(c->s_aux);
+  if (c->s_aux2) cudaStreamDestroy(c->s_aux2);
+  for (int i = 0; i < 2; ++i)
+    if (c->fork_ev2[i]) cudaEventDestroy(c->fork_ev2[i]);
   for (int i = 0; i < 6; ++i)
     if (c->fork_ev[i]) cudaEventDestroy(c->fork_ev[i]);
   if (c->s_in) cudaStreamDestroy(c->s_in);

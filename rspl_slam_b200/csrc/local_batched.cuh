@@ -1564,9 +1564,7 @@ __global__ void __launch_bounds__(256) kb_global_sums(const __grid_constant__ Ba
 // one WARP per window: the Levenberg accept / reject logic (§9.9) and the window's next stage (every lane takes
 // the same decision from the same warp-reduced sums; lane 0 writes the state, the lanes share the pose restore);
 // grid ceil(W / 4), 128 threads
-__global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= d.n_windows) return;
+BA_DEV void decide_window(const LocalDev& d, const BatchDev& b, int w, int lane) {
   WinState& s = b.ws[w];
   if (s.stage != STAGE_NEED_TRIAL) return;
   const bool ok = s.solve_ok;
@@ -1640,6 +1638,35 @@ __global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDe
   s.it = it + 1;
   const bool terminate = (q1 == 10 || rho == 0 || !isfinite(lambda));
   s.stage = (terminate || it + 1 >= iters) ? STAGE_DONE : STAGE_NEED_LIN;
+}
+
+// COND (the whole-schedule graph): the last warp of the grid to finish also evaluates the loop condition of the WHILE
+// node (any window still iterating?) and counts the super-step, which saves the separate one-CTA kernel on the
+// critical path of every super-step. ticket: d.err[3], zeroed with the error flags by the setup.
+template <bool COND>
+__global__ void __launch_bounds__(128) kb_decide(const __grid_constant__ LocalDev d, const __grid_constant__ BatchDev b,
+                                                 cudaGraphConditionalHandle h) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w < d.n_windows) decide_window(d, b, w, lane);
+  if (!COND) return;
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence();
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+    last = atomicAdd(d.err + 3, 1) == n_warps - 1 ? 1 : 0;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  int any = 0;
+  for (int i = lane; i < d.n_windows; i += 32) any |= *reinterpret_cast<volatile const int*>(&b.ws[i].stage) != STAGE_DONE ? 1 : 0;
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) {
+    d.err[3] = 0;
+    cudaGraphSetConditional(h, any ? 1u : 0u);
+    ++*b.n_active;
+  }
 }
 
 // grid (Cp + Cl, windows): chunk < Cp restores points, else lines

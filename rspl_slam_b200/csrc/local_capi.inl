@@ -542,6 +542,8 @@ void enqueue_local_setup(RsplBaContext* c, cudaStream_t s) {
 // context under the byte image of every kernel argument block, so a call with the same shapes and buffers is a
 // single cudaGraphLaunch. Used whenever the reduced systems fit shared memory (no HBM-resident solve, no NCCL in the loop)
 // and profiling is off.
+constexpr int POSE_BRANCH_MAX_W = 32; // batches up to this many windows run kb_pose_blocks on its own graph branch
+
 struct LocalGraphKey {
   ba::LocalDev d;
   ba::BatchDev b;
@@ -563,6 +565,10 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     CU_TRY(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
     for (int i = 0; i < 6; ++i) CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming));
   }
+  if (!c->s_aux2) {
+    CU_TRY(c, cudaStreamCreateWithFlags(&c->s_aux2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CU_TRY(c, cudaEventCreateWithFlags(&c->fork_ev2[i], cudaEventDisableTiming));
+  }
   const dim3 g_pt(b.Cp, W), g_ln(b.Cl, W), g_lm(b.C, W), g_pose(b.NFmax > 0 ? b.NFmax : 1, W), g_pair((b.Pmax + ba::BW - 1) / ba::BW, W),
       g_win((W + 127) / 128), g_winw((W + 3) / 4), g_tp(td.Tp > 0 ? td.Tp : 1, W), g_tl(td.Tl > 0 ? td.Tl : 1, W);
   const int edge_chunks = (c->l_max_edges + 256 * 8 - 1) / (256 * 8) > 0 ? (c->l_max_edges + 256 * 8 - 1) / (256 * 8) : 1;
@@ -577,7 +583,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
   } while (0)
   // one super-step on (sm, sl): the line kernels of a phase run beside the point kernels (fork / join events
   // become graph dependencies)
-  auto super_step = [&](cudaStream_t sm, cudaStream_t sl) {
+  auto super_step = [&](cudaStream_t sm, cudaStream_t sl, cudaGraphConditionalHandle cond) {
     auto fork = [&](int k) {
       if (!fork_lines) return;
       cudaEventRecord(c->fork_ev[2 * k], sm);
@@ -590,11 +596,20 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     };
     cudaStream_t sline = fork_lines ? sl : sm;
     fork(0);
-    // (the pose blocks follow the short line kernel on the second stream: they are independent of the point
-    // linearisation, and both are latency-bound at ~25 % resident warps, so they overlap well)
+    // (the pose blocks are independent of both linearisations; small batches are latency-bound, so they get a third
+    // branch of the graph there instead of following the line kernel)
+    const bool fork_pose = fork_lines && W <= POSE_BRANCH_MAX_W;
+    if (fork_pose) {
+      cudaEventRecord(c->fork_ev2[0], sm);
+      cudaStreamWaitEvent(c->s_aux2, c->fork_ev2[0], 0);
+    }
     if (b.Cp) GK(sm, ba::kb_linearize<0>, g_pt, ba::BT, 0, d, b, lo);
     if (b.Cl) GK(sline, ba::kb_linearize<1>, g_ln, ba::BT, 0, d, b, lo);
-    GK(sline, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    GK(fork_pose ? c->s_aux2 : sline, ba::kb_pose_blocks, g_pose, ba::BT, 0, d, b, lo);
+    if (fork_pose) {
+      cudaEventRecord(c->fork_ev2[1], c->s_aux2);
+      cudaStreamWaitEvent(sm, c->fork_ev2[1], 0);
+    }
     join(0);
     GK(sm, ba::kb_begin_trial, g_winw, 128, 0, d, b);
     fork(1);
@@ -607,7 +622,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
     if (b.Cp) GK(sm, ba::kt_backsub_rc<0>, g_pt, ba::BT, 0, d, b, lo, td);
     if (b.Cl) GK(sline, ba::kt_backsub_rc<1>, g_ln, ba::BT, 0, d, b, lo, td);
     join(2);
-    GK(sm, ba::kb_decide, g_winw, 128, 0, d, b);
+    GK(sm, ba::kb_decide<true>, g_winw, 128, 0, d, b, cond);
     if (b.C) GK(sm, ba::kb_restore, g_lm, ba::BT, 0, d, b);
   };
   cudaGraph_t graph = nullptr;
@@ -662,8 +677,7 @@ int capture_local_graph(RsplBaContext* c, const ba::LocalOpt& lo, size_t smem_so
            cudaStreamBeginCaptureToGraph(c->s_body, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
       if (!ok) break;
       const int before = n_launch;
-      super_step(c->s_body, c->s_aux);
-      GK(c->s_body, ba::kt_cond, 1, 256, 0, d, b, h, 1);
+      super_step(c->s_body, c->s_aux, h); // (kb_decide sets the loop condition and counts the super-step)
       launches_step = n_launch - before;
       n_launch = before;
       ok = cudaStreamEndCapture(c->s_body, nullptr) == cudaSuccess;
@@ -1006,7 +1020,7 @@ int local_solve_batched(RsplBaContext* c, const ba::LocalOpt& lo) {
       ProfScope ps_(c, PC_COLLECTIVE);
       if (coll_rc == RSPL_BA_OK) coll_rc = comm_all_reduce(c, b.gs_w + 4, b.gs + 4, 2, kNcclFloat64, kNcclSum);
     }
-    LAUNCH(PC_CONTROL, ba::kb_decide, g_winw, 128, 0, d, b);
+    LAUNCH(PC_CONTROL, ba::kb_decide<false>, g_winw, 128, 0, d, b, cudaGraphConditionalHandle{});
     if (b.C) LAUNCH(PC_CONTROL, ba::kb_restore, g_lm, ba::BT, 0, d, b);
   };
   // ... captured once into a CUDA graph and replayed (launch-bound for small batches: a C1 window
@@ -1296,7 +1310,7 @@ int local_batch_chunked(RsplBaContext* c, const RsplLocalBatch* in, const RsplBa
     kc->l_stride = RsplBaContext::LocalStrides();
     c->launches += kc->launches - launches0[k];
   }
-  c->local_uploaded = c->local_solved = false; // nothing stays resident in this context after a chunked call
+  // (the batch of an earlier rspl_ba_local_batch_upload stays resident in this context: the chunks lived in the children)
   if (rc != RSPL_BA_OK) return fail(c, rc, "%s", bad >= 0 ? c->kids[bad]->err : "local batch: chunk failed");
   return RSPL_BA_OK;
 }
