@@ -98,6 +98,9 @@ struct RsplBaContext {
   struct LocalStrides {
     size_t pose = 0, lm[2] = {0, 0}, cls[2][2] = {{0, 0}, {0, 0}};
   } l_stride;
+  void* l_stage = nullptr;           // pinned mirror of the input / output ranges of small local batches
+  size_t l_stage_cap = 0, l_in_end = 0, l_out_begin = 0, l_out_end = 0;
+  bool l_staged = false;
   std::vector<RsplBaContext*> kids; // child contexts of the chunked one-shot local call (own streams and workspaces)
   DevBuf local_buf;
   ba::LocalDev ld{};
@@ -327,6 +330,7 @@ extern "C" void rspl_ba_destroy(RsplBaContext* c) {
   cudaStreamSynchronize(c->stream);
   c->frame_buf.release();
   if (c->f_stage) cudaFreeHost(c->f_stage);
+  if (c->l_stage) cudaFreeHost(c->l_stage);
   c->local_buf.release();
   c->batch_buf.release();
   c->tile_buf.release();

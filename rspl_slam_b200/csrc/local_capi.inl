@@ -3,6 +3,8 @@
 
 namespace {
 
+constexpr size_t LOCAL_STAGE_MAX = 4 << 20; // input / output range of a batch that goes through the pinned mirror
+
 struct KindHost { // host view of one landmark kind of an RsplLocalBatch
   const int32_t* lm_begin;
   const int32_t* cls_begin[2];
@@ -137,15 +139,44 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
 
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  // Arena: every input first, then every output, then the work arrays — so that a small batch (the reference's call:
+  // one window) can go up in ONE copy from a pinned mirror of the input range and come back in ONE copy of the
+  // output range (local_stage_*), instead of ~30 + ~10 copies of a few KB each.
+  struct KOff {
+    size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
+    size_t meas, info, lm, src, chi2, lvl, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
+  } ko[2];
   Arena a;
   const size_t o_cam = a.take(sizeof(double) * 5 * in->n_cameras);
   const size_t o_pb = a.take(sizeof(int) * (W + 1));
   const size_t o_ptw = a.take(sizeof(double) * 7 * NP);
   const size_t o_pfx = a.take(NP);
-  const size_t o_tcw = a.take(sizeof(double) * 7 * NP);
+  for (int k = 0; k < 2; ++k) {
+    const int SD = k ? 6 : 3;
+    KOff& o = ko[k];
+    o.lm_begin = a.take(sizeof(int) * (W + 1));
+    for (int cl = 0; cl < 2; ++cl) {
+      o.cls_begin[cl] = a.take(sizeof(int) * (W + 1));
+      o.cls_pose[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_lm[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_cam[cl] = a.take(sizeof(int) * n_cls[k][cl]);
+      o.cls_meas[cl] = a.take(sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
+    }
+    o.lm_in = a.take(sizeof(double) * SD * n_lm[k]);
+  }
+  const size_t o_in_end = a.off;
+  // outputs
+  const size_t o_err = a.take(sizeof(int) * 4); // error flag, max degree of points / lines, decide ticket
   const size_t o_pout = a.take(sizeof(double) * 7 * NP);
   const size_t o_stats = a.take(sizeof(ba::DevStats) * W);
-  const size_t o_err = a.take(sizeof(int) * 4); // error flag, max degree of points / lines
+  for (int k = 0; k < 2; ++k) {
+    const int SD = k ? 6 : 3;
+    for (int cl = 0; cl < 2; ++cl) ko[k].out_inl[cl] = a.take(n_cls[k][cl]);
+    ko[k].lm_out = a.take(sizeof(double) * SD * n_lm[k]);
+  }
+  const size_t o_out_end = a.off;
+  // work
+  const size_t o_tcw = a.take(sizeof(double) * 7 * NP);
   const size_t o_sfi = a.take(sizeof(int) * NP);
   const int slot_stride = (max_free + 3) & ~3;
   // large-window setup variants (local_kernel.cuh): multi-CTA landmark ordering, pose lists by scatter + sort
@@ -158,24 +189,10 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     o_pcur[k] = a.take(sizeof(int) * (size_t)NP);
     o_ptmp[k] = a.take(sizeof(int) * ((size_t)n_cls[k][0] + n_cls[k][1] + 1));
   }
-  struct KOff {
-    size_t lm_begin, cls_begin[2], cls_pose[2], cls_lm[2], cls_cam[2], cls_meas[2], lm_in;
-    size_t meas, info, lm, src, chi2, lvl, Zb, ebeg, cursor, newidx, orig, x, xb, H, b, y, act, slot, plist, pbeg, out_inl[2], lm_out;
-  } ko[2];
   for (int k = 0; k < 2; ++k) {
     const int LD = k ? 4 : 3, SD = k ? 6 : 3, MD = k ? 8 : 3, HD = k ? 10 : 6, WD = 6 * LD;
     const size_t ne = (size_t)n_cls[k][0] + n_cls[k][1], nl = n_lm[k];
     KOff& o = ko[k];
-    o.lm_begin = a.take(sizeof(int) * (W + 1));
-    for (int cl = 0; cl < 2; ++cl) {
-      o.cls_begin[cl] = a.take(sizeof(int) * (W + 1));
-      o.cls_pose[cl] = a.take(sizeof(int) * n_cls[k][cl]);
-      o.cls_lm[cl] = a.take(sizeof(int) * n_cls[k][cl]);
-      o.cls_cam[cl] = a.take(sizeof(int) * n_cls[k][cl]);
-      o.cls_meas[cl] = a.take(sizeof(double) * kh[k].md[cl] * n_cls[k][cl]);
-      o.out_inl[cl] = a.take(n_cls[k][cl]);
-    }
-    o.lm_in = a.take(sizeof(double) * SD * nl);
     o.meas = a.take(sizeof(double) * MD * ne);
     o.info = a.take(sizeof(int) * ne);
     o.lm = a.take(sizeof(int) * ne);
@@ -196,14 +213,30 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
     o.slot = a.take(nl * (size_t)slot_stride);
     o.plist = a.take(sizeof(int) * ne);
     o.pbeg = a.take(sizeof(int) * (NP + 1));
-    o.lm_out = a.take(sizeof(double) * SD * nl);
   }
+  c->l_in_end = o_in_end;
+  c->l_out_begin = o_in_end;
+  c->l_out_end = o_out_end;
+  // small batches: stage the inputs in a pinned mirror of [0, o_in_end) and send it with one copy
+  const bool staged = o_out_end <= LOCAL_STAGE_MAX; // (inputs [0, o_in_end) and outputs [o_in_end, o_out_end) both inside the mirror)
+  if (staged && c->l_stage_cap < LOCAL_STAGE_MAX) {
+    if (c->l_stage) cudaFreeHost(c->l_stage);
+    c->l_stage = nullptr;
+    c->l_stage_cap = 0;
+    if (cudaHostAlloc(&c->l_stage, LOCAL_STAGE_MAX, cudaHostAllocDefault) == cudaSuccess) c->l_stage_cap = LOCAL_STAGE_MAX;
+    else cudaGetLastError();
+  }
+  c->l_staged = staged && c->l_stage_cap >= LOCAL_STAGE_MAX;
   CU_TRY(c, c->local_buf.reserve(a.off));
   char* base = c->local_buf.as<char>();
   cudaStream_t s = c->stream;
+  char* stage = c->l_staged ? (char*)c->l_stage : nullptr;
 #define H2D(off, src, bytes)                                                                              \
   do {                                                                                                    \
-    if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s)); \
+    if ((bytes) > 0) {                                                                                    \
+      if (stage) memcpy(stage + (off), (src), (bytes));                                                   \
+      else CU_TRY(c, cudaMemcpyAsync(base + (off), (src), (bytes), cudaMemcpyHostToDevice, s));           \
+    }                                                                                                     \
   } while (0)
   // component planes [comps][n]: one copy when the caller's planes are contiguous, one per component when the batch is
   // a window range of a larger one (stride = the plane length of the whole batch)
@@ -233,6 +266,7 @@ extern "C" int rspl_ba_local_batch_upload(RsplBaContext* c, const RsplLocalBatch
   }
 #undef H2D_PLANES
 #undef H2D
+  if (stage) CU_TRY(c, cudaMemcpyAsync(base, stage, o_in_end, cudaMemcpyHostToDevice, s));
   // index validation on the host while the DMA engine works (a rejected batch has been copied for nothing,
   // but is never solved: local_uploaded stays false)
   const char* bad = nullptr;
@@ -1156,6 +1190,31 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
   do {                                                                                              \
     if ((bytes) > 0) CU_TRY(c, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s)); \
   } while (0)
+  if (c->l_staged) {
+    // one copy of the output range into the pinned mirror, then host copies into the caller's arrays
+    char* base = c->local_buf.as<char>();
+    char* stage = (char*)c->l_stage;
+    CU_TRY(c, cudaMemcpyAsync(stage + c->l_out_begin, base + c->l_out_begin, c->l_out_end - c->l_out_begin, cudaMemcpyDeviceToHost, s));
+    if (c->l_graph_launches_step) CU_TRY(c, cudaMemcpyAsync(&steps, c->bd.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    auto hp = [&](const void* dev) { return stage + ((const char*)dev - base); };
+    auto planes = [&](double* dst, const double* dev, int comps, size_t n, size_t stride) {
+      if (!n) return;
+      const double* src = (const double*)hp(dev);
+      if (stride == 0 || stride == n) memcpy(dst, src, sizeof(double) * comps * n);
+      else
+        for (int q = 0; q < comps; ++q) memcpy(dst + (size_t)q * stride, src + (size_t)q * n, sizeof(double) * n);
+    };
+    err = *(const int*)hp(d.err);
+    planes(out->pose_twc, d.pose_out, 7, (size_t)c->l_np, c->l_stride.pose);
+    planes(out->point_xyz, d.k[0].lm_out, 3, (size_t)c->l_npt, c->l_stride.lm[0]);
+    planes(out->line_wd, d.k[1].lm_out, 6, (size_t)c->l_nln, c->l_stride.lm[1]);
+    if (c->l_n[0]) memcpy(out->mp_inlier, hp(d.k[0].out_inl[0]), (size_t)c->l_n[0]);
+    if (c->l_n[1]) memcpy(out->sp_inlier, hp(d.k[0].out_inl[1]), (size_t)c->l_n[1]);
+    if (c->l_n[2]) memcpy(out->ml_inlier, hp(d.k[1].out_inl[0]), (size_t)c->l_n[2]);
+    if (c->l_n[3]) memcpy(out->sl_inlier, hp(d.k[1].out_inl[1]), (size_t)c->l_n[3]);
+    if (out->stats) memcpy(out->stats, hp(d.stats), sizeof(RsplBaStats) * c->l_n_windows);
+  } else {
   D2H(&err, d.err, sizeof(int));
   if (c->l_graph_launches_step) D2H(&steps, c->bd.n_active, sizeof(int));
 #define D2H_PLANES(dst, src, comps, n, stride)                                                                       \
@@ -1173,8 +1232,9 @@ extern "C" int rspl_ba_local_batch_download(RsplBaContext* c, RsplLocalBatchResu
   D2H(out->ml_inlier, d.k[1].out_inl[0], (size_t)c->l_n[2]);
   D2H(out->sl_inlier, d.k[1].out_inl[1], (size_t)c->l_n[3]);
   if (out->stats) D2H(out->stats, d.stats, sizeof(RsplBaStats) * c->l_n_windows);
-#undef D2H
   CU_TRY(c, cudaStreamSynchronize(s));
+  }
+#undef D2H
   if (c->l_graph_launches_step) { // the graph's super-steps ran without the host counting them
     c->launches += (int64_t)steps * c->l_graph_launches_step;
     c->l_super_steps = steps;
