@@ -277,6 +277,11 @@ int rspl_ba_eval_edges(RsplBaContext* ctx, int edge_type, int32_t n, const doubl
 int rspl_ba_oplus(RsplBaContext* ctx, int kind, int32_t n, const double* state, const double* upd,
                   double* out);
 
+/* The kernels' reciprocal (op 0), reciprocal square root (op 1) and square root (op 2) without the CUDA library's
+ * range test (ba_math.cuh: rcp_nr / rsqrt_nr / sqrt_nr), evaluated on n host values (tests/test_edges_gpu.py: the
+ * reciprocal correctly rounded, rsqrt / sqrt within 2 ulp for normal arguments). */
+int rspl_ba_unit_math(RsplBaContext* ctx, int op, int32_t n, const double* in, double* out);
+
 #ifdef __cplusplus
 }
 #endif

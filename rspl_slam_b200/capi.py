@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points",
+    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points", "rspl_ba_unit_math",
     "rspl_ba_set_profiling", "rspl_ba_get_profile",
     "rspl_ba_comm_unique_id", "rspl_ba_comm_init", "rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank",
     "rspl_ba_collective_count", "rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download")
@@ -165,6 +165,8 @@ def load_library() -> C.CDLL:
     L.rspl_ba_triangulate_points.argtypes = [ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_f64p, C.c_int32,
                                              c_f64p, c_f64p, c_f64p, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
     L.rspl_ba_triangulate_points.restype = C.c_int
+    L.rspl_ba_unit_math.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p]
+    L.rspl_ba_unit_math.restype = C.c_int
     L.rspl_ba_oplus.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p, c_f64p]
     L.rspl_ba_oplus.restype = C.c_int
     L.rspl_ba_set_profiling.argtypes = [ctx, C.c_int]
@@ -452,6 +454,13 @@ class Context:
             self._ctx, n, _p(obs_begin, c_i32p), _p(obs_frame, c_i32p), _p(obs_uv, c_f64p), frame_twc.shape[1],
             _p(frame_twc, c_f64p), _p(cam5, c_f64p), _p(xyz, c_f64p), _p(ok, c_u8p), C.byref(cnt)))
         return xyz, ok, int(cnt.value)
+
+    def unit_math(self, op: int, x: np.ndarray) -> np.ndarray:
+        """rcp_nr (0) / rsqrt_nr (1) / sqrt_nr (2) of ba_math.cuh on the device."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros_like(x)
+        self._check(self._L.rspl_ba_unit_math(self._ctx, op, len(x), _p(x, c_f64p), _p(out, c_f64p)))
+        return out
 
     def oplus(self, kind: int, state: np.ndarray, upd: np.ndarray) -> np.ndarray:
         n = len(state)

@@ -55,8 +55,9 @@ BA_DEV void cross3(const double* a, const double* b, double* o) {
 // ------------------------------------------------------------------------------------------------
 // Reciprocal / reciprocal square root / square root without the library's range test (all hot loops). The CUDA library versions test the exponent range
 // and call an out-of-line slow path; that conditional call ends the basic block, so the compiler cannot interleave
-// the evaluation of several edges. These are the same MUFU seed + FMA refinement without the range test: results
-// within 1 ulp of the IEEE quotient for normal arguments (|x| in ~[1e-290, 1e290]); 0, denormals and infinities
+// the evaluation of several edges. These are the same MUFU seed + FMA refinement without the range test: for normal
+// arguments (|x| in ~[1e-280, 1e280]) the reciprocal came out correctly rounded on every one of 200 k samples over 560
+// decades and rsqrt / sqrt within 2 ulp (tests/test_edges_gpu.py); 0, denormals and infinities
 // give NaN instead of +-inf / 0 (a depth of exactly 0 or a chi2 of 0 under the square root never reach them:
 // see the callers).
 // ------------------------------------------------------------------------------------------------

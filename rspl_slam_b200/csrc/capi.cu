@@ -1064,6 +1064,34 @@ extern "C" int rspl_ba_oplus(RsplBaContext* c, int kind, int32_t n, const double
   return RSPL_BA_OK;
 }
 
+// Unit-level check of the range-test-free reciprocal / rsqrt / sqrt of ba_math.cuh: op 0 rcp_nr, 1 rsqrt_nr, 2 sqrt_nr.
+namespace ba {
+__global__ void unit_math_kernel(int op, int n, const double* in, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = in[i];
+  out[i] = op == 0 ? rcp_nr(x) : op == 1 ? rsqrt_nr(x) : sqrt_nr(x);
+}
+} // namespace ba
+
+extern "C" int rspl_ba_unit_math(RsplBaContext* c, int op, int32_t n, const double* in, double* out) {
+  if (!c || op < 0 || op > 2 || n < 0 || (n && (!in || !out))) return RSPL_BA_ERR_INVALID;
+  if (n == 0) return RSPL_BA_OK;
+  SetDevice guard(c->device);
+  Arena a;
+  const size_t o_i = a.take(sizeof(double) * n), o_o = a.take(sizeof(double) * n);
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_i, in, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+  ba::unit_math_kernel<<<(n + 255) / 256, 256, 0, s>>>(op, n, (const double*)(base + o_i), (double*)(base + o_o));
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(out, base + o_o, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  return RSPL_BA_OK;
+}
+
 // Batched Map::TriangulateMappoint (triangulate.cuh). Host arrays in, host arrays out; out_xyz of a point that is not
 // triangulated is left untouched. *n_done (optional) receives the number of points triangulated.
 extern "C" int rspl_ba_triangulate_points(RsplBaContext* c, int32_t n_points, const int32_t* obs_begin,
