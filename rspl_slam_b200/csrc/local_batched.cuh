@@ -809,15 +809,37 @@ BA_DEV void pose_block_kind(const LocalDev& d, const BatchDev& b, const LocalOpt
   const int a = k.pbeg[p0 + p], e_end = k.pbeg[p0 + p + 1];
   const double* R = b.P_R + 9 * (size_t)(p0 + p);
   const double* t = b.P_t + 3 * (size_t)(p0 + p);
+  // The pose-major list is an indirection (plist -> edge -> landmark -> state): three dependent loads per edge. The
+  // edge index is requested two iterations ahead and the edge header (level, info, landmark) one ahead, so that only
+  // the landmark state / measurement gather of the current edge is waited for.
+  int e_n = 0, e_nn = 0, info_n = 0, lm_n = 0;
+  unsigned char lvl_n = 1;
+  {
+    const int it0 = a + threadIdx.x;
+    if (it0 < e_end) {
+      e_n = k.plist[it0];
+      lvl_n = k.lvl[e_n];
+      info_n = k.info[e_n];
+      lm_n = k.lm[e_n];
+    }
+    if (it0 + BT < e_end) e_nn = k.plist[it0 + BT];
+  }
   for (int it = a + threadIdx.x; it < e_end; it += BT) {
-    const int e = k.plist[it];
-    if (k.lvl[e]) continue;
-    const int info = k.info[e];
+    const int e = e_n, info = info_n, lmi = lm_n;
+    const bool skip = lvl_n != 0;
+    if (it + BT < e_end) {
+      e_n = e_nn;
+      lvl_n = k.lvl[e_n];
+      info_n = k.info[e_n];
+      lm_n = k.lm[e_n];
+    }
+    if (it + 2 * BT < e_end) e_nn = k.plist[it + 2 * BT];
+    if (skip) continue;
     const bool stereo = (info >> 30) & 1;
     Cam cam;
     load_cam(d.cameras, (info >> 16) & 0xff, cam);
     double X[T::SD], m[T::MD], r[4], Jp[24], Jl[16];
-    load_lm<KIND>(k, l0 + k.lm[e], X);
+    load_lm<KIND>(k, l0 + lmi, X);
     load_edge<KIND>(k, e, m);
     eval_edge<KIND, true>(cam, o.bf_float, stereo, R, t, X, m, r, Jp, Jl);
     double wgt = 1.0;
