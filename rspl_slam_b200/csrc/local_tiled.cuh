@@ -578,12 +578,25 @@ BA_DEV void backsub_rc_one(const LocalDev& d, const BatchDev& b, const TileDev& 
 #pragma unroll
   for (int a = 0; a < LD; ++a) u[a] = 0.0;
   const int ea = k.ebeg[l], eb = k.ebeg[l + 1];
+  // (the header of the next edge and the slot of its pose are requested before this edge is evaluated)
+  int info_n = 0, fi_n = -1;
+  unsigned char lvl_n = 1;
+  if (ea < eb) {
+    lvl_n = k.lvl[ea];
+    info_n = k.info[ea];
+    fi_n = b.free_idx[p0 + (info_n & 0xffff)];
+  }
   for (int e = ea; e < eb; ++e) {
-    if (k.lvl[e]) continue;
-    const int info = k.info[e];
+    const int info = info_n, fi = fi_n;
+    const bool skip = lvl_n != 0;
+    if (e + 1 < eb) {
+      lvl_n = k.lvl[e + 1];
+      info_n = k.info[e + 1];
+      fi_n = b.free_idx[p0 + (info_n & 0xffff)];
+    }
+    if (skip) continue;
     const int p = info & 0xffff;
     BA_CHECK(p < d.pose_begin[w + 1] - d.pose_begin[w]);
-    const int fi = b.free_idx[p0 + p];
     if (fi < 0 || b.sys_idx[f0 + fi] < 0) continue;
     const bool stereo = (info >> 30) & 1;
     Cam cam;
