@@ -353,6 +353,107 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update(const __grid_constant_
   }
 }
 
+// ---- the same update with the three neighbour blocks resident in shared memory (bs <= BCR_RESIDENT_BS_MAX):
+// GR(Il) | GL(Ir) | GR(Ir) are fetched by cp.async in three groups when the kernel starts, so the CTA waits for one
+// global round trip instead of nine slab loads, and the k loops run without barriers. The per-tile sums are formed
+// in the same k order as bcr_update, so both give the same bits.
+// dynamic smem = (3 * bs * bs + 2 * bs) doubles
+constexpr int BCR_RESIDENT_BS_MAX = 96;
+__host__ __device__ constexpr size_t bcr_resident_smem(int bs) { return sizeof(double) * (3 * (size_t)bs * bs + 2 * (size_t)bs) + 64; }
+
+__device__ __forceinline__ void bcr_fetch_block(double* dst, const double* src, int n_doubles) {
+  for (int idx = 2 * threadIdx.x; idx < n_doubles; idx += 2 * blockDim.x) cp_async16(dst + idx, src + idx);
+}
+
+__device__ __forceinline__ void bcr_ata_resident(const double* As, const double* Bs, int bs, double (&acc)[18]) {
+  const int tc = bs / 6, tix = threadIdx.x;
+  if (tix >= (bs / 3) * tc) return;
+  const int r0 = 3 * (tix / tc), cl = tix % tc;
+#pragma unroll 6
+  for (int k = 0; k < bs; ++k) {
+    const double a0 = As[k * bs + r0], a1 = As[k * bs + r0 + 1], a2 = As[k * bs + r0 + 2];
+    double bv[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) bv[q] = Bs[k * bs + cl + q * tc];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      acc[q] += a0 * bv[q];
+      acc[6 + q] += a1 * bv[q];
+      acc[12 + q] += a2 * bv[q];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BCR_THREADS) bcr_update_resident(const __grid_constant__ BcrDev s, int level) {
+  extern __shared__ __align__(16) unsigned char bcr_smem[];
+  const int bs = s.bs, tid = threadIdx.x;
+  const size_t bb = (size_t)bs * bs;
+  double* S0 = reinterpret_cast<double*>(bcr_smem); // GR(Il)
+  double* S1 = S0 + bb;                             // GL(Ir)
+  double* S2 = S1 + bb;                             // GR(Ir)
+  double* gl = S2 + bb;                             // g(Il)
+  double* gr = gl + bs;                             // g(Ir)
+  if (*s.info) return;
+  const int h = 1 << level;
+  const int p = 2 * blockIdx.x;
+  const int J = p * h, Il = J - h, Ir = J + h;
+  const bool has_l = p > 0, has_r = Ir < s.M, has_n = has_r && J + 2 * h < s.M;
+  const int tc = bs / 6, ntiles = (bs / 3) * tc;
+  if (has_l) {
+    bcr_fetch_block(S0, s.GR + (size_t)Il * bb, (int)bb);
+    bcr_fetch_block(gl, s.g + (size_t)Il * bs, bs);
+  }
+  cp_async_commit();
+  if (has_r) {
+    bcr_fetch_block(S1, s.GL + (size_t)Ir * bb, (int)bb);
+    bcr_fetch_block(gr, s.g + (size_t)Ir * bs, bs);
+  }
+  cp_async_commit();
+  if (has_n) bcr_fetch_block(S2, s.GR + (size_t)Ir * bb, (int)bb);
+  cp_async_commit();
+  double acc[18];
+#pragma unroll
+  for (int q = 0; q < 18; ++q) acc[q] = 0.0;
+  double vl = 0.0, vr = 0.0;
+  cp_async_wait<2>();
+  __syncthreads();
+  if (has_l) {
+    if (tid < bs)
+      for (int k = 0; k < bs; ++k) vl += S0[k * bs + tid] * gl[k];
+    bcr_ata_resident(S0, S0, bs, acc);
+  }
+  cp_async_wait<1>();
+  __syncthreads();
+  if (has_r) {
+    if (tid < bs)
+      for (int k = 0; k < bs; ++k) vr += S1[k * bs + tid] * gr[k];
+    bcr_ata_resident(S1, S1, bs, acc);
+  }
+  if (tid < bs) s.x[(size_t)J * bs + tid] -= vl + vr;
+  const int r0 = 3 * (tid / tc), cl = tid % tc;
+  if (tid < ntiles) {
+    double* Dg = s.D + (size_t)J * bb;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) Dg[(size_t)(r0 + a) * bs + cl + q * tc] -= acc[a * 6 + q];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (has_n) {
+#pragma unroll
+    for (int q = 0; q < 18; ++q) acc[q] = 0.0;
+    bcr_ata_resident(S1, S2, bs, acc);
+    if (tid < ntiles) {
+      double* En = s.E + s.eoff[level + 1] + (size_t)(p / 2) * bb;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) En[(size_t)(r0 + a) * bs + cl + q * tc] = -acc[a * 6 + q];
+    }
+  }
+}
+
 // ---- root: the last active block (block 0). One CTA; dynamic smem = (bs * ld + 2 * bs) doubles + 16 bytes
 __global__ void __launch_bounds__(BCR_THREADS) bcr_root(const __grid_constant__ BcrDev s) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];

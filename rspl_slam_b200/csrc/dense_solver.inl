@@ -29,6 +29,12 @@ struct DenseLayout {
 };
 
 // Allocates the dense systems of the uploaded batch (grow-only) and the solver workspaces.
+// the resident update keeps three super-blocks in shared memory; RSPL_BA_BCR_SLABS=1 forces the slab-staged kernel
+static bool bcr_update_is_resident(const RsplBaContext* c, int bs) {
+  const bool slabs = getenv("RSPL_BA_BCR_SLABS") != nullptr;
+  return !slabs && bs <= ba::BCR_RESIDENT_BS_MAX && ba::bcr_tiles_per_thread(bs) == 1 && ba::bcr_resident_smem(bs) + 1024 <= (size_t)c->smem_optin;
+}
+
 int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band) {
   const int W = c->l_n_windows;
   L.off.assign(W, 0);
@@ -104,6 +110,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_backsub, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(lbytes + sizeof(double) * 4 * s.bs + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
     CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update<ba::BCR_TILES_PER_THREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64)));
+    if (bcr_update_is_resident(c, s.bs)) CU_TRY(c, cudaFuncSetAttribute(ba::bcr_update_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::bcr_resident_smem(s.bs)));
   } else {
     CU_TRY(c, cudaFuncSetAttribute(ba::dc_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba::DC_UPDATE_SMEM));
     CU_TRY(c, cudaFuncSetAttribute(ba::dc_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin - ba::DC_SOLVE_STATIC_SMEM)));
@@ -157,7 +164,8 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   for (int l = 0; l < levels; ++l) {
     const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
     if (n_odd > 0) ba::bcr_eliminate<<<n_odd, ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
-    if (ba::bcr_tiles_per_thread(s.bs) == 1) ba::bcr_update<1><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
+    if (bcr_update_is_resident(c, s.bs)) ba::bcr_update_resident<<<n_even, ba::BCR_THREADS, ba::bcr_resident_smem(s.bs), st>>>(s, l);
+    else if (ba::bcr_tiles_per_thread(s.bs) == 1) ba::bcr_update<1><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
     else ba::bcr_update<ba::BCR_TILES_PER_THREAD><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
     c->launches += 2;
     Ml = n_even;

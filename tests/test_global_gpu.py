@@ -166,6 +166,11 @@ def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
         other = gpu_ctx.local_batch(batch)
         monkeypatch.delenv(var)
         assert np.array_equal(other.sp_inlier, res.sp_inlier) and np.abs(other.pose_twc - res.pose_twc).max() < 1e-9
+    # the slab-staged cyclic-reduction update sums in the same order as the shared-memory-resident one: same bits
+    monkeypatch.setenv("RSPL_BA_BCR_SLABS", "1")
+    slabs = gpu_ctx.local_batch(batch)
+    monkeypatch.delenv("RSPL_BA_BCR_SLABS")
+    assert np.array_equal(slabs.pose_twc, res.pose_twc) and np.array_equal(slabs.sp_inlier, res.sp_inlier)
 
 
 def test_loop_closures_take_the_dense_cholesky(gpu_ctx, orc):
