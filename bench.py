@@ -50,7 +50,7 @@ BYTES_POSE_ONLY_MONO = 52
 BYTES_POSE_ONLY_STEREO_LINE = 124  # 64 meas + 48 world line + 4 flag + 8 chi2 (same accounting, line extension)
 BYTES_POSE_ONLY_MONO_LINE = 92
 C2_FRAMES, C2_POINTS, C2_LINES = 4096, 400, 60
-ALL_N1 = ["c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri"]
+ALL_N1 = ["c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri", "ends"]
 ALL_MULTI = ["c2", "c2p", "c4", "c5"]
 
 
@@ -76,7 +76,91 @@ def workload_name(key, args):
     if key == "tri":
         return (f"TRI batched Map::TriangulateMappoint (SURVEY 8f-4): {TRI_POINTS} new map points x 0-8 observations from "
                 f"{TRI_FRAMES} keyframes")
+    if key == "ends":
+        return (f"ENDS batched Map::UppdateMapline (SURVEY 8f-2): endpoint refresh of {ENDS_LINES} optimised lines "
+                f"(1024 windows x 300) x 0-{ENDS_MAX_PTS} map points")
     raise ValueError(key)
+
+
+ENDS_LINES, ENDS_MAX_PTS, ENDS_SAMPLE = 307_200, 24, 307_200
+ENDS_METRIC, ENDS_UNIT = "map lines refreshed/sec", "lines/s"
+
+
+def _ends_batch(n_lines):
+    from rspl_slam_b200 import synth
+    return synth.make_mapline_batch(20261018 + 7000, n_lines=n_lines, max_pts=ENDS_MAX_PTS)
+
+
+def _pin_arrays(b, capi):
+    """the numpy arrays of a dict copied into page-locked host memory"""
+    out = {}
+    for k, v in b.items():
+        if isinstance(v, np.ndarray) and v.size:
+            p = capi.pinned_empty(v.shape, v.dtype)
+            p[...] = v
+            out[k] = p
+        else:
+            out[k] = v
+    return out
+
+
+def bench_ends(env, steps, warmup, with_cpu):
+    """SURVEY 8(f) rank 2. value: lines per second of the kernel alone (event pair around the launch, inputs
+    resident); e2e: the same through rspl_ba_update_maplines with host arrays (copies inside)."""
+    from oracle import orc
+    ctx, args = env.ctx, env.args
+    b = _ends_batch(ENDS_LINES)
+    n, n_ref, n_pts = len(b["pt_begin"]) - 1, int(b["pt_begin"][-1]), b["point_xyz"].shape[1]
+    from rspl_slam_b200 import capi
+    b = _pin_arrays(b, capi)  # the e2e copies come from / go to page-locked host memory
+    out = (capi.pinned_empty((6, n), np.float64), capi.pinned_empty((n,), np.uint8))
+    out[0][:] = 0.0
+    call = lambda: ctx.update_maplines(b["line_wd"], b["pt_begin"], b["pt_index"], b["point_xyz"], out=out)
+    for _ in range(warmup):
+        call()
+    ctx.set_profiling(True)
+    t0 = time.perf_counter()
+    with ClockSampler(env.local_rank) as clk:
+        for _ in range(steps):
+            env.flush.zero_()
+            env.torch.cuda.synchronize(env.dev)
+            ends, ok, cnt = call()
+    wall = time.perf_counter() - t0
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    ms_kernel = prof["frame_opt"][0] / max(prof["frame_opt"][1], 1)
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    e2e_s = (time.perf_counter() - t1) / steps
+    # per line: Line3D (48) + offset (4) + endpoints (48) + flag (1); per reference: index (4) + position (24, each point
+    # is referenced once on average, so the point array is read once)
+    alg_bytes = 101.0 * n + 28.0 * n_ref
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    res = {
+        "metric": ENDS_METRIC, "value": n / (ms_kernel * 1e-3), "unit": ENDS_UNIT, "n_gpus": env.world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_kernel, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name("ends", args), "l2": "flushed (256 MiB write) between timed steps",
+                   "timing": "CUDA event pair around the kernel (profiling class of the C-ABI call)"},
+        "lines_ok": int(cnt), "point_references": n_ref,
+        "e2e": {"value": n / e2e_s, "unit": ENDS_UNIT, "h2d_bytes_per_step": int(100 * n + 4 + 4 * n_ref + 24 * n_pts),
+                "d2h_bytes_per_step": int(49 * n + 4), "ms_per_step": 1e3 * e2e_s,
+                "api": "rspl_ba_update_maplines (pinned host arrays in, pinned host arrays out)"},
+        "gpu_launches": int(prof["frame_opt"][1]),
+        "roofline": {"bound": "hbm", "kernel": "ba::line_endpoints_kernel", "achieved": achieved, "peak": env.peak,
+                     "unit": "GB/s", "frac": achieved / env.peak, "traffic": None, "peak_source": env.peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": ms_kernel},
+        "clocks": clk.summary(), "wall_s_timed_region": wall,
+    }
+    if with_cpu:
+        t2 = time.perf_counter()
+        ref_ends, ref_ok, _ = orc.update_maplines(b["line_wd"], b["pt_begin"], b["pt_index"], b["point_xyz"])
+        dt = time.perf_counter() - t2
+        res["cpu_baseline"] = {"value": n / dt, "unit": ENDS_UNIT, "cores": 1, "kind": "port",
+                               "sample": f"all {n} lines, 1 thread", "seconds": dt}
+        res["parity_check"] = bool(np.array_equal(ref_ok, ok) and np.array_equal(ref_ends, ends))
+    return res
 
 
 TRI_POINTS, TRI_FRAMES = 1_000_000, 16
@@ -105,7 +189,11 @@ def bench_tri(env, steps, warmup, with_cpu):
     ctx, args = env.ctx, env.args
     b = _tri_batch(TRI_POINTS)
     n, n_obs = len(b["obs_begin"]) - 1, int(b["obs_begin"][-1])
-    call = lambda: ctx.triangulate_points(b["obs_begin"], b["obs_frame"], b["obs_uv"], b["frame_twc"], b["cam5"])
+    from rspl_slam_b200 import capi
+    b = _pin_arrays(b, capi)  # the e2e copies come from / go to page-locked host memory
+    out = (capi.pinned_empty((3, n), np.float64), capi.pinned_empty((n,), np.uint8))
+    out[0][:] = 0.0
+    call = lambda: ctx.triangulate_points(b["obs_begin"], b["obs_frame"], b["obs_uv"], b["frame_twc"], b["cam5"], out=out)
     for _ in range(warmup):
         call()
     ctx.set_profiling(True)
@@ -134,7 +222,7 @@ def bench_tri(env, steps, warmup, with_cpu):
         "points_ok": int(cnt), "observations": n_obs,
         "e2e": {"value": n / e2e_s, "unit": TRI_UNIT, "h2d_bytes_per_step": int(20 * n_obs + 28 * n + 4 + 56 * TRI_FRAMES),
                 "d2h_bytes_per_step": int(25 * n), "ms_per_step": 1e3 * e2e_s,
-                "api": "rspl_ba_triangulate_points (pageable host arrays in, host arrays out)"},
+                "api": "rspl_ba_triangulate_points (pinned host arrays in, pinned host arrays out)"},
         "gpu_launches": int(prof["frame_opt"][1]),
         "roofline": {"bound": "hbm", "kernel": "ba::triangulate_points_kernel", "achieved": achieved, "peak": env.peak,
                      "unit": "GB/s", "frac": achieved / env.peak, "traffic": None, "peak_source": env.peak_src,
@@ -293,10 +381,31 @@ def reference_tri(args, steps, warmup):
             "e2e": {"value": value, "unit": TRI_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
+def reference_ends(args, steps, warmup):
+    from oracle import orc
+    b = _ends_batch(ENDS_SAMPLE)
+    ts = []
+    for step in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.update_maplines(b["line_wd"], b["pt_begin"], b["pt_index"], b["point_xyz"])
+        if step >= warmup:
+            ts.append(time.perf_counter() - t0)
+    value = ENDS_SAMPLE * len(ts) / float(sum(ts))
+    return {"impl": "reference", "metric": ENDS_METRIC, "value": value, "unit": ENDS_UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": 1e3 * float(sum(ts)) / len(ts), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name("ends", args),
+                       "reference_impl": "CPU oracle (restatement of map.cc:121-177 + g2o's Line3D::toCartesian with Eigen's LDLT)"},
+            "cpu_baseline": {"value": value, "unit": ENDS_UNIT, "cores": 1, "kind": "port", "sample": f"all {ENDS_SAMPLE} lines, 1 thread"},
+            "e2e": {"value": value, "unit": ENDS_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def reference_one(key, args, steps, warmup, budget):
     from oracle import orc
     if key == "tri":
         return reference_tri(args, steps, warmup)
+    if key == "ends":
+        return reference_ends(args, steps, warmup)
     threads = orc.max_threads()
     use = threads if key in ("c2", "c2p", "c4") else 1
     base, runner, desc = _oracle_sample(key, args, use, budget)
@@ -760,7 +869,7 @@ def sub_steps(key, args):
         return max(5, min(args.steps, 30)), 3
     if key == "c5":
         return max(1, min(args.steps, 3)), 1
-    if key == "tri":
+    if key in ("tri", "ends"):
         return max(2, min(args.steps, 5)), 2
     return args.steps, args.warmup
 
@@ -788,6 +897,8 @@ def run_ours(args):
             results[key] = bench_global(env, steps, warmup, with_cpu)
         elif key == "tri":
             results[key] = bench_tri(env, steps, warmup, with_cpu)
+        elif key == "ends":
+            results[key] = bench_ends(env, steps, warmup, with_cpu)
         else:
             results[key] = bench_units(env, key, steps, warmup, with_cpu)
         _log(f"workload {key} done")
@@ -808,7 +919,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri"],
+    ap.add_argument("--workload", default="all", choices=["all", "c2", "c2p", "c4", "c1", "c3", "frame1", "c5", "tri", "ends"],
                     help="all: C2 headline + every other configuration as `workloads` sub-objects")
     ap.add_argument("--frame-lines", type=int, default=C2_LINES, help="lines per frame (c2)")
     ap.add_argument("--kf", type=int, default=2000, help="keyframes of the global problem (c5)")

@@ -264,6 +264,20 @@ int rspl_ba_triangulate_points(RsplBaContext* ctx, int32_t n_points, const int32
                                const double* obs_uv, int32_t n_frames, const double* frame_twc, const double* cam5,
                                double* out_xyz, uint8_t* out_ok, int32_t* n_done);
 
+/* --- endpoint refresh of the optimised map lines ----------------------------
+ * Replaces the body of Map::UppdateMapline (/root/reference/src/map.cc:121-177), which Map::LocalMapOptimization
+ * calls for every line the local BA returned (map.cc:790-797), for a whole batch of lines. line_wd [6][n_lines] =
+ * g2o::Line3D [w, d] (what rspl_ba_local_batch_download returns); line l has the map points
+ * pt_index[pt_begin[l] .. pt_begin[l+1] - 1] (the valid map points on the line in its observing keyframes,
+ * map.cc:128-139) into point_xyz [3][n_points]. out_ok[l] is the reference's bool: 1 when a point within 0.2 of the
+ * line gave both ends, with the reference's quirk that the running maximum starts at DBL_MIN (no end from points
+ * whose main coordinate is not positive). endpoints [6][n_lines] (first the end at the largest main coordinate) is
+ * left untouched where out_ok[l] = 0, as the reference does not call SetEndpoints then. *n_done (may be null):
+ * number of lines refreshed. All pointers are host. */
+int rspl_ba_update_maplines(RsplBaContext* ctx, int32_t n_lines, const double* line_wd, const int32_t* pt_begin,
+                            const int32_t* pt_index, int32_t n_points, const double* point_xyz, double* endpoints,
+                            uint8_t* out_ok, int32_t* n_done);
+
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
  * line, 3 stereo line, 4 / 5 mono / stereo pose-only point edge (lm = the fixed world point Xw, Jl = 0). pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]

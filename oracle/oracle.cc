@@ -1704,3 +1704,119 @@ extern "C" int orc_triangulate_points(int32_t n_points, const int32_t* obs_begin
   }
   return n_done;
 }
+
+// ---- line endpoint refresh after the local BA (Map::UppdateMapline, map.cc:121-177) ----
+// g2o::Line3D::toCartesian (g2o types/slam3d_addons/line3d.cpp; g2o is not in the tree, see oracle.h): direction
+// d / |d|, anchor = (W^T W + 1e-9 I).ldlt().solve(W^T w) with W = -skew(d). Eigen's LDLT<Matrix3d> is restated as its
+// published unblocked algorithm: pivot on the largest |diagonal| of the not yet updated trailing part, left-looking
+// column update, unit-lower forward solve in axpy order, pseudo-inverse of D, unit-upper backward solve in dot order.
+static void ldlt3_solve(double A[3][3], const double b[3], double x[3]) {
+  int tr[3];
+  for (int k = 0; k < 3; ++k) {
+    int big = k;
+    for (int i = k + 1; i < 3; ++i)
+      if (std::fabs(A[i][i]) > std::fabs(A[big][big])) big = i; // maxCoeff: first maximum
+    tr[k] = big;
+    if (big != k) { // symmetric transposition on the lower triangle
+      for (int j = 0; j < k; ++j) std::swap(A[k][j], A[big][j]);
+      for (int i = big + 1; i < 3; ++i) std::swap(A[i][k], A[i][big]);
+      std::swap(A[k][k], A[big][big]);
+      for (int i = k + 1; i < big; ++i) std::swap(A[i][k], A[big][i]);
+    }
+    if (k > 0) {
+      double temp[2];
+      for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
+      double acc = A[k][0] * temp[0];
+      for (int j = 1; j < k; ++j) acc += A[k][j] * temp[j];
+      A[k][k] -= acc;
+      for (int i = k + 1; i < 3; ++i) {
+        double a2 = A[i][0] * temp[0];
+        for (int j = 1; j < k; ++j) a2 += A[i][j] * temp[j];
+        A[i][k] -= a2;
+      }
+    }
+    const double akk = A[k][k];
+    if (std::fabs(akk) > 0.0)
+      for (int i = k + 1; i < 3; ++i) A[i][k] /= akk;
+  }
+  double y[3] = {b[0], b[1], b[2]};
+  for (int k = 0; k < 3; ++k) std::swap(y[k], y[tr[k]]);
+  y[1] -= y[0] * A[1][0]; // L y' = y, column by column
+  y[2] -= y[0] * A[2][0];
+  y[2] -= y[1] * A[2][1];
+  const double tol = 1.0 / std::numeric_limits<double>::max();
+  for (int i = 0; i < 3; ++i) y[i] = std::fabs(A[i][i]) > tol ? y[i] / A[i][i] : 0.0;
+  y[1] -= A[2][1] * y[2]; // L^T x = y, row by row
+  y[0] -= A[1][0] * y[1] + A[2][0] * y[2];
+  for (int k = 2; k >= 0; --k) std::swap(y[k], y[tr[k]]);
+  x[0] = y[0];
+  x[1] = y[1];
+  x[2] = y[2];
+}
+
+static void line_to_cartesian(const double* wd, double* cart /* anchor(3), direction(3) */) {
+  const double w0 = wd[0], w1 = wd[1], w2 = wd[2], dx = wd[3], dy = wd[4], dz = wd[5];
+  const double nrm = std::sqrt(dx * dx + dy * dy + dz * dz);
+  cart[3] = dx / nrm;
+  cart[4] = dy / nrm;
+  cart[5] = dz / nrm;
+  // W = [[0, dz, -dy], [-dz, 0, dx], [dy, -dx, 0]]; A = W^T W + 1e-9 I, entries summed over k = 0, 1, 2
+  double A[3][3];
+  A[0][0] = (dz * dz + dy * dy) + 1e-9;
+  A[1][1] = (dz * dz + dx * dx) + 1e-9;
+  A[2][2] = (dy * dy + dx * dx) + 1e-9;
+  A[1][0] = A[0][1] = -(dx * dy);
+  A[2][0] = A[0][2] = -(dx * dz);
+  A[2][1] = A[1][2] = -(dy * dz);
+  const double b[3] = {-(dz * w1) + dy * w2, dz * w0 + -(dx * w2), -(dy * w0) + dx * w1};
+  ldlt3_solve(A, b, cart);
+}
+
+extern "C" void orc_line_to_cartesian(const double* wd6, double* cart6) { line_to_cartesian(wd6, cart6); }
+
+extern "C" int orc_update_maplines(int32_t n_lines, const double* line_wd, const int32_t* pt_begin, const int32_t* pt_index,
+                                   const double* point_xyz, int32_t n_points, double* endpoints, uint8_t* out_ok) {
+  int done = 0;
+  for (int l = 0; l < n_lines; ++l) {
+    out_ok[l] = 0;
+    double wd[6], cart[6];
+    for (int k = 0; k < 6; ++k) wd[k] = line_wd[(size_t)k * n_lines + l];
+    if (pt_begin[l + 1] == pt_begin[l]) continue; // map.cc:127 (no observers) and :166 (nothing found)
+    line_to_cartesian(wd, cart);
+    const double* lp = cart;
+    const double* v = cart + 3;
+    int md = 0; // array().abs().maxCoeff: first maximum
+    for (int k = 1; k < 3; ++k)
+      if (std::fabs(v[k]) > std::fabs(v[md])) md = k;
+    // (sic) DBL_MIN is the smallest POSITIVE double: a line whose nearby points all have a non-positive main
+    // coordinate finds no maximum and keeps its old endpoints (map.cc:153-166)
+    double max_d = DBL_MIN, min_d = DBL_MAX;
+    bool find_max = false, find_min = false;
+    for (int o = pt_begin[l]; o < pt_begin[l + 1]; ++o) {
+      const int pi = pt_index[o];
+      const double X[3] = {point_xyz[pi], point_xyz[(size_t)n_points + pi], point_xyz[2 * (size_t)n_points + pi]};
+      const double dp[3] = {X[0] - lp[0], X[1] - lp[1], X[2] - lp[2]};
+      const double c0 = v[1] * dp[2] - v[2] * dp[1], c1 = v[2] * dp[0] - v[0] * dp[2], c2 = v[0] * dp[1] - v[1] * dp[0];
+      const double dist = std::sqrt(c0 * c0 + c1 * c1 + c2 * c2); // line_processor.cc:77-90
+      if (dist > 0.2) continue;
+      const double di = X[md];
+      if (di > max_d) {
+        max_d = di;
+        find_max = true;
+      }
+      if (di < min_d) {
+        min_d = di;
+        find_min = true;
+      }
+    }
+    if (!find_max || !find_min) continue;
+    const double r1 = (max_d - lp[md]) / v[md], r2 = (min_d - lp[md]) / v[md];
+    for (int k = 0; k < 3; ++k) {
+      endpoints[(size_t)k * n_lines + l] = lp[k] + r1 * v[k];
+      endpoints[(size_t)(3 + k) * n_lines + l] = lp[k] + r2 * v[k];
+    }
+    out_ok[l] = 1;
+    ++done;
+  }
+  return done;
+}

@@ -174,6 +174,15 @@ int orc_triangulate_points(int32_t n_points, const int32_t* obs_begin, const int
                            int32_t n_obs, const double* frame_twc, int32_t n_frames, const double* cam5, double* out_xyz,
                            uint8_t* out_ok);
 
+/* --- Map::UppdateMapline (/root/reference/src/map.cc:121-177), the line endpoint refresh that follows the local BA
+ * (map.cc:797), for a batch of lines. line_wd [6][n_lines] g2o::Line3D [w, d]; line l has the map points
+ * pt_index[pt_begin[l] .. pt_begin[l+1] - 1] (the valid map points on the line in its observers, map.cc:128-139) in
+ * point_xyz [3][n_points]. endpoints [6][n_lines] (first the end at the largest main-direction coordinate) is written
+ * only where out_ok[l] = 1, the reference's return value. Returns the number of lines refreshed. */
+void orc_line_to_cartesian(const double* wd6, double* cart6);
+int orc_update_maplines(int32_t n_lines, const double* line_wd, const int32_t* pt_begin, const int32_t* pt_index,
+                        const double* point_xyz, int32_t n_points, double* endpoints, uint8_t* out_ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,6 +302,35 @@ def triangulate_points(obs_begin, obs_frame, obs_uv, frame_twc, cam5, xyz_init=N
     return xyz, ok, int(cnt)
 
 
+def line_to_cartesian(wd6) -> np.ndarray:
+    """g2o::Line3D::toCartesian: anchor (3), unit direction (3)."""
+    out = np.zeros(6)
+    L = lib()
+    L.orc_line_to_cartesian.argtypes = [c_f64p, c_f64p]
+    L.orc_line_to_cartesian.restype = None
+    L.orc_line_to_cartesian(_p(_arr(wd6, 6), c_f64p), _p(out, c_f64p))
+    return out
+
+
+def update_maplines(line_wd, pt_begin, pt_index, point_xyz, endpoints_init=None):
+    """Map::UppdateMapline (map.cc:121-177) for a batch of lines; same layout as rspl_ba_update_maplines.
+    Returns (endpoints [6][n], ok [n] uint8, number refreshed)."""
+    line_wd = np.ascontiguousarray(line_wd, dtype=np.float64)
+    pt_begin = np.ascontiguousarray(pt_begin, dtype=np.int32)
+    pt_index = np.ascontiguousarray(pt_index, dtype=np.int32)
+    point_xyz = np.ascontiguousarray(point_xyz, dtype=np.float64)
+    n = len(pt_begin) - 1
+    ends = np.zeros((6, n)) if endpoints_init is None else np.ascontiguousarray(endpoints_init, dtype=np.float64).copy()
+    ok = np.zeros(n, dtype=np.uint8)
+    L = lib()
+    c_i32p, c_u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    L.orc_update_maplines.argtypes = [C.c_int32, c_f64p, c_i32p, c_i32p, c_f64p, C.c_int32, c_f64p, c_u8p]
+    L.orc_update_maplines.restype = C.c_int
+    cnt = L.orc_update_maplines(n, _p(line_wd, c_f64p), _p(pt_begin, c_i32p), _p(pt_index, c_i32p), _p(point_xyz, c_f64p),
+                                point_xyz.shape[1], _p(ends, c_f64p), _p(ok, c_u8p))
+    return ends, ok, int(cnt)
+
+
 def huber(chi2: float, thr: float) -> np.ndarray:
     out = np.zeros(3)
     lib().orc_huber(chi2, thr, _p(out, c_f64p))

@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points", "rspl_ba_unit_math",
+    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points", "rspl_ba_update_maplines", "rspl_ba_unit_math",
     "rspl_ba_set_profiling", "rspl_ba_get_profile",
     "rspl_ba_comm_unique_id", "rspl_ba_comm_init", "rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank",
     "rspl_ba_collective_count", "rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download")
@@ -165,6 +165,9 @@ def load_library() -> C.CDLL:
     L.rspl_ba_triangulate_points.argtypes = [ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_f64p, C.c_int32,
                                              c_f64p, c_f64p, c_f64p, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
     L.rspl_ba_triangulate_points.restype = C.c_int
+    L.rspl_ba_update_maplines.argtypes = [ctx, C.c_int32, c_f64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, c_f64p,
+                                          c_f64p, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+    L.rspl_ba_update_maplines.restype = C.c_int
     L.rspl_ba_unit_math.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p]
     L.rspl_ba_unit_math.restype = C.c_int
     L.rspl_ba_oplus.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p, c_f64p]
@@ -437,23 +440,51 @@ class Context:
                                                _p(Jl, c_f64p), _p(Jp, c_f64p), _p(chi2, c_f64p)))
         return err, Jl, Jp, chi2
 
-    def triangulate_points(self, obs_begin, obs_frame, obs_uv, frame_twc, cam5, xyz_init=None):
+    def triangulate_points(self, obs_begin, obs_frame, obs_uv, frame_twc, cam5, xyz_init=None, out=None):
         """Batched Map::TriangulateMappoint (map.cc:292-339). obs_uv [2][n_obs], frame_twc [7][n_frames] (p, q xyzw).
-        Returns (xyz [3][n_points], ok [n_points] uint8, number triangulated); xyz of a failed point keeps xyz_init."""
+        Returns (xyz [3][n_points], ok [n_points] uint8, number triangulated); xyz of a failed point keeps xyz_init.
+        out = (xyz, ok): caller-owned result arrays (e.g. page-locked ones from pinned_empty), used in place."""
         obs_begin = np.ascontiguousarray(obs_begin, dtype=np.int32)
         obs_frame = np.ascontiguousarray(obs_frame, dtype=np.int32)
         obs_uv = np.ascontiguousarray(obs_uv, dtype=np.float64)
         frame_twc = np.ascontiguousarray(frame_twc, dtype=np.float64)
         cam5 = np.ascontiguousarray(cam5, dtype=np.float64)
         n = len(obs_begin) - 1
-        xyz = np.zeros((3, n)) if xyz_init is None else np.ascontiguousarray(xyz_init, dtype=np.float64).copy()
-        ok = np.zeros(n, dtype=np.uint8)
+        if out is not None:
+            xyz, ok = out
+            assert xyz.shape == (3, n) and xyz.dtype == np.float64 and xyz.flags.c_contiguous and ok.shape == (n,) and ok.dtype == np.uint8
+        else:
+            xyz = np.zeros((3, n)) if xyz_init is None else np.ascontiguousarray(xyz_init, dtype=np.float64).copy()
+            ok = np.zeros(n, dtype=np.uint8)
         cnt = C.c_int32(0)
         c_i32p, c_u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
         self._check(self._L.rspl_ba_triangulate_points(
             self._ctx, n, _p(obs_begin, c_i32p), _p(obs_frame, c_i32p), _p(obs_uv, c_f64p), frame_twc.shape[1],
             _p(frame_twc, c_f64p), _p(cam5, c_f64p), _p(xyz, c_f64p), _p(ok, c_u8p), C.byref(cnt)))
         return xyz, ok, int(cnt.value)
+
+    def update_maplines(self, line_wd, pt_begin, pt_index, point_xyz, endpoints_init=None, out=None):
+        """Batched Map::UppdateMapline (map.cc:121-177): endpoint refresh of optimised lines from their map points.
+        line_wd [6][n_lines], point_xyz [3][n_points], CSR pt_begin / pt_index. Returns (endpoints [6][n_lines],
+        ok [n_lines] uint8, number refreshed); endpoints of a line that is not refreshed keep endpoints_init.
+        out = (endpoints, ok): caller-owned result arrays (e.g. page-locked ones from pinned_empty), used in place."""
+        line_wd = np.ascontiguousarray(line_wd, dtype=np.float64)
+        pt_begin = np.ascontiguousarray(pt_begin, dtype=np.int32)
+        pt_index = np.ascontiguousarray(pt_index, dtype=np.int32)
+        point_xyz = np.ascontiguousarray(point_xyz, dtype=np.float64)
+        n = len(pt_begin) - 1
+        if out is not None:
+            ends, ok = out
+            assert ends.shape == (6, n) and ends.dtype == np.float64 and ends.flags.c_contiguous and ok.shape == (n,) and ok.dtype == np.uint8
+        else:
+            ends = np.zeros((6, n)) if endpoints_init is None else np.ascontiguousarray(endpoints_init, dtype=np.float64).copy()
+            ok = np.zeros(n, dtype=np.uint8)
+        cnt = C.c_int32(0)
+        c_i32p, c_u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        self._check(self._L.rspl_ba_update_maplines(
+            self._ctx, n, _p(line_wd, c_f64p), _p(pt_begin, c_i32p), _p(pt_index, c_i32p), point_xyz.shape[1],
+            _p(point_xyz, c_f64p), _p(ends, c_f64p), _p(ok, c_u8p), C.byref(cnt)))
+        return ends, ok, int(cnt.value)
 
     def unit_math(self, op: int, x: np.ndarray) -> np.ndarray:
         """rcp_nr (0) / rsqrt_nr (1) / sqrt_nr (2) of ba_math.cuh on the device."""

@@ -23,6 +23,7 @@
 #include "local_tiled.cuh"
 #include "dense_chol.cuh"
 #include "triangulate.cuh"
+#include "line_endpoints.cuh"
 
 static_assert(sizeof(RsplBaStats) == sizeof(ba::DevStats), "stats layout");
 
@@ -1104,8 +1105,6 @@ extern "C" int rspl_ba_triangulate_points(RsplBaContext* c, int32_t n_points, co
   if (!offsets_ok(obs_begin, n_points) || !out_xyz || !out_ok) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: bad offsets or null outputs");
   const int n_obs = obs_begin[n_points];
   if (n_obs > 0 && (!obs_frame || !obs_uv || !frame_twc)) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: null observation arrays");
-  for (int o = 0; o < n_obs; ++o)
-    if (obs_frame[o] < 0 || obs_frame[o] >= n_frames) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: keyframe index out of range");
   if (!(cam5[0] != 0.0) || !(cam5[1] != 0.0)) return fail(c, RSPL_BA_ERR_INVALID, "triangulate: zero focal length");
   SetDevice guard(c->device);
   if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
@@ -1124,6 +1123,10 @@ extern "C" int rspl_ba_triangulate_points(RsplBaContext* c, int32_t n_points, co
   if (n_frames > 0) CU_TRY(c, cudaMemcpyAsync(base + o_tw, frame_twc, sizeof(double) * 7 * (size_t)n_frames, cudaMemcpyHostToDevice, s));
   CU_TRY(c, cudaMemcpyAsync(base + o_xyz, out_xyz, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyHostToDevice, s)); // untouched where !ok
   CU_TRY(c, cudaMemsetAsync(base + o_cnt, 0, sizeof(int), s));
+  if (!cams_ok(obs_frame, n_obs, n_frames)) { // (threaded range check, behind the uploads already queued)
+    cudaStreamSynchronize(s);
+    return fail(c, RSPL_BA_ERR_INVALID, "triangulate: keyframe index out of range");
+  }
   ba::TriDev d;
   d.n_points = n_points;
   d.n_obs = n_obs;
@@ -1147,6 +1150,61 @@ extern "C" int rspl_ba_triangulate_points(RsplBaContext* c, int32_t n_points, co
   CU_TRY(c, cudaGetLastError());
   CU_TRY(c, cudaMemcpyAsync(out_xyz, base + o_xyz, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost, s));
   CU_TRY(c, cudaMemcpyAsync(out_ok, base + o_ok, (size_t)n_points, cudaMemcpyDeviceToHost, s));
+  int cnt = 0;
+  CU_TRY(c, cudaMemcpyAsync(&cnt, base + o_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  if (n_done) *n_done = cnt;
+  return RSPL_BA_OK;
+}
+
+extern "C" int rspl_ba_update_maplines(RsplBaContext* c, int32_t n_lines, const double* line_wd, const int32_t* pt_begin,
+                                       const int32_t* pt_index, int32_t n_points, const double* point_xyz,
+                                       double* endpoints, uint8_t* out_ok, int32_t* n_done) {
+  if (!c || n_lines < 0 || n_points < 0) return RSPL_BA_ERR_INVALID;
+  if (n_done) *n_done = 0;
+  if (n_lines == 0) return RSPL_BA_OK;
+  if (!offsets_ok(pt_begin, n_lines) || !line_wd || !endpoints || !out_ok) return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: bad offsets or null arrays");
+  const int n_ref = pt_begin[n_lines];
+  if (n_ref > 0 && (!pt_index || !point_xyz)) return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: null point arrays");
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  Arena a;
+  const size_t o_wd = a.take(sizeof(double) * 6 * (size_t)n_lines), o_beg = a.take(sizeof(int) * ((size_t)n_lines + 1));
+  const size_t o_idx = a.take(sizeof(int) * (size_t)n_ref), o_xyz = a.take(sizeof(double) * 3 * (size_t)n_points);
+  const size_t o_end = a.take(sizeof(double) * 6 * (size_t)n_lines), o_ok = a.take((size_t)n_lines), o_cnt = a.take(sizeof(int));
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_wd, line_wd, sizeof(double) * 6 * (size_t)n_lines, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemcpyAsync(base + o_beg, pt_begin, sizeof(int) * ((size_t)n_lines + 1), cudaMemcpyHostToDevice, s));
+  if (n_ref > 0) {
+    CU_TRY(c, cudaMemcpyAsync(base + o_idx, pt_index, sizeof(int) * (size_t)n_ref, cudaMemcpyHostToDevice, s));
+    CU_TRY(c, cudaMemcpyAsync(base + o_xyz, point_xyz, sizeof(double) * 3 * (size_t)n_points, cudaMemcpyHostToDevice, s));
+  }
+  CU_TRY(c, cudaMemcpyAsync(base + o_end, endpoints, sizeof(double) * 6 * (size_t)n_lines, cudaMemcpyHostToDevice, s)); // untouched where !ok
+  CU_TRY(c, cudaMemsetAsync(base + o_cnt, 0, sizeof(int), s));
+  if (!cams_ok(pt_index, n_ref, n_points)) { // (threaded range check, behind the uploads already queued)
+    cudaStreamSynchronize(s);
+    return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: point index out of range");
+  }
+  ba::LineEndpointsDev d;
+  d.n_lines = n_lines;
+  d.n_points = n_points;
+  d.line_wd = (const double*)(base + o_wd);
+  d.pt_begin = (const int*)(base + o_beg);
+  d.pt_index = (const int*)(base + o_idx);
+  d.point_xyz = (const double*)(base + o_xyz);
+  d.endpoints = (double*)(base + o_end);
+  d.out_ok = (uint8_t*)(base + o_ok);
+  d.n_done = (int*)(base + o_cnt);
+  {
+    ProfScope ps(c, PC_FRAME);
+    ba::line_endpoints_kernel<<<(n_lines + ba::LINE_EP_THREADS - 1) / ba::LINE_EP_THREADS, ba::LINE_EP_THREADS, 0, s>>>(d); // a thread per line
+  }
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(endpoints, base + o_end, sizeof(double) * 6 * (size_t)n_lines, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(out_ok, base + o_ok, (size_t)n_lines, cudaMemcpyDeviceToHost, s));
   int cnt = 0;
   CU_TRY(c, cudaMemcpyAsync(&cnt, base + o_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU_TRY(c, cudaStreamSynchronize(s));

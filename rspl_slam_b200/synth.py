@@ -503,3 +503,46 @@ def make_triangulation_batch(seed: int, n_points: int = 4096, n_frames: int = 12
     return dict(obs_begin=np.asarray(begin, dtype=I32), obs_frame=np.asarray(frames, dtype=I32),
                 obs_uv=np.ascontiguousarray(np.stack([np.asarray(us, dtype=F64), np.asarray(vs, dtype=F64)])),
                 frame_twc=np.ascontiguousarray(twc), cam5=EUROC_CAMERA.copy(), truth=truth)
+
+
+def make_mapline_batch(seed: int, n_lines: int = 4096, max_pts: int = 24, outlier_frac: float = 0.15, box: float = 6.0,
+                       lines_per_window: int = 300):
+    """Inputs of the batched Map::UppdateMapline (SURVEY 8(f) rank 2): optimised lines as g2o::Line3D [w, d] (d not
+    unit, as the BA leaves it) with 0..max_pts map points each: most within a few cm of the line, a fraction
+    0.1 - 1 m off it (the 0.2 m gate of map.cc:155 splits those), plus references to points of OTHER lines (far away).
+    Lines come in local maps of `lines_per_window`: the point array is ordered by map and shuffled inside each (a
+    line's points are map points of its own local map). The scene straddles the origin (box [-box / 3, box]^3), so a
+    share of the lines has only non-positive main coordinates (the reference's DBL_MIN quirk). Returns a dict of the
+    C-ABI arrays + the true segment ends `p1`, `p2`."""
+    rng = np.random.default_rng(seed)
+    p1 = rng.uniform(-box / 3.0, box, (n_lines, 3))
+    v = rng.normal(size=(n_lines, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    p2 = p1 + v * rng.uniform(0.5, 3.0, (n_lines, 1))
+    wd = line_from_cartesian(p1, p2 - p1) * rng.uniform(0.5, 2.0, (n_lines, 1))
+    cnt = rng.integers(0, max_pts + 1, n_lines)
+    cnt[rng.random(n_lines) < 0.03] = 0
+    begin = np.zeros(n_lines + 1, dtype=I32)
+    np.cumsum(cnt, out=begin[1:])
+    n_own = int(begin[-1])
+    owner = np.repeat(np.arange(n_lines), cnt)
+    t = rng.uniform(0.0, 1.0, (n_own, 1))
+    off = rng.normal(size=(n_own, 3))
+    off -= (off * v[owner]).sum(1, keepdims=True) * v[owner]  # perpendicular to the line
+    off /= np.maximum(np.linalg.norm(off, axis=1, keepdims=True), 1e-12)
+    far = rng.random(n_own) < outlier_frac
+    radius = np.where(far, rng.uniform(0.1, 1.0, n_own), np.abs(rng.normal(0.0, 0.03, n_own)))
+    xyz = p1[owner] + t * (p2 - p1)[owner] + off * radius[:, None]
+    win = owner // max(lines_per_window, 1)
+    index = np.argsort(win + rng.random(n_own), kind="stable").astype(I32)  # a permutation inside every local map
+    pts = np.zeros((n_own, 3))
+    pts[index] = xyz
+    # every eighth reference points at some other point of the same local map instead
+    if n_own:
+        n_win = int(win[-1]) + 1
+        w_start = np.searchsorted(win, np.arange(n_win), side="left")
+        w_len = np.searchsorted(win, np.arange(n_win), side="right") - w_start
+        other = w_start[win] + np.minimum((rng.random(n_own) * w_len[win]).astype(np.int64), w_len[win] - 1)
+        index = np.where(rng.random(n_own) < 0.125, other, index).astype(I32)
+    return dict(line_wd=np.ascontiguousarray(wd.T), pt_begin=begin, pt_index=index,
+                point_xyz=np.ascontiguousarray(pts.T), p1=p1, p2=p2)

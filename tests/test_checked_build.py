@@ -1,5 +1,5 @@
 """The library compiled with -DRSPL_BA_CHECKED (bounds / invariant asserts inside the kernels, `BA_CHECK` in
-ba_math.cuh) runs the frame, local, large-window and global paths on small problems without tripping an assert and
+ba_math.cuh) runs the frame, local, large-window, global, triangulation and line-endpoint paths on small problems without tripping an assert and
 with the same results as the shipped build. Substitute for compute-sanitizer memcheck, which is closed on the pool."""
 import json
 import os
@@ -32,6 +32,12 @@ out["local_inl"] = int(lr.sp_inlier.sum()) + int(lr.mp_inlier.sum()) + int(lr.sl
 big = synth.make_global_problem(synth.config_seed(5, 1), n_kf=80, n_points=6000, n_lines=600)
 gr = ctx.local_batch(LocalBatch.from_problems([big]))
 out["big_pose"] = gr.pose_twc.tolist()
+tb = synth.make_triangulation_batch(9, n_points=3000)
+tx, tok, _ = ctx.triangulate_points(tb["obs_begin"], tb["obs_frame"], tb["obs_uv"], tb["frame_twc"], tb["cam5"])
+out["tri"] = [tx.tolist(), int(tok.sum())]
+mb = synth.make_mapline_batch(10, n_lines=3000)
+me, mok, _ = ctx.update_maplines(mb["line_wd"], mb["pt_begin"], mb["pt_index"], mb["point_xyz"])
+out["ends"] = [me.tolist(), int(mok.sum())]
 ctx.close()
 print("RESULT" + json.dumps(out))
 """
