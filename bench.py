@@ -692,9 +692,41 @@ def bench_units(env, key, steps, warmup, with_cpu):
     }
     if key in ("c1", "c3", "frame1"):
         res["shim_latency"] = shim_latency(key)
+    if key == "c4" and world == 1:
+        res["post_ba_line_refresh"] = post_ba_line_refresh(env, ctx, batch, solve, opt)
     if with_cpu:
         res["cpu_baseline"] = cpu_baseline(key, args)
     return res
+
+
+def post_ba_line_refresh(env, ctx, batch, solve, opt, pts_per_line=12, reps=5):
+    """The step that follows the path (SURVEY 8f-2, Map::UppdateMapline for every optimised line) on the RESIDENT result
+    of the batch just solved: rspl_ba_local_batch_update_maplines, only the point lists travel. Every line gets
+    `pts_per_line` random map points of its own window (synthetic lists: the generator has no points-on-line relation,
+    so few of them pass the 0.2 m gate; the work per reference is the same)."""
+    try:
+        capi = env.capi
+        solve(opt)
+        env.torch.cuda.synchronize(env.dev)
+        nl = int(batch.line_begin[-1])
+        rng = np.random.default_rng(20261018)
+        win = np.repeat(np.searchsorted(batch.line_begin, np.arange(nl), side="right") - 1, pts_per_line)
+        span = (batch.point_begin[win + 1] - batch.point_begin[win]).astype(np.int64)
+        index = capi.pinned_empty((nl * pts_per_line,), np.int32)
+        index[:] = batch.point_begin[win] + rng.integers(0, 1 << 40, nl * pts_per_line) % np.maximum(span, 1)
+        begin = capi.pinned_empty((nl + 1,), np.int32)
+        begin[:] = np.arange(nl + 1, dtype=np.int64) * pts_per_line
+        out = (capi.pinned_empty((6, nl), np.float64), capi.pinned_empty((nl,), np.uint8))
+        ctx.local_update_maplines(begin, index, out=out)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            _, ok, cnt = ctx.local_update_maplines(begin, index, out=out)
+        dt = (time.perf_counter() - t0) / reps
+        return {"api": "rspl_ba_local_batch_update_maplines (lines and points resident from the solve; pinned lists in, pinned results out)",
+                "lines": nl, "point_references": int(nl * pts_per_line), "lines_refreshed": int(cnt), "ms_per_call": 1e3 * dt,
+                "h2d_bytes": int(4 * (nl + 1) + 4 * nl * pts_per_line), "d2h_bytes": int(49 * nl + 4)}
+    except Exception as e:  # an extra; it must not take the bench line down
+        return {"error": repr(e)[:300]}
 
 
 def shim_latency(key, reps=20):

@@ -278,6 +278,14 @@ int rspl_ba_update_maplines(RsplBaContext* ctx, int32_t n_lines, const double* l
                             const int32_t* pt_index, int32_t n_points, const double* point_xyz, double* endpoints,
                             uint8_t* out_ok, int32_t* n_done);
 
+/* The same refresh on the RESIDENT result of the local BA just solved on this context (after rspl_ba_local_batch_solve
+ * or an unchunked rspl_ba_local_batch): the optimised Line3Ds and map points are read where the solve left them in
+ * HBM, only the point lists travel. Line l = the l-th line of the batch (RsplLocalBatch::line_begin order),
+ * pt_index = batch-wide point indices (RsplLocalBatch::point_begin[w] + index in window w). endpoints [6][n_lines],
+ * out_ok [n_lines]; unlike above, endpoints of a line with out_ok[l] = 0 are written as 0. */
+int rspl_ba_local_batch_update_maplines(RsplBaContext* ctx, const int32_t* pt_begin, const int32_t* pt_index,
+                                        double* endpoints, uint8_t* out_ok, int32_t* n_done);
+
 /* --- unit-level device entry points (used by the parity tests) ------------------------------- */
 /* Evaluates n edges of one type on the device. edge_type: 0 mono point, 1 stereo point, 2 mono
  * line, 3 stereo line, 4 / 5 mono / stereo pose-only point edge (lm = the fixed world point Xw, Jl = 0). pose7 [n][7] = optimiser pose Tcw as qx,qy,qz,qw,tx,ty,tz; lm [n][6]

@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "rspl_ba_frame_batch_solve", "rspl_ba_frame_batch_download", "rspl_ba_local_batch",
     "rspl_ba_local_batch_upload", "rspl_ba_local_batch_solve", "rspl_ba_local_batch_download",
     "rspl_ba_alloc_pinned", "rspl_ba_free_pinned", "rspl_ba_launch_count", "rspl_ba_sync",
-    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points", "rspl_ba_update_maplines", "rspl_ba_unit_math",
+    "rspl_ba_eval_edges", "rspl_ba_oplus", "rspl_ba_triangulate_points", "rspl_ba_update_maplines", "rspl_ba_local_batch_update_maplines", "rspl_ba_unit_math",
     "rspl_ba_set_profiling", "rspl_ba_get_profile",
     "rspl_ba_comm_unique_id", "rspl_ba_comm_init", "rspl_ba_comm_destroy", "rspl_ba_comm_size", "rspl_ba_comm_rank",
     "rspl_ba_collective_count", "rspl_ba_global_upload", "rspl_ba_global_solve", "rspl_ba_global_download")
@@ -168,6 +168,9 @@ def load_library() -> C.CDLL:
     L.rspl_ba_update_maplines.argtypes = [ctx, C.c_int32, c_f64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, c_f64p,
                                           c_f64p, C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
     L.rspl_ba_update_maplines.restype = C.c_int
+    L.rspl_ba_local_batch_update_maplines.argtypes = [ctx, C.POINTER(C.c_int32), C.POINTER(C.c_int32), c_f64p,
+                                                      C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
+    L.rspl_ba_local_batch_update_maplines.restype = C.c_int
     L.rspl_ba_unit_math.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p]
     L.rspl_ba_unit_math.restype = C.c_int
     L.rspl_ba_oplus.argtypes = [ctx, C.c_int, C.c_int32, c_f64p, c_f64p, c_f64p]
@@ -484,6 +487,24 @@ class Context:
         self._check(self._L.rspl_ba_update_maplines(
             self._ctx, n, _p(line_wd, c_f64p), _p(pt_begin, c_i32p), _p(pt_index, c_i32p), point_xyz.shape[1],
             _p(point_xyz, c_f64p), _p(ends, c_f64p), _p(ok, c_u8p), C.byref(cnt)))
+        return ends, ok, int(cnt.value)
+
+    def local_update_maplines(self, pt_begin, pt_index, out=None):
+        """The endpoint refresh on the resident result of the local BA just solved on this context: pt_begin
+        [n_lines + 1] over all lines of the batch, pt_index batch-wide point indices. Returns (endpoints [6][n_lines]
+        (0 where not refreshed), ok [n_lines] uint8, number refreshed)."""
+        pt_begin = np.ascontiguousarray(pt_begin, dtype=np.int32)
+        pt_index = np.ascontiguousarray(pt_index, dtype=np.int32)
+        n = len(pt_begin) - 1
+        if out is not None:
+            ends, ok = out
+            assert ends.shape == (6, n) and ends.dtype == np.float64 and ends.flags.c_contiguous and ok.shape == (n,) and ok.dtype == np.uint8
+        else:
+            ends, ok = np.zeros((6, n)), np.zeros(n, dtype=np.uint8)
+        cnt = C.c_int32(0)
+        c_i32p, c_u8p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+        self._check(self._L.rspl_ba_local_batch_update_maplines(self._ctx, _p(pt_begin, c_i32p), _p(pt_index, c_i32p),
+                                                                _p(ends, c_f64p), _p(ok, c_u8p), C.byref(cnt)))
         return ends, ok, int(cnt.value)
 
     def unit_math(self, op: int, x: np.ndarray) -> np.ndarray:

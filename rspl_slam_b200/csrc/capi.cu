@@ -1190,6 +1190,8 @@ extern "C" int rspl_ba_update_maplines(RsplBaContext* c, int32_t n_lines, const 
   ba::LineEndpointsDev d;
   d.n_lines = n_lines;
   d.n_points = n_points;
+  d.line_stride = (size_t)n_lines;
+  d.point_stride = (size_t)n_points;
   d.line_wd = (const double*)(base + o_wd);
   d.pt_begin = (const int*)(base + o_beg);
   d.pt_index = (const int*)(base + o_idx);

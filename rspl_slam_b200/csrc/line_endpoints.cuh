@@ -28,10 +28,11 @@ constexpr int LINE_EP_THREADS = 128;
 
 struct LineEndpointsDev {
   int n_lines, n_points;
-  const double* line_wd;   // [6][n_lines] g2o::Line3D [w, d]
+  size_t line_stride, point_stride; // plane strides of line_wd and point_xyz (>= n_lines, >= n_points)
+  const double* line_wd;   // [6][line_stride] g2o::Line3D [w, d]
   const int* pt_begin;     // [n_lines + 1]
   const int* pt_index;     // [pt_begin[n_lines]] into point_xyz
-  const double* point_xyz; // [3][n_points]
+  const double* point_xyz; // [3][point_stride]
   double* endpoints;       // [6][n_lines], written where ok
   uint8_t* out_ok;         // [n_lines]
   int* n_done;
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(LINE_EP_THREADS) line_endpoints_kernel(const _
     double w[3], dd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      w[k] = d.line_wd[(size_t)k * d.n_lines + l];
-      dd[k] = d.line_wd[(size_t)(3 + k) * d.n_lines + l];
+      w[k] = d.line_wd[(size_t)k * d.line_stride + l];
+      dd[k] = d.line_wd[(size_t)(3 + k) * d.line_stride + l];
     }
     line_to_cartesian(w, dd, anchor, dir);
     if (fabs(dir[1]) > fabs(dir[0])) md = 1;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(LINE_EP_THREADS) line_endpoints_kernel(const _
     double max_d = DBL_MIN, min_d = DBL_MAX;
     while (pi >= 0) {
       BA_CHECK(pi < d.n_points);
-      const double X0 = d.point_xyz[pi], X1 = d.point_xyz[(size_t)d.n_points + pi], X2 = d.point_xyz[2 * (size_t)d.n_points + pi];
+      const double X0 = d.point_xyz[pi], X1 = d.point_xyz[d.point_stride + pi], X2 = d.point_xyz[2 * d.point_stride + pi];
       o += LINE_EP_LANES;
       pi = o < s_end ? d.pt_index[o] : -1;
       const double q0 = __dsub_rn(X0, a0), q1 = __dsub_rn(X1, a1), q2 = __dsub_rn(X2, a2);

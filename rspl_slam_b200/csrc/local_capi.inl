@@ -1402,6 +1402,61 @@ extern "C" int rspl_ba_local_batch(RsplBaContext* c, const RsplLocalBatch* in, c
   return rspl_ba_local_batch_download(c, out);
 }
 
+// ---- SURVEY 8(f) rank 2 on the resident result: the endpoint refresh of Map::UppdateMapline (map.cc:121-177) for
+// all lines of the batch just solved, reading the optimised Line3Ds and map points where the solve left them in HBM.
+// Only the CSR lists travel up (4 bytes per point reference), endpoints and flags come back.
+extern "C" int rspl_ba_local_batch_update_maplines(RsplBaContext* c, const int32_t* pt_begin, const int32_t* pt_index,
+                                                   double* endpoints, uint8_t* out_ok, int32_t* n_done) {
+  if (!c) return RSPL_BA_ERR_INVALID;
+  if (n_done) *n_done = 0;
+  if (!c->local_solved) return fail(c, RSPL_BA_ERR_STATE, "local_batch_update_maplines before solve");
+  const int n_lines = c->l_nln, n_points = c->l_npt;
+  if (n_lines == 0) return RSPL_BA_OK;
+  if (!offsets_ok(pt_begin, n_lines) || !endpoints || !out_ok) return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: bad offsets or null arrays");
+  const int n_ref = pt_begin[n_lines];
+  if (n_ref > 0 && !pt_index) return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: null point indices");
+  SetDevice guard(c->device);
+  if (!guard.ok) return fail(c, RSPL_BA_ERR_CUDA, "cudaSetDevice failed");
+  Arena a;
+  const size_t o_beg = a.take(sizeof(int) * ((size_t)n_lines + 1)), o_idx = a.take(sizeof(int) * (size_t)n_ref);
+  const size_t o_end = a.take(sizeof(double) * 6 * (size_t)n_lines), o_ok = a.take((size_t)n_lines), o_cnt = a.take(sizeof(int));
+  CU_TRY(c, c->unit_buf.reserve(a.off));
+  char* base = c->unit_buf.as<char>();
+  cudaStream_t s = c->stream;
+  CU_TRY(c, cudaMemcpyAsync(base + o_beg, pt_begin, sizeof(int) * ((size_t)n_lines + 1), cudaMemcpyHostToDevice, s));
+  if (n_ref > 0) CU_TRY(c, cudaMemcpyAsync(base + o_idx, pt_index, sizeof(int) * (size_t)n_ref, cudaMemcpyHostToDevice, s));
+  CU_TRY(c, cudaMemsetAsync(base + o_end, 0, a.off - o_end, s)); // endpoints of lines that are not refreshed read 0
+  if (!cams_ok(pt_index, n_ref, n_points)) { // (threaded range check, behind the uploads already queued)
+    cudaStreamSynchronize(s);
+    return fail(c, RSPL_BA_ERR_INVALID, "update_maplines: point index out of range");
+  }
+  ba::LineEndpointsDev d;
+  d.n_lines = n_lines;
+  d.n_points = n_points;
+  d.line_stride = (size_t)n_lines; // the result planes of the solve are dense
+  d.point_stride = (size_t)n_points;
+  d.line_wd = c->ld.k[1].lm_out;
+  d.pt_begin = (const int*)(base + o_beg);
+  d.pt_index = (const int*)(base + o_idx);
+  d.point_xyz = c->ld.k[0].lm_out;
+  d.endpoints = (double*)(base + o_end);
+  d.out_ok = (uint8_t*)(base + o_ok);
+  d.n_done = (int*)(base + o_cnt);
+  {
+    ProfScope ps(c, PC_FRAME);
+    ba::line_endpoints_kernel<<<(n_lines + ba::LINE_EP_THREADS - 1) / ba::LINE_EP_THREADS, ba::LINE_EP_THREADS, 0, s>>>(d);
+  }
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  CU_TRY(c, cudaMemcpyAsync(endpoints, base + o_end, sizeof(double) * 6 * (size_t)n_lines, cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaMemcpyAsync(out_ok, base + o_ok, (size_t)n_lines, cudaMemcpyDeviceToHost, s));
+  int cnt = 0;
+  CU_TRY(c, cudaMemcpyAsync(&cnt, base + o_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  if (n_done) *n_done = cnt;
+  return RSPL_BA_OK;
+}
+
 // ---- global BA: every rank uploads ONE window holding all poses (identical on every
 // rank) and its own share of the landmarks with all their constraints; the solve is collective over the
 // context's communicator (rspl_ba_comm_init). Upload and download are the local-batch calls.

@@ -28,6 +28,14 @@ out["frame1_pose"] = r1.pose_twc.tolist()
 probs = [synth.make_local_problem(synth.config_seed(1, 300 + i), n_kf=4 + i, n_points=120 + 40 * i, n_lines=15 + 5 * i) for i in range(3)]
 lr = ctx.local_batch(LocalBatch.from_problems(probs))
 out["local_pose"] = lr.pose_twc.tolist()
+lb = LocalBatch.from_problems(probs)
+nl, npnt = int(lb.line_begin[-1]), int(lb.point_begin[-1])
+rng = np.random.default_rng(3)
+pb = np.arange(nl + 1, dtype=np.int32) * 6
+pw = np.repeat(np.searchsorted(lb.line_begin, np.arange(nl), side="right") - 1, 6)
+pi = (lb.point_begin[pw] + rng.integers(0, 1 << 30, nl * 6) %% (lb.point_begin[pw + 1] - lb.point_begin[pw])).astype(np.int32)
+re_, rok, _ = ctx.local_update_maplines(pb, pi)
+out["resident_ends"] = [re_.tolist(), int(rok.sum())]
 out["local_inl"] = int(lr.sp_inlier.sum()) + int(lr.mp_inlier.sum()) + int(lr.sl_inlier.sum()) + int(lr.ml_inlier.sum())
 big = synth.make_global_problem(synth.config_seed(5, 1), n_kf=80, n_points=6000, n_lines=600)
 gr = ctx.local_batch(LocalBatch.from_problems([big]))

@@ -127,3 +127,44 @@ def test_update_maplines_edge_cases(gpu_ctx):
         gpu_ctx.update_maplines(wd, [0, 2, 2, 4], [0, 1, 1, 7], pts)  # point index out of range
     with pytest.raises(RsplBaError):
         gpu_ctx.update_maplines(wd, [0, 2, 1, 4], [0, 1, 1, 2], pts)  # offsets not monotone
+
+
+def _nearest_point_lists(batch, res, k=12):
+    """for every line of a solved local batch: the k map points of its own window closest to the optimised line, as
+    batch-wide indices (what Map::UppdateMapline gathers are the map points on the line in its observers)"""
+    begin, index = [0], []
+    for w in range(batch.n_windows):
+        p0, p1 = int(batch.point_begin[w]), int(batch.point_begin[w + 1])
+        X = res.point_xyz[:, p0:p1].T
+        for l in range(int(batch.line_begin[w]), int(batch.line_begin[w + 1])):
+            cart = orc.line_to_cartesian(res.line_wd[:, l])
+            dist = np.linalg.norm(np.cross(cart[3:], X - cart[:3]), axis=1)
+            near = np.argsort(dist)[:min(k, len(X)) if l % 7 else 0]  # every seventh line has no points
+            index.extend((p0 + near).tolist())
+            begin.append(len(index))
+    return np.asarray(begin, dtype=np.int32), np.asarray(index, dtype=np.int32)
+
+
+@pytest.mark.gpu
+def test_update_maplines_on_the_resident_local_ba_result(gpu_ctx):
+    """rspl_ba_local_batch_update_maplines reads the optimised lines and points where the solve left them in HBM: the
+    same bits as the host-array call on the downloaded result (and as the oracle), zeros where not refreshed."""
+    from rspl_slam_b200.problem import LocalBatch
+    probs = [synth.make_local_problem(synth.config_seed(1, 700 + i), n_kf=4 + i, n_points=400 + 100 * i, n_lines=40 + 10 * i) for i in range(4)]
+    batch = LocalBatch.from_problems(probs)
+    out = gpu_ctx.alloc_local_result(batch)
+    gpu_ctx.local_batch_upload(batch)
+    gpu_ctx.local_batch_solve()
+    gpu_ctx.local_batch_download(out)
+    begin, index = _nearest_point_lists(batch, out)
+    ends, ok, cnt = gpu_ctx.local_update_maplines(begin, index)
+    ref_ends, ref_ok, ref_cnt = orc.update_maplines(out.line_wd, begin, index, out.point_xyz)
+    assert np.array_equal(ok, ref_ok) and cnt == ref_cnt and 0 < cnt < len(ok)
+    assert np.array_equal(ends, ref_ends)  # (the oracle wrapper starts from zeros as well)
+    host_ends, host_ok, _ = gpu_ctx.update_maplines(out.line_wd, begin, index, out.point_xyz)
+    assert np.array_equal(host_ends, ends) and np.array_equal(host_ok, ok)
+    from rspl_slam_b200.capi import RsplBaError
+    bad = index.copy()
+    bad[0] = out.point_xyz.shape[1]
+    with pytest.raises(RsplBaError):
+        gpu_ctx.local_update_maplines(begin, bad)
