@@ -1,5 +1,8 @@
+#!/bin/bash
+# bcr_resident_ab.sh: global-BA tests + C5 with the cyclic-reduction variants (RSPL_BA_BCR_SLABS=1: slab-staged update kernel)
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out/bcr
-timeout 300 python -m pytest tests/test_global_gpu.py -m gpu -x -q > gpurun_out/bcr/test.log 2>&1; echo "tests rc=$?" >> gpurun_out/bcr/test.log
+timeout 600 python -m pytest tests/test_global_gpu.py tests/test_checked_build.py -m gpu -x -q > gpurun_out/bcr/test.log 2>&1; echo "tests rc=$?" >> gpurun_out/bcr/test.log
 for v in 0 1; do
   if [ $v = 1 ]; then export RSPL_BA_BCR_SLABS=1; else unset RSPL_BA_BCR_SLABS; fi
   timeout 300 python bench.py --workload c5 --steps 3 --warmup 3 > gpurun_out/bcr/c5_slabs$v.json 2> gpurun_out/bcr/c5_slabs$v.err

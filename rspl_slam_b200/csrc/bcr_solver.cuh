@@ -28,7 +28,22 @@ namespace ba {
 constexpr int BCR_THREADS = 512;
 constexpr int BCR_BS_MAX = 144;    // unknowns per super-block (24 poses): the factor of a block lives in shared memory
 constexpr int BCR_MAX_LEVELS = 20;
-constexpr int BCR_KC = 30;         // rows per staged slab of bcr_update
+constexpr int BCR_KC = 30;
+// -DRSPL_BCR_CLOCKS: phase clocks of CTA 0 of bcr_eliminate (profiles/scripts/bcr_phase_clocks.sh); off in the product
+#ifdef RSPL_BCR_CLOCKS
+__device__ long long bcr_clk[12];
+__device__ long long bcr_t0;
+#define BCR_CLK(i)                                 \
+  do {                                             \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {     \
+      const long long t_ = clock64();              \
+      bcr_clk[i] += t_ - bcr_t0;                   \
+      bcr_t0 = t_;                                 \
+    }                                              \
+  } while (0)
+#else
+#define BCR_CLK(i) do { } while (0)
+#endif         // rows per staged slab of bcr_update
 
 struct BcrDev {
   int M, bs, n;       // super-blocks, unknowns per super-block, system size
@@ -73,60 +88,142 @@ __device__ __forceinline__ bool bcr_chol6(const double* Ls, int ld, int k0, doub
   return ok;
 }
 
-// In-place lower Cholesky of the n x n matrix in shared memory (n a multiple of 6), whole CTA, three barriers per
-// 6-column panel. The strictly upper part is not touched; dinv [n] receives the reciprocal diagonal of the factor.
-// *s_fail is set on a pivot <= 0.
-__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s_fail) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  for (int k0 = 0; k0 < n; k0 += 6) {
-    double Lk[6][6], inv[6];
-    if (!bcr_chol6(Ls, ld, k0, Lk, inv)) *s_fail = 1; // (benign race: every thread writes the same value)
-    __syncthreads();                                  // everyone has read the diagonal block
-    // (static indices, one writer: a thread-dependent index into Lk moves the whole block to local memory -- 336 bytes
-    // of stack traffic per thread and panel; it made kb_solve, bcr_eliminate and bcr_root 1.3 - 1.6 x slower)
-    {
-      // thread r * 6 + c publishes L[r][c]: the value is picked with a select chain over static indices, the store
-      // itself has a computed address
-      double v = 0.0, iv = 0.0;
+// Factor of the 6 x 6 diagonal block at k0 by ONE warp (every lane redundantly, in registers), written back in place
+// together with the reciprocal diagonal and, when LinvS != null, the inverse of the block's factor (lower triangle
+// of LinvS[(k0 / 6) * 36 + r * 6 + c]; the entries above the diagonal are never read).
+// (static register indices only: the published value is picked with a select chain, the store has a computed address
+// -- a lane-dependent index into Lk moves the whole block to local memory, 1.3 - 1.6 x slower kernels)
+__device__ __forceinline__ void bcr_diag_block(double* Ls, int ld, int k0, double* dinv, int* s_fail, double* LinvS) {
+  const int lane = threadIdx.x & 31;
+  double Lk[6][6], inv[6];
+  if (!bcr_chol6(Ls, ld, k0, Lk, inv)) *s_fail = 1; // (benign race: every lane writes the same value)
+  __syncwarp();                                     // every lane has read the block
+  // lane e < 21 owns the lower-triangle entry (r, c), e = r (r + 1) / 2 + c; lanes 21..26 own inv[lane - 21]
+  const int r = (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15), c = lane - r * (r + 1) / 2;
+  double v = 0.0, iv = 0.0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
+  for (int rr = 0; rr < 6; ++rr) {
 #pragma unroll
-        for (int c = 0; c <= r; ++c) v = tid == r * 6 + c ? Lk[r][c] : v;
-        iv = tid == r * 7 ? inv[r] : iv;
-      }
-      const int r = tid / 6, c = tid - 6 * r;
-      if (tid < 36 && c <= r) {
-        Ls[(k0 + r) * ld + k0 + c] = v;
-        if (c == r) dinv[k0 + r] = iv;
+    for (int cc = 0; cc <= rr; ++cc) v = lane == rr * (rr + 1) / 2 + cc ? Lk[rr][cc] : v;
+    iv = lane == 21 + rr ? inv[rr] : iv;
+  }
+  if (lane < 21) Ls[(k0 + r) * ld + k0 + c] = v;
+  else if (lane < 27) dinv[k0 + lane - 21] = iv;
+  if (LinvS != nullptr) {
+    double Li[6][6];
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) {
+#pragma unroll
+      for (int rr = 0; rr < 6; ++rr) Li[rr][cc] = 0.0;
+      Li[cc][cc] = inv[cc];
+#pragma unroll
+      for (int rr = cc + 1; rr < 6; ++rr) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = cc; q < rr; ++q) acc += Lk[rr][q] * Li[q][cc];
+        Li[rr][cc] = -acc * inv[rr];
       }
     }
-    for (int i = k0 + 6 + tid; i < n; i += nt) { // panel: X Lkk^T = A, one thread per row
-      double xr[6];
+    double w = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+      for (int cc = 0; cc <= rr; ++cc) w = lane == rr * (rr + 1) / 2 + cc ? Li[rr][cc] : w;
+    if (lane < 21) LinvS[(k0 / 6) * 36 + r * 6 + c] = w;
+  }
+}
+
+// In-place lower Cholesky of the n x n matrix in shared memory (n a multiple of 6), whole CTA, two barriers per
+// 6-column panel. The strictly upper part is not touched; dinv [n] receives the reciprocal diagonal of the factor.
+// *s_fail is set on a pivot <= 0. LinvS != null: also receives the inverses of the 6 x 6 diagonal blocks of the factor
+// (what bcr_cta_forward_inv multiplies with instead of substituting).
+// Look-ahead: while warps 1.. apply the trailing update of panel k, warp 0 updates the NEXT diagonal block first and
+// factorises it, so the serial 6 x 6 factorisation (six dependent rsqrt chains, formerly run redundantly by all
+// warps between two barriers: 2100 of the 5500 cycles of a panel step in bcr_eliminate) is off the critical path.
+// Every entry sees the same operations in the same order as before: same bits.
+__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s_fail, double* LinvS = nullptr) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  if (warp == 0) bcr_diag_block(Ls, ld, 0, dinv, s_fail, LinvS);
+  __syncthreads();
+  BCR_CLK(1);
+  for (int k0 = 0; k0 < n; k0 += 6) {
+    if (k0 + 6 + tid < n) { // panel: X Lkk^T = A, one thread per row; Lkk broadcast from shared memory
+      double Lk[6][6], inv[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        double v = Ls[i * ld + k0 + c];
+        inv[c] = dinv[k0 + c];
 #pragma unroll
-        for (int q = 0; q < c; ++q) v -= xr[q] * Lk[c][q];
-        xr[c] = v * inv[c];
+        for (int q = 0; q < c; ++q) Lk[c][q] = Ls[(k0 + c) * ld + k0 + q];
       }
+      for (int i = k0 + 6 + tid; i < n; i += nt) {
+        double xr[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) Ls[i * ld + k0 + c] = xr[c];
-    }
-    __syncthreads();
-    // trailing update of the lower triangle: a warp per row i, lanes over the columns j <= i
-    for (int i = k0 + 6 + warp; i < n; i += nw) {
-      double pi[6];
+        for (int c = 0; c < 6; ++c) {
+          double v = Ls[i * ld + k0 + c];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) pi[q] = Ls[i * ld + k0 + q];
-      for (int j = k0 + 6 + lane; j <= i; j += 32) {
-        const double* pj = Ls + j * ld + k0;
-        double v = Ls[i * ld + j];
+          for (int q = 0; q < c; ++q) v -= xr[q] * Lk[c][q];
+          xr[c] = v * inv[c];
+        }
 #pragma unroll
-        for (int q = 0; q < 6; ++q) v -= pi[q] * pj[q];
-        Ls[i * ld + j] = v;
+        for (int c = 0; c < 6; ++c) Ls[i * ld + k0 + c] = xr[c];
       }
     }
     __syncthreads();
+    BCR_CLK(2);
+    const int k1 = k0 + 6;
+    if (warp == 0 || nw == 1) {
+      if (k1 < n) { // the next diagonal block: lane e < 21 updates its entry (r, c), then the warp factorises it
+        const int r = (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15), c = lane - r * (r + 1) / 2;
+        if (lane < 21) {
+          double v = Ls[(k1 + r) * ld + k1 + c];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) v -= Ls[(k1 + r) * ld + k0 + q] * Ls[(k1 + c) * ld + k0 + q];
+          Ls[(k1 + r) * ld + k1 + c] = v;
+        }
+        __syncwarp();
+        bcr_diag_block(Ls, ld, k1, dinv, s_fail, LinvS);
+      }
+    }
+    if (warp != 0 || nw == 1) {
+      // trailing update of the rows below the next diagonal block: a warp per row pair, lanes over the columns j <= i
+      const int w = nw == 1 ? 0 : warp - 1, wn = nw == 1 ? 1 : nw - 1;
+      for (int i = k1 + 6 + 2 * w; i < n; i += 2 * wn) {
+        const bool two = i + 1 < n;
+        double p0[6], p1[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          p0[q] = Ls[i * ld + k0 + q];
+          p1[q] = two ? Ls[(i + 1) * ld + k0 + q] : 0.0;
+        }
+        for (int jb = k1 + lane; jb <= i + 1; jb += 64) { // two column chunks at a time (independent FMA chains)
+          double v0[2], v1[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = jb + 32 * u;
+            v0[u] = j <= i ? Ls[i * ld + j] : 0.0;
+            v1[u] = two && j <= i + 1 ? Ls[(i + 1) * ld + j] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = jb + 32 * u;
+              const double pq = j <= i + 1 ? Ls[j * ld + k0 + q] : 0.0;
+              v0[u] -= p0[q] * pq;
+              v1[u] -= p1[q] * pq;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = jb + 32 * u;
+            if (j <= i) Ls[i * ld + j] = v0[u];
+            if (two && j <= i + 1) Ls[(i + 1) * ld + j] = v1[u];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    BCR_CLK(3);
   }
 }
 
@@ -174,6 +271,77 @@ __device__ void bcr_cta_forward(const double* Ls, int ld, const double* dinv, in
   }
 }
 
+// The same with the inverted diagonal blocks of bcr_cta_cholesky: Y_k = Linv_kk X_k is a 6 x 6 product per column
+// spread over all threads (thread = (row, column)) instead of a six-step substitution on one thread per column;
+// results are held in registers across a barrier (the product is not in place). (Forming Y_{k+1} in registers by the
+// two warps that have just updated those rows saves the phase and its barriers but puts 21 more dependent FMAs and
+// broadcast loads on the step's slowest warps: measured 1.143 instead of 1.125 ms per solve -- not kept.)
+constexpr int BCR_FWD_ROUNDS = (6 * (2 * BCR_BS_MAX + 1) + BCR_THREADS - 1) / BCR_THREADS;
+__device__ void bcr_cta_forward_inv(const double* Ls, int ld, const double* LinvS, int n, double* P, int pld, int nc) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  int rr[BCR_FWD_ROUNDS], cc[BCR_FWD_ROUNDS];
+#pragma unroll
+  for (int u = 0; u < BCR_FWD_ROUNDS; ++u) {
+    const int t = tid + u * nt;
+    rr[u] = t < 6 * nc ? t / nc : -1;
+    cc[u] = t - (t / nc) * nc;
+  }
+  for (int k0 = 0; k0 < n; k0 += 6) {
+    const double* Li = LinvS + (k0 / 6) * 36;
+    double yv[BCR_FWD_ROUNDS];
+#pragma unroll
+    for (int u = 0; u < BCR_FWD_ROUNDS; ++u) {
+      double acc = 0.0;
+      if (rr[u] >= 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          if (q <= rr[u]) acc += Li[rr[u] * 6 + q] * P[(k0 + q) * pld + cc[u]];
+      }
+      yv[u] = acc;
+    }
+    __syncthreads();
+    BCR_CLK(5);
+#pragma unroll
+    for (int u = 0; u < BCR_FWD_ROUNDS; ++u)
+      if (rr[u] >= 0) P[(k0 + rr[u]) * pld + cc[u]] = yv[u];
+    __syncthreads();
+    BCR_CLK(6);
+    // X_i -= L_ik Y_k. This phase is bound by shared-memory bandwidth, not latency (unrolling three column chunks for
+    // ILP changed nothing): per updated entry the row-pair version moves 40 bytes (P in, P out, three Y loads). A warp
+    // now takes a whole 6-row block (n is a multiple of 6) and half of the columns: the six Y values of a column serve
+    // six rows -- 24 bytes per entry -- and the 6 x 6 block of L stays in registers.
+    {
+      const int ntile = (n - k0 - 6) / 6;
+      const int half = ((nc + 63) / 64) * 32;
+      for (int wi = warp; wi < 2 * ntile; wi += nw) {
+        const int i = k0 + 6 + 6 * (wi >> 1);
+        const int cbeg = (wi & 1) ? half : 0, cend = (wi & 1) ? nc : (half < nc ? half : nc);
+        double l[6][6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) l[a][q] = Ls[(i + a) * ld + k0 + q];
+        for (int c = cbeg + lane; c < cend; c += 32) {
+          double y[6], v[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            y[q] = P[(k0 + q) * pld + c];
+            v[q] = P[(i + q) * pld + c];
+          }
+#pragma unroll
+          for (int q = 0; q < 6; ++q)
+#pragma unroll
+            for (int a = 0; a < 6; ++a) v[a] -= l[a][q] * y[q];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) P[(i + a) * pld + c] = v[a];
+        }
+      }
+    }
+    __syncthreads();
+    BCR_CLK(7);
+  }
+}
+
 // x = L^-T y in place (one warp, column-oriented); y in shared memory
 __device__ void bcr_warp_backward(const double* Ls, int ld, const double* dinv, int n, double* y) {
   const int lane = threadIdx.x & 31;
@@ -187,62 +355,91 @@ __device__ void bcr_warp_backward(const double* Ls, int ld, const double* dinv, 
 }
 
 // ---- level l, odd blocks: factorise and form GL, GR, g. grid = number of odd active blocks; dynamic smem =
-// (bs * ld + bs + bs * pch) doubles + 16 bytes, pch = columns of one panel chunk (>= 1, odd)
+// (bs * ld + 7 * bs + bs * pch) doubles + 16 bytes, pch = columns of one panel chunk (>= 1, odd)
 __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_constant__ BcrDev s, int level, int pch) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
-  const int bs = s.bs, ld = bcr_ld(bs), tid = threadIdx.x, nt = blockDim.x;
+  const int bs = s.bs, ld = bcr_ld(bs), tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   double* Ls = reinterpret_cast<double*>(bcr_smem);
   double* dinv = Ls + (size_t)bs * ld;
-  double* P = dinv + bs;
+  double* Linv = dinv + bs;            // [bs / 6][36]
+  double* P = Linv + (size_t)6 * bs;
   int* s_fail = reinterpret_cast<int*>(P + (size_t)bs * pch);
   const int h = 1 << level;
   const int p = 2 * blockIdx.x + 1;
-  const int I = p * h, Il = I - h, Ir = I + h;
+  const int I = p * h, Ir = I + h;
   const bool has_r = Ir < s.M;
   const size_t bb = (size_t)bs * bs;
   double* Dg = s.D + (size_t)I * bb;
   if (tid == 0) *s_fail = 0;
-  for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = Dg[idx];
-  __syncthreads();
-  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail);
-  if (*s_fail) {
-    if (tid == 0) atomicOr(s.info, 1);
-    return; // (uniform) the solve is rejected as a whole
-  }
-  for (int idx = tid; idx < bs * bs; idx += nt) { // keep the factor for the back substitution
-    const int r = idx / bs, c = idx % bs;
-    Dg[idx] = c <= r ? Ls[r * ld + c] : 0.0;
-  }
+#ifdef RSPL_BCR_CLOCKS
+  if (tid == 0 && blockIdx.x == 0) bcr_t0 = clock64();
+#endif
+  // (all copies below: a warp per row, lanes along it -- no integer division per element)
+  // The diagonal block and the first panel chunk are fetched with cp.async when the kernel starts (8-byte copies: the
+  // odd leading dimensions leave the shared-memory rows 8-byte aligned only); the panel lands under the factorisation.
+  for (int r = warp; r < bs; r += nw)
+    for (int c = lane; c < bs; c += 32) cp_async8(&Ls[r * ld + c], &Dg[(size_t)r * bs + c]);
+  cp_async_commit();
   const double* El = s.E + s.eoff[level] + (size_t)(p - 1) * bb; // rows Il, columns I
   const double* Er = s.E + s.eoff[level] + (size_t)p * bb;       // rows I, columns Ir
   double* GLg = s.GL + (size_t)I * bb;
   double* GRg = s.GR + (size_t)I * bb;
   const int ncol = 2 * bs + 1; // [ E(Il,I)^T | E(I,Ir) | b_I ]
+  // panel chunk [c0, c0 + nc): columns of E(Il,I)^T are rows of E(Il,I) -- a warp per such row keeps the global reads
+  // coalesced; pch is odd, so the transposing shared-memory writes are conflict-free
+  auto stage_panel = [&](int c0, int nc) {
+    const int c1 = c0 + nc;
+    const int la = c0, lb = c1 < bs ? c1 : bs;                        // columns of E(Il,I)^T in this chunk
+    const int ra = c0 > bs ? c0 : bs, rb = c1 < 2 * bs ? c1 : 2 * bs; // columns of E(I,Ir)
+    for (int c = la + warp; c < lb; c += nw)
+      for (int r = lane; r < bs; r += 32) cp_async8(&P[r * pch + c - c0], &El[(size_t)c * bs + r]);
+    for (int r = warp; r < bs; r += nw)
+      for (int c = ra + lane; c < rb; c += 32) {
+        if (has_r) cp_async8(&P[r * pch + c - c0], &Er[(size_t)r * bs + c - bs]);
+        else P[r * pch + c - c0] = 0.0;
+      }
+    if (c1 > 2 * bs)
+      for (int r = tid; r < bs; r += nt) cp_async8(&P[r * pch + 2 * bs - c0], &s.x[(size_t)I * bs + r]);
+    cp_async_commit();
+  };
+  stage_panel(0, ncol < pch ? ncol : pch);
+  cp_async_wait<1>(); // the diagonal block
+  __syncthreads();
+  BCR_CLK(0);
+  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail, Linv);
+  if (*s_fail) {
+    cp_async_wait<0>();
+    if (tid == 0) atomicOr(s.info, 1);
+    return; // (uniform) the solve is rejected as a whole
+  }
+  for (int r = warp; r < bs; r += nw) // keep the factor for the back substitution
+    for (int c = lane; c < bs; c += 32) Dg[(size_t)r * bs + c] = c <= r ? Ls[r * ld + c] : 0.0;
   for (int c0 = 0; c0 < ncol; c0 += pch) {
     const int nc = ncol - c0 < pch ? ncol - c0 : pch;
-    // (columns of E(Il,I)^T are rows of E(Il,I): r fastest keeps those global reads coalesced; pch is odd, so the
-    // transposing shared-memory writes are conflict-free)
-    for (int idx = tid; idx < bs * nc; idx += nt) {
-      const int cl = idx / bs, r = idx - cl * bs, c = c0 + cl;
-      if (c < bs) P[r * pch + cl] = El[(size_t)c * bs + r];
-    }
-    for (int idx = tid; idx < bs * nc; idx += nt) {
-      const int r = idx / nc, cl = idx - r * nc, c = c0 + cl;
-      if (c >= 2 * bs) P[r * pch + cl] = s.x[(size_t)I * bs + r];
-      else if (c >= bs) P[r * pch + cl] = has_r ? Er[(size_t)r * bs + c - bs] : 0.0;
-    }
+    const int c1 = c0 + nc;
+    const int la = c0, lb = c1 < bs ? c1 : bs;
+    const int ra = c0 > bs ? c0 : bs, rb = c1 < 2 * bs ? c1 : 2 * bs;
+    if (c0 > 0) stage_panel(c0, nc);
+    cp_async_wait<0>();
     __syncthreads();
-    bcr_cta_forward(Ls, ld, dinv, bs, P, pch, nc);
-    for (int idx = tid; idx < bs * nc; idx += nt) {
-      const int r = idx / nc, c = c0 + idx % nc;
-      const double v = P[r * pch + idx % nc];
-      if (c < bs) GLg[(size_t)r * bs + c] = v;
-      else if (c < 2 * bs) GRg[(size_t)r * bs + c - bs] = v;
-      else s.g[(size_t)I * bs + r] = v;
+    BCR_CLK(4);
+    bcr_cta_forward_inv(Ls, ld, Linv, bs, P, pch, nc);
+    for (int r = warp; r < bs; r += nw) {
+      for (int c = la + lane; c < lb; c += 32) GLg[(size_t)r * bs + c] = P[r * pch + c - c0];
+      for (int c = ra + lane; c < rb; c += 32) GRg[(size_t)r * bs + c - bs] = P[r * pch + c - c0];
     }
+    if (c1 > 2 * bs)
+      for (int r = tid; r < bs; r += nt) s.g[(size_t)I * bs + r] = P[r * pch + 2 * bs - c0];
     __syncthreads();
+    BCR_CLK(8);
   }
-  (void)Il;
+#ifdef RSPL_BCR_CLOCKS
+  if (tid == 0 && blockIdx.x == 0 && level == 0) {
+    printf("bcr_eliminate phase clocks (CTA 0, accumulated): load %lld | chol6 %lld panel %lld trailing %lld | stage %lld | fwdA %lld fwdA-write %lld fwdB %lld | store %lld\n",
+           bcr_clk[0], bcr_clk[1], bcr_clk[2], bcr_clk[3], bcr_clk[4], bcr_clk[5], bcr_clk[6], bcr_clk[7], bcr_clk[8]);
+    for (int i = 0; i < 12; ++i) bcr_clk[i] = 0;
+  }
+#endif
 }
 
 // C[r][c] += sum_k A[k][r] B[k][c] over the bs rows of the global blocks A, B (both [bs][bs] row-major), for the

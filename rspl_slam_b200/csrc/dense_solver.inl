@@ -154,11 +154,11 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   ProfScope ps(c, PC_SOLVE);
   const size_t ld = s.bs + 1;
   const size_t lbytes = sizeof(double) * s.bs * ld;
-  int pch = (int)(((long long)c->smem_optin - 2048 - (long long)lbytes - (long long)sizeof(double) * s.bs) / (long long)(sizeof(double) * s.bs));
+  int pch = (int)(((long long)c->smem_optin - 2048 - (long long)lbytes - (long long)sizeof(double) * 7 * s.bs) / (long long)(sizeof(double) * s.bs));
   if (pch > 2 * s.bs + 1) pch = 2 * s.bs + 1;
   if (!(pch & 1)) --pch; // odd: conflict-free transposed staging
   if (pch < 1) return fail(c, RSPL_BA_ERR_UNSUPPORTED, "cyclic-reduction solver: super-block does not fit shared memory");
-  const size_t smem_el = lbytes + sizeof(double) * s.bs * (pch + 1) + 64;
+  const size_t smem_el = lbytes + sizeof(double) * s.bs * (pch + 7) + 64; // factor, dinv, inverse diagonal blocks, panel
   const size_t smem_up = sizeof(double) * (2 * ba::BCR_KC * s.bs + ba::BCR_KC) + 64;
   Ml = s.M;
   for (int l = 0; l < levels; ++l) {
