@@ -562,9 +562,9 @@ __device__ __forceinline__ void bcr_fetch_block(double* dst, const double* src, 
   for (int idx = 2 * threadIdx.x; idx < n_doubles; idx += 2 * blockDim.x) cp_async16(dst + idx, src + idx);
 }
 
-__device__ __forceinline__ void bcr_ata_resident(const double* As, const double* Bs, int bs, double (&acc)[18]) {
-  const int tc = bs / 6, tix = threadIdx.x;
-  if (tix >= (bs / 3) * tc) return;
+__device__ __forceinline__ void bcr_ata_resident(const double* As, const double* Bs, int bs, int tix, double (&acc)[18]) {
+  const int tc = bs / 6;
+  if (tix < 0) return;
   const int r0 = 3 * (tix / tc), cl = tix % tc;
 #pragma unroll 6
   for (int k = 0; k < bs; ++k) {
@@ -581,6 +581,9 @@ __device__ __forceinline__ void bcr_ata_resident(const double* As, const double*
   }
 }
 
+// grid = (even active blocks, slices): the 3 x 6 output tiles of a block are split over `slices` CTAs (blockIdx.y) when
+// the level has fewer blocks than the GPU has SMs -- the products are bound by the FP64 rate of ONE SM (2.2 M FMAs
+// per block), and every CTA fetches the same three input blocks from L2. Tiles are computed exactly as by one CTA.
 __global__ void __launch_bounds__(BCR_THREADS) bcr_update_resident(const __grid_constant__ BcrDev s, int level) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
   const int bs = s.bs, tid = threadIdx.x;
@@ -596,6 +599,9 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update_resident(const __grid_
   const int J = p * h, Il = J - h, Ir = J + h;
   const bool has_l = p > 0, has_r = Ir < s.M, has_n = has_r && J + 2 * h < s.M;
   const int tc = bs / 6, ntiles = (bs / 3) * tc;
+  const int per = (ntiles + (int)gridDim.y - 1) / (int)gridDim.y; // tiles of this slice: [slice * per, ...)
+  const int tix = tid < per && (int)blockIdx.y * per + tid < ntiles ? (int)blockIdx.y * per + tid : -1;
+  const bool vec = blockIdx.y == 0 && tid < bs; // slice 0 also updates the right-hand side
   if (has_l) {
     bcr_fetch_block(S0, s.GR + (size_t)Il * bb, (int)bb);
     bcr_fetch_block(gl, s.g + (size_t)Il * bs, bs);
@@ -615,20 +621,20 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update_resident(const __grid_
   cp_async_wait<2>();
   __syncthreads();
   if (has_l) {
-    if (tid < bs)
+    if (vec)
       for (int k = 0; k < bs; ++k) vl += S0[k * bs + tid] * gl[k];
-    bcr_ata_resident(S0, S0, bs, acc);
+    bcr_ata_resident(S0, S0, bs, tix, acc);
   }
   cp_async_wait<1>();
   __syncthreads();
   if (has_r) {
-    if (tid < bs)
+    if (vec)
       for (int k = 0; k < bs; ++k) vr += S1[k * bs + tid] * gr[k];
-    bcr_ata_resident(S1, S1, bs, acc);
+    bcr_ata_resident(S1, S1, bs, tix, acc);
   }
-  if (tid < bs) s.x[(size_t)J * bs + tid] -= vl + vr;
-  const int r0 = 3 * (tid / tc), cl = tid % tc;
-  if (tid < ntiles) {
+  if (vec) s.x[(size_t)J * bs + tid] -= vl + vr;
+  const int r0 = tix >= 0 ? 3 * (tix / tc) : 0, cl = tix >= 0 ? tix % tc : 0;
+  if (tix >= 0) {
     double* Dg = s.D + (size_t)J * bb;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -640,8 +646,8 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_update_resident(const __grid_
   if (has_n) {
 #pragma unroll
     for (int q = 0; q < 18; ++q) acc[q] = 0.0;
-    bcr_ata_resident(S1, S2, bs, acc);
-    if (tid < ntiles) {
+    bcr_ata_resident(S1, S2, bs, tix, acc);
+    if (tix >= 0) {
       double* En = s.E + s.eoff[level + 1] + (size_t)(p / 2) * bb;
 #pragma unroll
       for (int a = 0; a < 3; ++a)

@@ -164,7 +164,11 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   for (int l = 0; l < levels; ++l) {
     const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
     if (n_odd > 0) ba::bcr_eliminate<<<n_odd, ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
-    if (bcr_update_is_resident(c, s.bs)) ba::bcr_update_resident<<<n_even, ba::BCR_THREADS, ba::bcr_resident_smem(s.bs), st>>>(s, l);
+    if (bcr_update_is_resident(c, s.bs)) {
+      int slices = 1; // output tiles of a block over several CTAs while the level leaves SMs idle
+      while (slices < 4 && n_even * slices * 2 <= c->num_sms) slices *= 2;
+      ba::bcr_update_resident<<<dim3(n_even, slices), ba::BCR_THREADS, ba::bcr_resident_smem(s.bs), st>>>(s, l);
+    }
     else if (ba::bcr_tiles_per_thread(s.bs) == 1) ba::bcr_update<1><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
     else ba::bcr_update<ba::BCR_TILES_PER_THREAD><<<n_even, ba::BCR_THREADS, smem_up, st>>>(s, l);
     c->launches += 2;
