@@ -1,5 +1,5 @@
 mkdir -p gpurun_out/la
-timeout 900 python -m pytest tests/test_global_gpu.py -m gpu -x -q > gpurun_out/la/test2.log 2>&1; echo "tests rc=$?" >> gpurun_out/la/test2.log
+timeout 900 python -m pytest tests/test_global_gpu.py tests/test_checked_build.py -m gpu -x -q > gpurun_out/la/test2.log 2>&1; echo "tests rc=$?" >> gpurun_out/la/test2.log
 timeout 300 python bench.py --workload c5 --steps 3 --warmup 3 > gpurun_out/la/c5.json 2> gpurun_out/la/c5.err
 timeout 300 python bench.py --workload c1 --steps 20 --warmup 3 > gpurun_out/la/c1.json 2> gpurun_out/la/c1.err
 bash profiles/scripts/bcr_phase_clocks.sh | tail -1

@@ -35,7 +35,7 @@ __device__ long long bcr_clk[12];
 __device__ long long bcr_t0;
 #define BCR_CLK(i)                                 \
   do {                                             \
-    if (threadIdx.x == 0 && blockIdx.x == 0) {     \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { \
       const long long t_ = clock64();              \
       bcr_clk[i] += t_ - bcr_t0;                   \
       bcr_t0 = t_;                                 \
@@ -48,7 +48,9 @@ __device__ long long bcr_t0;
 struct BcrDev {
   int M, bs, n;       // super-blocks, unknowns per super-block, system size
   int levels;
-  double* D;          // [M][bs*bs] row-major, full storage; overwritten by the lower Cholesky factor when eliminated
+  double* D;          // [M][bs*bs] row-major, full storage
+  double* F;          // [M][bs*bs] lower Cholesky factor of an eliminated block (its own array: the column slices of
+                      // bcr_eliminate all read D while slice 0 writes the factor)
   double* E;          // coupling blocks of every level: E + eoff[l] + p * bs*bs = rows of active block p, columns of p + 1
   long long eoff[BCR_MAX_LEVELS];
   double* GL;         // [M][bs*bs]  L^-1 E(Il,I)^T   (rows I, columns Il)
@@ -354,7 +356,8 @@ __device__ void bcr_warp_backward(const double* Ls, int ld, const double* dinv, 
   }
 }
 
-// ---- level l, odd blocks: factorise and form GL, GR, g. grid = number of odd active blocks; dynamic smem =
+// ---- level l, odd blocks: factorise and form GL, GR, g. grid = (number of odd active blocks, column slices: the
+// 2 bs + 1 panel columns are split over the slices while the level leaves SMs idle); dynamic smem =
 // (bs * ld + 7 * bs + bs * pch) doubles + 16 bytes, pch = columns of one panel chunk (>= 1, odd)
 __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_constant__ BcrDev s, int level, int pch) {
   extern __shared__ __align__(16) unsigned char bcr_smem[];
@@ -369,10 +372,10 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
   const int I = p * h, Ir = I + h;
   const bool has_r = Ir < s.M;
   const size_t bb = (size_t)bs * bs;
-  double* Dg = s.D + (size_t)I * bb;
+  const double* Dg = s.D + (size_t)I * bb;
   if (tid == 0) *s_fail = 0;
 #ifdef RSPL_BCR_CLOCKS
-  if (tid == 0 && blockIdx.x == 0) bcr_t0 = clock64();
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) bcr_t0 = clock64();
 #endif
   // (all copies below: a warp per row, lanes along it -- no integer division per element)
   // The diagonal block and the first panel chunk are fetched with cp.async when the kernel starts (8-byte copies: the
@@ -402,7 +405,10 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
       for (int r = tid; r < bs; r += nt) cp_async8(&P[r * pch + 2 * bs - c0], &s.x[(size_t)I * bs + r]);
     cp_async_commit();
   };
-  stage_panel(0, ncol < pch ? ncol : pch);
+  // column slice of this CTA (gridDim.y slices; every slice factorises the block itself)
+  const int per = (ncol + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int cA = (int)blockIdx.y * per, cB = cA + per < ncol ? cA + per : ncol;
+  stage_panel(cA, cB - cA < pch ? cB - cA : pch);
   cp_async_wait<1>(); // the diagonal block
   __syncthreads();
   BCR_CLK(0);
@@ -412,14 +418,17 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
     if (tid == 0) atomicOr(s.info, 1);
     return; // (uniform) the solve is rejected as a whole
   }
-  for (int r = warp; r < bs; r += nw) // keep the factor for the back substitution
-    for (int c = lane; c < bs; c += 32) Dg[(size_t)r * bs + c] = c <= r ? Ls[r * ld + c] : 0.0;
-  for (int c0 = 0; c0 < ncol; c0 += pch) {
-    const int nc = ncol - c0 < pch ? ncol - c0 : pch;
+  if (blockIdx.y == 0) { // keep the factor for the back substitution
+    double* Fg = s.F + (size_t)I * bb;
+    for (int r = warp; r < bs; r += nw)
+      for (int c = lane; c < bs; c += 32) Fg[(size_t)r * bs + c] = c <= r ? Ls[r * ld + c] : 0.0;
+  }
+  for (int c0 = cA; c0 < cB; c0 += pch) {
+    const int nc = cB - c0 < pch ? cB - c0 : pch;
     const int c1 = c0 + nc;
     const int la = c0, lb = c1 < bs ? c1 : bs;
     const int ra = c0 > bs ? c0 : bs, rb = c1 < 2 * bs ? c1 : 2 * bs;
-    if (c0 > 0) stage_panel(c0, nc);
+    if (c0 > cA) stage_panel(c0, nc);
     cp_async_wait<0>();
     __syncthreads();
     BCR_CLK(4);
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_eliminate(const __grid_consta
     BCR_CLK(8);
   }
 #ifdef RSPL_BCR_CLOCKS
-  if (tid == 0 && blockIdx.x == 0 && level == 0) {
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && level == 0) {
     printf("bcr_eliminate phase clocks (CTA 0, accumulated): load %lld | chol6 %lld panel %lld trailing %lld | stage %lld | fwdA %lld fwdA-write %lld fwdB %lld | store %lld\n",
            bcr_clk[0], bcr_clk[1], bcr_clk[2], bcr_clk[3], bcr_clk[4], bcr_clk[5], bcr_clk[6], bcr_clk[7], bcr_clk[8]);
     for (int i = 0; i < 12; ++i) bcr_clk[i] = 0;
@@ -696,8 +705,11 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant
   const int I = (2 * blockIdx.x + 1) * h, Il = I - h, Ir = I + h;
   const bool has_r = Ir < s.M;
   const size_t bb = (size_t)bs * bs;
-  const double* Dg = s.D + (size_t)I * bb;
-  for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = Dg[idx];
+  const double* Dg = s.F + (size_t)I * bb;
+  // the factor lands in shared memory (cp.async) while the warps form g - GL x_Il - GR x_Ir from global memory
+  for (int r = warp; r < bs; r += nt / 32)
+    for (int c = lane; c <= r; c += 32) cp_async8(&Ls[r * ld + c], &Dg[(size_t)r * bs + c]);
+  cp_async_commit();
   for (int r = tid; r < bs; r += nt) {
     dinv[r] = 1.0 / Dg[(size_t)r * bs + r];
     xl[r] = s.x[(size_t)Il * bs + r];
@@ -706,13 +718,27 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_backsub(const __grid_constant
   __syncthreads();
   const double* GLg = s.GL + (size_t)I * bb;
   const double* GRg = s.GR + (size_t)I * bb;
-  for (int r = warp; r < bs; r += nt / 32) { // one warp per row: coalesced rows of GL / GR, fixed butterfly
-    double v = 0.0;
-    for (int c = lane; c < bs; c += 32) v += GLg[(size_t)r * bs + c] * xl[c] + (has_r ? GRg[(size_t)r * bs + c] * xr[c] : 0.0);
+  // one warp per row (coalesced rows of GL / GR, fixed butterfly), three rows in flight
+  const int nw = nt / 32;
+  for (int r0 = warp; r0 < bs; r0 += 3 * nw) {
+    double v[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) y[r] = s.g[(size_t)I * bs + r] - v;
+    for (int u = 0; u < 3; ++u) {
+      const int r = r0 + u * nw;
+      if (r < bs)
+        for (int c = lane; c < bs; c += 32) v[u] += GLg[(size_t)r * bs + c] * xl[c] + (has_r ? GRg[(size_t)r * bs + c] * xr[c] : 0.0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 3; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int r = r0 + u * nw;
+      if (lane == 0 && r < bs) y[r] = s.g[(size_t)I * bs + r] - v[u];
+    }
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (tid < 32) bcr_warp_backward(Ls, ld, dinv, bs, y);
   __syncthreads();

@@ -69,13 +69,14 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
   const size_t o_dinv = a.take(sizeof(double) * ((size_t)n_max + 8));
   const size_t o_yw = a.take(sizeof(double) * ((size_t)n_max + 8));
   L.bcr_bsp = bcr_bsp;
-  size_t o_bD = 0, o_bE = 0, o_bGL = 0, o_bGR = 0, o_bg = 0;
+  size_t o_bD = 0, o_bF = 0, o_bE = 0, o_bGL = 0, o_bGR = 0, o_bg = 0;
   int bcr_M = 0;
   if (bcr_bsp) {
     const int nf = c->l_nf_begin[1] - c->l_nf_begin[0];
     bcr_M = (nf + bcr_bsp - 1) / bcr_bsp;
     const size_t bb = (size_t)36 * bcr_bsp * bcr_bsp;
     o_bD = a.take(sizeof(double) * bb * bcr_M);
+    o_bF = a.take(sizeof(double) * bb * bcr_M);
     o_bE = a.take(sizeof(double) * bb * (2 * (size_t)bcr_M + ba::BCR_MAX_LEVELS));
     o_bGL = a.take(sizeof(double) * bb * bcr_M);
     o_bGR = a.take(sizeof(double) * bb * bcr_M);
@@ -97,6 +98,7 @@ int dense_prepare(RsplBaContext* c, DenseLayout& L, const std::vector<int>& band
     s.n = 0;
     s.levels = 0;
     s.D = (double*)(base + o_bD);
+    s.F = (double*)(base + o_bF);
     s.E = (double*)(base + o_bE);
     s.GL = (double*)(base + o_bGL);
     s.GR = (double*)(base + o_bGR);
@@ -163,7 +165,11 @@ int bcr_assemble_solve(RsplBaContext* c, DenseLayout& L, int n_sys, int n_ne) {
   Ml = s.M;
   for (int l = 0; l < levels; ++l) {
     const int n_odd = Ml / 2, n_even = (Ml + 1) / 2;
-    if (n_odd > 0) ba::bcr_eliminate<<<n_odd, ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
+    if (n_odd > 0) {
+      int slices = 1; // panel columns of a block over several CTAs while the level leaves SMs idle
+      while (slices < 4 && n_odd * slices * 2 <= c->num_sms) slices *= 2;
+      ba::bcr_eliminate<<<dim3(n_odd, slices), ba::BCR_THREADS, smem_el, st>>>(s, l, pch);
+    }
     if (bcr_update_is_resident(c, s.bs)) {
       int slices = 1; // output tiles of a block over several CTAs while the level leaves SMs idle
       while (slices < 4 && n_even * slices * 2 <= c->num_sms) slices *= 2;
