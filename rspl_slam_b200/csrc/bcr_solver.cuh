@@ -143,13 +143,17 @@ __device__ __forceinline__ void bcr_diag_block(double* Ls, int ld, int k0, doubl
 // factorises it, so the serial 6 x 6 factorisation (six dependent rsqrt chains, formerly run redundantly by all
 // warps between two barriers: 2100 of the 5500 cycles of a panel step in bcr_eliminate) is off the critical path.
 // Every entry sees the same operations in the same order as before: same bits.
-__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s_fail, double* LinvS = nullptr) {
+// extra = 1: row n of the array holds a right-hand side b^T; it is carried through the panel solves and trailing
+// updates like any row below the diagonal and ends as (L^-1 b)^T -- the forward substitution without a sweep of its
+// own (same products in the same order as bcr_cta_forward: same bits).
+__device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s_fail, double* LinvS = nullptr, int extra = 0) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int nr = n + extra; // rows carried
   if (warp == 0) bcr_diag_block(Ls, ld, 0, dinv, s_fail, LinvS);
   __syncthreads();
   BCR_CLK(1);
   for (int k0 = 0; k0 < n; k0 += 6) {
-    if (k0 + 6 + tid < n) { // panel: X Lkk^T = A, one thread per row; Lkk broadcast from shared memory
+    if (k0 + 6 + tid < nr) { // panel: X Lkk^T = A, one thread per row; Lkk broadcast from shared memory
       double Lk[6][6], inv[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
@@ -157,7 +161,7 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s
 #pragma unroll
         for (int q = 0; q < c; ++q) Lk[c][q] = Ls[(k0 + c) * ld + k0 + q];
       }
-      for (int i = k0 + 6 + tid; i < n; i += nt) {
+      for (int i = k0 + 6 + tid; i < nr; i += nt) {
         double xr[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
@@ -189,28 +193,29 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s
     if (warp != 0 || nw == 1) {
       // trailing update of the rows below the next diagonal block: a warp per row pair, lanes over the columns j <= i
       const int w = nw == 1 ? 0 : warp - 1, wn = nw == 1 ? 1 : nw - 1;
-      for (int i = k1 + 6 + 2 * w; i < n; i += 2 * wn) {
-        const bool two = i + 1 < n;
+      for (int i = k1 + 6 + 2 * w; i < nr; i += 2 * wn) {
+        const bool two = i + 1 < nr;
+        const int j0max = i < n ? i : n - 1, j1max = i + 1 < n ? i + 1 : n - 1; // (a right-hand-side row has n columns)
         double p0[6], p1[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
           p0[q] = Ls[i * ld + k0 + q];
           p1[q] = two ? Ls[(i + 1) * ld + k0 + q] : 0.0;
         }
-        for (int jb = k1 + lane; jb <= i + 1; jb += 64) { // two column chunks at a time (independent FMA chains)
+        for (int jb = k1 + lane; jb <= j1max; jb += 64) { // two column chunks at a time (independent FMA chains)
           double v0[2], v1[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int j = jb + 32 * u;
-            v0[u] = j <= i ? Ls[i * ld + j] : 0.0;
-            v1[u] = two && j <= i + 1 ? Ls[(i + 1) * ld + j] : 0.0;
+            v0[u] = j <= j0max ? Ls[i * ld + j] : 0.0;
+            v1[u] = two && j <= j1max ? Ls[(i + 1) * ld + j] : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int j = jb + 32 * u;
-              const double pq = j <= i + 1 ? Ls[j * ld + k0 + q] : 0.0;
+              const double pq = j <= j1max ? Ls[j * ld + k0 + q] : 0.0;
               v0[u] -= p0[q] * pq;
               v1[u] -= p1[q] * pq;
             }
@@ -218,8 +223,8 @@ __device__ void bcr_cta_cholesky(double* Ls, int ld, int n, double* dinv, int* s
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int j = jb + 32 * u;
-            if (j <= i) Ls[i * ld + j] = v0[u];
-            if (two && j <= i + 1) Ls[(i + 1) * ld + j] = v1[u];
+            if (j <= j0max) Ls[i * ld + j] = v0[u];
+            if (two && j <= j1max) Ls[(i + 1) * ld + j] = v1[u];
           }
         }
       }
@@ -344,9 +349,39 @@ __device__ void bcr_cta_forward_inv(const double* Ls, int ld, const double* Linv
   }
 }
 
-// x = L^-T y in place (one warp, column-oriented); y in shared memory
+// x = L^-T y in place (one warp, column-oriented); y in shared memory. For n <= 160 the vector lives in registers
+// (entry j in lane j % 32, slot j / 32) and x_i is broadcast by a shuffle: the dependent chain of a step is
+// FMA -> SHFL -> MUL instead of two shared-memory round trips and two warp barriers (60 - 156 serial steps per solve
+// of a local window). Same operations on every entry in the same order: same bits.
+constexpr int BCR_BACK_SLOTS = 5;
 __device__ void bcr_warp_backward(const double* Ls, int ld, const double* dinv, int n, double* y) {
   const int lane = threadIdx.x & 31;
+  if (n <= 32 * BCR_BACK_SLOTS) {
+    double yr[BCR_BACK_SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < BCR_BACK_SLOTS; ++sl) yr[sl] = sl * 32 + lane < n ? y[sl * 32 + lane] : 0.0;
+#pragma unroll
+    for (int sl = BCR_BACK_SLOTS - 1; sl >= 0; --sl) {
+      if (sl * 32 >= n) continue; // (uniform)
+      const int top = n - 1 - sl * 32 < 31 ? n - 1 - sl * 32 : 31;
+      for (int il = top; il >= 0; --il) {
+        const int i = sl * 32 + il;
+        const double* Li = Ls + i * ld;
+        const double xi = __shfl_sync(0xffffffffu, yr[sl], il) * dinv[i];
+        if (lane == il) yr[sl] = xi;
+#pragma unroll
+        for (int s2 = 0; s2 <= sl; ++s2) {
+          const int j = s2 * 32 + lane;
+          if (j < i) yr[s2] -= Li[j] * xi;
+        }
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < BCR_BACK_SLOTS; ++sl)
+      if (sl * 32 + lane < n) y[sl * 32 + lane] = yr[sl];
+    __syncwarp();
+    return;
+  }
   for (int i = n - 1; i >= 0; --i) {
     const double xi = y[i] * dinv[i];
     __syncwarp();
@@ -679,12 +714,11 @@ __global__ void __launch_bounds__(BCR_THREADS) bcr_root(const __grid_constant__ 
   for (int idx = tid; idx < bs * bs; idx += nt) Ls[(idx / bs) * ld + idx % bs] = s.D[idx];
   for (int r = tid; r < bs; r += nt) y[r] = s.x[r];
   __syncthreads();
-  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail);
+  bcr_cta_cholesky(Ls, ld, bs, dinv, s_fail, nullptr, 1); // (y is row bs of the array: forward substitution included)
   if (*s_fail) {
     if (tid == 0) atomicOr(s.info, 1);
     return;
   }
-  bcr_cta_forward(Ls, ld, dinv, bs, y, 1, 1);
   if (tid < 32) bcr_warp_backward(Ls, ld, dinv, bs, y);
   __syncthreads();
   for (int r = tid; r < bs; r += nt) s.x[r] = y[r];

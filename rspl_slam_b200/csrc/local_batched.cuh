@@ -1265,11 +1265,10 @@ __global__ void __launch_bounds__(256) kb_solve(const __grid_constant__ LocalDev
   }
   __syncthreads();
   if (n > 0) {
-    bcr_cta_cholesky(Hs, ld, n, dinv, &s_fail); // fails iff a pivot <= 0, like LinearSolverEigen (§9.11)
-    if (!s_fail) {
-      bcr_cta_forward(Hs, ld, dinv, n, xs, 1, 1);
-      if (tid < 32) bcr_warp_backward(Hs, ld, dinv, n, xs);
-    }
+    // fails iff a pivot <= 0, like LinearSolverEigen (§9.11); xs is row n of the array: the right-hand side rides
+    // through the factorisation (forward substitution included)
+    bcr_cta_cholesky(Hs, ld, n, dinv, &s_fail, nullptr, 1);
+    if (!s_fail && tid < 32) bcr_warp_backward(Hs, ld, dinv, n, xs);
     __syncthreads();
     if (tid == 0) s_ok = !s_fail && !s.prep_fail;
   } else if (tid == 0) {
