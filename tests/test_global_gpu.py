@@ -166,6 +166,14 @@ def test_block_tridiagonal_reduced_solve(gpu_ctx, orc, monkeypatch):
         other = gpu_ctx.local_batch(batch)
         monkeypatch.delenv(var)
         assert np.array_equal(other.sp_inlier, res.sp_inlier) and np.abs(other.pose_twc - res.pose_twc).max() < 1e-9
+    # larger super-blocks take other code paths of the cyclic reduction: 16 poses (bs = 96, the largest block the
+    # resident update kernel holds), 24 poses (bs = 144: slab-staged update with three tiles per thread, and a panel of
+    # bcr_eliminate that no longer fits shared memory in one chunk, so the column slices loop over staged chunks)
+    for poses in ("16", "24"):
+        monkeypatch.setenv("RSPL_BA_BCR_POSES", poses)
+        other = gpu_ctx.local_batch(batch)
+        monkeypatch.delenv("RSPL_BA_BCR_POSES")
+        assert np.array_equal(other.sp_inlier, res.sp_inlier) and np.abs(other.pose_twc - res.pose_twc).max() < 1e-9
     # the slab-staged cyclic-reduction update sums in the same order as the shared-memory-resident one: same bits
     monkeypatch.setenv("RSPL_BA_BCR_SLABS", "1")
     slabs = gpu_ctx.local_batch(batch)
