@@ -25,9 +25,12 @@ namespace ba {
 
 constexpr int LINE_EP_LANES = 8;
 constexpr int LINE_EP_THREADS = 128;
-#ifndef LINE_EP_MIN_BLOCKS
-#define LINE_EP_MIN_BLOCKS 1 // (register cap A/B, profiles/scripts/ends_regcap_ab.sh: 80 registers 72 us; capped to 64 / 48
-                             // registers -- 8 / 10 CTAs per SM, 40 / 96 bytes of spills -- 77 us both: not kept)
+// (register cap A/B with -DLINE_EP_MIN_BLOCKS=8 / 10, profiles/scripts/ends_regcap_ab.sh: 80 registers 72 us; capped to
+// 64 / 48 registers -- 8 / 10 CTAs per SM, 40 / 96 bytes of spills -- 77 us both: not kept)
+#ifdef LINE_EP_MIN_BLOCKS
+#define LINE_EP_BOUNDS __launch_bounds__(LINE_EP_THREADS, LINE_EP_MIN_BLOCKS)
+#else
+#define LINE_EP_BOUNDS __launch_bounds__(LINE_EP_THREADS)
 #endif
 
 struct LineEndpointsDev {
@@ -105,7 +108,7 @@ BA_DEV void line_to_cartesian(const double (&w)[3], const double (&d)[3], double
 // and later writes the endpoints (coalesced). The point segments are walked in 8 rounds of 4 lines, LINE_EP_LANES lanes
 // per line, with the owner's anchor / direction broadcast by shuffles; the first point index of every round is
 // fetched up front so that only the gathers of a round wait for each other.
-__global__ void __launch_bounds__(LINE_EP_THREADS, LINE_EP_MIN_BLOCKS) line_endpoints_kernel(const __grid_constant__ LineEndpointsDev d) {
+__global__ void LINE_EP_BOUNDS line_endpoints_kernel(const __grid_constant__ LineEndpointsDev d) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int GROUPS = 32 / LINE_EP_LANES, ROUNDS = 32 / GROUPS;
   const int lane = threadIdx.x & 31, sub = lane % LINE_EP_LANES, grp = lane / LINE_EP_LANES;
